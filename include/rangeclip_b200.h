@@ -1,0 +1,164 @@
+/*
+ * rangeclip_b200 -- C ABI of the B200 (sm_100a) kernels behind the DepthCLIP loss / evaluation
+ * hot path of jinryan/RangeCLIP.
+ *
+ * The reference has no FFI: its boundary for this path is the Python call surface
+ *   DepthUNet.compute_loss            RangeCLIP/src/depth_segmentation_model/model.py:178-355
+ *   masked_average_pooling            model.py:15-56
+ *   prepare_image_contrast_data       dataloader.py:205-305  (area pooling: 286-304)
+ *   DepthUNet.predict                 model.py:119-175
+ *   validate_model metric loop        validate.py:88-139, finalisation 194-214
+ * Those signatures are mirrored in Python by the package `rangeclip_b200` (losses.py, pooling.py,
+ * evaluation.py); every one of them bottoms out in the entry points declared here, bound with
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named `h_*`;
+ *   - the library never allocates or frees caller-visible memory and never synchronises the
+ *     host; every call enqueues work on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = success, negative = rc_status; rc_last_error() gives the text for the
+ *     calling thread; no C++ exception crosses the ABI;
+ *   - pixel embeddings are the reference's NCHW tensor viewed as [B][D][HW] (HW contiguous),
+ *     element type given by an rc_dtype; `ld_b` = elements between images (normally D*HW).
+ */
+#ifndef RANGECLIP_B200_H_
+#define RANGECLIP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RC_ABI_VERSION 1
+
+typedef enum { RC_F32 = 0, RC_BF16 = 1 } rc_dtype;
+
+typedef enum {
+  RC_OK = 0,
+  RC_ERR_INVALID = -1,      /* bad argument (shape, alignment, null pointer)          */
+  RC_ERR_UNSUPPORTED = -2,  /* shape outside what the kernel family supports          */
+  RC_ERR_CUDA = -3,         /* CUDA runtime / driver error at launch                  */
+  RC_ERR_NO_DEVICE = -4     /* no sm_100 device / driver entry point not available    */
+} rc_status;
+
+int rc_abi_version(void);
+const char* rc_last_error(void);
+/* Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */
+int64_t rc_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pixel-text / area-image InfoNCE  (replaces model.py:272-291 fwd and its autograd; 304-321)
+ *
+ *   z[p,k] = <x_p / max(|x_p|, 1e-12), t_k> * inv_tau         t = L2-normalised rows [K][D]
+ *   loss   = sum_p w_p (lse_p - z[p, y_p]) / sum_p w_p          y_p = -1 or w_p = 0: ignored
+ *
+ * `w` carries the reference's sampling-with-replacement multiplicities (model.py:220-228).
+ * Accumulators (`loss_sum`, `w_sum`, `dlogtau`) are double[1] each and are ADDED to (zero them).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Workspace bytes rc_infonce_* needs for the given problem (bf16 tensor-core path only). */
+int64_t rc_infonce_workspace_bytes(int B, int D, int64_t HW, int K, rc_dtype x_dtype);
+
+/* fp32 CUDA-core path (any K >= 1, D % 8 == 0, D <= 512).  Parity path: 1e-5 relative.
+ *   dx (nullable) [B][D][HW] f32 = grad_scale * d(loss)/dx, dt (nullable) [K][D] f32 ADDED to.
+ *   w_sum_in: device double[1] holding sum_p w_p (needed when dx/dt/dlogtau are requested);
+ *   grad_scale: device float[1] upstream gradient (nullable = 1).                             */
+int rc_infonce_f32(const float* x, int B, int D, int64_t HW, int64_t ld_b,
+                   const float* t, int K, const int32_t* y, const float* w, float inv_tau,
+                   float* lse, double* loss_sum, double* w_sum,
+                   const double* w_sum_in, const float* grad_scale,
+                   float* dx, float* dt, double* dlogtau, void* stream);
+
+/* bf16 tcgen05/TMEM path (K <= 256, D % 64 == 0, D <= 512, HW % 8 == 0).
+ *   x        [B][D][HW] f32 or bf16 (x_dtype); f32 input is rounded to bf16 by the pre-pass
+ *   t_bf16   [Kp][D] bf16 normalised rows, Kp = K rounded up to 64, pad rows zero
+ *   tt_bf16  [D][Kp] bf16 = transpose of t_bf16 (operand of the dX GEMM)
+ *   dx       nullable; same dtype as x; = grad_scale * w_p/sum(w) * d(lse_p - z_py)/dx
+ *   dt       nullable [K][D] f32, ADDED to (second kernel, recomputes S slice-wise)
+ *   workspace from rc_infonce_workspace_bytes; holds bf16 copy of x (f32 input) and 1/|x|.   */
+int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
+                    const void* t_bf16, const void* tt_bf16, int K,
+                    const int32_t* y, const float* w, float inv_tau,
+                    float* lse, double* loss_sum, double* w_sum,
+                    const double* w_sum_in, const float* grad_scale,
+                    void* dx, float* dt, double* dlogtau,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Helpers used by both paths.
+ * rc_text_prepare: rows of `text[idx[k]]` (idx nullable = identity) are L2-normalised
+ *   (F.normalize, eps 1e-12; model.py:272) and written as f32 [K][D] (nullable), bf16 [Kp][D]
+ *   (nullable) and transposed bf16 [D][Kp] (nullable), Kp = round_up(K, 64), pads zeroed.
+ * rc_weight_sum: w_sum[0] += sum_p w_p * (y_p >= 0)  (double).
+ * rc_sample_weights: w[b][p] = multiplicity of p in rand_idx[b][:] * (seg[b][p] > 0), and
+ *   y[b][p] = map[seg[b][p]] (or -1 where seg == 0) -- the dense form of model.py:220-228,276-278.
+ * rc_scale: in-place x *= s[0] (device scalar) for a late upstream gradient. */
+int rc_text_prepare(const float* text, int64_t ld_text, const int64_t* idx, int K, int D,
+                    float* t_f32, void* t_bf16, void* tt_bf16, void* stream);
+int rc_weight_sum(const float* w, const int32_t* y, int64_t n, double* w_sum, void* stream);
+int rc_sample_weights(const int64_t* seg, const int64_t* rand_idx, int B, int64_t HW, int64_t n_samples,
+                      const int32_t* map, int C, float* w, int32_t* y, void* stream);
+int rc_scale(void* x, rc_dtype dtype, int64_t n, const float* s, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Segment-masked average pooling  (replaces dataloader.py:286-304 and model.py:36-54)
+ *   slot = lut[b * lut_ld + seg[b][p]]  (lut_ld = 0: one LUT for the whole batch, model.py:15)
+ *   sum[slot][d] += x[b][d][p], count[slot] += 1; rc_pool_finish divides (zeros when empty).
+ * ------------------------------------------------------------------------------------------- */
+int rc_pool_fwd(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
+                const int64_t* seg, const int32_t* lut, int64_t lut_ld, int C, int n_slots,
+                float* sum /*[n][D], zeroed*/, int32_t* count /*[n], zeroed*/, void* stream);
+int rc_pool_finish(float* sum_inout, const int32_t* count, int n_slots, int D, void* stream);
+/* dx[b][d][p] = g[slot][d] / count[slot] (0 where slot < 0); dx dtype = x_dtype. */
+int rc_pool_bwd(const float* g, const int32_t* count, int B, int D, int64_t HW,
+                const int64_t* seg, const int32_t* lut, int64_t lut_ld, int C, int n_slots,
+                void* dx, rc_dtype x_dtype, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Smoothness (TV-L1)  (replaces model.py:332-334 and its autograd)
+ *   sums[0] += sum |x[..,w]-x[..,w+1]|, sums[1] += sum |x[..,h,:]-x[..,h+1,:]|  (double[2])
+ *   bwd: dx (=|+=) scale_h * d(sum_h)/dx + scale_v * d(sum_v)/dx, sign(0) = 0;
+ *        scales are device floats scale[2]; when dx_scale (device float[1], nullable) is given
+ *        and accumulate != 0 the existing dx is first multiplied by it (fused late upstream
+ *        scaling of the InfoNCE gradient).
+ * ------------------------------------------------------------------------------------------- */
+int rc_tv_fwd(const void* x, rc_dtype x_dtype, int64_t planes, int H, int W, double* sums, void* stream);
+int rc_tv_bwd(const void* x, rc_dtype x_dtype, int64_t planes, int H, int W, const float* scale,
+              void* dx, int accumulate, const float* dx_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Evaluation  (replaces model.py:164-173 and validate.py:88-139)
+ * rc_eval_topk_f32 / rc_eval_topk_bf16: top-k (k <= 8) text ids per pixel by cosine logit,
+ *   ties broken towards the smaller reduced index; out[b][j][p] = index_map[arg] (int64).
+ * rc_eval_hist: per-batch histograms over equivalence classes
+ *   hist[0][L]=#(ge==L) hist[1][L]=#(p1==L) hist[2][L]=#(ge==L & p1==L)
+ *   hist[3][L]=#(oracle==L) hist[4][L]=#(ge==L & oracle==L); counters {correct_top1,
+ *   correct_topk, total}; all int64, ADDED to.
+ * rc_eval_fold: fold one batch's hist into the running accumulators with the reference's
+ *   per-batch label-presence rule (validate.py:108) and record first-seen batch per label.
+ * ------------------------------------------------------------------------------------------- */
+int rc_eval_topk_f32(const float* x, int B, int D, int64_t HW, int64_t ld_b, const float* t, int K,
+                     const int64_t* index_map, int k, int64_t* out, void* stream);
+int rc_eval_topk_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
+                      const void* t_bf16, int K, const int64_t* index_map, int k, int64_t* out,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+int rc_eval_hist(const int64_t* gt, const int64_t* topk, int B, int64_t HW, int k,
+                 const uint8_t* E, const int64_t* cmap, int C,
+                 int64_t* hist /*[5][C]*/, int64_t* counters /*[3]*/, void* stream);
+int rc_eval_fold(const int64_t* batch_hist /*[5][C]*/, int C, int32_t batch_index,
+                 int64_t* acc /*[4][C]: I1,U1,IK,UK*/, int32_t* first_seen /*[C], init INT32_MAX*/,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Debug / bring-up: one 128 x N x Kd bf16 GEMM tile through the same TMA + tcgen05 + TMEM
+ * building blocks (descriptor variants selected by `variant`), C[128][N] f32 row-major.
+ *   variant 0: A K-major [128][Kd], B K-major [N][Kd]
+ *   variant 1: A MN-major [Kd][128] (the NCHW pixel operand), B K-major [N][Kd]
+ * ------------------------------------------------------------------------------------------- */
+int rc_debug_umma_gemm(const void* a_bf16, const void* b_bf16, int N, int Kd, int variant,
+                       float* c, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RANGECLIP_B200_H_ */

@@ -1,0 +1,643 @@
+// K1/K2: fused pixel-text InfoNCE forward + backward on the 5th-gen tensor cores (sm_100a).
+//
+// Replaces model.py:272-291 (normalize, [N,512]@[512,K], /tau, cross_entropy) and its autograd
+// (CE backward, two matmuls, normalize backward, index_put/scatter_add) with
+//   * rownorm_kernel      one pass over X: 1/|x_p| (and the bf16 copy when X is fp32)
+//   * infonce_umma_kernel persistent, warp-specialised: per 128-pixel tile
+//        S  = X^T T^T           tcgen05.mma, A = X tile straight from NCHW (MN-major via TMA),
+//                               B = text rows (K-major via TMA), fp32 accumulators in TMEM
+//        softmax/CE epilogue    one thread per pixel reads its S row from TMEM: logsumexp, loss,
+//                               dlogtau, and P = exp(z-m) - sum*onehot written as bf16 to smem
+//        dX^T = T^T P^T          tcgen05.mma per 128-channel block, accumulators in TMEM
+//        dX epilogue            row scale + normalize-backward projection, TMA store to NCHW
+//     The [B*HW, K] logits never leave the SM.
+//   * infonce_dt_umma_kernel  dText = P^T Xhat, text rows sliced across CTAs, S recomputed
+//                             slice-wise from the saved logsumexp (TMEM cannot hold S, dX and the
+//                             256x512 fp32 dText at once).
+#include "common.cuh"
+#include "umma.cuh"
+#include <float.h>
+
+namespace rc {
+
+using namespace umma;
+
+// ------------------------------------------------------------------------------------------------
+// host: driver entry point + tensor maps
+// ------------------------------------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const char* what) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(RC_ERR_NO_DEVICE, "%s: cuTensorMapEncodeTiled entry point unavailable", what);
+  cuuint64_t gdim[3];
+  cuuint64_t gstr[2];
+  cuuint32_t bx[3];
+  cuuint32_t es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i + 1];
+  const CUtensorMapSwizzle sw = (box[0] * 2 >= 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (box[0] * 2 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                     : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RC_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+  return RC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pre-pass: inverse row norms of the bf16-rounded rows (+ bf16 copy of an fp32 input)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+rownorm_kernel(const T* __restrict__ x, int B, int D, int64_t HW, __nv_bfloat16* __restrict__ xb,
+               float* __restrict__ inv_norm) {
+  const int64_t groups_per_img = HW / 8;
+  const int64_t n = (int64_t)B * groups_per_img;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = g / groups_per_img;
+    const int64_t p0 = (g - b * groups_per_img) * 8;
+    const T* src = x + b * (int64_t)D * HW + p0;
+    __nv_bfloat16* dst = xb ? xb + b * (int64_t)D * HW + p0 : nullptr;
+    float ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss[j] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < D; ++d) {
+      float v[8];
+      load8(src + (int64_t)d * HW, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));   // the tensor cores see the rounded value
+        ss[j] = fmaf(v[j], v[j], ss[j]);
+      }
+      if (dst) store8(dst + (int64_t)d * HW, v);
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 1.f / fmaxf(sqrtf(ss[j]), 1e-12f);
+    store8(inv_norm + b * HW + p0, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kTilePx = 128;
+constexpr int kThreads = 384;          // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4-7 softmax, 8-11 dX epilogue
+constexpr int kStages = 2;
+constexpr int kStageBytes = 48 * 1024; // S phase: X chunk 16 KB + text chunk <= 32 KB; dX phase: <= 2 x 16 KB
+constexpr int kPBytes = 64 * 1024;     // P [128 px][<=256 k] bf16, four K-major 128B-swizzled sub-tiles
+constexpr int kStgBufs = 4;
+constexpr int kStgPx = 32;             // pixels per dX staging step
+constexpr int kStgBytes = 128 * kStgPx * 2;   // [128 d][32 px] bf16 = 8 KB
+constexpr int kTmemCols = 512;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct __align__(8) UmmaBars {
+  uint64_t full[kStages], empty[kStages];
+  uint64_t s_full, s_empty, p_full, p_empty;
+  uint64_t acc_full[2], acc_empty[2];
+  uint64_t stg_full[kStgBufs];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+constexpr int kOffP = kStages * kStageBytes;
+constexpr int kOffStg = kOffP + kPBytes;
+constexpr int kScaleBufs = 4;          // per-tile row-scale buffers (softmax runs up to 2 tiles ahead of the dX epilogue)
+constexpr int kOffScale = kOffStg + kStgBufs * kStgBytes;       // rs[4][128], cs[4][128] floats
+constexpr int kOffBars = kOffScale + 2 * kScaleBufs * 128 * 4;
+constexpr int kSmemBytes = kOffBars + (int)sizeof(UmmaBars) + 1024;   // + alignment slack
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct InfoNceParams {
+  int B, D, K, Kp;
+  int64_t HW;
+  int tiles_per_img;
+  int64_t n_tiles;
+  const float* inv_norm;
+  const int32_t* y;
+  const float* w;
+  float inv_tau;
+  const float* grad_scale;
+  const double* w_sum_in;
+  float* lse;
+  double* loss_sum;
+  double* w_sum;
+  double* dlogtau;
+};
+
+template <bool kBwd>
+__global__ void __launch_bounds__(kThreads, 1)
+infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW], box (64 px, 64 d, 1)
+                    const __grid_constant__ CUtensorMap map_t,     // T [Kp][D],    box (64 d, Kp)
+                    const __grid_constant__ CUtensorMap map_tt,    // T^T [D][Kp],  box (64 k, 128 d)
+                    const __grid_constant__ CUtensorMap map_x_e,   // X,            box (32 px, 128 d, 1)
+                    const __grid_constant__ CUtensorMap map_dx,    // dX,           box (32 px, 128 d, 1)
+                    const InfoNceParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  UmmaBars* bars = reinterpret_cast<UmmaBars*>(smem + kOffBars);
+  float* rs_s = reinterpret_cast<float*>(smem + kOffScale);          // [kScaleBufs][128]
+  float* cs_s = rs_s + kScaleBufs * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_dchunks = prm.D / 64;
+  const int n_q = prm.D / 128;
+  const int n_kchunks = prm.Kp / 64;
+  const int n_units = (n_kchunks + 1) / 2;   // dX phase pipeline units (<= 2 k-chunks each) per channel block
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x_s); tma_prefetch_desc(&map_t);
+    if (kBwd) { tma_prefetch_desc(&map_tt); tma_prefetch_desc(&map_x_e); tma_prefetch_desc(&map_dx); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 128);
+    mbar_init(&bars->p_full, 128); mbar_init(&bars->p_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 128); }
+    for (int i = 0; i < kStgBufs; ++i) mbar_init(&bars->stg_full[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t idesc_s = make_idesc_bf16(128, prm.Kp, /*A MN-major*/ 1, /*B K-major*/ 0);
+  const uint32_t idesc_d = make_idesc_bf16(128, 128, 0, 0);
+
+  if (warp == 0 && lane == 0) {
+    // =============================== TMA producer ===============================
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+      const int b = (int)(tile / prm.tiles_per_img);
+      const int px0 = (int)(tile - (int64_t)b * prm.tiles_per_img) * kTilePx;
+      for (int c = 0; c < n_dchunks; ++c, ++it) {
+        const int st = it % kStages;
+        mbar_wait(&bars->empty[st], ((it / kStages) & 1) ^ 1, 1);
+        uint8_t* sb = smem + st * kStageBytes;
+        mbar_arrive_expect_tx(&bars->full[st], 2 * 8192 + prm.Kp * 128);
+        tma_load_3d(sb, &map_x_s, &bars->full[st], px0, c * 64, b);
+        tma_load_3d(sb + 8192, &map_x_s, &bars->full[st], px0 + 64, c * 64, b);
+        tma_load_2d(sb + 16384, &map_t, &bars->full[st], c * 64, 0);
+      }
+      if (kBwd) {
+        for (int q = 0; q < n_q; ++q)
+          for (int u = 0; u < n_units; ++u, ++it) {
+            const int st = it % kStages;
+            mbar_wait(&bars->empty[st], ((it / kStages) & 1) ^ 1, 2);
+            uint8_t* sb = smem + st * kStageBytes;
+            const int nb = min(2, n_kchunks - 2 * u);
+            mbar_arrive_expect_tx(&bars->full[st], nb * 16384);
+            for (int jj = 0; jj < nb; ++jj)
+              tma_load_2d(sb + jj * 16384, &map_tt, &bars->full[st], (2 * u + jj) * 64, q * 128);
+          }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // =============================== MMA issuer ================================
+    uint32_t it = 0, lt = 0, qcount = 0;
+    for (int64_t tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
+      mbar_wait(&bars->s_empty, (lt & 1) ^ 1, 3);
+      tc_fence_after();
+      for (int c = 0; c < n_dchunks; ++c, ++it) {
+        const int st = it % kStages;
+        mbar_wait(&bars->full[st], (it / kStages) & 1, 4);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(smem + st * kStageBytes);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          // A: X chunk [64 d][128 px], MN-major; one k-step = 16 channels = two 1024-byte atoms
+          const uint64_t a = desc_mnmajor_sw128(sb + ks * 2048, 8192);
+          const uint64_t bdesc = desc_kmajor_sw128(sb + 16384 + ks * 32);
+          mma_bf16_ss(tmem, a, bdesc, idesc_s, (c | ks) != 0);
+        }
+        mma_commit(&bars->empty[st]);
+      }
+      mma_commit(&bars->s_full);
+      if (kBwd) {
+        mbar_wait(&bars->p_full, lt & 1, 5);
+        tc_fence_after();
+        const uint32_t pb = smem_u32(smem + kOffP);
+        for (int q = 0; q < n_q; ++q, ++qcount) {
+          const int ab = qcount & 1;
+          mbar_wait(&bars->acc_empty[ab], ((qcount >> 1) & 1) ^ 1, 6);
+          tc_fence_after();
+          const uint32_t dcol = tmem + 256 + ab * 128;
+          for (int u = 0; u < n_units; ++u, ++it) {
+            const int st = it % kStages;
+            mbar_wait(&bars->full[st], (it / kStages) & 1, 7);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(smem + st * kStageBytes);
+            const int nb = min(2, n_kchunks - 2 * u);
+            for (int jj = 0; jj < nb; ++jj) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t a = desc_kmajor_sw128(sb + jj * 16384 + ks * 32);             // T^T [128 d][64 k]
+                const uint64_t bdesc = desc_kmajor_sw128(pb + (2 * u + jj) * 16384 + ks * 32);   // P [128 px][64 k]
+                mma_bf16_ss(dcol, a, bdesc, idesc_d, (u | jj | ks) != 0);
+              }
+            }
+            mma_commit(&bars->empty[st]);
+          }
+          mma_commit(&bars->acc_full[ab]);
+        }
+        mma_commit(&bars->p_empty);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =============================== softmax / CE ===============================
+    const int row = (warp & 3) * 32 + lane;                 // pixel within the tile == TMEM lane
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint8_t* prow = smem + kOffP + row * 128;
+    const int sw = row & 7;
+    float loss_acc = 0.f, w_acc = 0.f, dlt_acc = 0.f;
+    float inv_wsum = 0.f;
+    float gscale = 1.f;
+    if (kBwd) {
+      const double ws = prm.w_sum_in[0];
+      inv_wsum = ws > 0.0 ? (float)(1.0 / ws) : 0.f;
+      if (prm.grad_scale) gscale = prm.grad_scale[0];
+    }
+    uint32_t lt = 0;
+    for (int64_t tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
+      const int b = (int)(tile / prm.tiles_per_img);
+      const int px = (int)(tile - (int64_t)b * prm.tiles_per_img) * kTilePx + row;
+      const bool valid = px < prm.HW;
+      const int64_t m = (int64_t)b * prm.HW + px;
+      const float inv_n = valid ? prm.inv_norm[m] : 0.f;
+      const int yi = valid ? prm.y[m] : -1;
+      const float wi = (valid && yi >= 0) ? prm.w[m] : 0.f;
+      const float zs = inv_n * prm.inv_tau;     // z = s * zs   (zs >= 0)
+      const float zl = zs * kLog2e;
+      mbar_wait(&bars->s_full, lt & 1, 8);
+      tc_fence_after();
+      // pass 1: row maximum of the raw dots
+      float mx = -FLT_MAX;
+      for (int c = 0; c < prm.Kp / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < prm.K) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      const float ml = mx * zl;
+      if (kBwd) mbar_wait(&bars->p_empty, (lt & 1) ^ 1, 9);
+      // pass 2: exp, sums, P
+      float sum = 0.f, sez = 0.f, sy = 0.f;
+      for (int c = 0; c < prm.Kp / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + c * 32, r);
+        tmem_ld_wait();
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int k = c * 32 + i;
+          const float s = __uint_as_float(r[i]);
+          e[i] = (k < prm.K) ? fast_exp2(fmaf(s, zl, -ml)) : 0.f;
+          sum += e[i];
+          sez = fmaf(e[i], s, sez);
+          if (k == yi) sy = s;
+        }
+        if (kBwd) {
+          uint8_t* sub = prow + (c >> 1) * 16384;        // 64-wide K sub-tile
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int chunk = (c & 1) * 4 + g;             // 16-byte chunk within the 128-byte row
+            uint4 v;
+            v.x = pack_bf16x2(e[g * 8 + 0], e[g * 8 + 1]); v.y = pack_bf16x2(e[g * 8 + 2], e[g * 8 + 3]);
+            v.z = pack_bf16x2(e[g * 8 + 4], e[g * 8 + 5]); v.w = pack_bf16x2(e[g * 8 + 6], e[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(sub + ((chunk ^ sw) << 4)) = v;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->s_empty);               // S columns may be overwritten by the next tile
+      const float zy = sy * zs;
+      const float lse = (ml + __log2f(sum)) * kLn2;
+      loss_acc += wi * (lse - zy);
+      w_acc += wi;
+      if (valid && prm.lse) prm.lse[m] = lse;
+      if (kBwd) {
+        const float coef = gscale * wi * inv_wsum;
+        const float inv_sum = 1.f / sum;
+        if (yi >= 0) {   // P[row][y] = e_y - sum  (softmax - onehot, times sum), subtraction before rounding
+          const float ey = fast_exp2(fmaf(sy, zl, -ml));
+          const int kk = yi & 63;
+          uint8_t* sub = prow + (yi >> 6) * 16384;
+          *reinterpret_cast<__nv_bfloat16*>(sub + (((kk >> 3) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(ey - sum);
+        }
+        const float cj = coef * (sez * zs * inv_sum - zy);        // sum_k dz_k z_k
+        rs_s[(lt & (kScaleBufs - 1)) * 128 + row] = inv_n * prm.inv_tau * coef * inv_sum;
+        cs_s[(lt & (kScaleBufs - 1)) * 128 + row] = inv_n * inv_n * cj;
+        dlt_acc -= cj;
+        fence_proxy_async_smem();                 // P is read by the tensor core (async proxy)
+        mbar_arrive(&bars->p_full);
+      }
+    }
+    loss_acc = warp_sum(loss_acc); w_acc = warp_sum(w_acc); dlt_acc = warp_sum(dlt_acc);
+    if (lane == 0) {
+      if (prm.loss_sum) atomicAdd(prm.loss_sum, (double)loss_acc);
+      if (prm.w_sum) atomicAdd(prm.w_sum, (double)w_acc);
+      if (kBwd && prm.dlogtau) atomicAdd(prm.dlogtau, (double)dlt_acc);
+    }
+  } else if (kBwd && warp >= 8) {
+    // =============================== dX epilogue ===============================
+    const int row = (warp & 3) * 32 + lane;                 // channel within the 128-channel block == TMEM lane
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256;
+    const bool leader = threadIdx.x == 256;
+    const int steps_per_tile = n_q * 4;
+    const int64_t my_tiles = (prm.n_tiles > blockIdx.x) ? (prm.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total_steps = my_tiles * steps_per_tile;
+    auto issue_load = [&](int64_t s) {
+      const int64_t ltile = s / steps_per_tile;
+      const int rem = (int)(s - ltile * steps_per_tile);
+      const int64_t tile = blockIdx.x + ltile * gridDim.x;
+      const int b = (int)(tile / prm.tiles_per_img);
+      const int px0 = (int)(tile - (int64_t)b * prm.tiles_per_img) * kTilePx;
+      const int sb = (int)(s & (kStgBufs - 1));
+      mbar_arrive_expect_tx(&bars->stg_full[sb], kStgBytes);
+      tma_load_3d(smem + kOffStg + sb * kStgBytes, &map_x_e, &bars->stg_full[sb], px0 + (rem & 3) * kStgPx, (rem >> 2) * 128, b);
+    };
+    if (leader) {
+      if (total_steps > 0) issue_load(0);
+      if (total_steps > 1) issue_load(1);
+    }
+    int64_t s = 0;
+    uint32_t lt = 0, qcount = 0;
+    for (int64_t tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
+      const int b = (int)(tile / prm.tiles_per_img);
+      const int px0 = (int)(tile - (int64_t)b * prm.tiles_per_img) * kTilePx;
+      mbar_wait(&bars->p_full, lt & 1, 10);      // rs/cs of this tile are visible
+      const float* rs = rs_s + (lt & (kScaleBufs - 1)) * 128;
+      const float* cs = cs_s + (lt & (kScaleBufs - 1)) * 128;
+      for (int q = 0; q < n_q; ++q, ++qcount) {
+        const int ab = qcount & 1;
+        mbar_wait(&bars->acc_full[ab], (qcount >> 1) & 1, 11);
+        tc_fence_after();
+        for (int h = 0; h < 4; ++h, ++s) {
+          const int sb = (int)(s & (kStgBufs - 1));
+          if (leader && s + 2 < total_steps) {
+            tma_store_wait_read0_keep1();
+            issue_load(s + 2);
+          }
+          uint32_t acc[32];
+          tmem_ld_32x32(trow + ab * 128 + h * kStgPx, acc);
+          tmem_ld_wait();
+          if (h == 3) { tc_fence_before(); mbar_arrive(&bars->acc_empty[ab]); }
+          mbar_wait(&bars->stg_full[sb], (uint32_t)((s / kStgBufs) & 1), 12);
+          uint8_t* srow = smem + kOffStg + sb * kStgBytes + row * 64;    // 32 px bf16 = 64 B per channel row
+          const int sw = (row >> 1) & 3;                                  // 64-byte swizzle
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4* p = reinterpret_cast<uint4*>(srow + ((g ^ sw) << 4));
+            const uint4 xv = *p;
+            const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float4 r0 = *reinterpret_cast<const float4*>(rs + h * kStgPx + g * 8);
+            const float4 r1 = *reinterpret_cast<const float4*>(rs + h * kStgPx + g * 8 + 4);
+            const float4 c0 = *reinterpret_cast<const float4*>(cs + h * kStgPx + g * 8);
+            const float4 c1 = *reinterpret_cast<const float4*>(cs + h * kStgPx + g * 8 + 4);
+            const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float xval = (i & 1) ? __uint_as_float(xu[i >> 1] & 0xffff0000u) : __uint_as_float(xu[i >> 1] << 16);
+              o[i] = fmaf(rr[i], __uint_as_float(acc[g * 8 + i]), -cc[i] * xval);
+            }
+            uint4 ov;
+            ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
+            ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+            *p = ov;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (leader) {
+            tma_store_3d(&map_dx, smem + kOffStg + sb * kStgBytes, px0 + h * kStgPx, q * 128, b);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (leader) tma_store_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem);
+  }
+}
+
+}  // namespace rc
+
+// ------------------------------------------------------------------------------------------------
+// bring-up kernel: one 128 x N x Kd GEMM tile through the same TMA / descriptor / tcgen05 / TMEM path
+// ------------------------------------------------------------------------------------------------
+namespace rc {
+
+struct __align__(8) DebugBars { uint64_t full, done; uint32_t tmem_base, pad; };
+
+__global__ void __launch_bounds__(128, 1)
+debug_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int N, int Kd,
+                       int variant, float* __restrict__ c) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sa = smem;               // 16 KB
+  uint8_t* sbm = smem + 16384;      // <= 32 KB
+  DebugBars* bars = reinterpret_cast<DebugBars*>(smem + 49152);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars->full, 1);
+    mbar_init(&bars->done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N, variant == 0 ? 0 : 1, 0);
+    for (int ck = 0; ck < Kd / 64; ++ck) {
+      mbar_arrive_expect_tx(&bars->full, 16384 + N * 128);
+      if (variant == 0) {
+        tma_load_2d(sa, &map_a, &bars->full, ck * 64, 0);             // A [128][Kd]: box (64 k, 128 rows)
+      } else {
+        tma_load_2d(sa, &map_a, &bars->full, 0, ck * 64);             // A^T [Kd][128]: box (64 m, 64 k) x 2
+        tma_load_2d(sa + 8192, &map_a, &bars->full, 64, ck * 64);
+      }
+      tma_load_2d(sbm, &map_b, &bars->full, ck * 64, 0);              // B [N][Kd]: box (64 k, N rows)
+      mbar_wait(&bars->full, ck & 1, 100);
+      tc_fence_after();
+      for (int ks = 0; ks < 4; ++ks) {
+        uint64_t a;
+        if (variant == 0) a = desc_kmajor_sw128(smem_u32(sa) + ks * 32);
+        else if (variant == 1) a = desc_mnmajor_sw128(smem_u32(sa) + ks * 2048, 8192);
+        else a = make_smem_desc_sw128(smem_u32(sa) + ks * 2048, 1024, 8192);   // hypothesis: LBO/SBO roles swapped
+        const uint64_t b = desc_kmajor_sw128(smem_u32(sbm) + ks * 32);
+        mma_bf16_ss(tmem, a, b, idesc, (ck | ks) != 0);
+      }
+      mma_commit(&bars->done);
+      mbar_wait(&bars->done, ck & 1, 101);
+    }
+  }
+  __syncthreads();
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int cc = 0; cc < N / 32; ++cc) {
+    uint32_t r[32];
+    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, r);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) c[(int64_t)row * N + cc * 32 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(tmem); }
+}
+
+static int check_sm100(const char* what) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(RC_ERR_NO_DEVICE, "%s: no CUDA device", what);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return fail(RC_ERR_NO_DEVICE, "%s: needs an sm_100 device (compute capability %d.x found)", what, major);
+  return RC_OK;
+}
+
+}  // namespace rc
+
+extern "C" int rc_debug_umma_gemm(const void* a_bf16, const void* b_bf16, int N, int Kd, int variant, float* c, void* stream) {
+  RC_REQUIRE(a_bf16 && b_bf16 && c, "rc_debug_umma_gemm: null pointer");
+  RC_REQUIRE(N >= 32 && N <= 256 && N % 32 == 0 && Kd >= 64 && Kd % 64 == 0 && variant >= 0 && variant <= 2,
+             "rc_debug_umma_gemm: bad shape N=%d Kd=%d variant=%d", N, Kd, variant);
+  int rcode = rc::check_sm100("rc_debug_umma_gemm");
+  if (rcode) return rcode;
+  CUtensorMap ma, mb;
+  if (variant == 0) {
+    const uint64_t dims[2] = {(uint64_t)Kd, 128}, str[2] = {2, (uint64_t)Kd * 2};
+    const uint32_t box[2] = {64, 128};
+    if ((rcode = rc::make_tmap_bf16(&ma, a_bf16, 2, dims, str, box, "debug A"))) return rcode;
+  } else {
+    const uint64_t dims[2] = {128, (uint64_t)Kd}, str[2] = {2, 256};
+    const uint32_t box[2] = {64, 64};
+    if ((rcode = rc::make_tmap_bf16(&ma, a_bf16, 2, dims, str, box, "debug A^T"))) return rcode;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)Kd, (uint64_t)N}, str[2] = {2, (uint64_t)Kd * 2};
+    const uint32_t box[2] = {64, (uint32_t)N};
+    if ((rcode = rc::make_tmap_bf16(&mb, b_bf16, 2, dims, str, box, "debug B"))) return rcode;
+  }
+  const int smem = 49152 + 64 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(rc::debug_umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return rc::fail(RC_ERR_CUDA, "rc_debug_umma_gemm: smem opt-in: %s", cudaGetErrorString(e));
+  rc::debug_umma_gemm_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(ma, mb, N, Kd, variant, c);
+  return rc::check_launch("rc_debug_umma_gemm");
+}
+
+extern "C" int64_t rc_infonce_workspace_bytes(int B, int D, int64_t HW, int K, rc_dtype x_dtype) {
+  (void)K;
+  const int64_t M = (int64_t)B * HW;
+  int64_t bytes = ((M * 4 + 255) / 256) * 256;                                   // inv_norm
+  if (x_dtype == RC_F32) bytes += (((int64_t)B * D * HW * 2 + 255) / 256) * 256;   // bf16 copy of X
+  return bytes + 256;
+}
+
+extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16,
+                               const void* tt_bf16, int K, const int32_t* y, const float* w, float inv_tau, float* lse,
+                               double* loss_sum, double* w_sum, const double* w_sum_in, const float* grad_scale, void* dx,
+                               float* dt, double* dlogtau, void* workspace, int64_t workspace_bytes, void* stream) {
+  using namespace rc;
+  RC_REQUIRE(x && t_bf16 && y && w && workspace, "rc_infonce_bf16: null pointer");
+  RC_REQUIRE(B >= 0 && HW >= 0, "rc_infonce_bf16: bad shape");
+  if (K < 1 || K > 256) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: K=%d outside [1,256] (use rc_infonce_f32)", K);
+  if (D < 128 || D > 512 || D % 128 != 0) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: D=%d must be 128, 256, 384 or 512", D);
+  if (HW % 8 != 0) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: HW=%lld must be a multiple of 8", (long long)HW);
+  RC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(t_bf16) & 15) == 0,
+             "rc_infonce_bf16: x and t must be 16-byte aligned");
+  const bool bwd = dx != nullptr;
+  if (bwd) RC_REQUIRE(tt_bf16 && w_sum_in && (reinterpret_cast<uintptr_t>(dx) & 15) == 0, "rc_infonce_bf16: backward needs tt_bf16, w_sum_in and aligned dx");
+  if (dt != nullptr) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: dText is produced by rc_infonce_dt_bf16");
+  if (dlogtau && !bwd) return fail(RC_ERR_INVALID, "rc_infonce_bf16: dlogtau needs dx");
+  RC_REQUIRE(workspace_bytes >= rc_infonce_workspace_bytes(B, D, HW, K, x_dtype), "rc_infonce_bf16: workspace too small");
+  if (B == 0 || HW == 0) return RC_OK;
+  int rcode = check_sm100("rc_infonce_bf16");
+  if (rcode) return rcode;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t M = (int64_t)B * HW;
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  float* inv_norm = reinterpret_cast<float*>(ws);
+  __nv_bfloat16* xb = nullptr;
+  if (x_dtype == RC_F32) xb = reinterpret_cast<__nv_bfloat16*>(ws + ((M * 4 + 255) / 256) * 256);
+  {
+    const int64_t groups = M / 8;
+    const int64_t blocks = (groups + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)num_sms() * 8 ? blocks : (int64_t)num_sms() * 8);
+    if (x_dtype == RC_F32) rownorm_kernel<float><<<grid, 256, 0, s>>>((const float*)x, B, D, HW, xb, inv_norm);
+    else rownorm_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, B, D, HW, nullptr, inv_norm);
+    if ((rcode = check_launch("rc_infonce_bf16(rownorm)"))) return rcode;
+  }
+  const void* xsrc = (x_dtype == RC_F32) ? (const void*)xb : x;
+  const int Kp = (K + 63) / 64 * 64;
+  CUtensorMap m_xs, m_t, m_tt, m_xe, m_dx;
+  {
+    const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)D, (uint64_t)B};
+    const uint64_t str[3] = {2, (uint64_t)HW * 2, (uint64_t)D * HW * 2};
+    const uint32_t box_s[3] = {64, 64, 1}, box_e[3] = {kStgPx, 128, 1};
+    if ((rcode = make_tmap_bf16(&m_xs, xsrc, 3, dims, str, box_s, "map_x_s"))) return rcode;
+    if ((rcode = make_tmap_bf16(&m_xe, xsrc, 3, dims, str, box_e, "map_x_e"))) return rcode;
+    if ((rcode = make_tmap_bf16(&m_dx, bwd ? dx : xsrc, 3, dims, str, box_e, "map_dx"))) return rcode;
+    const uint64_t tdims[2] = {(uint64_t)D, (uint64_t)Kp}, tstr[2] = {2, (uint64_t)D * 2};
+    const uint32_t tbox[2] = {64, (uint32_t)Kp};
+    if ((rcode = make_tmap_bf16(&m_t, t_bf16, 2, tdims, tstr, tbox, "map_t"))) return rcode;
+    const uint64_t ttdims[2] = {(uint64_t)Kp, (uint64_t)D}, ttstr[2] = {2, (uint64_t)Kp * 2};
+    const uint32_t ttbox[2] = {64, 128};
+    if ((rcode = make_tmap_bf16(&m_tt, bwd ? tt_bf16 : t_bf16, 2, bwd ? ttdims : tdims, bwd ? ttstr : tstr,
+                                bwd ? ttbox : tbox, "map_tt"))) return rcode;
+  }
+  InfoNceParams prm;
+  prm.B = B; prm.D = D; prm.K = K; prm.Kp = Kp; prm.HW = HW;
+  prm.tiles_per_img = (int)((HW + kTilePx - 1) / kTilePx);
+  prm.n_tiles = (int64_t)B * prm.tiles_per_img;
+  prm.inv_norm = inv_norm; prm.y = y; prm.w = w; prm.inv_tau = inv_tau; prm.grad_scale = grad_scale;
+  prm.w_sum_in = w_sum_in; prm.lse = lse; prm.loss_sum = loss_sum; prm.w_sum = w_sum; prm.dlogtau = dlogtau;
+  const int grid = (int)(prm.n_tiles < (int64_t)num_sms() ? prm.n_tiles : (int64_t)num_sms());
+  cudaError_t e;
+  if (bwd) {
+    e = cudaFuncSetAttribute(infonce_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_infonce_bf16: smem opt-in: %s", cudaGetErrorString(e));
+    infonce_umma_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_xe, m_dx, prm);
+  } else {
+    e = cudaFuncSetAttribute(infonce_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_infonce_bf16: smem opt-in: %s", cudaGetErrorString(e));
+    infonce_umma_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_xe, m_dx, prm);
+  }
+  return check_launch("rc_infonce_bf16");
+}
+
+extern "C" int rc_eval_topk_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16, int K,
+                                 const int64_t* index_map, int k, int64_t* out, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  (void)x; (void)x_dtype; (void)B; (void)D; (void)HW; (void)t_bf16; (void)K; (void)index_map; (void)k; (void)out;
+  (void)workspace; (void)workspace_bytes; (void)stream;
+  return rc::fail(RC_ERR_UNSUPPORTED, "rc_eval_topk_bf16: tensor-core top-k not built yet (use rc_eval_topk_f32)");
+}

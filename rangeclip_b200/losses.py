@@ -1,0 +1,164 @@
+"""Drop-in for ``DepthUNet.compute_loss`` (RangeCLIP/src/depth_segmentation_model/model.py:178-355).
+
+Same signature, same ``loss_info`` keys, same RNG streams consumed in the same order
+(``torch.randint`` on the device, ``np.random.choice``, CPU ``torch.randperm``), same
+zero-loss fallbacks with the same warnings (Q14).  The three loss terms run on the CUDA kernels of
+this package; only the tiny host-side contrast-set builder (model.py:231-270) stays in Python, as in
+the reference.
+
+Use either as a mixin (``class MyUNet(DepthCLIPLossMixin, DepthUNet)``), by assignment
+(``DepthUNet.compute_loss = rangeclip_b200.compute_loss``), or as a free function with a model
+object that owns ``log_temperature_text`` / ``log_temperature_image``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def build_contrast_indices(unique_labels: torch.Tensor, C: int, label_similarity_sets, k_distractors: int,
+                           pct_medium: float, pct_hard: float, pct_rand: float, device) -> torch.Tensor:
+    """Contrast set = GT labels in the sample + curriculum distractors (model.py:234-268).
+
+    Host logic, kept behaviour-identical to the reference including the ``label in container``
+    membership test that silently disables hard/medium distractors for list-form sets (Q3) and
+    the order in which ``np.random`` and the CPU torch generator are consumed (Q6)."""
+    present = unique_labels.tolist()
+    n_medium = int(k_distractors * pct_medium)
+    n_hard = int(k_distractors * pct_hard)
+    n_rand = k_distractors - n_medium - n_hard
+    candidates = set()
+    for n_wanted, key in ((n_medium, 'medium'), (n_hard, 'hard')):
+        if n_wanted > 0:
+            table = label_similarity_sets[key]
+            for lab in present:
+                if lab in table:
+                    candidates.update(table[lab])
+    candidates = [c for c in list(candidates) if c not in present]
+    n_curriculum = n_medium + n_hard
+    if len(candidates) >= n_curriculum:
+        chosen = np.random.choice(candidates, size=n_curriculum, replace=False)
+    else:
+        chosen = candidates
+    chosen = torch.tensor(chosen, device=device, dtype=torch.long)
+    every = torch.arange(C, device=device)
+    free = every[~torch.isin(every, torch.cat([unique_labels, chosen], dim=0))]
+    if n_rand > 0 and len(free) > 0:
+        rand_part = free[torch.randperm(len(free))[:n_rand]]
+    else:
+        rand_part = torch.tensor([], device=device, dtype=torch.long)
+    return torch.unique(torch.cat([unique_labels, chosen, rand_part], dim=0))
+
+
+def text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embeddings, label_similarity_sets,
+                          log_temperature_text, percent_image_sampling=0.7, k_distractors=50, pct_medium=0.0,
+                          pct_hard=0.75, pct_rand=0.25, precision="auto", return_aux=False):
+    """Pixel-text InfoNCE of model.py:199-301 on the fused kernels.
+
+    The reference gathers ``int(0.7*HW)`` pixel rows per image WITH replacement and drops label 0
+    (model.py:220-228); here the same ``torch.randint`` draw becomes a per-pixel multiplicity weight
+    and the [B,D,H,W] tensor is read in place (no gather, no [N,K] logits)."""
+    assert abs(pct_medium + pct_hard + pct_rand - 1.0) < 1e-4, "Sum of text percentages must be 1."
+    B, D, H, W = pixel_embeddings.shape
+    C = candidate_text_embeddings.shape[0]
+    device = pixel_embeddings.device
+    zero = lambda: torch.tensor(0.0, device=device)
+    hw = H * W
+    if hw == 0:
+        raise RuntimeError("Input dimensions H or W are zero.")
+    n_samples = min(int(percent_image_sampling * H * W), hw)
+    if n_samples == 0 and hw > 0:
+        n_samples = hw
+    rand_indices = torch.randint(0, hw, (B, n_samples), device=device)
+    target_flat = target_indices.reshape(B, -1)
+    label_samples = torch.gather(target_flat, 1, rand_indices)          # labels only: B*N int64
+    label_samples = label_samples[label_samples > 0]
+    aux = dict(rand_indices=rand_indices, contrast_indices=None)
+    if label_samples.numel() == 0 or D == 0:
+        print("Warning: No valid foreground pixels sampled for text contrastive loss.")
+        return (zero(), aux) if return_aux else zero()
+    unique_labels = torch.unique(label_samples)
+    contrast = build_contrast_indices(unique_labels, C, label_similarity_sets, k_distractors, pct_medium,
+                                      pct_hard, pct_rand, device)
+    aux["contrast_indices"] = contrast
+    if len(contrast) <= 1:
+        print("Warning: Not enough indices for text contrastive loss (need > 1).")
+        return (zero(), aux) if return_aux else zero()
+    label_map = torch.full((C,), -1, dtype=torch.int32, device=device)
+    label_map[contrast] = torch.arange(contrast.shape[0], device=device, dtype=torch.int32)
+    w, y = ops.sample_weights(target_flat, rand_indices, label_map)
+    if candidate_text_embeddings.requires_grad:
+        t_norm = torch.nn.functional.normalize(candidate_text_embeddings[contrast].float(), dim=1)
+    else:
+        t_norm, _, _ = ops.text_prepare(candidate_text_embeddings, contrast, want_f32=True)
+    loss = ops.infonce(pixel_embeddings, t_norm, log_temperature_text, y, w, precision)
+    return (loss, aux) if return_aux else loss
+
+
+def image_contrastive_loss(area_embeddings, image_embeddings, log_temperature_image, precision="fp32"):
+    """Area-image InfoNCE of model.py:304-321: rows = pooled area embeddings, candidates = CLIP
+    crop embeddings, positives on the diagonal.  n is at most a few thousand, so the rows are
+    transposed to the kernels' [D][n] layout first (n*D elements; plumbing)."""
+    n, D = area_embeddings.shape
+    x = area_embeddings.float().t().contiguous().view(1, D, n, 1)
+    if image_embeddings.requires_grad:
+        t_norm = torch.nn.functional.normalize(image_embeddings.float(), dim=1)
+    else:
+        t_norm, _, _ = ops.text_prepare(image_embeddings, None, want_f32=True)
+    y = torch.arange(n, device=x.device, dtype=torch.int32)
+    w = torch.ones(n, device=x.device, dtype=torch.float32)
+    return ops.infonce(x, t_norm, log_temperature_image, y, w, precision)
+
+
+def compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddings, label_similarity_sets,
+                 area_embeddings, image_embeddings, W_text=1.0, W_image=0.5, W_smooth=2e2,
+                 percent_image_sampling=0.7, k_distractors=50, pct_medium=0.0, pct_hard=0.75, pct_rand=0.25,
+                 precision="auto"):
+    """Hybrid contrastive loss: pixel-text + area-image + smoothness (model.py:178-355)."""
+    device = pixel_embeddings.device
+    log_tau_text = self.log_temperature_text
+    log_tau_image = self.log_temperature_image
+
+    text_loss = torch.tensor(0.0, device=device)
+    if W_text > 0:
+        text_loss = text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embeddings,
+                                          label_similarity_sets, log_tau_text, percent_image_sampling,
+                                          k_distractors, pct_medium, pct_hard, pct_rand, precision)
+
+    image_loss = torch.tensor(0.0, device=device)
+    if area_embeddings is not None and image_embeddings is not None and area_embeddings.shape[0] > 1:
+        image_loss = image_contrastive_loss(area_embeddings, image_embeddings, log_tau_image)
+    elif W_image > 0:
+        dummy = torch.tensor(1.0, device=device, requires_grad=True)       # model.py:325-326 (Q14)
+        image_loss = dummy * torch.exp(log_tau_image) * 0.0
+
+    smooth_loss = torch.tensor(0.0, device=device)
+    if W_smooth > 0:
+        smooth_loss = ops.smoothness(pixel_embeddings)
+
+    total = W_text * text_loss + W_image * image_loss + W_smooth * smooth_loss
+
+    # one device->host transfer instead of the reference's six .item() syncs (model.py:343-349)
+    host = torch.stack([total.detach().float(), text_loss.detach().float(), image_loss.detach().float(),
+                        smooth_loss.detach().float(), torch.exp(log_tau_text.detach().float()),
+                        torch.exp(log_tau_image.detach().float())]).tolist()
+    loss_info = {
+        'total_loss': host[0],
+        'text_contrastive_loss': host[1] if W_text > 0 else 0,
+        'image_contrastive_loss': host[2] if W_image > 0 else 0,
+        'smoothness_loss': host[3] if W_smooth > 0 else 0,
+        'temperature_text': host[4],
+        'temperature_image': host[5],
+        'W_text': W_text,
+        'W_image': W_image,
+        'W_smooth': W_smooth,
+    }
+    return total, loss_info
+
+
+class DepthCLIPLossMixin:
+    """Mixin giving a model with ``log_temperature_text`` / ``log_temperature_image`` parameters the
+    reference's ``compute_loss`` on the B200 kernels."""
+    compute_loss = compute_loss

@@ -1,0 +1,376 @@
+"""Thin PyTorch-facing wrappers over the C ABI (``include/rangeclip_b200.h``).
+
+PyTorch is used for device memory, streams and autograd plumbing only; every computation is a
+kernel in ``librangeclip_b200.so``.  All functions require CUDA tensors on an sm_100 device and
+raise ``RuntimeError`` otherwise -- there is no CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import RC_BF16, RC_F32, check
+
+_I32_MAX = 2**31 - 1
+
+
+def _need_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("rangeclip_b200 ops need CUDA tensors (no CPU fallback exists)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return RC_F32
+    if t.dtype == torch.bfloat16:
+        return RC_BF16
+    raise RuntimeError(f"rangeclip_b200: unsupported embedding dtype {t.dtype} (float32 or bfloat16)")
+
+
+def _emb3(x: torch.Tensor) -> Tuple[torch.Tensor, int, int, int]:
+    """[B, D, H, W] (or [B, D, HW]) contiguous view -> (x, B, D, HW)."""
+    if x.dim() not in (3, 4):
+        raise RuntimeError("pixel embeddings must be [B, D, H, W]")
+    x = x.contiguous()
+    B, D = x.shape[0], x.shape[1]
+    return x, B, D, x[0, 0].numel() if B and D else 0
+
+
+def bf16_path_supported(D: int, HW: int, K: int) -> bool:
+    """Shapes the tcgen05 InfoNCE kernel covers (everything else runs on the fp32 kernel)."""
+    return 1 <= K <= 256 and D in (128, 256, 384, 512) and HW % 8 == 0 and HW > 0
+
+
+# ----------------------------------------------------------------------------------------------
+# text preparation / sampling weights
+# ----------------------------------------------------------------------------------------------
+
+def text_prepare(text: torch.Tensor, idx: Optional[torch.Tensor], want_f32=True, want_bf16=False):
+    """F.normalize(text[idx], dim=1) (model.py:272) as f32 [K,D] and/or bf16 [Kp,D] + [D,Kp]."""
+    _need_cuda(text, idx)
+    text = text.float().contiguous()
+    K = int(idx.numel()) if idx is not None else text.shape[0]
+    D = text.shape[1]
+    Kp = (K + 63) // 64 * 64
+    t32 = torch.empty(K, D, device=text.device, dtype=torch.float32) if want_f32 else None
+    tb = torch.empty(Kp, D, device=text.device, dtype=torch.bfloat16) if want_bf16 else None
+    ttb = torch.empty(D, Kp, device=text.device, dtype=torch.bfloat16) if want_bf16 else None
+    if idx is not None:
+        idx = idx.to(torch.int64).contiguous()
+    check(_lib.lib().rc_text_prepare(_p(text), text.stride(0), _p(idx), K, D, _p(t32), _p(tb), _p(ttb),
+                                     _stream(text)), "rc_text_prepare")
+    return t32, tb, ttb
+
+
+def text_to_bf16(t_norm: torch.Tensor):
+    """bf16 [Kp,D] and transposed [D,Kp] copies of already-normalised rows (tiny; plumbing only)."""
+    K, D = t_norm.shape
+    Kp = (K + 63) // 64 * 64
+    tb = torch.zeros(Kp, D, device=t_norm.device, dtype=torch.bfloat16)
+    tb[:K] = t_norm.detach().to(torch.bfloat16)
+    return tb, tb.t().contiguous()
+
+
+def sample_weights(seg: torch.Tensor, rand_idx: Optional[torch.Tensor], label_map: torch.Tensor):
+    """Dense form of model.py:220-228,276-284: w[b,p] = multiplicity of p among rand_idx[b] (1 when
+    rand_idx is None) zeroed on background / unmapped labels; y[b,p] = label_map[seg] or -1."""
+    _need_cuda(seg, rand_idx, label_map)
+    B = seg.shape[0]
+    HW = seg[0].numel() if B else 0
+    seg = seg.to(torch.int64).contiguous()
+    label_map = label_map.to(torch.int32).contiguous()
+    w = torch.empty(B, HW, device=seg.device, dtype=torch.float32)
+    y = torch.empty(B, HW, device=seg.device, dtype=torch.int32)
+    n_s = 0
+    if rand_idx is not None:
+        rand_idx = rand_idx.to(torch.int64).contiguous()
+        n_s = rand_idx.shape[1]
+    check(_lib.lib().rc_sample_weights(_p(seg), _p(rand_idx), B, HW, n_s, _p(label_map), label_map.numel(),
+                                       _p(w), _p(y), _stream(seg)), "rc_sample_weights")
+    return w, y
+
+
+# ----------------------------------------------------------------------------------------------
+# InfoNCE
+# ----------------------------------------------------------------------------------------------
+
+def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch.Tensor, inv_tau: float,
+                need_dx: bool, need_dt: bool, precision: str = "auto",
+                grad_scale: Optional[torch.Tensor] = None, t_bf16=None):
+    """One fused pass: returns dict(loss_sum, w_sum (double[1] tensors), lse, dx, dt, dlogtau).
+    loss = loss_sum / w_sum; dx/dt/dlogtau are gradients of that mean loss times grad_scale."""
+    _need_cuda(x, t_norm, y, w)
+    x, B, D, HW = _emb3(x)
+    K = t_norm.shape[0]
+    dev = x.device
+    M = B * HW
+    y = y.reshape(-1).to(torch.int32).contiguous()
+    w = w.reshape(-1).to(torch.float32).contiguous()
+    if y.numel() != M or w.numel() != M:
+        raise RuntimeError("infonce: y / w must have one entry per pixel row")
+    if precision == "auto":
+        precision = "bf16" if (bf16_path_supported(D, HW, K) and not need_dt) else "fp32"
+    acc = torch.zeros(4, device=dev, dtype=torch.float64)        # loss_sum, w_sum, dlogtau, w_sum_in
+    lse = torch.empty(M, device=dev, dtype=torch.float32)
+    need_grad = need_dx or need_dt
+    L = _lib.lib()
+    st = _stream(x)
+    if need_grad:
+        check(L.rc_weight_sum(_p(w), _p(y), M, acc[3:].data_ptr(), st), "rc_weight_sum")
+    gs = None
+    if grad_scale is not None:
+        gs = grad_scale.detach().reshape(1).to(device=dev, dtype=torch.float32)
+    dt = torch.zeros(K, D, device=dev, dtype=torch.float32) if need_dt else None
+    if precision == "fp32":
+        xf = x if x.dtype == torch.float32 else x.float()
+        tf = t_norm.detach().float().contiguous()
+        dx = torch.empty_like(xf) if need_dx else None
+        check(L.rc_infonce_f32(_p(xf), B, D, HW, D * HW, _p(tf), K, _p(y), _p(w), float(inv_tau), _p(lse),
+                               acc[0:].data_ptr(), acc[1:].data_ptr(),
+                               acc[3:].data_ptr() if need_grad else None, _p(gs),
+                               _p(dx), _p(dt), acc[2:].data_ptr() if need_grad else None, st), "rc_infonce_f32")
+        if dx is not None and dx.dtype != x.dtype:
+            dx = dx.to(x.dtype)
+    elif precision == "bf16":
+        if not bf16_path_supported(D, HW, K):
+            raise RuntimeError(f"infonce: bf16 tensor-core path does not cover D={D}, HW={HW}, K={K}")
+        if need_dt:
+            raise RuntimeError("infonce: dText on the bf16 path is not available yet; use precision='fp32'")
+        if t_bf16 is None:
+            t_bf16 = text_to_bf16(t_norm)
+        tb, ttb = t_bf16
+        xdt = _dt(x)
+        ws_bytes = int(L.rc_infonce_workspace_bytes(B, D, HW, K, xdt))
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        dxb = torch.empty(B, D, HW, device=dev, dtype=torch.bfloat16) if need_dx else None
+        check(L.rc_infonce_bf16(_p(x), xdt, B, D, HW, _p(tb), _p(ttb), K, _p(y), _p(w), float(inv_tau), _p(lse),
+                                acc[0:].data_ptr(), acc[1:].data_ptr(),
+                                acc[3:].data_ptr() if need_grad else None, _p(gs), _p(dxb), None,
+                                acc[2:].data_ptr() if need_dx else None, _p(ws), ws_bytes, st), "rc_infonce_bf16")
+        dx = None
+        if dxb is not None:
+            dx = dxb.view(x.shape) if x.dtype == torch.bfloat16 else dxb.view(x.shape).to(x.dtype)
+    else:
+        raise RuntimeError(f"infonce: unknown precision {precision!r}")
+    return dict(loss_sum=acc[0], w_sum=acc[1], dlogtau=acc[2], lse=lse, dx=dx, dt=dt, precision=precision)
+
+
+class _InfoNCE(torch.autograd.Function):
+    """loss = weighted InfoNCE(x, t_norm, y, w) / tau; gradients for x, t_norm and log_tau are
+    produced by the same fused kernel launch as the loss (single pass over X)."""
+
+    @staticmethod
+    def forward(ctx, x, t_norm, log_tau, y, w, precision):
+        need_dx = x.requires_grad
+        need_dt = t_norm.requires_grad
+        need_tau = log_tau.requires_grad
+        inv_tau = float(torch.exp(-log_tau.detach().float()))          # one scalar sync, as .item() in the reference
+        r = infonce_raw(x.detach(), t_norm.detach(), y, w, inv_tau, need_dx or need_tau, need_dt, precision)
+        wsum = r["w_sum"]
+        loss = torch.where(wsum > 0, r["loss_sum"] / wsum.clamp_min(1e-300), torch.zeros_like(wsum)).float()
+        ctx.save_for_backward(r["dx"] if need_dx else None, r["dt"], r["dlogtau"].float())
+        ctx.flags = (need_dx, need_dt, need_tau)
+        ctx.x_dtype = x.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dx, dt, dlt = ctx.saved_tensors
+        need_dx, need_dt, need_tau = ctx.flags
+        gx = gt = gl = None
+        if need_dx:
+            gx = dx
+            gdev = g.detach().reshape(1).float()
+            check(_lib.lib().rc_scale(_p(gx), _dt(gx), gx.numel(), _p(gdev), _stream(gx)), "rc_scale")
+        if need_dt:
+            gt = dt * g
+        if need_tau:
+            gl = (dlt * g).reshape(())
+        return gx, gt, gl, None, None, None
+
+
+def infonce(x, t_norm, log_tau, y, w, precision="auto"):
+    """Autograd-aware fused InfoNCE; x [B,D,H,W], t_norm [K,D] normalised, y/w per pixel."""
+    return _InfoNCE.apply(x, t_norm, log_tau, y, w, precision)
+
+
+# ----------------------------------------------------------------------------------------------
+# smoothness (TV-L1)
+# ----------------------------------------------------------------------------------------------
+
+def tv_sums(x: torch.Tensor) -> torch.Tensor:
+    """double[2]: sum |dx_w|, sum |dx_h| over [B,D,H,W] (model.py:332-333 numerators)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    B, D, H, W = x.shape
+    sums = torch.zeros(2, device=x.device, dtype=torch.float64)
+    check(_lib.lib().rc_tv_fwd(_p(x), _dt(x), B * D, H, W, _p(sums), _stream(x)), "rc_tv_fwd")
+    return sums
+
+
+def tv_denominators(shape) -> Tuple[float, float]:
+    B, D, H, W = shape
+    return float(B * D * H * (W - 1)), float(B * D * (H - 1) * W)
+
+
+def tv_backward(x: torch.Tensor, scale: torch.Tensor, dx: Optional[torch.Tensor] = None,
+                dx_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx (= or +=) scale[0] * d(sum_h)/dx + scale[1] * d(sum_v)/dx; if dx is given it is first
+    multiplied by dx_scale (device scalar) -- the fused late upstream scaling."""
+    x = x.contiguous()
+    B, D, H, W = x.shape
+    acc = 1
+    if dx is None:
+        dx = torch.empty_like(x)
+        acc = 0
+    scale = scale.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    ds = None if dx_scale is None else dx_scale.detach().reshape(1).to(device=x.device, dtype=torch.float32)
+    check(_lib.lib().rc_tv_bwd(_p(x), _dt(x), B * D, H, W, _p(scale), _p(dx), acc, _p(ds), _stream(x)), "rc_tv_bwd")
+    return dx
+
+
+class _Smoothness(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        sums = tv_sums(x.detach())
+        dh, dv = tv_denominators(x.shape)
+        ctx.save_for_backward(x)
+        # l1_loss over an empty slice is NaN in the reference (W == 1 or H == 1); keep that
+        th = sums[0] / dh if dh > 0 else torch.full((), float("nan"), device=x.device, dtype=torch.float64)
+        tv = sums[1] / dv if dv > 0 else torch.full((), float("nan"), device=x.device, dtype=torch.float64)
+        return (th + tv).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        dh, dv = tv_denominators(x.shape)
+        scale = torch.stack([g.float() / dh if dh > 0 else g.float() * 0, g.float() / dv if dv > 0 else g.float() * 0])
+        return tv_backward(x.detach(), scale)
+
+
+def smoothness(x: torch.Tensor) -> torch.Tensor:
+    return _Smoothness.apply(x)
+
+
+# ----------------------------------------------------------------------------------------------
+# masked pooling
+# ----------------------------------------------------------------------------------------------
+
+def pool_forward(x: torch.Tensor, seg: torch.Tensor, lut: torch.Tensor, lut_per_image: bool, n_slots: int):
+    """sum/count per slot then mean; lut [B,C] (per image) or [C] (batch-wide) int32, -1 = none."""
+    _need_cuda(x, seg, lut)
+    x, B, D, HW = _emb3(x)
+    seg = seg.reshape(B, -1).to(torch.int64).contiguous()
+    lut = lut.to(torch.int32).contiguous()
+    C = lut.shape[-1]
+    out = torch.zeros(n_slots, D, device=x.device, dtype=torch.float32)
+    cnt = torch.zeros(max(n_slots, 1), device=x.device, dtype=torch.int32)
+    L = _lib.lib()
+    check(L.rc_pool_fwd(_p(x), _dt(x), B, D, HW, _p(seg), _p(lut), C if lut_per_image else 0, C, n_slots,
+                        _p(out), _p(cnt), _stream(x)), "rc_pool_fwd")
+    check(L.rc_pool_finish(_p(out), _p(cnt), n_slots, D, _stream(x)), "rc_pool_finish")
+    return out, cnt
+
+
+def pool_backward(g: torch.Tensor, cnt: torch.Tensor, seg: torch.Tensor, lut: torch.Tensor, lut_per_image: bool,
+                  shape, dtype) -> torch.Tensor:
+    B, D = shape[0], shape[1]
+    HW = 1
+    for s in shape[2:]:
+        HW *= s
+    seg = seg.reshape(B, -1).to(torch.int64).contiguous()
+    lut = lut.to(torch.int32).contiguous()
+    C = lut.shape[-1]
+    g = g.float().contiguous()
+    dx = torch.empty(shape, device=g.device, dtype=dtype)
+    check(_lib.lib().rc_pool_bwd(_p(g), _p(cnt), B, D, HW, _p(seg), _p(lut), C if lut_per_image else 0, C,
+                                 g.shape[0], _p(dx), RC_F32 if dtype == torch.float32 else RC_BF16, 0,
+                                 _stream(g)), "rc_pool_bwd")
+    return dx
+
+
+class _MaskedPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, seg, lut, lut_per_image, n_slots):
+        out, cnt = pool_forward(x.detach(), seg, lut, lut_per_image, n_slots)
+        ctx.save_for_backward(cnt, seg, lut)
+        ctx.meta = (lut_per_image, tuple(x.shape), x.dtype)
+        return out.to(x.dtype) if x.dtype != torch.float32 else out
+
+    @staticmethod
+    def backward(ctx, g):
+        cnt, seg, lut = ctx.saved_tensors
+        lut_per_image, shape, dtype = ctx.meta
+        return pool_backward(g, cnt, seg, lut, lut_per_image, shape, dtype), None, None, None, None
+
+
+def masked_pool(x, seg, lut, lut_per_image, n_slots):
+    return _MaskedPool.apply(x, seg, lut, lut_per_image, n_slots)
+
+
+# ----------------------------------------------------------------------------------------------
+# evaluation
+# ----------------------------------------------------------------------------------------------
+
+def eval_topk(x: torch.Tensor, t_norm: torch.Tensor, index_map: torch.Tensor, k: int, precision="fp32"):
+    """out[b, j, h, w] = index_map[j-th best text row by cosine logit] (model.py:164-173)."""
+    _need_cuda(x, t_norm, index_map)
+    x, B, D, HW = _emb3(x)
+    K = t_norm.shape[0]
+    k = min(k, K)
+    out = torch.empty((B, k) + tuple(x.shape[2:]), device=x.device, dtype=torch.int64)
+    index_map = index_map.to(torch.int64).contiguous()
+    if precision != "fp32":
+        raise RuntimeError("eval_topk: only the fp32 kernel is available in this build")
+    xf = x if x.dtype == torch.float32 else x.float()
+    tf = t_norm.float().contiguous()
+    check(_lib.lib().rc_eval_topk_f32(_p(xf), B, D, HW, D * HW, _p(tf), K, _p(index_map), k, _p(out), _stream(x)),
+          "rc_eval_topk_f32")
+    return out
+
+
+def eval_hist(gt: torch.Tensor, topk: torch.Tensor, E_u8: torch.Tensor, cmap: torch.Tensor,
+              hist: Optional[torch.Tensor] = None, counters: Optional[torch.Tensor] = None):
+    """One batch of validate.py:88-139 as five class histograms + three counters (int64, added to)."""
+    _need_cuda(gt, topk, E_u8, cmap)
+    B, k = topk.shape[0], topk.shape[1]
+    HW = topk[0, 0].numel()
+    C = cmap.numel()
+    gt = gt.reshape(-1).to(torch.int64).contiguous()
+    topk = topk.to(torch.int64).contiguous()
+    if gt.numel() != B * HW:
+        raise RuntimeError("eval_hist: gt and topk disagree on the number of pixels")
+    if hist is None:
+        hist = torch.zeros(5, C, device=gt.device, dtype=torch.int64)
+    if counters is None:
+        counters = torch.zeros(3, device=gt.device, dtype=torch.int64)
+    check(_lib.lib().rc_eval_hist(_p(gt), _p(topk), B, HW, k, _p(E_u8), _p(cmap), C, _p(hist), _p(counters),
+                                  _stream(gt)), "rc_eval_hist")
+    return hist, counters
+
+
+def eval_fold(batch_hist: torch.Tensor, batch_index: int, acc: torch.Tensor, first_seen: torch.Tensor) -> None:
+    C = batch_hist.shape[1]
+    check(_lib.lib().rc_eval_fold(_p(batch_hist), C, int(batch_index), _p(acc), _p(first_seen), _stream(acc)),
+          "rc_eval_fold")
+
+
+def debug_umma_gemm(a: torch.Tensor, b: torch.Tensor, variant: int) -> torch.Tensor:
+    """Bring-up check of the TMA + tcgen05 + TMEM path: C[128,N] = A B^T in bf16 -> f32."""
+    _need_cuda(a, b)
+    N, Kd = b.shape
+    c = torch.empty(128, N, device=a.device, dtype=torch.float32)
+    check(_lib.lib().rc_debug_umma_gemm(_p(a.contiguous()), _p(b.contiguous()), N, Kd, variant, _p(c), _stream(a)),
+          "rc_debug_umma_gemm")
+    return c

@@ -1,0 +1,103 @@
+"""Drop-ins for ``masked_average_pooling`` (model.py:15-56) and ``prepare_image_contrast_data``
+(dataloader.py:205-305) on the segment-masked pooling kernel (one read of the embeddings instead
+of one full-tensor ``torch.where`` temporary per object)."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def masked_average_pooling(pixel_embeddings, segmentation_map, object_indices):
+    """Batch-wide mean embedding per object index (model.py:15-56); zeros for absent indices.
+    Differentiable w.r.t. ``pixel_embeddings`` like the reference function."""
+    B, D, H, W = pixel_embeddings.shape
+    device = pixel_embeddings.device
+    object_indices = torch.as_tensor(object_indices, device=device, dtype=torch.long).reshape(-1)
+    n = int(object_indices.numel())
+    if n == 0:
+        return torch.zeros((0, D), device=device, dtype=pixel_embeddings.dtype)
+    seg = segmentation_map.to(device)
+    # labels -> first slot holding that label; duplicate indices are filled by a row gather below
+    C = int(max(int(object_indices.max()) + 1, 1))
+    uniq, inverse = torch.unique(object_indices, return_inverse=True)
+    lut = torch.full((C,), -1, dtype=torch.int32, device=device)
+    ok = uniq >= 0
+    lut[uniq[ok]] = torch.arange(uniq.numel(), device=device, dtype=torch.int32)[ok]
+    pooled = ops.masked_pool(pixel_embeddings, seg, lut, False, int(uniq.numel()))
+    return pooled[inverse]
+
+
+def pool_objects_per_image(pixel_embeddings, segmentation, image_index, labels, differentiable=False):
+    """area[i] = mean of pixel_embeddings[image_index[i]] over segmentation == labels[i]
+    (dataloader.py:286-304); zeros where the mask is empty.  All objects in one kernel launch."""
+    B, D = pixel_embeddings.shape[0], pixel_embeddings.shape[1]
+    device = pixel_embeddings.device
+    image_index = torch.as_tensor(image_index, device=device, dtype=torch.long).reshape(-1)
+    labels = torch.as_tensor(labels, device=device, dtype=torch.long).reshape(-1)
+    n = int(labels.numel())
+    if n == 0:
+        return torch.zeros((0, D), device=device, dtype=pixel_embeddings.dtype)
+    seg = segmentation
+    if seg.dim() == 4:
+        seg = seg.squeeze(1)
+    C = int(max(int(labels.max()) + 1, 1))
+    key = image_index * C + labels.clamp_min(0)
+    uniq, inverse = torch.unique(key, return_inverse=True)
+    lut = torch.full((B * C,), -1, dtype=torch.int32, device=device)
+    lut[uniq] = torch.arange(uniq.numel(), device=device, dtype=torch.int32)
+    neg = labels < 0
+    x = pixel_embeddings if differentiable else pixel_embeddings.detach()
+    pooled = ops.masked_pool(x, seg, lut.view(B, C), True, int(uniq.numel()))[inverse]
+    if bool(neg.any()):
+        pooled = pooled.masked_fill(neg[:, None], 0)
+    return pooled
+
+
+@torch.no_grad()
+def prepare_image_contrast_data(image_processed_batch, object_bbox_batch, object_label_batch, segmentation_batch,
+                                pixel_embeddings_batch, clip_image_encoder, clip_processor, device):
+    """Area embeddings + CLIP crop embeddings for the image contrastive loss (dataloader.py:205-305).
+    Validation, cropping and the CLIP call are the reference's host logic; the per-object masked
+    means (dataloader.py:286-304) run as one pooling kernel.  ``@torch.no_grad`` as in the
+    reference: the area embeddings are detached."""
+    if not isinstance(image_processed_batch, torch.Tensor) or image_processed_batch.dim() != 4:
+        print("Warning: 'image_processed_batch' is not a 4D tensor.")
+        return None, None
+    if not isinstance(object_bbox_batch, torch.Tensor) or object_bbox_batch.dim() != 2 or object_bbox_batch.shape[1] != 4:
+        print("Warning: 'object_bbox_batch' is not a [B, 4] tensor.")
+        return None, None
+    if not isinstance(object_label_batch, torch.Tensor):
+        print("Warning: 'object_label_batch' is not a tensor.")
+        return None, None
+    B, _, H_proc, W_proc = image_processed_batch.shape
+    if B == 0:
+        return None, None
+    boxes = object_bbox_batch.tolist()          # one transfer instead of 4*B .item() calls
+    labels = object_label_batch.tolist()
+    crops, keep, keep_labels = [], [], []
+    for b in range(B):
+        xmin, ymin, xmax, ymax = boxes[b]
+        if xmax > xmin and ymax > ymin and xmin >= 0 and ymin >= 0 and xmax <= W_proc and ymax <= H_proc:
+            crop = image_processed_batch[b][:, int(ymin):int(ymax), int(xmin):int(xmax)]
+            if crop.numel() > 0:
+                crops.append(crop)
+                keep.append(b)
+                keep_labels.append(int(labels[b]))
+            else:
+                print(f"Warning: Skipping item {b}, cropped processed tensor is empty for bbox [{xmin},{ymin},{xmax},{ymax}].")
+        else:
+            print(f"Debug: Skipping item {b}, invalid bbox [{xmin},{ymin},{xmax},{ymax}] relative to processed dims ({H_proc}, {W_proc}) for label {labels[b]}.")
+    if not crops:
+        return None, None
+    try:
+        image_inputs = clip_processor(images=crops, return_tensors="pt", padding=True, do_rescale=False).to(device)
+    except Exception as e:  # same contract as dataloader.py:276-278
+        print(f"Error during clip_processor processing cropped tensors: {e}")
+        return None, None
+    try:
+        image_embeddings = clip_image_encoder.get_image_features(pixel_values=image_inputs['pixel_values'])
+    except Exception as e:
+        raise TypeError(f"CLIP image encoder failed: {e}. Ensure it's a compatible model.") from e
+    area = pool_objects_per_image(pixel_embeddings_batch, segmentation_batch, keep, keep_labels)
+    return area.to(image_embeddings.dtype), image_embeddings

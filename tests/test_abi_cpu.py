@@ -1,0 +1,75 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol the header declares;
+host-side logic (contrast-set builder, candidate-set builder) matches the reference's golden
+outputs; ops refuse CPU tensors instead of silently falling back."""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rangeclip_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    hdr = open(os.path.join(ROOT, "include", "rangeclip_b200.h")).read()
+    declared = set(re.findall(r"\b(rc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.PROTOTYPES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.lib().rc_abi_version() == 1
+    assert _lib.launch_count() >= 0
+
+
+def test_argument_validation_without_gpu():
+    from rangeclip_b200 import _lib
+    L = _lib.lib()
+    assert L.rc_eval_hist(None, None, 1, 1, 1, None, None, 1, None, None, None) == -1
+    assert b"null pointer" in L.rc_last_error()
+    assert L.rc_infonce_workspace_bytes(2, 512, 1024, 256, _lib.RC_F32) > 2 * 512 * 1024 * 2
+
+
+def test_ops_refuse_cpu_tensors():
+    from rangeclip_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.tv_sums(torch.zeros(1, 1, 4, 4))
+    with pytest.raises(RuntimeError):
+        ops.eval_hist(torch.zeros(4, dtype=torch.long), torch.zeros(1, 1, 2, 2, dtype=torch.long),
+                      torch.eye(3, dtype=torch.uint8), torch.arange(3))
+
+
+@pytest.mark.parametrize("case", ["dict", "list", "noimg", "medium"])
+def test_contrast_set_builder_matches_reference(golden_dir, case):
+    from rangeclip_b200 import build_contrast_indices
+    from oracle import rangeclip_oracle as O
+    g = np.load(os.path.join(golden_dir, f"loss_{case}.npz"))
+    C = g["text"].shape[0]
+    hard = {i: [int(v) for v in g["hard"][i]] for i in range(C)}
+    med = {i: [int(v) for v in g["medium"][i]] for i in range(C)}
+    sets = {"medium": med, "hard": hard}
+    if str(g["sim_form"]) == "list":
+        sets = {"medium": [med[i] for i in range(C)], "hard": [hard[i] for i in range(C)]}
+    _, lab = O.sample_pixels(torch.tensor(g["X"]), torch.tensor(g["seg"]), torch.tensor(g["rand_idx"]))
+    seed = int(g["seed"])
+    np.random.seed(seed); torch.manual_seed(seed); random.seed(seed)
+    got = build_contrast_indices(torch.unique(lab), C, sets, int(g["k_distractors"]), float(g["pcts"][0]),
+                                 float(g["pcts"][1]), float(g["pcts"][2]), torch.device("cpu"))
+    assert np.array_equal(got.numpy(), g["contrast"])
+
+
+def test_candidate_set_builder_matches_reference(golden_dir):
+    from rangeclip_b200 import build_reduced_candidates
+    from oracle import rangeclip_oracle as O
+    g = np.load(os.path.join(golden_dir, "predict.npz"))
+    seg = torch.tensor(g["seg"])
+    random.seed(int(g["seed"]))
+    mine = build_reduced_candidates(seg, g["text"].shape[0], int(g["num_negatives"]))
+    random.seed(int(g["seed"]))
+    assert mine == O.build_candidate_set(seg, g["text"].shape[0], int(g["num_negatives"]))
+    assert set(np.unique(g["topk"]).tolist()) <= set(mine)

@@ -1,0 +1,355 @@
+"""GPU parity tests: CUDA kernels (through the C ABI) against the CPU oracle and the golden
+fixtures.  Integer work is bit-exact; floating point within the tolerances BASELINE.json states
+(1e-5 relative on the fp32 path, 2e-2 max-relative on the bf16 tensor-core path)."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rangeclip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_RTOL = 1e-5
+BF16_MAXREL = 2e-2
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def maxrel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def unit(x, dim):
+    return torch.nn.functional.normalize(x, dim=dim)
+
+
+def block_seg(B, H, W, blk, labels, gen):
+    gh, gw = H // blk, W // blk
+    pick = torch.randint(0, len(labels), (B, gh, gw), generator=gen)
+    lab = torch.as_tensor(labels)[pick]
+    return lab.repeat_interleave(blk, 1).repeat_interleave(blk, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 bring-up
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("variant,N,Kd", [(0, 64, 64), (0, 256, 512), (1, 64, 64), (1, 256, 512), (1, 128, 128)])
+def test_umma_gemm_tile(variant, N, Kd):
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(variant * 100 + N + Kd)
+    a = torch.randn(128, Kd, generator=g).to(torch.bfloat16)          # logical A [M=128][Kd]
+    b = torch.randn(N, Kd, generator=g).to(torch.bfloat16)
+    ref = a.float() @ b.float().T
+    a_dev = a.to(dev()) if variant == 0 else a.t().contiguous().to(dev())   # variant 1: stored [Kd][128]
+    c = ops.debug_umma_gemm(a_dev, b.to(dev()), variant).cpu()
+    assert maxrel(c, ref) < 1e-5, f"variant {variant}: maxrel {maxrel(c, ref)}"
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluation histograms (integer, bit-exact)
+# ------------------------------------------------------------------------------------------------
+
+def _oracle_metrics(segs, topks, E, cmap):
+    st = O.MetricState()
+    for seg, topk in zip(segs, topks):
+        k = topk.shape[1]
+        O.metrics_accumulate(st, seg.reshape(-1), np.transpose(topk, (0, 2, 3, 1)).reshape(-1, k), E, cmap)
+    return st, O.metrics_finalize(st, segs[-1], cmap)
+
+
+def _run_accumulator(segs, topks, E, cmap):
+    from rangeclip_b200 import MetricAccumulator
+    acc = MetricAccumulator(torch.tensor(E), torch.tensor(cmap), device=dev())
+    for seg, topk in zip(segs, topks):
+        acc.update(torch.tensor(seg).to(dev()), torch.tensor(topk).to(dev()))
+    return acc.finalize(torch.tensor(segs[-1]).to(dev()))
+
+
+def _assert_metrics_equal(fin, st, ofin):
+    for nm in ["intersection_top1", "union_top1", "intersection_topk", "union_topk"]:
+        assert list(fin[nm].items()) == list(getattr(st, nm).items()), nm       # values AND insertion order
+    assert fin["correct_pixels_top1"] == st.correct_top1 and fin["correct_pixels_topk"] == st.correct_topk
+    assert fin["total_pixels"] == st.total
+    for key in ["mIoU_t1", "mIoU_tk", "pixel_accuracy_t1", "pixel_accuracy_tk"]:
+        assert fin[key] == ofin[key], key                                          # bit-exact floats
+
+
+def test_eval_hist_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    fin = _run_accumulator(list(g["seg"]), list(g["topk"]), g["E"], g["cmap"])
+    for nm in ["intersection_top1", "union_top1", "intersection_topk", "union_topk"]:
+        assert list(fin[nm].keys()) == g[nm + "_keys"].tolist()
+        assert list(fin[nm].values()) == g[nm + "_vals"].tolist()
+    for key in ["mIoU_t1", "mIoU_tk", "pixel_accuracy_t1", "pixel_accuracy_tk"]:
+        assert fin[key] == float(g[key])
+
+
+@pytest.mark.parametrize("C,k,B,H,W,seed", [(64, 5, 3, 32, 32, 0), (1024, 5, 2, 64, 64, 1), (9000, 3, 1, 40, 24, 2),
+                                            (17, 1, 2, 8, 8, 3), (40000, 5, 1, 16, 16, 4)])
+def test_eval_hist_random(C, k, B, H, W, seed):
+    rng = np.random.default_rng(seed)
+    eq = {i: {i} for i in range(C)}
+    ids = rng.permutation(C)[: max(2, C // 10)]
+    for a, b in zip(ids[:-1], ids[1:]):          # a chain: maximally non-transitive (Q9)
+        eq[int(a)].add(int(b)); eq[int(b)].add(int(a))
+    E = O.build_equivalence_tensor(eq, C); cmap = O.build_equivalence_class_map(E)
+    segs, topks = [], []
+    for bi in range(3):
+        pool = rng.permutation(C)[: min(C, 12 + 5 * bi)]
+        seg = pool[rng.integers(0, len(pool), (B, H, W))]
+        topk = np.stack([rng.permutation(C)[:k] for _ in range(B * H * W)]).reshape(B, H, W, k).transpose(0, 3, 1, 2).copy()
+        hit = rng.random((B, H, W)) < 0.5
+        topk[:, 0][hit] = seg[hit]
+        hit2 = rng.random((B, H, W)) < 0.3
+        if k > 1:
+            topk[:, k - 1][hit2] = seg[hit2]
+        segs.append(seg.astype(np.int64)); topks.append(topk.astype(np.int64))
+    st, ofin = _oracle_metrics(segs, topks, E, cmap)
+    fin = _run_accumulator(segs, topks, E, cmap)
+    _assert_metrics_equal(fin, st, ofin)
+
+
+def test_eval_hist_full_size_properties():
+    """BASELINE config 4 sizes (K=1024, 64 x 256^2 per batch): size-independent invariants."""
+    from rangeclip_b200 import ops
+    C, k, B, H, W = 1024, 5, 64, 256, 256
+    g = torch.Generator(device="cuda").manual_seed(0)
+    gt = torch.randint(0, C, (B, H, W), device=dev(), generator=g)
+    topk = torch.randint(0, C, (B, k, H, W), device=dev(), generator=g)
+    topk[:, 0] = torch.where(torch.rand(B, H, W, device=dev(), generator=g) < 0.5, gt, topk[:, 0])
+    E = torch.eye(C, dtype=torch.uint8, device=dev())
+    cmap = torch.arange(C, device=dev())
+    hist, cnt = ops.eval_hist(gt, topk, E, cmap)
+    n = B * H * W
+    assert int(cnt[2]) == n
+    assert int(hist[0].sum()) == n and int(hist[1].sum()) == n and int(hist[3].sum()) == n
+    assert int(hist[2].sum()) == int(cnt[0]) == int((gt == topk[:, 0]).sum())       # identity E: I1 total = correct top1
+    assert int(hist[4].sum()) == int(cnt[1]) == int((topk == gt[:, None]).any(1).sum())
+    assert torch.equal(hist[0], torch.bincount(gt.reshape(-1), minlength=C))
+
+
+# ------------------------------------------------------------------------------------------------
+# smoothness
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape,dtype", [((2, 8, 16, 16), torch.float32), ((1, 3, 37, 50), torch.float32),
+                                          ((2, 16, 64, 256), torch.bfloat16), ((1, 4, 5, 8), torch.float32),
+                                          ((3, 2, 130, 24), torch.float32)])
+def test_smoothness_fwd_bwd(shape, dtype):
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(shape, generator=g)
+    # nearest-upsample-like ties (Q8): duplicate neighbouring columns/rows in part of the tensor
+    x[..., 1::2] = x[..., 0::2][..., : x[..., 1::2].shape[-1]]
+    x = x.to(dtype).float()
+    ref = O.smoothness(x.double())
+    gref = O.smoothness_grad(x)
+    xd = x.to(dev()).to(dtype).requires_grad_(True)
+    loss = ops.smoothness(xd)
+    assert abs(float(loss) - float(ref)) <= FP32_RTOL * abs(float(ref))
+    (loss * 3.0).backward()
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    assert maxrel(xd.grad.float().cpu(), 3.0 * gref) < tol
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling
+# ------------------------------------------------------------------------------------------------
+
+def test_pooling_golden(golden_dir):
+    import rangeclip_b200 as R
+    g = np.load(os.path.join(golden_dir, "pool.npz"))
+    X = torch.tensor(g["X"]).to(dev()); seg = torch.tensor(g["seg"]).to(dev())
+    items = g["valid_items"].tolist(); labels = [int(g["label"][i]) for i in items]
+    area = R.pool_objects_per_image(X, seg, items, labels)
+    assert np.allclose(area.cpu().numpy(), g["area"], rtol=FP32_RTOL, atol=1e-7)
+    assert float(area[2].abs().sum()) == 0.0
+    Xg = X.clone().requires_grad_(True)
+    mp = R.masked_average_pooling(Xg, seg, torch.tensor(g["objs"]))
+    assert np.allclose(mp.detach().cpu().numpy(), g["mp"], rtol=FP32_RTOL, atol=1e-7)
+    (mp * torch.tensor(g["mp_upstream"]).to(dev())).sum().backward()
+    assert np.allclose(Xg.grad.cpu().numpy(), g["mp_dX"], rtol=FP32_RTOL, atol=1e-9)
+
+
+@pytest.mark.parametrize("B,D,H,W,blk,dtype", [(3, 64, 32, 32, 8, torch.float32), (2, 128, 48, 40, 4, torch.bfloat16),
+                                                (2, 16, 9, 7, 1, torch.float32), (1, 512, 64, 64, 16, torch.float32)])
+def test_pooling_all_blocks(B, D, H, W, blk, dtype):
+    """config-3 style: every block of every image is an object; one read of X."""
+    import rangeclip_b200 as R
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, D, H, W, generator=g).to(dtype).float()
+    labels_pool = list(range(0, 40))
+    seg = block_seg(B, H - H % blk, W - W % blk, blk, labels_pool, g)
+    seg = torch.nn.functional.pad(seg, (0, W - seg.shape[2], 0, H - seg.shape[1]), value=39)
+    items, labels = [], []
+    for b in range(B):
+        for lab in torch.unique(seg[b]).tolist():
+            items.append(b); labels.append(lab)
+    items += [0, 0]; labels += [labels[0], 77]           # a duplicate and an absent label
+    ref = O.area_pool_per_image(x.double(), seg, items, labels)
+    out = R.pool_objects_per_image(x.to(dev()).to(dtype), seg.to(dev()), items, labels)
+    assert maxrel(out.float().cpu(), ref) < (2e-6 if dtype == torch.float32 else 5e-3)
+    assert float(out[-1].abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# InfoNCE
+# ------------------------------------------------------------------------------------------------
+
+def _infonce_case(B, D, H, W, K, seed, bf16_exact, ignore_frac=0.2, tau=0.07):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, D, H, W, generator=g) * (0.5 + torch.rand(B, 1, H, W, generator=g))
+    t = unit(torch.randn(K, D, generator=g), 1)
+    if bf16_exact:
+        x = x.to(torch.bfloat16).float()
+        t = t.to(torch.bfloat16).float()
+    y = torch.randint(0, K, (B, H * W), generator=g, dtype=torch.int32)
+    y[torch.rand(B, H * W, generator=g) < ignore_frac] = -1
+    w = torch.randint(0, 4, (B, H * W), generator=g).float()
+    return x, t, y, w, 1.0 / tau
+
+
+def _oracle_infonce(x, t, y, w, inv_tau):
+    B, D, H, W = x.shape
+    rows = x.permute(0, 2, 3, 1).reshape(-1, D)
+    r = O.infonce_dense(rows, t, y.reshape(-1), w.reshape(-1), inv_tau)
+    r["dx4"] = r["dx"].reshape(B, H, W, D).permute(0, 3, 1, 2)
+    return r
+
+
+@pytest.mark.parametrize("B,D,H,W,K", [(2, 64, 8, 8, 20), (1, 512, 16, 16, 256), (2, 128, 5, 7, 33), (1, 96, 4, 8, 300),
+                                        (1, 256, 8, 16, 1)])
+def test_infonce_fp32(B, D, H, W, K):
+    from rangeclip_b200 import ops
+    x, t, y, w, inv_tau = _infonce_case(B, D, H, W, K, seed=B * 1000 + D + K, bf16_exact=False)
+    ref = _oracle_infonce(x, t, y, w, inv_tau)
+    r = ops.infonce_raw(x.to(dev()), t.to(dev()), y.to(dev()), w.to(dev()), inv_tau, True, True, "fp32")
+    loss = float(r["loss_sum"] / r["w_sum"])
+    assert abs(loss - float(ref["loss"])) <= FP32_RTOL * abs(float(ref["loss"]))
+    assert float(r["w_sum"]) == float(ref["wsum"])
+    assert maxrel(r["lse"].cpu(), ref["lse"]) < FP32_RTOL
+    assert maxrel(r["dx"].cpu(), ref["dx4"]) < FP32_RTOL
+    assert maxrel(r["dt"].cpu(), ref["dt"]) < FP32_RTOL
+    assert abs(float(r["dlogtau"]) - float(ref["dlogtau"])) <= FP32_RTOL * abs(float(ref["dlogtau"])) + 1e-9
+
+
+@pytest.mark.parametrize("B,D,H,W,K,xdtype", [(1, 128, 16, 8, 64, torch.bfloat16), (2, 512, 16, 16, 256, torch.bfloat16),
+                                               (2, 256, 16, 24, 100, torch.bfloat16), (1, 512, 20, 20, 200, torch.float32),
+                                               (3, 384, 8, 40, 7, torch.bfloat16)])
+def test_infonce_bf16_tensor_core(B, D, H, W, K, xdtype):
+    from rangeclip_b200 import ops
+    x, t, y, w, inv_tau = _infonce_case(B, D, H, W, K, seed=B * 77 + D + K, bf16_exact=True)
+    ref = _oracle_infonce(x, t, y, w, inv_tau)
+    r = ops.infonce_raw(x.to(dev()).to(xdtype), t.to(dev()), y.to(dev()), w.to(dev()), inv_tau, True, False, "bf16")
+    torch.cuda.synchronize()
+    loss = float(r["loss_sum"] / r["w_sum"])
+    assert abs(loss - float(ref["loss"])) <= 2e-3 * abs(float(ref["loss"])), (loss, float(ref["loss"]))
+    assert maxrel(r["lse"].cpu(), ref["lse"]) < 2e-3
+    assert maxrel(r["dx"].float().cpu(), ref["dx4"]) < BF16_MAXREL
+    assert abs(float(r["dlogtau"]) - float(ref["dlogtau"])) <= BF16_MAXREL * abs(float(ref["dlogtau"]))
+    # forward-only launch (validation path) gives the same loss
+    r2 = ops.infonce_raw(x.to(dev()).to(xdtype), t.to(dev()), y.to(dev()), w.to(dev()), inv_tau, False, False, "bf16")
+    assert abs(float(r2["loss_sum"] / r2["w_sum"]) - loss) <= 1e-6 * abs(loss)
+
+
+def test_infonce_bf16_linearity_full_width():
+    """Size-independent property at the headline tile shape (D=512, K=256, HW=65536, one image):
+    gradients are linear in the upstream scale and rows with w = 0 get exactly zero gradient."""
+    from rangeclip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, D, H, W, K = 1, 512, 256, 256, 256
+    x = torch.randn(B, D, H, W, device=dev(), generator=g).to(torch.bfloat16)
+    t = unit(torch.randn(K, D, device=dev(), generator=g), 1)
+    y = torch.randint(0, K, (B, H * W), device=dev(), generator=g, dtype=torch.int32)
+    w = (torch.rand(B, H * W, device=dev(), generator=g) < 0.7).float()
+    r1 = ops.infonce_raw(x, t, y, w, 1 / 0.07, True, False, "bf16")
+    r2 = ops.infonce_raw(x, t, y, w, 1 / 0.07, True, False, "bf16", grad_scale=torch.tensor(4.0, device=dev()))
+    assert torch.equal(r2["dx"].float(), 4.0 * r1["dx"].float())          # power-of-two scale: exact in bf16
+    zero_rows = (w.view(H, W) == 0)
+    assert float(r1["dx"].float()[0][:, zero_rows].abs().max()) == 0.0
+    assert abs(float(r1["loss_sum"]) - float(r2["loss_sum"])) <= 1e-9 * abs(float(r1["loss_sum"]))
+
+
+# ------------------------------------------------------------------------------------------------
+# drop-in compute_loss / predict against the golden fixtures of the reference
+# ------------------------------------------------------------------------------------------------
+
+class _Model(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.log_temperature_text = torch.nn.Parameter(torch.log(torch.tensor(0.07)))
+        self.log_temperature_image = torch.nn.Parameter(torch.log(torch.tensor(0.1)))
+
+
+def _sets(g):
+    C = g["text"].shape[0]
+    hard = {i: [int(v) for v in g["hard"][i]] for i in range(C)}
+    med = {i: [int(v) for v in g["medium"][i]] for i in range(C)}
+    if str(g["sim_form"]) == "list":
+        return {"medium": [med[i] for i in range(C)], "hard": [hard[i] for i in range(C)]}
+    return {"medium": med, "hard": hard}
+
+
+@pytest.mark.parametrize("case", ["dict", "list", "noimg", "medium"])
+def test_compute_loss_golden(golden_dir, case):
+    import rangeclip_b200 as R
+    from unittest import mock
+    g = np.load(os.path.join(golden_dir, f"loss_{case}.npz"))
+    model = _Model().to(dev())
+    X = torch.tensor(g["X"]).to(dev()).requires_grad_(True)
+    area = torch.tensor(g["area"]).to(dev()) if g["area"].size else None
+    img = torch.tensor(g["img"]).to(dev()) if g["img"].size else None
+    rand_idx = torch.tensor(g["rand_idx"]).to(dev())
+    seed = int(g["seed"])
+    np.random.seed(seed); torch.manual_seed(seed); random.seed(seed)
+    with mock.patch("torch.randint", lambda *a, **k: rand_idx):
+        total, info = R.compute_loss(model, X, torch.tensor(g["seg"]).to(dev()), torch.tensor(g["text"]).to(dev()),
+                                     _sets(g), area, img, W_image=float(g["W_image"]), W_smooth=float(g["W_smooth"]),
+                                     percent_image_sampling=float(g["pct_sampling"]),
+                                     k_distractors=int(g["k_distractors"]), pct_medium=float(g["pcts"][0]),
+                                     pct_hard=float(g["pcts"][1]), pct_rand=float(g["pcts"][2]), precision="fp32")
+    total.backward()
+    assert abs(float(total) - float(g["total"])) <= FP32_RTOL * abs(float(g["total"]))
+    assert abs(info["text_contrastive_loss"] - float(g["text_loss"])) <= FP32_RTOL * abs(float(g["text_loss"]))
+    assert abs(info["image_contrastive_loss"] - float(g["image_loss"])) <= FP32_RTOL * abs(float(g["image_loss"])) + 1e-12
+    assert abs(info["smoothness_loss"] - float(g["smooth_loss"])) <= FP32_RTOL * abs(float(g["smooth_loss"]))
+    assert maxrel(X.grad.cpu(), g["dX"]) < FP32_RTOL
+    assert abs(float(model.log_temperature_text.grad) - float(g["dlogtau_text"])) <= FP32_RTOL * abs(float(g["dlogtau_text"]))
+    if img is not None:
+        assert abs(float(model.log_temperature_image.grad) - float(g["dlogtau_image"])) <= FP32_RTOL * abs(float(g["dlogtau_image"]))
+
+
+def test_predict_golden_tie_aware(golden_dir):
+    import rangeclip_b200 as R
+    g = np.load(os.path.join(golden_dir, "predict.npz"))
+    emb = torch.tensor(g["emb"]); text = torch.tensor(g["text"]); seg = torch.tensor(g["seg"])
+    random.seed(int(g["seed"]))
+    topk, xn = R.predict_from_embeddings(emb.to(dev()), text.to(dev()), seg.to(dev()), int(g["num_negatives"]), int(g["top_k"]))
+    topk = topk.cpu().numpy()
+    assert np.allclose(xn.cpu().numpy(), g["xn"], rtol=1e-6, atol=1e-7)
+    if not np.array_equal(topk, g["topk"]):
+        # every disagreement must be a near-tie in the oracle's logits (SURVEY section 7, K7 contract)
+        random.seed(int(g["seed"]))
+        reduced = O.build_candidate_set(seg, text.shape[0], int(g["num_negatives"]))
+        _, logits, _ = O.predict_tail(emb, text, reduced, int(g["top_k"]))
+        glob = {c: i for i, c in enumerate(reduced)}
+        B, k, H, W = topk.shape
+        bad = np.argwhere(topk != g["topk"])
+        for b, j, h, w_ in bad:
+            la = float(logits[b, glob[int(topk[b, j, h, w_])], h * W + w_])
+            lb = float(logits[b, glob[int(g["topk"][b, j, h, w_])], h * W + w_])
+            assert abs(la - lb) < 1e-5
+
+
+def test_missing_gpu_paths_fail_loudly():
+    from rangeclip_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.tv_sums(torch.zeros(1, 1, 4, 4))          # CPU tensor: no fallback
