@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the DepthCLIP pixel-text InfoNCE hot path (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU port, host cores
+
+Workload (one "step" = one fused forward+backward pass over one batch): B=64 images of 256x256
+pixel embeddings, D=512, bf16, K=256 text rows (63 ground-truth labels + 193 curriculum
+distractors), sampling weights as in model.py:220-228.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(B=64, H=256, W=256, D=512, K=256, C=1024, G=63, tau=0.07, pct_sampling=0.7)
+METRIC = "pixel_text_infonce_fwd_bwd_throughput"
+UNIT = "Mpix/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------------
+
+def make_labels(B, H, W, G, gen):
+    """Per image an 8x8 grid of 32x32 blocks; labels from a pool of G foreground ids, id 0 once."""
+    gh, gw = H // 32, W // 32
+    pick = torch.randint(1, G + 1, (B, gh, gw), generator=gen)
+    pick[:, 0, 0] = 0
+    return pick.repeat_interleave(32, 1).repeat_interleave(32, 2).contiguous()
+
+
+def make_device_workload(device, seed, B):
+    c = CFG
+    g = torch.Generator(device=device).manual_seed(seed)
+    D, H, W, K, C = c["D"], c["H"], c["W"], c["K"], c["C"]
+    x = torch.empty(B, D, H, W, device=device, dtype=torch.bfloat16)
+    for b in range(B):                                    # unit-norm rows, generated per image to bound memory
+        xb = torch.randn(D, H, W, device=device, generator=g)
+        x[b] = (xb / xb.norm(dim=0, keepdim=True)).to(torch.bfloat16)
+    text = torch.nn.functional.normalize(torch.randn(C, D, device=device, generator=g), dim=1)
+    seg = make_labels(B, H, W, c["G"], torch.Generator().manual_seed(seed)).to(device)
+    # contrast set: the G ground-truth ids + (K - G) distractor ids  (curriculum 0/0.75/0.25, Q3 dict form)
+    gt_ids = torch.arange(1, c["G"] + 1, device=device)
+    rest = torch.arange(c["G"] + 1, C, device=device)
+    distract = rest[torch.randperm(rest.numel(), device=device, generator=g)[: K - c["G"]]]
+    contrast = torch.unique(torch.cat([gt_ids, distract]))
+    assert contrast.numel() == K
+    n_samples = int(c["pct_sampling"] * H * W)
+    rand_idx = torch.randint(0, H * W, (B, n_samples), device=device, generator=g)
+    return dict(x=x, text=text, seg=seg, contrast=contrast, rand_idx=rand_idx)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                    str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([v.strip() for v in o.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline = the oracle port (reference op sequence on torch CPU), bounded sample
+# ------------------------------------------------------------------------------------------------
+
+def cpu_reference_step(Bc, seed=0):
+    """One fwd+bwd of the reference's pixel-text InfoNCE (model.py:204-291 op sequence) on CPU."""
+    from oracle import rangeclip_oracle as O
+    c = CFG
+    g = torch.Generator().manual_seed(seed)
+    D, H, W, K, C = c["D"], c["H"], c["W"], c["K"], c["C"]
+    x = torch.nn.functional.normalize(torch.randn(Bc, D, H, W, generator=g), dim=1).requires_grad_(True)
+    text = torch.nn.functional.normalize(torch.randn(C, D, generator=g), dim=1)
+    seg = make_labels(Bc, H, W, c["G"], g)
+    contrast = torch.unique(torch.cat([torch.arange(1, c["G"] + 1), torch.arange(c["G"] + 1, c["G"] + 1 + K - c["G"])]))
+    rand_idx = torch.randint(0, H * W, (Bc, int(c["pct_sampling"] * H * W)), generator=g)
+    log_tau = torch.log(torch.tensor(c["tau"])).requires_grad_(True)
+
+    def step():
+        x.grad = None
+        loss = O.text_infonce_sampled(x, seg, text, rand_idx, contrast, log_tau)
+        loss.backward()
+        return float(loss.detach())
+
+    return step, Bc * H * W
+
+
+def time_cpu(Bc, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, pix = cpu_reference_step(Bc)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    return pix / t / 1e6, t, torch.get_num_threads()
+
+
+# ------------------------------------------------------------------------------------------------
+# main
+# ------------------------------------------------------------------------------------------------
+
+def dist_env():
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    c = CFG
+    Bc = 2
+    val, t, cores = time_cpu(Bc, max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)))
+    sample = f"B={Bc} of the B={c['B']} batch per step (same 256x256, D=512, K=256, 0.7 sampling), torch CPU fp32"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": min(args.steps, 5),
+        "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: pixel-text InfoNCE fwd+bwd, 256x256, D=512, K=256", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    from rangeclip_b200 import _lib, ops
+    import rangeclip_b200 as R
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    c = CFG
+    B, D, H, W, K = c["B"], c["D"], c["H"], c["W"], c["K"]
+    HW, M = H * W, c["B"] * H * W
+    wl = make_device_workload(device, 1234 + rank, B)
+    x, text, seg = wl["x"], wl["text"], wl["seg"]
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    inv_tau = 1.0 / c["tau"]
+
+    # per-step inputs that the loss wrapper derives from (seg, rand_idx, contrast): part of the step
+    label_map = torch.full((c["C"],), -1, dtype=torch.int32, device=device)
+    label_map[wl["contrast"]] = torch.arange(K, device=device, dtype=torch.int32)
+    _, tb, ttb = ops.text_prepare(text, wl["contrast"], want_f32=False, want_bf16=True)
+    ws_bytes = int(L.rc_infonce_workspace_bytes(B, D, HW, K, _lib.RC_BF16))
+    ws = torch.empty(ws_bytes, device=device, dtype=torch.uint8)
+    dx = torch.empty(B, D, HW, device=device, dtype=torch.bfloat16)
+    lse = torch.empty(M, device=device, dtype=torch.float32)
+    acc = torch.zeros(4, device=device, dtype=torch.float64)
+
+    def step(flags=0, prepass_only=False):
+        """sampling weights -> weight sum -> pre-pass -> fused fwd+bwd kernel (loss, lse, dX, dlogtau)."""
+        w, y = ops.sample_weights(seg.view(B, HW), wl["rand_idx"], label_map)
+        acc.zero_()
+        _lib.check(L.rc_weight_sum(w.data_ptr(), y.data_ptr(), M, acc[3:].data_ptr(), st), "rc_weight_sum")
+        _lib.check(L.rc_infonce_bf16(x.data_ptr(), _lib.RC_BF16, B, D, HW, tb.data_ptr(), ttb.data_ptr(), K,
+                                     y.data_ptr(), w.data_ptr(), inv_tau, lse.data_ptr(), acc[0:].data_ptr(),
+                                     acc[1:].data_ptr(), acc[3:].data_ptr(), None, dx.data_ptr(), None,
+                                     acc[2:].data_ptr(), ws.data_ptr(), ws_bytes, flags, st), "rc_infonce_bf16")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    n0 = _lib.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    with ClockSampler(local) as clk:
+        barrier()
+        ev[0].record()
+        for _ in range(args.steps):
+            step()
+        ev[1].record()
+        barrier()
+    launches = _lib.launch_count() - n0
+    ms = ev[0].elapsed_time(ev[1])
+    tmax = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax)
+    loss = float(acc[0] / acc[1])
+    value = world * M * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- dominant kernel alone (pre-pass already in the workspace): CUDA events on the launch stream
+    w, y = ops.sample_weights(seg.view(B, HW), wl["rand_idx"], label_map)
+    kev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    kreps = max(3, args.steps)
+    kev[0].record()
+    for _ in range(kreps):
+        _lib.check(L.rc_infonce_bf16(x.data_ptr(), _lib.RC_BF16, B, D, HW, tb.data_ptr(), ttb.data_ptr(), K,
+                                     y.data_ptr(), w.data_ptr(), inv_tau, lse.data_ptr(), acc[0:].data_ptr(),
+                                     acc[1:].data_ptr(), acc[3:].data_ptr(), None, dx.data_ptr(), None,
+                                     acc[2:].data_ptr(), ws.data_ptr(), ws_bytes, 1, st), "rc_infonce_bf16")
+    kev[1].record()
+    torch.cuda.synchronize()
+    k_ms = kev[0].elapsed_time(kev[1]) / kreps
+    pk = peaks()
+    flops = 4.0 * M * K * D                      # S = X T^T and dX = P T: 2 GEMM units (dText not produced by this kernel)
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    long_region = ms > 2000.0
+    peak = pk["tf_sust"] if long_region else pk["tf_burst"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("infonce_umma_kernel_bytes_per_launch")
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "infonce_umma_kernel<true>", "kernel_ms": k_ms,
+                "peak_source": f"{pk['src']} {'sustained' if long_region else 'burst'} cuBLAS bf16",
+                "algorithmic_flops_per_launch": flops}
+
+    # ---- end to end through the public drop-in API with HOST buffers (pinned), loss read back
+    e2e = None
+    if not args.no_e2e:
+        class M_(torch.nn.Module):
+            def __init__(s):
+                super().__init__()
+                s.log_temperature_text = torch.nn.Parameter(torch.log(torch.tensor(c["tau"])))
+                s.log_temperature_image = torch.nn.Parameter(torch.log(torch.tensor(0.1)))
+        model = M_().to(device)
+        xh = x.cpu().pin_memory()
+        segh = seg.cpu().pin_memory()
+        sets = {"medium": {}, "hard": {i: [] for i in range(c["C"])}}
+        # hard sets: every GT label lists the benchmark's distractor ids so that the reference's own
+        # builder (model.py:240-268) yields exactly K = 256 contrast rows
+        gt = set(range(1, c["G"] + 1))
+        dis = [int(v) for v in wl["contrast"].tolist() if int(v) not in gt]
+        for lab in gt:
+            sets["hard"][lab] = dis
+        e_steps = max(2, min(args.steps, 5))
+        h2d = xh.numel() * 2 + segh.numel() * 8
+        d2h = 6 * 4
+
+        def e2e_step():
+            xd = xh.to(device, non_blocking=True).requires_grad_(True)
+            sd = segh.to(device, non_blocking=True)
+            total, info = R.compute_loss(model, xd, sd, text, sets, None, None, W_text=1.0, W_image=0.0, W_smooth=0.0,
+                                         percent_image_sampling=c["pct_sampling"], k_distractors=K - c["G"],
+                                         pct_medium=0.0, pct_hard=1.0, pct_rand=0.0, precision="bf16")
+            total.backward()
+            return info["total_loss"]
+
+        np.random.seed(0); torch.manual_seed(0)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        barrier()
+        dt_e = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * M * e_steps / float(dt_e) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e_steps,
+               "api": "rangeclip_b200.compute_loss(...)+backward, pinned host X/seg, loss_info read back"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, t, cores = time_cpu(2, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "B=2 of the B=64 batch (256x256, D=512, K=256, 0.7 sampling), torch CPU fp32, median of 3",
+               "s_per_step": t}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1]: pixel-text InfoNCE fwd+bwd, B=64/GPU, 256x256, D=512, K=256 (63 GT + 193 distractors), "
+                                   "0.7 sampling with replacement", "outputs": "loss, lse, dX (bf16), dlogtau",
+                       "l2": "inputs (4.3 GB bf16 per step) exceed the 126 MB L2; no flush needed",
+                       "step": "rc_sample_weights + rc_weight_sum + pre-pass (1/|x|) + fused tcgen05 kernel"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "loss": loss,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -76,14 +76,20 @@ int rc_infonce_f32(const float* x, int B, int D, int64_t HW, int64_t ld_b,
  *   tt_bf16  [D][Kp] bf16 = transpose of t_bf16 (operand of the dX GEMM)
  *   dx       nullable; same dtype as x; = grad_scale * w_p/sum(w) * d(lse_p - z_py)/dx
  *   dt       nullable [K][D] f32, ADDED to (second kernel, recomputes S slice-wise)
- *   workspace from rc_infonce_workspace_bytes; holds bf16 copy of x (f32 input) and 1/|x|.   */
+ *   workspace from rc_infonce_workspace_bytes; holds bf16 copy of x (f32 input) and 1/|x|.
+ *   flags    RC_INFONCE_PREPASS_DONE: the workspace already holds the pre-pass results for this
+ *            x (written by rc_infonce_prepass or an earlier call); skip the pre-pass kernel.      */
+#define RC_INFONCE_PREPASS_DONE 1
 int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
                     const void* t_bf16, const void* tt_bf16, int K,
                     const int32_t* y, const float* w, float inv_tau,
                     float* lse, double* loss_sum, double* w_sum,
                     const double* w_sum_in, const float* grad_scale,
                     void* dx, float* dt, double* dlogtau,
-                    void* workspace, int64_t workspace_bytes, void* stream);
+                    void* workspace, int64_t workspace_bytes, int flags, void* stream);
+/* The pre-pass alone: 1/|x_p| of the bf16-rounded rows (+ bf16 copy of an f32 x) into workspace. */
+int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
+                       void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Helpers used by both paths.
  * rc_text_prepare: rows of `text[idx[k]]` (idx nullable = identity) are L2-normalised

@@ -562,40 +562,56 @@ extern "C" int64_t rc_infonce_workspace_bytes(int B, int D, int64_t HW, int K, r
   return bytes + 256;
 }
 
+namespace rc {
+static int infonce_prepass_impl(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, void* workspace,
+                                int64_t workspace_bytes, cudaStream_t s, float** inv_norm_out, __nv_bfloat16** xb_out) {
+  RC_REQUIRE(x && workspace, "rc_infonce_prepass: null pointer");
+  if (HW % 8 != 0) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: HW=%lld must be a multiple of 8", (long long)HW);
+  RC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "rc_infonce_bf16: x must be 16-byte aligned");
+  RC_REQUIRE(workspace_bytes >= rc_infonce_workspace_bytes(B, D, HW, 0, x_dtype), "rc_infonce_bf16: workspace too small");
+  const int64_t M = (int64_t)B * HW;
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  *inv_norm_out = reinterpret_cast<float*>(ws);
+  *xb_out = (x_dtype == RC_F32) ? reinterpret_cast<__nv_bfloat16*>(ws + ((M * 4 + 255) / 256) * 256) : nullptr;
+  if (s == (cudaStream_t)-1 || M == 0) return RC_OK;   // pointers only
+  const int64_t groups = M / 8;
+  const int64_t blocks = (groups + 255) / 256;
+  const int grid = (int)(blocks < (int64_t)num_sms() * 8 ? blocks : (int64_t)num_sms() * 8);
+  if (x_dtype == RC_F32) rownorm_kernel<float><<<grid, 256, 0, s>>>((const float*)x, B, D, HW, *xb_out, *inv_norm_out);
+  else rownorm_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, B, D, HW, nullptr, *inv_norm_out);
+  return check_launch("rc_infonce_prepass");
+}
+}  // namespace rc
+
+extern "C" int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+  float* inv_norm; __nv_bfloat16* xb;
+  int rcode = rc::check_sm100("rc_infonce_prepass");
+  if (rcode) return rcode;
+  return rc::infonce_prepass_impl(x, x_dtype, B, D, HW, workspace, workspace_bytes, (cudaStream_t)stream, &inv_norm, &xb);
+}
+
 extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16,
                                const void* tt_bf16, int K, const int32_t* y, const float* w, float inv_tau, float* lse,
                                double* loss_sum, double* w_sum, const double* w_sum_in, const float* grad_scale, void* dx,
-                               float* dt, double* dlogtau, void* workspace, int64_t workspace_bytes, void* stream) {
+                               float* dt, double* dlogtau, void* workspace, int64_t workspace_bytes, int flags, void* stream) {
   using namespace rc;
   RC_REQUIRE(x && t_bf16 && y && w && workspace, "rc_infonce_bf16: null pointer");
   RC_REQUIRE(B >= 0 && HW >= 0, "rc_infonce_bf16: bad shape");
   if (K < 1 || K > 256) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: K=%d outside [1,256] (use rc_infonce_f32)", K);
   if (D < 128 || D > 512 || D % 128 != 0) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: D=%d must be 128, 256, 384 or 512", D);
-  if (HW % 8 != 0) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: HW=%lld must be a multiple of 8", (long long)HW);
-  RC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(t_bf16) & 15) == 0,
-             "rc_infonce_bf16: x and t must be 16-byte aligned");
+  RC_REQUIRE((reinterpret_cast<uintptr_t>(t_bf16) & 15) == 0, "rc_infonce_bf16: t must be 16-byte aligned");
   const bool bwd = dx != nullptr;
   if (bwd) RC_REQUIRE(tt_bf16 && w_sum_in && (reinterpret_cast<uintptr_t>(dx) & 15) == 0, "rc_infonce_bf16: backward needs tt_bf16, w_sum_in and aligned dx");
   if (dt != nullptr) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: dText is produced by rc_infonce_dt_bf16");
   if (dlogtau && !bwd) return fail(RC_ERR_INVALID, "rc_infonce_bf16: dlogtau needs dx");
-  RC_REQUIRE(workspace_bytes >= rc_infonce_workspace_bytes(B, D, HW, K, x_dtype), "rc_infonce_bf16: workspace too small");
   if (B == 0 || HW == 0) return RC_OK;
   int rcode = check_sm100("rc_infonce_bf16");
   if (rcode) return rcode;
   cudaStream_t s = (cudaStream_t)stream;
-  const int64_t M = (int64_t)B * HW;
-  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  float* inv_norm = reinterpret_cast<float*>(ws);
-  __nv_bfloat16* xb = nullptr;
-  if (x_dtype == RC_F32) xb = reinterpret_cast<__nv_bfloat16*>(ws + ((M * 4 + 255) / 256) * 256);
-  {
-    const int64_t groups = M / 8;
-    const int64_t blocks = (groups + 255) / 256;
-    const int grid = (int)(blocks < (int64_t)num_sms() * 8 ? blocks : (int64_t)num_sms() * 8);
-    if (x_dtype == RC_F32) rownorm_kernel<float><<<grid, 256, 0, s>>>((const float*)x, B, D, HW, xb, inv_norm);
-    else rownorm_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, B, D, HW, nullptr, inv_norm);
-    if ((rcode = check_launch("rc_infonce_bf16(rownorm)"))) return rcode;
-  }
+  float* inv_norm; __nv_bfloat16* xb;
+  if ((rcode = infonce_prepass_impl(x, x_dtype, B, D, HW, workspace, workspace_bytes,
+                                    (flags & RC_INFONCE_PREPASS_DONE) ? (cudaStream_t)-1 : s, &inv_norm, &xb))) return rcode;
   const void* xsrc = (x_dtype == RC_F32) ? (const void*)xb : x;
   const int Kp = (K + 63) / 64 * 64;
   CUtensorMap m_xs, m_t, m_tt, m_xe, m_dx;

@@ -157,7 +157,7 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
         check(L.rc_infonce_bf16(_p(x), xdt, B, D, HW, _p(tb), _p(ttb), K, _p(y), _p(w), float(inv_tau), _p(lse),
                                 acc[0:].data_ptr(), acc[1:].data_ptr(),
                                 acc[3:].data_ptr() if need_grad else None, _p(gs), _p(dxb), None,
-                                acc[2:].data_ptr() if need_dx else None, _p(ws), ws_bytes, st), "rc_infonce_bf16")
+                                acc[2:].data_ptr() if need_dx else None, _p(ws), ws_bytes, 0, st), "rc_infonce_bf16")
         dx = None
         if dxb is not None:
             dx = dxb.view(x.shape) if x.dtype == torch.bfloat16 else dxb.view(x.shape).to(x.dtype)
