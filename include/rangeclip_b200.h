@@ -161,6 +161,9 @@ int rc_eval_fold(const int64_t* batch_hist /*[5][C]*/, int C, int32_t batch_inde
  *   variant 0: A K-major [128][Kd], B K-major [N][Kd]
  *   variant 1: A MN-major [Kd][128] (the NCHW pixel operand), B K-major [N][Kd]
  * ------------------------------------------------------------------------------------------- */
+/* Bring-up instrumentation: when set (device int64[32]), CTA 0 of rc_infonce_bf16 records per-barrier
+ * wait cycles of its producer / MMA / softmax / epilogue roles; index 0 = role lifetime. NULL disables. */
+int rc_debug_set_timing_buffer(int64_t* dev_buf);
 int rc_debug_umma_gemm(const void* a_bf16, const void* b_bf16, int N, int Kd, int variant,
                        float* c, void* stream);
 

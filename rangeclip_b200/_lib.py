@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librangeclip_b200.so")
+LIB_PATH = os.environ.get("RANGECLIP_B200_LIB", os.path.join(_HERE, "librangeclip_b200.so"))
 CSRC = os.path.join(_HERE, "csrc")
 
 RC_F32, RC_BF16 = 0, 1
@@ -42,6 +42,7 @@ PROTOTYPES = {
     "rc_eval_topk_bf16": [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _vp],
     "rc_eval_hist": [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "rc_eval_fold": [_vp, _i32, _i32, _vp, _vp, _vp],
+    "rc_debug_set_timing_buffer": [_vp],
     "rc_debug_umma_gemm": [_vp, _vp, _i32, _i32, _i32, _vp, _vp],
 }
 _RESTYPES = {"rc_last_error": C.c_char_p, "rc_launch_count": _i64, "rc_infonce_workspace_bytes": _i64}

@@ -98,11 +98,11 @@ rownorm_kernel(const T* __restrict__ x, int B, int D, int64_t HW, __nv_bfloat16*
 // main kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kTilePx = 128;
-constexpr int kThreads = 384;          // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4-7 softmax, 8-11 dX epilogue
-constexpr int kStages = 2;
-constexpr int kStageBytes = 48 * 1024; // S phase: X chunk 16 KB + text chunk <= 32 KB; dX phase: <= 2 x 16 KB
+constexpr int kThreads = 384;          // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4-11 compute (softmax, then dX epilogue)
+constexpr int kStages = 4;             // ring of 32 KB slots, each with its own full/empty barrier
+constexpr int kStageBytes = 32 * 1024; // one slot = two X chunks (2 x 16 KB) | one text chunk (<= 32 KB) | T^T [128 d][<=128 k]
 constexpr int kPBytes = 64 * 1024;     // P [128 px][<=256 k] bf16, four K-major 128B-swizzled sub-tiles
-constexpr int kStgBufs = 4;
+constexpr int kStgBufs = 3;
 constexpr int kStgPx = 32;             // pixels per dX staging step
 constexpr int kStgBytes = 128 * kStgPx * 2;   // [128 d][32 px] bf16 = 8 KB
 constexpr int kTmemCols = 512;
@@ -122,7 +122,8 @@ constexpr int kOffP = kStages * kStageBytes;
 constexpr int kOffStg = kOffP + kPBytes;
 constexpr int kScaleBufs = 4;          // per-tile row-scale buffers (softmax runs up to 2 tiles ahead of the dX epilogue)
 constexpr int kOffScale = kOffStg + kStgBufs * kStgBytes;       // rs[4][128], cs[4][128] floats
-constexpr int kOffBars = kOffScale + 2 * kScaleBufs * 128 * 4;
+constexpr int kOffXch = kOffScale + 2 * kScaleBufs * 128 * 4;   // softmax half<->half exchange: max, sum, sez, sy [2][128] each
+constexpr int kOffBars = kOffXch + 4 * 2 * 128 * 4;
 constexpr int kSmemBytes = kOffBars + (int)sizeof(UmmaBars) + 1024;   // + alignment slack
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -131,11 +132,28 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// mbar_wait that also accumulates the cycles spent waiting (per role, reported for CTA 0)
+#ifdef RC_TIMING
+#define RC_T0(name) const long long name = clock64()
+#define RC_TACC(idx, name) wt[idx] += clock64() - name
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, int tag, long long* acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, tag);
+  acc[tag] += clock64() - t0;
+}
+#else
+#define RC_T0(name)
+#define RC_TACC(idx, name)
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, int tag, long long*) {
+  mbar_wait(bar, parity, tag);
+}
+#endif
+
 struct InfoNceParams {
   int B, D, K, Kp;
   int64_t HW;
   int tiles_per_img;
-  int64_t n_tiles;
+  int n_tiles;
   const float* inv_norm;
   const int32_t* y;
   const float* w;
@@ -146,6 +164,7 @@ struct InfoNceParams {
   double* loss_sum;
   double* w_sum;
   double* dlogtau;
+  long long* dbg;   // optional [32] per-tag wait-cycle counters of CTA 0 (bring-up instrumentation)
 };
 
 template <bool kBwd>
@@ -156,8 +175,9 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
                     const __grid_constant__ CUtensorMap map_x_e,   // X,            box (32 px, 128 d, 1)
                     const __grid_constant__ CUtensorMap map_dx,    // dX,           box (32 px, 128 d, 1)
                     const InfoNceParams prm) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (128B-swizzle atoms) comes from the declaration, so that the compiler keeps the
+  // shared address space (LDS/STS instead of generic LD/ST) for every access derived from `smem`.
+  extern __shared__ __align__(1024) uint8_t smem[];
   UmmaBars* bars = reinterpret_cast<UmmaBars*>(smem + kOffBars);
   float* rs_s = reinterpret_cast<float*>(smem + kOffScale);          // [kScaleBufs][128]
   float* cs_s = rs_s + kScaleBufs * 128;
@@ -171,40 +191,62 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
     tma_prefetch_desc(&map_x_s); tma_prefetch_desc(&map_t);
     if (kBwd) { tma_prefetch_desc(&map_tt); tma_prefetch_desc(&map_x_e); tma_prefetch_desc(&map_dx); }
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-    mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 128);
-    mbar_init(&bars->p_full, 128); mbar_init(&bars->p_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 128); }
+    mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 256);
+    mbar_init(&bars->p_full, 256); mbar_init(&bars->p_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 256); }
     for (int i = 0; i < kStgBufs; ++i) mbar_init(&bars->stg_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(&bars->tmem_base);
+  if (kBwd) {
+    for (int i = threadIdx.x; i < kPBytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem + kOffP)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+#ifdef RC_TIMING
+  long long wt[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) wt[i] = 0;
+  const long long t_start = clock64();
+#else
+  long long* wt = nullptr;
+#endif
   const uint32_t idesc_s = make_idesc_bf16(128, prm.Kp, /*A MN-major*/ 1, /*B K-major*/ 0);
   const uint32_t idesc_d = make_idesc_bf16(128, 128, 0, 0);
 
   if (warp == 0 && lane == 0) {
     // =============================== TMA producer ===============================
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
-      const int b = (int)(tile / prm.tiles_per_img);
-      const int px0 = (int)(tile - (int64_t)b * prm.tiles_per_img) * kTilePx;
-      for (int c = 0; c < n_dchunks; ++c, ++it) {
-        const int st = it % kStages;
-        mbar_wait(&bars->empty[st], ((it / kStages) & 1) ^ 1, 1);
-        uint8_t* sb = smem + st * kStageBytes;
-        mbar_arrive_expect_tx(&bars->full[st], 2 * 8192 + prm.Kp * 128);
-        tma_load_3d(sb, &map_x_s, &bars->full[st], px0, c * 64, b);
-        tma_load_3d(sb + 8192, &map_x_s, &bars->full[st], px0 + 64, c * 64, b);
-        tma_load_2d(sb + 16384, &map_t, &bars->full[st], c * 64, 0);
+    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+      const int b = tile / prm.tiles_per_img;
+      const int px0 = (tile - b * prm.tiles_per_img) * kTilePx;
+      for (int cp = 0; cp < n_dchunks / 2; ++cp) {
+        {   // slot A: X chunks 2cp, 2cp+1 -- [64 d][128 px] each, as two 64-pixel boxes
+          const int st = it % kStages;
+          mbar_wait_t(&bars->empty[st], ((it / kStages) & 1) ^ 1, 1, wt);
+          uint8_t* sb = smem + st * kStageBytes;
+          mbar_arrive_expect_tx(&bars->full[st], 4 * 8192);
+          for (int cc = 0; cc < 2; ++cc) {
+            tma_load_3d(sb + cc * 16384, &map_x_s, &bars->full[st], px0, (2 * cp + cc) * 64, b);
+            tma_load_3d(sb + cc * 16384 + 8192, &map_x_s, &bars->full[st], px0 + 64, (2 * cp + cc) * 64, b);
+          }
+          ++it;
+        }
+        for (int cc = 0; cc < 2; ++cc, ++it) {   // slots B, C: text chunks [Kp][64 d]
+          const int st = it % kStages;
+          mbar_wait_t(&bars->empty[st], ((it / kStages) & 1) ^ 1, 1, wt);
+          mbar_arrive_expect_tx(&bars->full[st], prm.Kp * 128);
+          tma_load_2d(smem + st * kStageBytes, &map_t, &bars->full[st], (2 * cp + cc) * 64, 0);
+        }
       }
       if (kBwd) {
         for (int q = 0; q < n_q; ++q)
           for (int u = 0; u < n_units; ++u, ++it) {
             const int st = it % kStages;
-            mbar_wait(&bars->empty[st], ((it / kStages) & 1) ^ 1, 2);
+            mbar_wait_t(&bars->empty[st], ((it / kStages) & 1) ^ 1, 2, wt);
             uint8_t* sb = smem + st * kStageBytes;
             const int nb = min(2, n_kchunks - 2 * u);
             mbar_arrive_expect_tx(&bars->full[st], nb * 16384);
@@ -216,36 +258,43 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
   } else if (warp == 1 && lane == 0) {
     // =============================== MMA issuer ================================
     uint32_t it = 0, lt = 0, qcount = 0;
-    for (int64_t tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
-      mbar_wait(&bars->s_empty, (lt & 1) ^ 1, 3);
+    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
+      mbar_wait_t(&bars->s_empty, (lt & 1) ^ 1, 3, wt);
       tc_fence_after();
-      for (int c = 0; c < n_dchunks; ++c, ++it) {
-        const int st = it % kStages;
-        mbar_wait(&bars->full[st], (it / kStages) & 1, 4);
-        tc_fence_after();
-        const uint32_t sb = smem_u32(smem + st * kStageBytes);
+      for (int cp = 0; cp < n_dchunks / 2; ++cp, it += 3) {
+        const int sa = it % kStages;
+        mbar_wait_t(&bars->full[sa], (it / kStages) & 1, 4, wt);
+        const uint32_t xa = smem_u32(smem + sa * kStageBytes);
+        for (int cc = 0; cc < 2; ++cc) {
+          const uint32_t jt = it + 1 + cc;
+          const int sbt = jt % kStages;
+          mbar_wait_t(&bars->full[sbt], (jt / kStages) & 1, 4, wt);
+          tc_fence_after();
+          const uint32_t tb = smem_u32(smem + sbt * kStageBytes);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          // A: X chunk [64 d][128 px], MN-major; one k-step = 16 channels = two 1024-byte atoms
-          const uint64_t a = desc_mnmajor_sw128(sb + ks * 2048, 8192);
-          const uint64_t bdesc = desc_kmajor_sw128(sb + 16384 + ks * 32);
-          mma_bf16_ss(tmem, a, bdesc, idesc_s, (c | ks) != 0);
+          for (int ks = 0; ks < 4; ++ks) {
+            // A: X chunk [64 d][128 px], MN-major; one k-step = 16 channels = two 1024-byte atoms
+            const uint64_t a = desc_mnmajor_sw128(xa + cc * 16384 + ks * 2048, 8192);
+            const uint64_t bdesc = desc_kmajor_sw128(tb + ks * 32);
+            mma_bf16_ss(tmem, a, bdesc, idesc_s, (cp | cc | ks) != 0);
+          }
+          mma_commit(&bars->empty[sbt]);
         }
-        mma_commit(&bars->empty[st]);
+        mma_commit(&bars->empty[sa]);
       }
       mma_commit(&bars->s_full);
       if (kBwd) {
-        mbar_wait(&bars->p_full, lt & 1, 5);
+        mbar_wait_t(&bars->p_full, lt & 1, 5, wt);
         tc_fence_after();
         const uint32_t pb = smem_u32(smem + kOffP);
         for (int q = 0; q < n_q; ++q, ++qcount) {
           const int ab = qcount & 1;
-          mbar_wait(&bars->acc_empty[ab], ((qcount >> 1) & 1) ^ 1, 6);
+          mbar_wait_t(&bars->acc_empty[ab], ((qcount >> 1) & 1) ^ 1, 6, wt);
           tc_fence_after();
           const uint32_t dcol = tmem + 256 + ab * 128;
           for (int u = 0; u < n_units; ++u, ++it) {
             const int st = it % kStages;
-            mbar_wait(&bars->full[st], (it / kStages) & 1, 7);
+            mbar_wait_t(&bars->full[st], (it / kStages) & 1, 7, wt);
             tc_fence_after();
             const uint32_t sb = smem_u32(smem + st * kStageBytes);
             const int nb = min(2, n_kchunks - 2 * u);
@@ -264,12 +313,18 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
         mma_commit(&bars->p_empty);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // =============================== softmax / CE ===============================
+  } else if (warp >= 4) {
+    // ============ compute warps: softmax / CE of the tile, then its dX epilogue ============
+    // Two warps per TMEM lane quarter: half 0 (warps 4-7) owns text columns [0, Kp/2) in the softmax and pixels
+    // [0,16) of every 32-pixel staging step in the epilogue; half 1 (warps 8-11) the rest.
+    const int half = warp >= 8 ? 1 : 0;
     const int row = (warp & 3) * 32 + lane;                 // pixel within the tile == TMEM lane
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int Kh = prm.Kp >> 1;                             // columns per half (multiple of 32)
+    const int cb = half * Kh;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + cb;
     uint8_t* prow = smem + kOffP + row * 128;
     const int sw = row & 7;
+    float* xch = reinterpret_cast<float*>(smem + kOffXch);  // [4][2][128]
     float loss_acc = 0.f, w_acc = 0.f, dlt_acc = 0.f;
     float inv_wsum = 0.f;
     float gscale = 1.f;
@@ -278,10 +333,39 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
       inv_wsum = ws > 0.0 ? (float)(1.0 / ws) : 0.f;
       if (prm.grad_scale) gscale = prm.grad_scale[0];
     }
+    // epilogue state
+    const uint32_t trow_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256 + half * 16;
+    const bool leader = threadIdx.x == 128;
+    const int steps_per_tile = n_q * 4;
+    const int64_t my_tiles = (prm.n_tiles > (int)blockIdx.x) ? (prm.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int64_t total_steps = kBwd ? my_tiles * steps_per_tile : 0;
+    // load cursor (leader only): runs two staging steps ahead of the compute cursor; no divisions per step
+    int lc_tile = blockIdx.x, lc_rem = 0, lc_buf = 0;
+    int lc_b = lc_tile / prm.tiles_per_img, lc_px0 = (lc_tile - lc_b * prm.tiles_per_img) * kTilePx;
+    auto issue_next_load = [&]() {
+      mbar_arrive_expect_tx(&bars->stg_full[lc_buf], kStgBytes);
+      tma_load_3d(smem + kOffStg + lc_buf * kStgBytes, &map_x_e, &bars->stg_full[lc_buf], lc_px0 + (lc_rem & 3) * kStgPx,
+                  (lc_rem >> 2) * 128, lc_b);
+      lc_buf = (lc_buf + 1 == kStgBufs) ? 0 : lc_buf + 1;
+      if (++lc_rem == steps_per_tile) {
+        lc_rem = 0;
+        lc_tile += gridDim.x;
+        lc_b = lc_tile / prm.tiles_per_img;
+        lc_px0 = (lc_tile - lc_b * prm.tiles_per_img) * kTilePx;
+      }
+    };
+    if (leader) {
+      if (total_steps > 0) issue_next_load();
+      if (total_steps > 1) issue_next_load();
+    }
+    int64_t s = 0;
+    int sb = 0;
+    uint32_t sb_par = 0, qcount = 0;
     uint32_t lt = 0;
-    for (int64_t tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
-      const int b = (int)(tile / prm.tiles_per_img);
-      const int px = (int)(tile - (int64_t)b * prm.tiles_per_img) * kTilePx + row;
+    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
+      RC_T0(tg0);
+      const int b = tile / prm.tiles_per_img;
+      const int px = (tile - b * prm.tiles_per_img) * kTilePx + row;
       const bool valid = px < prm.HW;
       const int64_t m = (int64_t)b * prm.HW + px;
       const float inv_n = valid ? prm.inv_norm[m] : 0.f;
@@ -289,134 +373,147 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
       const float wi = (valid && yi >= 0) ? prm.w[m] : 0.f;
       const float zs = inv_n * prm.inv_tau;     // z = s * zs   (zs >= 0)
       const float zl = zs * kLog2e;
-      mbar_wait(&bars->s_full, lt & 1, 8);
+      RC_TACC(5, tg0);
+      mbar_wait_t(&bars->s_full, lt & 1, 8, wt);
       tc_fence_after();
-      // pass 1: row maximum of the raw dots
+      RC_T0(tp1);
+      // pass 1: maximum of the raw dots over this half's valid columns
       float mx = -FLT_MAX;
-      for (int c = 0; c < prm.Kp / 32; ++c) {
+      for (int c = 0; c * 32 < Kh; ++c) {
+        const int nvalid = prm.K - (cb + c * 32);
+        if (nvalid <= 0) break;
         uint32_t r[32];
         tmem_ld_32x32(trow + c * 32, r);
         tmem_ld_wait();
+        float m0 = -FLT_MAX, m1 = -FLT_MAX, m2 = -FLT_MAX, m3 = -FLT_MAX;
+        if (nvalid >= 32) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < prm.K) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(r[i])); m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(r[i + 2])); m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < nvalid) m0 = fmaxf(m0, __uint_as_float(r[i]));
+        }
+        mx = fmaxf(fmaxf(mx, fmaxf(m0, m1)), fmaxf(m2, m3));
       }
+      xch[(0 * 2 + half) * 128 + row] = mx;
+      named_bar_sync(2, 256);
+      mx = fmaxf(mx, xch[(0 * 2 + (half ^ 1)) * 128 + row]);
       const float ml = mx * zl;
-      if (kBwd) mbar_wait(&bars->p_empty, (lt & 1) ^ 1, 9);
-      // pass 2: exp, sums, P
-      float sum = 0.f, sez = 0.f, sy = 0.f;
-      for (int c = 0; c < prm.Kp / 32; ++c) {
+      RC_TACC(6, tp1);
+      if (kBwd) mbar_wait_t(&bars->p_empty, (lt & 1) ^ 1, 9, wt);
+      RC_T0(tp2);
+      // pass 2: e = exp(z - m), partial sums, P (bf16, K-major 128B-swizzled sub-tiles)
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, sy = 0.f;
+      for (int c = 0; c * 32 < Kh; ++c) {
+        const int k0 = cb + c * 32;
+        const int nvalid = prm.K - k0;
+        if (nvalid <= 0) break;
         uint32_t r[32];
         tmem_ld_32x32(trow + c * 32, r);
         tmem_ld_wait();
-        float e[32];
+        const int yrel = yi - k0;
+        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = c * 32 + i;
-          const float s = __uint_as_float(r[i]);
-          e[i] = (k < prm.K) ? fast_exp2(fmaf(s, zl, -ml)) : 0.f;
-          sum += e[i];
-          sez = fmaf(e[i], s, sez);
-          if (k == yi) sy = s;
+        for (int i = 0; i < 32; i += 4) {
+          const float a0 = __uint_as_float(r[i]), a1 = __uint_as_float(r[i + 1]);
+          const float a2 = __uint_as_float(r[i + 2]), a3 = __uint_as_float(r[i + 3]);
+          float e0 = fast_exp2(fmaf(a0, zl, -ml)), e1 = fast_exp2(fmaf(a1, zl, -ml));
+          float e2 = fast_exp2(fmaf(a2, zl, -ml)), e3 = fast_exp2(fmaf(a3, zl, -ml));
+          if (nvalid < 32) {      // warp-uniform; only the chunk that straddles K
+            e0 = (i < nvalid) ? e0 : 0.f; e1 = (i + 1 < nvalid) ? e1 : 0.f;
+            e2 = (i + 2 < nvalid) ? e2 : 0.f; e3 = (i + 3 < nvalid) ? e3 : 0.f;
+          }
+          s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+          q0 = fmaf(e0, a0, q0); q1 = fmaf(e1, a1, q1); q2 = fmaf(e2, a2, q2); q3 = fmaf(e3, a3, q3);
+          sy = (yrel == i) ? a0 : sy; sy = (yrel == i + 1) ? a1 : sy;
+          sy = (yrel == i + 2) ? a2 : sy; sy = (yrel == i + 3) ? a3 : sy;
+          pk[i >> 1] = pack_bf16x2(e0, e1);
+          pk[(i >> 1) + 1] = pack_bf16x2(e2, e3);
         }
         if (kBwd) {
-          uint8_t* sub = prow + (c >> 1) * 16384;        // 64-wide K sub-tile
+          uint8_t* sub = prow + (k0 >> 6) * 16384;          // 64-wide K sub-tile
+          const int cbase = (k0 & 32) >> 3;                 // first 16-byte chunk of this 32-column group
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int chunk = (c & 1) * 4 + g;             // 16-byte chunk within the 128-byte row
-            uint4 v;
-            v.x = pack_bf16x2(e[g * 8 + 0], e[g * 8 + 1]); v.y = pack_bf16x2(e[g * 8 + 2], e[g * 8 + 3]);
-            v.z = pack_bf16x2(e[g * 8 + 4], e[g * 8 + 5]); v.w = pack_bf16x2(e[g * 8 + 6], e[g * 8 + 7]);
-            *reinterpret_cast<uint4*>(sub + ((chunk ^ sw) << 4)) = v;
-          }
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(sub + (((cbase + g) ^ sw) << 4)) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
         }
       }
       tc_fence_before();
       mbar_arrive(&bars->s_empty);               // S columns may be overwritten by the next tile
+      RC_TACC(7, tp2);
+      RC_T0(tp3);
+      float sum = (s0 + s1) + (s2 + s3);
+      float sez = (q0 + q1) + (q2 + q3);
+      const bool mine_y = yi >= cb && yi < cb + Kh;
+      xch[(1 * 2 + half) * 128 + row] = sum;
+      xch[(2 * 2 + half) * 128 + row] = sez;
+      xch[(3 * 2 + half) * 128 + row] = mine_y ? sy : 0.f;
+      named_bar_sync(2, 256);
+      sum += xch[(1 * 2 + (half ^ 1)) * 128 + row];
+      sez += xch[(2 * 2 + (half ^ 1)) * 128 + row];
+      sy = mine_y ? sy : xch[(3 * 2 + (half ^ 1)) * 128 + row];
       const float zy = sy * zs;
-      const float lse = (ml + __log2f(sum)) * kLn2;
-      loss_acc += wi * (lse - zy);
-      w_acc += wi;
-      if (valid && prm.lse) prm.lse[m] = lse;
+      if (half == 0) {
+        const float lse = (ml + __log2f(sum)) * kLn2;
+        loss_acc += wi * (lse - zy);
+        w_acc += wi;
+        if (valid && prm.lse) prm.lse[m] = lse;
+      }
       if (kBwd) {
         const float coef = gscale * wi * inv_wsum;
         const float inv_sum = 1.f / sum;
-        if (yi >= 0) {   // P[row][y] = e_y - sum  (softmax - onehot, times sum), subtraction before rounding
+        if (mine_y) {    // P[row][y] = e_y - sum  (softmax - onehot, times sum), subtraction before rounding
           const float ey = fast_exp2(fmaf(sy, zl, -ml));
           const int kk = yi & 63;
           uint8_t* sub = prow + (yi >> 6) * 16384;
           *reinterpret_cast<__nv_bfloat16*>(sub + (((kk >> 3) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(ey - sum);
         }
-        const float cj = coef * (sez * zs * inv_sum - zy);        // sum_k dz_k z_k
-        rs_s[(lt & (kScaleBufs - 1)) * 128 + row] = inv_n * prm.inv_tau * coef * inv_sum;
-        cs_s[(lt & (kScaleBufs - 1)) * 128 + row] = inv_n * inv_n * cj;
-        dlt_acc -= cj;
+        if (half == 0) {
+          const float cj = coef * (sez * zs * inv_sum - zy);        // sum_k dz_k z_k
+          rs_s[(lt & (kScaleBufs - 1)) * 128 + row] = inv_n * prm.inv_tau * coef * inv_sum;
+          cs_s[(lt & (kScaleBufs - 1)) * 128 + row] = inv_n * inv_n * cj;
+          dlt_acc -= cj;
+        }
         fence_proxy_async_smem();                 // P is read by the tensor core (async proxy)
         mbar_arrive(&bars->p_full);
+        named_bar_sync(2, 256);                   // rs/cs written by half 0 are visible to all compute warps
       }
-    }
-    loss_acc = warp_sum(loss_acc); w_acc = warp_sum(w_acc); dlt_acc = warp_sum(dlt_acc);
-    if (lane == 0) {
-      if (prm.loss_sum) atomicAdd(prm.loss_sum, (double)loss_acc);
-      if (prm.w_sum) atomicAdd(prm.w_sum, (double)w_acc);
-      if (kBwd && prm.dlogtau) atomicAdd(prm.dlogtau, (double)dlt_acc);
-    }
-  } else if (kBwd && warp >= 8) {
-    // =============================== dX epilogue ===============================
-    const int row = (warp & 3) * 32 + lane;                 // channel within the 128-channel block == TMEM lane
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256;
-    const bool leader = threadIdx.x == 256;
-    const int steps_per_tile = n_q * 4;
-    const int64_t my_tiles = (prm.n_tiles > blockIdx.x) ? (prm.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total_steps = my_tiles * steps_per_tile;
-    auto issue_load = [&](int64_t s) {
-      const int64_t ltile = s / steps_per_tile;
-      const int rem = (int)(s - ltile * steps_per_tile);
-      const int64_t tile = blockIdx.x + ltile * gridDim.x;
-      const int b = (int)(tile / prm.tiles_per_img);
-      const int px0 = (int)(tile - (int64_t)b * prm.tiles_per_img) * kTilePx;
-      const int sb = (int)(s & (kStgBufs - 1));
-      mbar_arrive_expect_tx(&bars->stg_full[sb], kStgBytes);
-      tma_load_3d(smem + kOffStg + sb * kStgBytes, &map_x_e, &bars->stg_full[sb], px0 + (rem & 3) * kStgPx, (rem >> 2) * 128, b);
-    };
-    if (leader) {
-      if (total_steps > 0) issue_load(0);
-      if (total_steps > 1) issue_load(1);
-    }
-    int64_t s = 0;
-    uint32_t lt = 0, qcount = 0;
-    for (int64_t tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
-      const int b = (int)(tile / prm.tiles_per_img);
-      const int px0 = (int)(tile - (int64_t)b * prm.tiles_per_img) * kTilePx;
-      mbar_wait(&bars->p_full, lt & 1, 10);      // rs/cs of this tile are visible
+      RC_TACC(10, tp3);
+      if (!kBwd) continue;
+      // ------------------------------ dX epilogue of this tile ------------------------------
+      const int px0 = (tile - b * prm.tiles_per_img) * kTilePx;
       const float* rs = rs_s + (lt & (kScaleBufs - 1)) * 128;
       const float* cs = cs_s + (lt & (kScaleBufs - 1)) * 128;
       for (int q = 0; q < n_q; ++q, ++qcount) {
         const int ab = qcount & 1;
-        mbar_wait(&bars->acc_full[ab], (qcount >> 1) & 1, 11);
+        mbar_wait_t(&bars->acc_full[ab], (qcount >> 1) & 1, 11, wt);
         tc_fence_after();
         for (int h = 0; h < 4; ++h, ++s) {
-          const int sb = (int)(s & (kStgBufs - 1));
-          if (leader && s + 2 < total_steps) {
-            tma_store_wait_read0_keep1();
-            issue_load(s + 2);
-          }
-          uint32_t acc[32];
-          tmem_ld_32x32(trow + ab * 128 + h * kStgPx, acc);
+          // this thread: channel row `row`, pixels [h*32 + half*16, +16) of the tile
+          uint32_t acc[16];
+          RC_T0(tl0);
+          tmem_ld_32x16(trow_acc + ab * 128 + h * kStgPx, acc);
           tmem_ld_wait();
+          RC_TACC(15, tl0);
           if (h == 3) { tc_fence_before(); mbar_arrive(&bars->acc_empty[ab]); }
-          mbar_wait(&bars->stg_full[sb], (uint32_t)((s / kStgBufs) & 1), 12);
+          mbar_wait_t(&bars->stg_full[sb], sb_par, 12, wt);
+          RC_T0(tc0);
           uint8_t* srow = smem + kOffStg + sb * kStgBytes + row * 64;    // 32 px bf16 = 64 B per channel row
-          const int sw = (row >> 1) & 3;                                  // 64-byte swizzle
+          const int sw64 = (row >> 1) & 3;                                // 64-byte swizzle
+          const float* rsp = rs + h * kStgPx + half * 16;
+          const float* csp = cs + h * kStgPx + half * 16;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4* p = reinterpret_cast<uint4*>(srow + ((g ^ sw) << 4));
+          for (int g = 0; g < 2; ++g) {
+            uint4* p = reinterpret_cast<uint4*>(srow + (((half * 2 + g) ^ sw64) << 4));
             const uint4 xv = *p;
             const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
-            const float4 r0 = *reinterpret_cast<const float4*>(rs + h * kStgPx + g * 8);
-            const float4 r1 = *reinterpret_cast<const float4*>(rs + h * kStgPx + g * 8 + 4);
-            const float4 c0 = *reinterpret_cast<const float4*>(cs + h * kStgPx + g * 8);
-            const float4 c1 = *reinterpret_cast<const float4*>(cs + h * kStgPx + g * 8 + 4);
+            const float4 r0 = *reinterpret_cast<const float4*>(rsp + g * 8);
+            const float4 r1 = *reinterpret_cast<const float4*>(rsp + g * 8 + 4);
+            const float4 c0 = *reinterpret_cast<const float4*>(csp + g * 8);
+            const float4 c1 = *reinterpret_cast<const float4*>(csp + g * 8 + 4);
             const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
             const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
             float o[8];
@@ -430,17 +527,48 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
             ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
             *p = ov;
           }
+          RC_TACC(1, tc0);
+          RC_T0(tf0);
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          RC_TACC(2, tf0);
+          named_bar_sync(1, 256);
+          RC_TACC(13, tf0);
           if (leader) {
+            RC_T0(ts0);
             tma_store_3d(&map_dx, smem + kOffStg + sb * kStgBytes, px0 + h * kStgPx, q * 128, b);
             tma_store_commit();
+            RC_TACC(3, ts0);
+            if (s + 2 < total_steps) {
+              RC_T0(tw0);
+              tma_store_wait_read0_keep1();     // the store of step s-1 has finished reading buffer (s+2) % 3
+              RC_TACC(14, tw0);
+              RC_T0(ti0);
+              issue_next_load();
+              RC_TACC(4, ti0);
+            }
           }
+          if (++sb == kStgBufs) { sb = 0; sb_par ^= 1; }
         }
       }
     }
-    if (leader) tma_store_wait_all0();
+    if (kBwd && leader) tma_store_wait_all0();
+    if (half == 0) {
+      loss_acc = warp_sum(loss_acc); w_acc = warp_sum(w_acc); dlt_acc = warp_sum(dlt_acc);
+      if (lane == 0) {
+        if (prm.loss_sum) atomicAdd(prm.loss_sum, (double)loss_acc);
+        if (prm.w_sum) atomicAdd(prm.w_sum, (double)w_acc);
+        if (kBwd && prm.dlogtau) atomicAdd(prm.dlogtau, (double)dlt_acc);
+      }
+    }
   }
+#ifdef RC_TIMING
+  if (prm.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
+    wt[0] = clock64() - t_start;
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) prm.dbg[role * 16 + i] = wt[i];
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -461,8 +589,9 @@ struct __align__(8) DebugBars { uint64_t full, done; uint32_t tmem_base, pad; };
 __global__ void __launch_bounds__(128, 1)
 debug_umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int N, int Kd,
                        int variant, float* __restrict__ c) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (128B-swizzle atoms) comes from the declaration, so that the compiler keeps the
+  // shared address space (LDS/STS instead of generic LD/ST) for every access derived from `smem`.
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sa = smem;               // 16 KB
   uint8_t* sbm = smem + 16384;      // <= 32 KB
   DebugBars* bars = reinterpret_cast<DebugBars*>(smem + 49152);
@@ -583,6 +712,9 @@ static int infonce_prepass_impl(const void* x, rc_dtype x_dtype, int B, int D, i
 }
 }  // namespace rc
 
+namespace rc { static long long* g_dbg_buf = nullptr; }
+extern "C" int rc_debug_set_timing_buffer(int64_t* dev_buf) { rc::g_dbg_buf = (long long*)dev_buf; return RC_OK; }
+
 extern "C" int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, void* workspace,
                                   int64_t workspace_bytes, void* stream) {
   float* inv_norm; __nv_bfloat16* xb;
@@ -633,10 +765,11 @@ extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, in
   InfoNceParams prm;
   prm.B = B; prm.D = D; prm.K = K; prm.Kp = Kp; prm.HW = HW;
   prm.tiles_per_img = (int)((HW + kTilePx - 1) / kTilePx);
-  prm.n_tiles = (int64_t)B * prm.tiles_per_img;
+  if ((int64_t)B * prm.tiles_per_img > 0x7fffffff) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: too many tiles");
+  prm.n_tiles = B * prm.tiles_per_img;
   prm.inv_norm = inv_norm; prm.y = y; prm.w = w; prm.inv_tau = inv_tau; prm.grad_scale = grad_scale;
-  prm.w_sum_in = w_sum_in; prm.lse = lse; prm.loss_sum = loss_sum; prm.w_sum = w_sum; prm.dlogtau = dlogtau;
-  const int grid = (int)(prm.n_tiles < (int64_t)num_sms() ? prm.n_tiles : (int64_t)num_sms());
+  prm.w_sum_in = w_sum_in; prm.lse = lse; prm.loss_sum = loss_sum; prm.w_sum = w_sum; prm.dlogtau = dlogtau; prm.dbg = g_dbg_buf;
+  const int grid = prm.n_tiles < num_sms() ? prm.n_tiles : num_sms();
   cudaError_t e;
   if (bwd) {
     e = cudaFuncSetAttribute(infonce_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
