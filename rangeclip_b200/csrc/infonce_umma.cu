@@ -102,7 +102,7 @@ constexpr int kThreads = 384;          // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 
 constexpr int kStages = 4;             // ring of 32 KB slots, each with its own full/empty barrier
 constexpr int kStageBytes = 32 * 1024; // one slot = two X chunks (2 x 16 KB) | one text chunk (<= 32 KB) | T^T [128 d][<=128 k]
 constexpr int kPBytes = 64 * 1024;     // P [128 px][<=256 k] bf16, four K-major 128B-swizzled sub-tiles
-constexpr int kStgBufs = 3;
+constexpr int kStgBufs = 3;             // dX staging buffers; X for the epilogue is prefetched kStgBufs-1 steps ahead
 constexpr int kStgPx = 32;             // pixels per dX staging step
 constexpr int kStgBytes = 128 * kStgPx * 2;   // [128 d][32 px] bf16 = 8 KB
 constexpr int kTmemCols = 512;
@@ -113,7 +113,7 @@ struct __align__(8) UmmaBars {
   uint64_t full[kStages], empty[kStages];
   uint64_t s_full, s_empty, p_full, p_empty;
   uint64_t acc_full[2], acc_empty[2];
-  uint64_t stg_full[kStgBufs];
+  uint64_t stg_full[kStgBufs], stg_done[kStgBufs];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -194,7 +194,7 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
     mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 256);
     mbar_init(&bars->p_full, 256); mbar_init(&bars->p_empty, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 256); }
-    for (int i = 0; i < kStgBufs; ++i) mbar_init(&bars->stg_full[i], 1);
+    for (int i = 0; i < kStgBufs; ++i) { mbar_init(&bars->stg_full[i], 1); mbar_init(&bars->stg_done[i], 256); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(&bars->tmem_base);
@@ -313,6 +313,46 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
         mma_commit(&bars->p_empty);
       }
     }
+  } else if (kBwd && warp == 3 && lane == 0) {
+    // ================= staging DMA: TMA loads of X for the dX epilogue, TMA stores of dX =================
+    const int steps_per_tile = n_q * 4;
+    const int64_t my_tiles = (prm.n_tiles > (int)blockIdx.x) ? (prm.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int64_t total_steps = my_tiles * steps_per_tile;
+    struct Cursor { int tile, rem, buf, b, px0; };
+    auto init = [&](Cursor& c) {
+      c.tile = blockIdx.x; c.rem = 0; c.buf = 0;
+      c.b = c.tile / prm.tiles_per_img; c.px0 = (c.tile - c.b * prm.tiles_per_img) * kTilePx;
+    };
+    auto advance = [&](Cursor& c) {
+      c.buf = (c.buf + 1 == kStgBufs) ? 0 : c.buf + 1;
+      if (++c.rem == steps_per_tile) {
+        c.rem = 0; c.tile += gridDim.x;
+        c.b = c.tile / prm.tiles_per_img; c.px0 = (c.tile - c.b * prm.tiles_per_img) * kTilePx;
+      }
+    };
+    Cursor ld, stc;
+    init(ld); init(stc);
+    auto issue_next_load = [&]() {
+      mbar_arrive_expect_tx(&bars->stg_full[ld.buf], kStgBytes);
+      tma_load_3d(smem + kOffStg + ld.buf * kStgBytes, &map_x_e, &bars->stg_full[ld.buf], ld.px0 + (ld.rem & 3) * kStgPx,
+                  (ld.rem >> 2) * 128, ld.b);
+      advance(ld);
+    };
+    for (int i = 0; i < kStgBufs - 1; ++i)
+      if (i < total_steps) issue_next_load();
+    uint32_t par = 0;
+    for (int64_t s = 0; s < total_steps; ++s) {
+      mbar_wait_t(&bars->stg_done[stc.buf], par, 13, wt);
+      tma_store_3d(&map_dx, smem + kOffStg + stc.buf * kStgBytes, stc.px0 + (stc.rem & 3) * kStgPx, (stc.rem >> 2) * 128, stc.b);
+      tma_store_commit();
+      if (stc.buf + 1 == kStgBufs) par ^= 1;
+      advance(stc);
+      if (s + kStgBufs - 1 < total_steps) {
+        tma_store_wait_read0_keep1();     // the store of step s-1 has finished reading the buffer being refilled
+        issue_next_load();
+      }
+    }
+    tma_store_wait_all0();
   } else if (warp >= 4) {
     // ============ compute warps: softmax / CE of the tile, then its dX epilogue ============
     // Two warps per TMEM lane quarter: half 0 (warps 4-7) owns text columns [0, Kp/2) in the softmax and pixels
@@ -335,32 +375,28 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
     }
     // epilogue state
     const uint32_t trow_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256 + half * 16;
-    const bool leader = threadIdx.x == 128;
-    const int steps_per_tile = n_q * 4;
-    const int64_t my_tiles = (prm.n_tiles > (int)blockIdx.x) ? (prm.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int64_t total_steps = kBwd ? my_tiles * steps_per_tile : 0;
-    // load cursor (leader only): runs two staging steps ahead of the compute cursor; no divisions per step
-    int lc_tile = blockIdx.x, lc_rem = 0, lc_buf = 0;
-    int lc_b = lc_tile / prm.tiles_per_img, lc_px0 = (lc_tile - lc_b * prm.tiles_per_img) * kTilePx;
-    auto issue_next_load = [&]() {
-      mbar_arrive_expect_tx(&bars->stg_full[lc_buf], kStgBytes);
-      tma_load_3d(smem + kOffStg + lc_buf * kStgBytes, &map_x_e, &bars->stg_full[lc_buf], lc_px0 + (lc_rem & 3) * kStgPx,
-                  (lc_rem >> 2) * 128, lc_b);
-      lc_buf = (lc_buf + 1 == kStgBufs) ? 0 : lc_buf + 1;
-      if (++lc_rem == steps_per_tile) {
-        lc_rem = 0;
-        lc_tile += gridDim.x;
-        lc_b = lc_tile / prm.tiles_per_img;
-        lc_px0 = (lc_tile - lc_b * prm.tiles_per_img) * kTilePx;
-      }
-    };
-    if (leader) {
-      if (total_steps > 0) issue_next_load();
-      if (total_steps > 1) issue_next_load();
-    }
-    int64_t s = 0;
     int sb = 0;
     uint32_t sb_par = 0, qcount = 0;
+    float nx_inv_n = 0.f, nx_w = 0.f;
+    int nx_y = -1;
+    auto load_pixel_scalars = [&](int t) {
+      nx_inv_n = 0.f; nx_w = 0.f; nx_y = -1;
+      if (t < prm.n_tiles) {
+        const int tb = t / prm.tiles_per_img;
+        const int tpx = (t - tb * prm.tiles_per_img) * kTilePx + row;
+        if (tpx < prm.HW) {
+          const int64_t tm = (int64_t)tb * prm.HW + tpx;
+          nx_inv_n = __ldg(prm.inv_norm + tm);
+          nx_y = __ldg(prm.y + tm);
+          nx_w = __ldg(prm.w + tm);
+        }
+      }
+    };
+    load_pixel_scalars(blockIdx.x);
+    // exp(z - m) needs m >= max z for range only.  Cosine logits are bounded: |z| <= |t_k| / tau, so for
+    // tau not too small the constant m = 1.01 / tau replaces the row-maximum pass over TMEM.
+    const bool use_bound = prm.inv_tau * (2.02f * kLog2e) < 100.f;
+    const float ml_bound = prm.inv_tau * (1.01f * kLog2e);
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
       RC_T0(tg0);
@@ -368,18 +404,19 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
       const int px = (tile - b * prm.tiles_per_img) * kTilePx + row;
       const bool valid = px < prm.HW;
       const int64_t m = (int64_t)b * prm.HW + px;
-      const float inv_n = valid ? prm.inv_norm[m] : 0.f;
-      const int yi = valid ? prm.y[m] : -1;
-      const float wi = (valid && yi >= 0) ? prm.w[m] : 0.f;
+      const float inv_n = nx_inv_n;
+      const int yi = nx_y;
+      const float wi = yi >= 0 ? nx_w : 0.f;
+      load_pixel_scalars(tile + (int)gridDim.x);          // next tile's scalars: latency hidden behind this tile
       const float zs = inv_n * prm.inv_tau;     // z = s * zs   (zs >= 0)
       const float zl = zs * kLog2e;
       RC_TACC(5, tg0);
       mbar_wait_t(&bars->s_full, lt & 1, 8, wt);
       tc_fence_after();
       RC_T0(tp1);
-      // pass 1: maximum of the raw dots over this half's valid columns
+      // pass 1: maximum of the raw dots over this half's valid columns (skipped when the bound applies)
       float mx = -FLT_MAX;
-      for (int c = 0; c * 32 < Kh; ++c) {
+      for (int c = 0; !use_bound && c * 32 < Kh; ++c) {
         const int nvalid = prm.K - (cb + c * 32);
         if (nvalid <= 0) break;
         uint32_t r[32];
@@ -398,10 +435,13 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
         }
         mx = fmaxf(fmaxf(mx, fmaxf(m0, m1)), fmaxf(m2, m3));
       }
-      xch[(0 * 2 + half) * 128 + row] = mx;
-      named_bar_sync(2, 256);
-      mx = fmaxf(mx, xch[(0 * 2 + (half ^ 1)) * 128 + row]);
-      const float ml = mx * zl;
+      float ml = ml_bound;
+      if (!use_bound) {
+        xch[(0 * 2 + half) * 128 + row] = mx;
+        named_bar_sync(2, 256);
+        mx = fmaxf(mx, xch[(0 * 2 + (half ^ 1)) * 128 + row]);
+        ml = mx * zl;
+      }
       RC_TACC(6, tp1);
       if (kBwd) mbar_wait_t(&bars->p_empty, (lt & 1) ^ 1, 9, wt);
       RC_T0(tp2);
@@ -420,8 +460,8 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
         for (int i = 0; i < 32; i += 4) {
           const float a0 = __uint_as_float(r[i]), a1 = __uint_as_float(r[i + 1]);
           const float a2 = __uint_as_float(r[i + 2]), a3 = __uint_as_float(r[i + 3]);
-          float e0 = fast_exp2(fmaf(a0, zl, -ml)), e1 = fast_exp2(fmaf(a1, zl, -ml));
-          float e2 = fast_exp2(fmaf(a2, zl, -ml)), e3 = fast_exp2(fmaf(a3, zl, -ml));
+          float e0 = fast_exp2(fminf(fmaf(a0, zl, -ml), 64.f)), e1 = fast_exp2(fminf(fmaf(a1, zl, -ml), 64.f));
+          float e2 = fast_exp2(fminf(fmaf(a2, zl, -ml), 64.f)), e3 = fast_exp2(fminf(fmaf(a3, zl, -ml), 64.f));
           if (nvalid < 32) {      // warp-uniform; only the chunk that straddles K
             e0 = (i < nvalid) ? e0 : 0.f; e1 = (i + 1 < nvalid) ? e1 : 0.f;
             e2 = (i + 2 < nvalid) ? e2 : 0.f; e3 = (i + 3 < nvalid) ? e3 : 0.f;
@@ -466,7 +506,7 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
         const float coef = gscale * wi * inv_wsum;
         const float inv_sum = 1.f / sum;
         if (mine_y) {    // P[row][y] = e_y - sum  (softmax - onehot, times sum), subtraction before rounding
-          const float ey = fast_exp2(fmaf(sy, zl, -ml));
+          const float ey = fast_exp2(fminf(fmaf(sy, zl, -ml), 64.f));
           const int kk = yi & 63;
           uint8_t* sub = prow + (yi >> 6) * 16384;
           *reinterpret_cast<__nv_bfloat16*>(sub + (((kk >> 3) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(ey - sum);
@@ -491,7 +531,7 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
         const int ab = qcount & 1;
         mbar_wait_t(&bars->acc_full[ab], (qcount >> 1) & 1, 11, wt);
         tc_fence_after();
-        for (int h = 0; h < 4; ++h, ++s) {
+        for (int h = 0; h < 4; ++h) {
           // this thread: channel row `row`, pixels [h*32 + half*16, +16) of the tile
           uint32_t acc[16];
           RC_T0(tl0);
@@ -528,30 +568,12 @@ infonce_umma_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][H
             *p = ov;
           }
           RC_TACC(1, tc0);
-          RC_T0(tf0);
-          fence_proxy_async_smem();
-          RC_TACC(2, tf0);
-          named_bar_sync(1, 256);
-          RC_TACC(13, tf0);
-          if (leader) {
-            RC_T0(ts0);
-            tma_store_3d(&map_dx, smem + kOffStg + sb * kStgBytes, px0 + h * kStgPx, q * 128, b);
-            tma_store_commit();
-            RC_TACC(3, ts0);
-            if (s + 2 < total_steps) {
-              RC_T0(tw0);
-              tma_store_wait_read0_keep1();     // the store of step s-1 has finished reading buffer (s+2) % 3
-              RC_TACC(14, tw0);
-              RC_T0(ti0);
-              issue_next_load();
-              RC_TACC(4, ti0);
-            }
-          }
+          fence_proxy_async_smem();                 // staged dX is read by the TMA store (async proxy)
+          mbar_arrive(&bars->stg_done[sb]);         // the DMA thread stores this buffer and refills it
           if (++sb == kStgBufs) { sb = 0; sb_par ^= 1; }
         }
       }
     }
-    if (kBwd && leader) tma_store_wait_all0();
     if (half == 0) {
       loss_acc = warp_sum(loss_acc); w_acc = warp_sum(w_acc); dlt_acc = warp_sum(dlt_acc);
       if (lane == 0) {
