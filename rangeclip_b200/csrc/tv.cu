@@ -108,6 +108,151 @@ tv_bwd_kernel(const T* __restrict__ x, int64_t planes, int H, int W, int TH, con
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// vectorised shared-memory tiled kernels (W % 8 == 0, 16-byte aligned base): the tile is filled with
+// 16-byte cp.async copies in the tensor's own dtype; every thread then owns groups of 8 consecutive
+// pixels of one row (one 16/32-byte shared load per row it touches).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void tv_fill_tile(const T* __restrict__ plane, int H, int W, int h_first, int n_rows, T* __restrict__ tile) {
+  const int lo = h_first < 0 ? 0 : h_first;
+  const int hi = (h_first + n_rows) > H ? H : (h_first + n_rows);
+  if (hi > lo) {
+    const char* src = reinterpret_cast<const char*>(plane + (int64_t)lo * W);
+    char* dst = reinterpret_cast<char*>(tile + (int64_t)(lo - h_first) * W);
+    const int bytes = (hi - lo) * W * (int)sizeof(T);
+    for (int i = threadIdx.x * 16; i < bytes; i += kTvThreads * 16) {
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + i);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void lds8(const float* p, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void lds8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ float lds1(const float* p) { return *p; }
+__device__ __forceinline__ float lds1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__global__ void __launch_bounds__(kTvThreads)
+tv_fwd_vec_kernel(const T* __restrict__ x, int64_t planes, int H, int W, int TH, double* __restrict__ sums) {
+  extern __shared__ __align__(16) unsigned char tv_smem[];
+  T* tile = reinterpret_cast<T*>(tv_smem);   // [(TH+1)][W]
+  const int tiles_per_plane = (H + TH - 1) / TH;
+  const int64_t n_tiles = planes * tiles_per_plane;
+  const int gpr = W >> 3;   // groups of 8 pixels per row
+  double acc_h = 0.0, acc_v = 0.0;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t pl = t / tiles_per_plane;
+    const int h0 = (int)(t - pl * tiles_per_plane) * TH;
+    const int rows = min(TH, H - h0);
+    __syncthreads();
+    tv_fill_tile(x + pl * (int64_t)H * W, H, W, h0, rows + 1, tile);
+    __syncthreads();
+    const bool has_below = (h0 + rows) < H;
+    float sh = 0.f, sv = 0.f;
+    for (int gi = threadIdx.x; gi < rows * gpr; gi += kTvThreads) {
+      const int r = gi / gpr, c0 = (gi - r * gpr) << 3;
+      const T* p = tile + r * W + c0;
+      float v[8];
+      lds8(p, v);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) sh += fabsf(v[i] - v[i + 1]);
+      if (c0 + 8 < W) sh += fabsf(v[7] - lds1(p + 8));
+      if (r + 1 < rows || has_below) {
+        float b[8];
+        lds8(p + W, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sv += fabsf(v[i] - b[i]);
+      }
+    }
+    acc_h += (double)sh;
+    acc_v += (double)sv;
+  }
+  acc_h = warp_sum(acc_h);
+  acc_v = warp_sum(acc_v);
+  __shared__ double red[2][kTvThreads / 32];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][wid] = acc_h; red[1][wid] = acc_v; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < kTvThreads / 32; ++i) { a += red[0][i]; b += red[1][i]; }
+    atomicAdd(&sums[0], a);
+    atomicAdd(&sums[1], b);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTvThreads)
+tv_bwd_vec_kernel(const T* __restrict__ x, int64_t planes, int H, int W, int TH, const float* __restrict__ scale,
+                  T* __restrict__ dx, int accumulate, const float* __restrict__ dx_scale) {
+  extern __shared__ __align__(16) unsigned char tv_smem[];
+  T* tile = reinterpret_cast<T*>(tv_smem);   // [(TH+2)][W], row 0 = h0-1
+  const int tiles_per_plane = (H + TH - 1) / TH;
+  const int64_t n_tiles = planes * tiles_per_plane;
+  const int gpr = W >> 3;
+  const float sh = scale[0], sv = scale[1];
+  const float ds = (dx_scale != nullptr) ? dx_scale[0] : 1.f;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t pl = t / tiles_per_plane;
+    const int h0 = (int)(t - pl * tiles_per_plane) * TH;
+    const int rows = min(TH, H - h0);
+    __syncthreads();
+    tv_fill_tile(x + pl * (int64_t)H * W, H, W, h0 - 1, rows + 2, tile);
+    __syncthreads();
+    T* out = dx + pl * (int64_t)H * W + (int64_t)h0 * W;
+    for (int gi = threadIdx.x; gi < rows * gpr; gi += kTvThreads) {
+      const int r = gi / gpr, c0 = (gi - r * gpr) << 3;
+      const int h = h0 + r;
+      const T* p = tile + (r + 1) * W + c0;
+      float v[8], g[8];
+      lds8(p, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const float sg = sh * sgnf(v[i] - v[i + 1]);
+        g[i] += sg;
+        g[i + 1] -= sg;
+      }
+      if (c0 + 8 < W) g[7] += sh * sgnf(v[7] - lds1(p + 8));
+      if (c0 > 0) g[0] -= sh * sgnf(lds1(p - 1) - v[0]);
+      if (h + 1 < H) {
+        float b[8];
+        lds8(p + W, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] += sv * sgnf(v[i] - b[i]);
+      }
+      if (h >= 1) {
+        float a[8];
+        lds8(p - W, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] -= sv * sgnf(a[i] - v[i]);
+      }
+      T* o = out + r * W + c0;
+      if (accumulate) {
+        float e[8];
+        load8(o, e);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = fmaf(ds, e[i], g[i]);
+      }
+      store8(o, g);
+    }
+  }
+}
+
 static int tv_tile_rows(int H, int W, int halo) {
   int r = kTvSmemFloats / W - halo;
   if (r > 32) r = 32;
@@ -128,7 +273,14 @@ extern "C" int rc_tv_fwd(const void* x, rc_dtype x_dtype, int64_t planes, int H,
   const int grid = (int)(n_tiles < cap ? n_tiles : cap);
   const size_t smem = (size_t)(TH + 1) * W * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
-  if (x_dtype == RC_F32)
+  const bool vec = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (vec) {
+    const size_t vsmem = (size_t)(TH + 1) * W * (x_dtype == RC_F32 ? 4 : 2);
+    if (x_dtype == RC_F32)
+      rc::tv_fwd_vec_kernel<float><<<grid, rc::kTvThreads, vsmem, s>>>((const float*)x, planes, H, W, TH, sums);
+    else
+      rc::tv_fwd_vec_kernel<__nv_bfloat16><<<grid, rc::kTvThreads, vsmem, s>>>((const __nv_bfloat16*)x, planes, H, W, TH, sums);
+  } else if (x_dtype == RC_F32)
     rc::tv_fwd_kernel<float><<<grid, rc::kTvThreads, smem, s>>>((const float*)x, planes, H, W, TH, sums);
   else
     rc::tv_fwd_kernel<__nv_bfloat16><<<grid, rc::kTvThreads, smem, s>>>((const __nv_bfloat16*)x, planes, H, W, TH, sums);
@@ -147,7 +299,15 @@ extern "C" int rc_tv_bwd(const void* x, rc_dtype x_dtype, int64_t planes, int H,
   const int grid = (int)(n_tiles < cap ? n_tiles : cap);
   const size_t smem = (size_t)(TH + 2) * W * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
-  if (x_dtype == RC_F32)
+  const bool vec = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+  if (vec) {
+    const size_t vsmem = (size_t)(TH + 2) * W * (x_dtype == RC_F32 ? 4 : 2);
+    if (x_dtype == RC_F32)
+      rc::tv_bwd_vec_kernel<float><<<grid, rc::kTvThreads, vsmem, s>>>((const float*)x, planes, H, W, TH, scale, (float*)dx, accumulate, dx_scale);
+    else
+      rc::tv_bwd_vec_kernel<__nv_bfloat16><<<grid, rc::kTvThreads, vsmem, s>>>((const __nv_bfloat16*)x, planes, H, W, TH, scale,
+                                                                                (__nv_bfloat16*)dx, accumulate, dx_scale);
+  } else if (x_dtype == RC_F32)
     rc::tv_bwd_kernel<float><<<grid, rc::kTvThreads, smem, s>>>((const float*)x, planes, H, W, TH, scale, (float*)dx, accumulate, dx_scale);
   else
     rc::tv_bwd_kernel<__nv_bfloat16><<<grid, rc::kTvThreads, smem, s>>>((const __nv_bfloat16*)x, planes, H, W, TH, scale,
