@@ -13,12 +13,13 @@ The CUDA code lives in ``csrc/`` and is reached through the C ABI in ``include/r
 from .losses import (DepthCLIPLossMixin, build_contrast_indices, compute_loss, image_contrastive_loss,
                      text_contrastive_loss)
 from .pooling import masked_average_pooling, pool_objects_per_image, prepare_image_contrast_data
-from .evaluation import MetricAccumulator, build_reduced_candidates, predict, predict_from_embeddings
+from .evaluation import (MetricAccumulator, build_reduced_candidates, finalize_metrics, predict,
+                         predict_from_embeddings, validate_model)
 from . import ops
 
 __all__ = [
     "DepthCLIPLossMixin", "build_contrast_indices", "compute_loss", "image_contrastive_loss",
     "text_contrastive_loss", "masked_average_pooling", "pool_objects_per_image",
     "prepare_image_contrast_data", "MetricAccumulator", "build_reduced_candidates", "predict",
-    "predict_from_embeddings", "ops",
+    "predict_from_embeddings", "finalize_metrics", "validate_model", "ops",
 ]

@@ -44,6 +44,9 @@ inline int num_sms() {
   return n;
 }
 
+// fp32 -> bf16 copy + inverse row norms (defined in infonce_umma.cu, shared with eval_topk_umma.cu)
+int launch_rownorm_f32(const float* x, int B, int D, int64_t HW, __nv_bfloat16* xb, float* inv_norm, cudaStream_t s);
+
 // ---- device helpers ---------------------------------------------------------------------------
 template <typename T> struct ElemIO;
 template <> struct ElemIO<float> {

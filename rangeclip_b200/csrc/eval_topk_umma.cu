@@ -1,0 +1,231 @@
+// K7: top-k text ids per pixel on the tensor cores (evaluation, model.py:164-173).
+//
+// Replaces `einsum('bdn,cd->bcn')` (a materialised [B, Kr, HW] logit tensor) followed by a sort-based
+// `topk(k, dim=1)` and an index gather with one persistent kernel: per 128-pixel tile the bf16 pixel
+// rows stay resident in shared memory while the text rows stream past in blocks of 256; the fp32
+// logits live only in TMEM (two 256-column buffers, so the scan of block j overlaps the MMA of block
+// j+1) and every thread keeps the running top-k of its pixel in registers.
+// The ranking by cosine similarity equals the ranking by raw dot product (the per-pixel norm is a
+// positive constant), so no normalisation pass over X is needed; ties go to the smaller text index.
+#include "common.cuh"
+#include "umma.cuh"
+#include <float.h>
+
+namespace rc {
+using namespace umma;
+
+
+namespace topk {
+
+constexpr int kThreads = 256;            // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4-7 top-k scan (one thread per pixel)
+constexpr int kTilePx = 128;
+constexpr int kXBytes = 128 * 1024;      // X tile [D <= 512][128 px] bf16: D/64 chunks of 16 KB
+constexpr int kStages = 3;
+constexpr int kStageBytes = 32 * 1024;   // text block chunk [256 k][64 d]
+constexpr int kNB = 256;                 // text rows per block (MMA N)
+constexpr int kTmemCols = 512;
+constexpr int kMaxK = 8;
+
+struct __align__(8) Bars {
+  uint64_t full[kStages], empty[kStages];
+  uint64_t x_full, x_empty;
+  uint64_t s_full[2], s_empty[2];
+  uint32_t tmem_base, pad;
+};
+constexpr int kOffRing = kXBytes;
+constexpr int kOffBars = kOffRing + kStages * kStageBytes;
+constexpr int kSmemBytes = kOffBars + (int)sizeof(Bars);
+
+struct Params {
+  int B, D, K, k;
+  int64_t HW;
+  int tiles_per_img, n_tiles, n_blocks;
+  const int64_t* index_map;
+  int64_t* out;
+};
+
+__device__ __forceinline__ void topk_insert(float (&bv)[kMaxK], int (&bi)[kMaxK], int k, float v, int id) {
+  // strict '>' keeps the earlier (smaller) index on ties
+#pragma unroll
+  for (int j = 0; j < kMaxK; ++j) {
+    if (j < k && v > bv[j]) {
+      const float tv = bv[j]; const int ti = bi[j];
+      bv[j] = v; bi[j] = id; v = tv; id = ti;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][HW], box (64 px, 64 d, 1)
+                      const __grid_constant__ CUtensorMap map_t,    // T [Kp][D], box (64 d, 256 rows), OOB rows = 0
+                      const Params prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Bars* bars = reinterpret_cast<Bars*>(smem + kOffBars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_dchunks = prm.D / 64;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_t);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    mbar_init(&bars->x_full, 1); mbar_init(&bars->x_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t idesc = make_idesc_bf16(128, kNB, /*A MN-major*/ 1, /*B K-major*/ 0);
+
+  if (warp == 0 && lane == 0) {
+    // =============================== TMA producer ===============================
+    uint32_t it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
+      const int b = tile / prm.tiles_per_img;
+      const int px0 = (tile - b * prm.tiles_per_img) * kTilePx;
+      mbar_wait(&bars->x_empty, (lt & 1) ^ 1, 1);
+      mbar_arrive_expect_tx(&bars->x_full, n_dchunks * 16384);
+      for (int c = 0; c < n_dchunks; ++c) {
+        tma_load_3d(smem + c * 16384, &map_x, &bars->x_full, px0, c * 64, b);
+        tma_load_3d(smem + c * 16384 + 8192, &map_x, &bars->x_full, px0 + 64, c * 64, b);
+      }
+      for (int nb = 0; nb < prm.n_blocks; ++nb)
+        for (int c = 0; c < n_dchunks; ++c, ++it) {
+          const int st = it % kStages;
+          mbar_wait(&bars->empty[st], ((it / kStages) & 1) ^ 1, 2);
+          mbar_arrive_expect_tx(&bars->full[st], kStageBytes);
+          tma_load_2d(smem + kOffRing + st * kStageBytes, &map_t, &bars->full[st], c * 64, nb * kNB);
+        }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // =============================== MMA issuer ================================
+    uint32_t it = 0, lt = 0, nbc = 0;
+    const uint32_t xs = smem_u32(smem);
+    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
+      mbar_wait(&bars->x_full, lt & 1, 3);
+      for (int nb = 0; nb < prm.n_blocks; ++nb, ++nbc) {
+        const int sbuf = nbc & 1;
+        mbar_wait(&bars->s_empty[sbuf], ((nbc >> 1) & 1) ^ 1, 4);
+        tc_fence_after();
+        for (int c = 0; c < n_dchunks; ++c, ++it) {
+          const int st = it % kStages;
+          mbar_wait(&bars->full[st], (it / kStages) & 1, 5);
+          tc_fence_after();
+          const uint32_t tb = smem_u32(smem + kOffRing + st * kStageBytes);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t a = desc_mnmajor_sw128(xs + c * 16384 + ks * 2048, 8192);
+            const uint64_t bdesc = desc_kmajor_sw128(tb + ks * 32);
+            mma_bf16_ss(tmem + sbuf * kNB, a, bdesc, idesc, (c | ks) != 0);
+          }
+          mma_commit(&bars->empty[st]);
+        }
+        mma_commit(&bars->s_full[sbuf]);
+      }
+      mma_commit(&bars->x_empty);       // all MMAs reading this X tile have completed
+    }
+  } else if (warp >= 4) {
+    // =============================== top-k scan ================================
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t nbc = 0;
+    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+      const int b = tile / prm.tiles_per_img;
+      const int px = (tile - b * prm.tiles_per_img) * kTilePx + row;
+      float bv[kMaxK];
+      int bi[kMaxK];
+#pragma unroll
+      for (int j = 0; j < kMaxK; ++j) { bv[j] = -FLT_MAX; bi[j] = -1; }
+      float kth = -FLT_MAX;              // current k-th best: cheap reject before the insertion network
+      for (int nb = 0; nb < prm.n_blocks; ++nb, ++nbc) {
+        const int sbuf = nbc & 1;
+        mbar_wait(&bars->s_full[sbuf], (nbc >> 1) & 1, 6);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < kNB / 32; ++c) {
+          const int k0 = nb * kNB + c * 32;
+          if (k0 >= prm.K) break;
+          uint32_t r[32];
+          tmem_ld_32x32(trow + sbuf * kNB + c * 32, r);
+          tmem_ld_wait();
+          const int nvalid = prm.K - k0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float v = __uint_as_float(r[i]);
+            if (i < nvalid && v > kth) {
+              topk_insert(bv, bi, prm.k, v, k0 + i);
+              kth = bv[0];
+#pragma unroll
+              for (int j = 1; j < kMaxK; ++j) if (j < prm.k) kth = bv[j];
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bars->s_empty[sbuf]);
+      }
+      if (px < prm.HW) {
+#pragma unroll
+        for (int j = 0; j < kMaxK; ++j)
+          if (j < prm.k) prm.out[((int64_t)b * prm.k + j) * prm.HW + px] = bi[j] >= 0 ? __ldg(prm.index_map + bi[j]) : -1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem); }
+}
+
+}  // namespace topk
+}  // namespace rc
+
+extern "C" int rc_eval_topk_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16, int K,
+                                 const int64_t* index_map, int k, int64_t* out, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  using namespace rc;
+  RC_REQUIRE(x && t_bf16 && index_map && out, "rc_eval_topk_bf16: null pointer");
+  RC_REQUIRE(B >= 0 && HW >= 0 && K >= 1 && k >= 1 && k <= topk::kMaxK && k <= K, "rc_eval_topk_bf16: bad shape (k=%d K=%d)", k, K);
+  if (D < 64 || D > 512 || D % 64 != 0) return fail(RC_ERR_UNSUPPORTED, "rc_eval_topk_bf16: D=%d must be a multiple of 64 and <= 512", D);
+  if (HW % 8 != 0) return fail(RC_ERR_UNSUPPORTED, "rc_eval_topk_bf16: HW=%lld must be a multiple of 8", (long long)HW);
+  RC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(t_bf16) & 15) == 0,
+             "rc_eval_topk_bf16: x and t must be 16-byte aligned");
+  if (B == 0 || HW == 0) return RC_OK;
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return fail(RC_ERR_NO_DEVICE, "rc_eval_topk_bf16: needs an sm_100 device");
+  cudaStream_t s = (cudaStream_t)stream;
+  const void* xsrc = x;
+  int rcode;
+  if (x_dtype == RC_F32) {
+    const int64_t M = (int64_t)B * HW;
+    RC_REQUIRE(workspace && workspace_bytes >= rc_infonce_workspace_bytes(B, D, HW, K, RC_F32), "rc_eval_topk_bf16: workspace too small for the bf16 copy");
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    float* inv_norm = reinterpret_cast<float*>(ws);
+    __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + ((M * 4 + 255) / 256) * 256);
+    if ((rcode = launch_rownorm_f32((const float*)x, B, D, HW, xb, inv_norm, s))) return rcode;
+    xsrc = xb;
+  }
+  const int Kp = (K + 63) / 64 * 64;
+  CUtensorMap m_x, m_t;
+  {
+    const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)D, (uint64_t)B};
+    const uint64_t str[3] = {2, (uint64_t)HW * 2, (uint64_t)D * HW * 2};
+    const uint32_t box[3] = {64, 64, 1};
+    if ((rcode = make_tmap_bf16(&m_x, xsrc, 3, dims, str, box, "topk map_x"))) return rcode;
+    const uint64_t tdims[2] = {(uint64_t)D, (uint64_t)Kp}, tstr[2] = {2, (uint64_t)D * 2};
+    const uint32_t tbox[2] = {64, (uint32_t)topk::kNB};
+    if ((rcode = make_tmap_bf16(&m_t, t_bf16, 2, tdims, tstr, tbox, "topk map_t"))) return rcode;
+  }
+  topk::Params prm;
+  prm.B = B; prm.D = D; prm.K = K; prm.k = k; prm.HW = HW;
+  prm.tiles_per_img = (int)((HW + topk::kTilePx - 1) / topk::kTilePx);
+  if ((int64_t)B * prm.tiles_per_img > 0x7fffffff) return fail(RC_ERR_UNSUPPORTED, "rc_eval_topk_bf16: too many tiles");
+  prm.n_tiles = B * prm.tiles_per_img;
+  prm.n_blocks = (K + topk::kNB - 1) / topk::kNB;
+  prm.index_map = index_map; prm.out = out;
+  const int grid = prm.n_tiles < num_sms() ? prm.n_tiles : num_sms();
+  cudaError_t e = cudaFuncSetAttribute(topk::eval_topk_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, topk::kSmemBytes);
+  if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_eval_topk_bf16: smem opt-in: %s", cudaGetErrorString(e));
+  topk::eval_topk_umma_kernel<<<grid, topk::kThreads, topk::kSmemBytes, s>>>(m_x, m_t, prm);
+  return check_launch("rc_eval_topk_bf16");
+}

@@ -714,6 +714,12 @@ extern "C" int64_t rc_infonce_workspace_bytes(int B, int D, int64_t HW, int K, r
 }
 
 namespace rc {
+int launch_rownorm_f32(const float* x, int B, int D, int64_t HW, __nv_bfloat16* xb, float* inv_norm, cudaStream_t s) {
+  const int64_t blocks = ((int64_t)B * HW / 8 + 255) / 256;
+  const int grid = (int)(blocks < (int64_t)num_sms() * 8 ? blocks : (int64_t)num_sms() * 8);
+  rownorm_kernel<float><<<grid, 256, 0, s>>>(x, B, D, HW, xb, inv_norm);
+  return check_launch("rownorm(f32 -> bf16)");
+}
 static int infonce_prepass_impl(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, void* workspace,
                                 int64_t workspace_bytes, cudaStream_t s, float** inv_norm_out, __nv_bfloat16** xb_out) {
   RC_REQUIRE(x && workspace, "rc_infonce_prepass: null pointer");
@@ -803,12 +809,4 @@ extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, in
     infonce_umma_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_xe, m_dx, prm);
   }
   return check_launch("rc_infonce_bf16");
-}
-
-extern "C" int rc_eval_topk_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16, int K,
-                                 const int64_t* index_map, int k, int64_t* out, void* workspace, int64_t workspace_bytes,
-                                 void* stream) {
-  (void)x; (void)x_dtype; (void)B; (void)D; (void)HW; (void)t_bf16; (void)K; (void)index_map; (void)k; (void)out;
-  (void)workspace; (void)workspace_bytes; (void)stream;
-  return rc::fail(RC_ERR_UNSUPPORTED, "rc_eval_topk_bf16: tensor-core top-k not built yet (use rc_eval_topk_f32)");
 }

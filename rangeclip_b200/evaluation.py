@@ -29,7 +29,7 @@ def build_reduced_candidates(segmentation: torch.Tensor, total_candidates: int, 
 
 
 def predict_from_embeddings(pixel_embeddings, candidate_text_embeddings, segmentation, num_negatives=300, top_k=5,
-                            precision="fp32"):
+                            precision="auto"):
     """model.py:144-173 given the decoder output: returns (topk ids [B,k,H,W] int64 in the ORIGINAL
     index space, L2-normalised embeddings).  The [B,Kr,HW] logits are never materialised."""
     total = candidate_text_embeddings.shape[0]
@@ -80,28 +80,123 @@ class MetricAccumulator:
     def finalize(self, last_segmentation: torch.Tensor) -> Dict[str, object]:
         """validate.py:194-214: mIoU over labels present in the LAST batch's GT (Q11), averaged in the
         reference's dict insertion order (batch of first appearance, then label id); accuracies."""
-        acc = self.acc.cpu().tolist()
-        counters = self.counters.cpu().tolist()
-        first = self.first_seen.cpu().tolist()
         valid = set(self.cmap[last_segmentation.reshape(-1).to(self.cmap.device)].tolist())
-        order = sorted((fs, lab) for lab, fs in enumerate(first) if fs != INT32_MAX)
-        dicts = {name: {} for name in ("intersection_top1", "union_top1", "intersection_topk", "union_topk")}
-        for _, lab in order:
-            dicts["intersection_top1"][lab] = acc[0][lab]
-            dicts["union_top1"][lab] = acc[1][lab]
-            dicts["intersection_topk"][lab] = acc[2][lab]
-            dicts["union_topk"][lab] = acc[3][lab]
+        return finalize_metrics(self.acc, self.counters, self.first_seen, valid)
 
-        def miou(inter, union):
-            ious = [inter[lab] / union[lab] for lab in union if lab in valid and union[lab] > 0]
-            return sum(ious) / len(ious) if ious else 0.0
 
-        total = counters[2]
-        return {
-            "mIoU_t1": miou(dicts["intersection_top1"], dicts["union_top1"]),
-            "mIoU_tk": miou(dicts["intersection_topk"], dicts["union_topk"]),
-            "pixel_accuracy_t1": counters[0] / total if total > 0 else 0.0,
-            "pixel_accuracy_tk": counters[1] / total if total > 0 else 0.0,
-            "correct_pixels_top1": counters[0], "correct_pixels_topk": counters[1], "total_pixels": total,
-            **dicts,
-        }
+def finalize_metrics(acc_t: torch.Tensor, counters_t: torch.Tensor, first_seen_t: torch.Tensor, valid: set) -> Dict[str, object]:
+    """Host-side finalisation (validate.py:194-214) from the integer state; one device->host transfer."""
+    acc = acc_t.cpu().tolist()
+    counters = counters_t.cpu().tolist()
+    first = first_seen_t.cpu().tolist()
+    order = sorted((fs, lab) for lab, fs in enumerate(first) if fs != INT32_MAX)
+    dicts = {name: {} for name in ("intersection_top1", "union_top1", "intersection_topk", "union_topk")}
+    for _, lab in order:
+        dicts["intersection_top1"][lab] = acc[0][lab]
+        dicts["union_top1"][lab] = acc[1][lab]
+        dicts["intersection_topk"][lab] = acc[2][lab]
+        dicts["union_topk"][lab] = acc[3][lab]
+
+    def miou(inter, union):
+        ious = [inter[lab] / union[lab] for lab in union if lab in valid and union[lab] > 0]
+        return sum(ious) / len(ious) if ious else 0.0
+
+    total = counters[2]
+    return {
+        "mIoU_t1": miou(dicts["intersection_top1"], dicts["union_top1"]),
+        "mIoU_tk": miou(dicts["intersection_topk"], dicts["union_topk"]),
+        "pixel_accuracy_t1": counters[0] / total if total > 0 else 0.0,
+        "pixel_accuracy_tk": counters[1] / total if total > 0 else 0.0,
+        "correct_pixels_top1": counters[0], "correct_pixels_topk": counters[1], "total_pixels": total,
+        **dicts,
+    }
+
+
+def _log(s: str, filepath: Optional[str] = None) -> None:
+    """Same contract as utils/src/log_utils.py:7-30: print, and append to ``filepath`` when given."""
+    print(s)
+    if filepath is not None:
+        import os
+        os.makedirs(os.path.dirname(filepath) or ".", exist_ok=True)
+        with open(filepath, "a+") as f:
+            f.write(s + "\n")
+
+
+def _unwrap(model):
+    return model.module if hasattr(model, "module") else model
+
+
+def validate_model(model, clip_model, clip_processor, candidate_text_embeddings, candidate_labels, equivalence_tensor,
+                   equiv_class_map, similarity_sets, curriculum, dataloader, step, best_results, device, w_text=1.0,
+                   w_image=0.5, w_smooth=2e2, summary_writer=None, n_sample_per_summary=16, log_path=None,
+                   all_reduce=False):
+    """Drop-in for ``validate_model`` (validate.py:34-266).  Same arguments, same ``best_results`` keys and log
+    lines; the per-batch metric loops (validate.py:88-139) run as two kernels per batch with no host sync, and the
+    finalisation (validate.py:194-214) reads the integer state back once.  ``all_reduce=True`` (an addition) sums
+    the state over the default process group first, so that every rank may validate its own shard."""
+    from .losses import compute_loss as _compute_loss
+    from .pooling import prepare_image_contrast_data as _prepare
+
+    model.eval()
+    acc = MetricAccumulator(equivalence_tensor, equiv_class_map, device=device)
+    totals = [0.0, 0.0, 0.0, 0.0]
+    n_batches = 0
+    segmentation = None
+    temperature_text = None
+    core = _unwrap(model)
+    with torch.no_grad():
+        for batch in dataloader:
+            depth = batch['depth'].to(device, non_blocking=True)
+            image_processed = batch['image'].to(device, non_blocking=True)
+            segmentation = batch['segmentation'].to(device, non_blocking=True)
+            object_bbox = batch['object_bbox'].to(device, non_blocking=True)
+            object_label = batch['object_label']
+            pred_topk, pixel_embeddings, temperature_text = core.predict(
+                depth_maps=depth, candidate_text_embeddings=candidate_text_embeddings, segmentation=segmentation,
+                num_negatives=50, top_k=5)
+            acc.update(segmentation, pred_topk)
+            area_embeddings, image_embeddings = _prepare(
+                image_processed_batch=image_processed, object_bbox_batch=object_bbox, object_label_batch=object_label,
+                segmentation_batch=segmentation, pixel_embeddings_batch=pixel_embeddings, clip_image_encoder=clip_model,
+                clip_processor=clip_processor, device=device)
+            loss_fn = core.compute_loss if hasattr(core, "compute_loss") else (lambda **kw: _compute_loss(core, **kw))
+            _, loss_info = loss_fn(
+                pixel_embeddings=pixel_embeddings, target_indices=segmentation,
+                candidate_text_embeddings=candidate_text_embeddings, label_similarity_sets=similarity_sets,
+                area_embeddings=area_embeddings, image_embeddings=image_embeddings, W_text=w_text, W_image=w_image,
+                W_smooth=w_smooth, k_distractors=50, pct_medium=curriculum['pct_medium'], pct_hard=curriculum['pct_hard'],
+                pct_rand=curriculum['pct_rand'])
+            totals[0] += loss_info['total_loss']
+            totals[1] += loss_info.get('text_contrastive_loss', 0)
+            totals[2] += loss_info.get('image_contrastive_loss', 0)
+            totals[3] += loss_info.get('smoothness_loss', 0)
+            n_batches += 1
+    if all_reduce:
+        from .distributed import all_reduce_metrics
+        all_reduce_metrics(acc)
+    fin = acc.finalize(segmentation) if segmentation is not None else finalize_metrics(acc.acc, acc.counters, acc.first_seen, set())
+    miou_top1, miou_topk = fin["mIoU_t1"], fin["mIoU_tk"]
+    pixel_acc_top1, pixel_acc_topk = fin["pixel_accuracy_t1"], fin["pixel_accuracy_tk"]
+    avg = [t / max(n_batches, 1) for t in totals]
+    _log(f"[Val] [Step {step}] Top-1 pixel accuracy (equiv): {pixel_acc_top1:.4f}", log_path)
+    _log(f"[Val] [Step {step}] Top-k pixel accuracy (equiv): {pixel_acc_topk:.4f}", log_path)
+    _log(f"[Val] [Step {step}] Top-1 mIoU (equiv): {miou_top1:.4f}", log_path)
+    _log(f"[Val] [Step {step}] Top-k mIoU (equiv): {miou_topk:.4f}", log_path)
+    _log(f"[Val] Step {step} | # of labels in Top-1 mIoU: {len(fin['intersection_top1'])}", log_path)
+    _log(f"[Val] Step {step} | # of labels in Top-k mIoU: {len(fin['intersection_topk'])}", log_path)
+    _log(f"[Val] Step {step} | Loss: {avg[0]:.4f}, Text Contrastive: {avg[1]:.4f}, Image Contrastive: {avg[2]:.4f}, "
+         f"Smoothness: {avg[3]:.4f}", log_path)
+    if best_results.get("mIoU_tk", 0) < miou_topk:
+        best_results.update({
+            "loss": avg[0], "step": step, "mIoU_t1": miou_top1, "mIoU_tk": miou_topk,
+            "pixel_accuracy_t1": pixel_acc_top1, "pixel_accuracy_tk": pixel_acc_topk, "temperature": temperature_text,
+            "avg_text_contrastive_loss": avg[1], "avg_image_contrastive_loss": avg[2], "avg_smoothness_loss": avg[3]})
+    _log(f"Best validation loss: {best_results['loss']:.4f} at step {best_results['step']}", log_path)
+    if summary_writer is not None:
+        summary_writer.add_scalar("val/loss", avg[0], global_step=step)
+        for name, val in (("val/pixel_accuracy", pixel_acc_top1), ("val/pixel_accuracy_tk", pixel_acc_topk),
+                          ("val/mIoU", miou_top1), ("val/mIoU_tk", miou_topk),
+                          ("val/avg_text_contrastive_loss", avg[1]), ("val/avg_image_contrastive_loss", avg[2]),
+                          ("val/avg_smoothness_loss", avg[3])):
+            summary_writer.add_scalar(name, val, global_step=step)
+    return best_results

@@ -323,20 +323,41 @@ def masked_pool(x, seg, lut, lut_per_image, n_slots):
 # evaluation
 # ----------------------------------------------------------------------------------------------
 
-def eval_topk(x: torch.Tensor, t_norm: torch.Tensor, index_map: torch.Tensor, k: int, precision="fp32"):
-    """out[b, j, h, w] = index_map[j-th best text row by cosine logit] (model.py:164-173)."""
+def topk_bf16_supported(D: int, HW: int) -> bool:
+    return D % 64 == 0 and 64 <= D <= 512 and HW % 8 == 0 and HW > 0
+
+
+def eval_topk(x: torch.Tensor, t_norm: torch.Tensor, index_map: torch.Tensor, k: int, precision="auto", t_bf16=None):
+    """out[b, j, h, w] = index_map[j-th best text row by cosine logit] (model.py:164-173).
+    precision 'fp32' = CUDA-core kernel (reference arithmetic), 'bf16' = tcgen05 kernel, 'auto' = bf16 when
+    the shape allows it."""
     _need_cuda(x, t_norm, index_map)
     x, B, D, HW = _emb3(x)
     K = t_norm.shape[0]
     k = min(k, K)
     out = torch.empty((B, k) + tuple(x.shape[2:]), device=x.device, dtype=torch.int64)
     index_map = index_map.to(torch.int64).contiguous()
-    if precision != "fp32":
-        raise RuntimeError("eval_topk: only the fp32 kernel is available in this build")
-    xf = x if x.dtype == torch.float32 else x.float()
-    tf = t_norm.float().contiguous()
-    check(_lib.lib().rc_eval_topk_f32(_p(xf), B, D, HW, D * HW, _p(tf), K, _p(index_map), k, _p(out), _stream(x)),
-          "rc_eval_topk_f32")
+    if precision == "auto":
+        precision = "bf16" if topk_bf16_supported(D, HW) else "fp32"
+    L = _lib.lib()
+    if precision == "fp32":
+        xf = x if x.dtype == torch.float32 else x.float()
+        tf = t_norm.float().contiguous()
+        check(L.rc_eval_topk_f32(_p(xf), B, D, HW, D * HW, _p(tf), K, _p(index_map), k, _p(out), _stream(x)),
+              "rc_eval_topk_f32")
+    elif precision == "bf16":
+        if not topk_bf16_supported(D, HW):
+            raise RuntimeError(f"eval_topk: bf16 tensor-core path does not cover D={D}, HW={HW}")
+        tb = t_bf16 if t_bf16 is not None else text_to_bf16(t_norm)[0]
+        xdt = _dt(x)
+        ws, ws_bytes = None, 0
+        if xdt == RC_F32:
+            ws_bytes = int(L.rc_infonce_workspace_bytes(B, D, HW, K, xdt))
+            ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+        check(L.rc_eval_topk_bf16(_p(x), xdt, B, D, HW, _p(tb), K, _p(index_map), k, _p(out), _p(ws), ws_bytes, _stream(x)),
+              "rc_eval_topk_bf16")
+    else:
+        raise RuntimeError(f"eval_topk: unknown precision {precision!r}")
     return out
 
 

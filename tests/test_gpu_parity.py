@@ -332,7 +332,8 @@ def test_predict_golden_tie_aware(golden_dir):
     g = np.load(os.path.join(golden_dir, "predict.npz"))
     emb = torch.tensor(g["emb"]); text = torch.tensor(g["text"]); seg = torch.tensor(g["seg"])
     random.seed(int(g["seed"]))
-    topk, xn = R.predict_from_embeddings(emb.to(dev()), text.to(dev()), seg.to(dev()), int(g["num_negatives"]), int(g["top_k"]))
+    topk, xn = R.predict_from_embeddings(emb.to(dev()), text.to(dev()), seg.to(dev()), int(g["num_negatives"]), int(g["top_k"]),
+                                         precision="fp32")
     topk = topk.cpu().numpy()
     assert np.allclose(xn.cpu().numpy(), g["xn"], rtol=1e-6, atol=1e-7)
     if not np.array_equal(topk, g["topk"]):
@@ -347,6 +348,74 @@ def test_predict_golden_tie_aware(golden_dir):
             la = float(logits[b, glob[int(topk[b, j, h, w_])], h * W + w_])
             lb = float(logits[b, glob[int(g["topk"][b, j, h, w_])], h * W + w_])
             assert abs(la - lb) < 1e-5
+
+
+def _tie_aware_equal(topk, ref_topk, logits, reduced, tol):
+    """Every disagreement must be a near-tie in the oracle's logits."""
+    if np.array_equal(topk, ref_topk):
+        return 0
+    glob = {c: i for i, c in enumerate(reduced)}
+    B, k, H, W = topk.shape
+    bad = np.argwhere(topk != ref_topk)
+    for b, j, h, w_ in bad:
+        la = float(logits[b, glob[int(topk[b, j, h, w_])], h * W + w_])
+        lb = float(logits[b, glob[int(ref_topk[b, j, h, w_])], h * W + w_])
+        assert abs(la - lb) < tol, (b, j, h, w_, la, lb)
+    return len(bad)
+
+
+@pytest.mark.parametrize("B,D,H,W,K,k,xdtype", [(2, 512, 16, 16, 1024, 5, torch.bfloat16), (1, 128, 8, 24, 300, 5, torch.bfloat16),
+                                                 (2, 64, 16, 8, 40, 3, torch.float32), (1, 256, 20, 20, 257, 8, torch.bfloat16),
+                                                 (1, 512, 16, 16, 5, 5, torch.bfloat16)])
+def test_eval_topk_tensor_core(B, D, H, W, K, k, xdtype):
+    """tcgen05 top-k against the oracle on bf16-exact inputs (differences = accumulation order only)."""
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(B + D + K)
+    text = unit(torch.randn(K, D, generator=g), 1).to(torch.bfloat16).float()
+    lab = torch.randint(0, K, (B, H, W), generator=g)
+    emb = (text[lab].permute(0, 3, 1, 2) + 0.3 * torch.randn(B, D, H, W, generator=g)).to(torch.bfloat16).float()
+    reduced = list(range(K))
+    # oracle on the same bf16-exact rows (text is NOT re-normalised by ops.eval_topk)
+    logits = torch.einsum('bdn,cd->bcn', unit(emb, 1).view(B, D, H * W).double(), text.double())
+    ref = logits.topk(k, dim=1).indices.view(B, k, H, W).numpy()
+    index_map = torch.arange(K) * 3 + 1                      # non-trivial reduced -> global map
+    out = ops.eval_topk(emb.to(dev()).to(xdtype), text.to(dev()), index_map.to(dev()), k, "bf16").cpu().numpy()
+    assert out.shape == (B, k, H, W)
+    n_bad = _tie_aware_equal((out - 1) // 3, ref, logits, reduced, 1e-5)
+    assert n_bad <= 0.001 * out.size + 2
+    out32 = ops.eval_topk(emb.to(dev()), text.to(dev()), index_map.to(dev()), k, "fp32").cpu().numpy()
+    _tie_aware_equal((out32 - 1) // 3, ref, logits, reduced, 1e-5)
+
+
+def test_validate_model_golden(golden_dir):
+    """Drop-in validate_model against the reference's recorded run (fake model, three batches)."""
+    import rangeclip_b200 as R
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    segs, preds = list(g["seg"]), list(g["topk"])
+    B, H, W = segs[0].shape
+
+    class FakeModel:
+        def __init__(self):
+            self.i = 0
+
+        def eval(self):
+            return self
+
+        def predict(self, depth_maps, candidate_text_embeddings, segmentation, num_negatives, top_k):
+            t = torch.tensor(preds[self.i]).to(dev())
+            self.i += 1
+            return t, torch.zeros(B, 4, H, W, device=dev()), torch.tensor(0.07)
+
+        def compute_loss(self, **kw):
+            return torch.tensor(0.0), {"total_loss": 0.0}
+
+    batches = [{"depth": torch.zeros(B, 1, H, W), "image": torch.zeros(B, 3, H, W), "segmentation": torch.tensor(s_),
+                "object_bbox": torch.zeros(B, 4, dtype=torch.long), "object_label": "x"} for s_ in segs]
+    best = R.validate_model(FakeModel(), None, None, None, [str(i) for i in range(int(g["C"]))], torch.tensor(g["E"]),
+                            torch.tensor(g["cmap"]), None, dict(pct_medium=0.0, pct_hard=0.5, pct_rand=0.5), batches, 0,
+                            {"step": -1, "loss": float("inf")}, dev())
+    for key in ("mIoU_t1", "mIoU_tk", "pixel_accuracy_t1", "pixel_accuracy_tk"):
+        assert best[key] == float(g[key]), key
 
 
 def test_missing_gpu_paths_fail_loudly():
