@@ -55,6 +55,20 @@ __device__ __forceinline__ void topk_insert(float (&bv)[kMaxK], int (&bi)[kMaxK]
   }
 }
 
+// r[i] for a per-thread dynamic i: binary select tree (registers cannot be indexed dynamically)
+__device__ __forceinline__ float select32(const uint32_t (&r)[32], int i) {
+  float a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = __uint_as_float((i & 1) ? r[2 * j + 1] : r[2 * j]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = (i & 2) ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] = (i & 4) ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) a[j] = (i & 8) ? a[2 * j + 1] : a[2 * j];
+  return (i & 16) ? a[1] : a[0];
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][HW], box (64 px, 64 d, 1)
                       const __grid_constant__ CUtensorMap map_t,    // T [Kp][D], box (64 d, 256 rows), OOB rows = 0
@@ -149,10 +163,18 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
           tmem_ld_32x32(trow + sbuf * kNB + c * 32, r);
           tmem_ld_wait();
           const int nvalid = prm.K - k0;
+          // Per thread only ~k ln(K/k) values ever enter the top-k, but with 32 pixels per warp some lane qualifies at
+          // almost every column.  So: a branch-free candidate bitmask first (2 instructions per value), then a short
+          // per-thread loop over the set bits -- the warp iterates max-over-lanes(#candidates), not once per column.
+          uint32_t mask = 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = __uint_as_float(r[i]);
-            if (i < nvalid && v > kth) {
+          for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(r[i]) > kth) ? (1u << i) : 0u;
+          if (nvalid < 32) mask &= (1u << nvalid) - 1u;
+          while (mask) {
+            const int i = __ffs(mask) - 1;       // ascending column order: the earlier index wins ties
+            mask &= mask - 1;
+            const float v = select32(r, i);
+            if (v > kth) {
               topk_insert(bv, bi, prm.k, v, k0 + i);
               kth = bv[0];
 #pragma unroll
