@@ -74,26 +74,30 @@ def make_device_workload(device, seed, B):
 # ------------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled every 20 ms DURING the timed region (NVML)."""
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], threading.Event()
         self.t = threading.Thread(target=self._run, daemon=True)
+        self.max_mhz = None
 
     def _run(self):
-        while not self.stop.is_set():
-            try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                    str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([v.strip() for v in o.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.1)
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            while not self.stop.is_set():
+                self.rows.append((float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), N.nvmlDeviceGetPowerUsage(h) / 1e3,
+                                  int(N.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                self.stop.wait(0.02)
+        except Exception as e:  # pragma: no cover
+            self.rows.append((float("nan"), float("nan"), -1))
+            self.err = repr(e)
 
     def __enter__(self):
         self.t.start()
+        time.sleep(0.05)
         return self
 
     def __exit__(self, *a):
@@ -101,13 +105,16 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+        rows = [r for r in self.rows if r[2] >= 0]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        sm = sorted(r[0] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "power_w_max": max(r[1] for r in rows),
+                "samples": len(rows), "reasons": [n for b_, n in names.items() if bits & b_]}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -54,7 +54,7 @@ def build_contrast_indices(unique_labels: torch.Tensor, C: int, label_similarity
 
 def text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embeddings, label_similarity_sets,
                           log_temperature_text, percent_image_sampling=0.7, k_distractors=50, pct_medium=0.0,
-                          pct_hard=0.75, pct_rand=0.25, precision="auto", return_aux=False):
+                          pct_hard=0.75, pct_rand=0.25, precision="auto", return_aux=False, with_smoothness=False):
     """Pixel-text InfoNCE of model.py:199-301 on the fused kernels.
 
     The reference gathers ``int(0.7*HW)`` pixel rows per image WITH replacement and drops label 0
@@ -93,6 +93,10 @@ def text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embed
         t_norm = torch.nn.functional.normalize(candidate_text_embeddings[contrast].float(), dim=1)
     else:
         t_norm, _, _ = ops.text_prepare(candidate_text_embeddings, contrast, want_f32=True)
+    if with_smoothness:      # one autograd node for both terms -> one fused backward pass over X / dX
+        loss, smooth = ops.pixel_losses(pixel_embeddings, t_norm, log_temperature_text, y, w, precision)
+        aux["smoothness"] = smooth
+        return loss, aux
     loss = ops.infonce(pixel_embeddings, t_norm, log_temperature_text, y, w, precision)
     return (loss, aux) if return_aux else loss
 
@@ -122,10 +126,15 @@ def compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddin
     log_tau_image = self.log_temperature_image
 
     text_loss = torch.tensor(0.0, device=device)
+    fused_smooth = None
     if W_text > 0:
-        text_loss = text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embeddings,
-                                          label_similarity_sets, log_tau_text, percent_image_sampling,
-                                          k_distractors, pct_medium, pct_hard, pct_rand, precision)
+        fuse = W_smooth > 0 and pixel_embeddings.requires_grad
+        out = text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embeddings,
+                                    label_similarity_sets, log_tau_text, percent_image_sampling,
+                                    k_distractors, pct_medium, pct_hard, pct_rand, precision, return_aux=True,
+                                    with_smoothness=fuse)
+        text_loss = out[0]
+        fused_smooth = out[1].get("smoothness")
 
     image_loss = torch.tensor(0.0, device=device)
     if area_embeddings is not None and image_embeddings is not None and area_embeddings.shape[0] > 1:
@@ -136,7 +145,7 @@ def compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddin
 
     smooth_loss = torch.tensor(0.0, device=device)
     if W_smooth > 0:
-        smooth_loss = ops.smoothness(pixel_embeddings)
+        smooth_loss = fused_smooth if fused_smooth is not None else ops.smoothness(pixel_embeddings)
 
     total = W_text * text_loss + W_image * image_loss + W_smooth * smooth_loss
 

@@ -200,6 +200,51 @@ class _InfoNCE(torch.autograd.Function):
         return gx, gt, gl, None, None, None
 
 
+class _PixelLosses(torch.autograd.Function):
+    """Text InfoNCE + smoothness of the SAME pixel embeddings as one autograd node, so that the backward is a
+    single pass: dX = g_text * dX_text (computed in the forward launch) + g_smooth * d(TV)/dX, written in
+    place by rc_tv_bwd(accumulate, dx_scale) -- X is read once, dX read and written once (model.py:272-291,
+    332-334 and their autograd)."""
+
+    @staticmethod
+    def forward(ctx, x, t_norm, log_tau, y, w, precision):
+        need_dx = x.requires_grad
+        need_dt = t_norm.requires_grad
+        need_tau = log_tau.requires_grad
+        inv_tau = float(torch.exp(-log_tau.detach().float()))
+        r = infonce_raw(x.detach(), t_norm.detach(), y, w, inv_tau, need_dx or need_tau, need_dt, precision)
+        wsum = r["w_sum"]
+        text = torch.where(wsum > 0, r["loss_sum"] / wsum.clamp_min(1e-300), torch.zeros_like(wsum)).float()
+        sums = tv_sums(x.detach())
+        dh, dv = tv_denominators(x.shape)
+        nan = torch.full((), float("nan"), device=x.device, dtype=torch.float64)
+        smooth = ((sums[0] / dh if dh > 0 else nan) + (sums[1] / dv if dv > 0 else nan)).float()
+        ctx.save_for_backward(x, r["dx"] if need_dx else None, r["dt"], r["dlogtau"].float())
+        ctx.flags = (need_dx, need_dt, need_tau)
+        return text, smooth
+
+    @staticmethod
+    def backward(ctx, g_text, g_smooth):
+        x, dx, dt, dlt = ctx.saved_tensors
+        need_dx, need_dt, need_tau = ctx.flags
+        gx = gt = gl = None
+        if need_dx:
+            dh, dv = tv_denominators(x.shape)
+            gs = g_smooth.float()
+            scale = torch.stack([gs / dh if dh > 0 else gs * 0, gs / dv if dv > 0 else gs * 0])
+            gx = tv_backward(x.detach(), scale, dx=dx, dx_scale=g_text.float())
+        if need_dt:
+            gt = dt * g_text
+        if need_tau:
+            gl = (dlt * g_text).reshape(())
+        return gx, gt, gl, None, None, None
+
+
+def pixel_losses(x, t_norm, log_tau, y, w, precision="auto"):
+    """(text InfoNCE, smoothness) with a fused single-pass backward."""
+    return _PixelLosses.apply(x, t_norm, log_tau, y, w, precision)
+
+
 def infonce(x, t_norm, log_tau, y, w, precision="auto"):
     """Autograd-aware fused InfoNCE; x [B,D,H,W], t_norm [K,D] normalised, y/w per pixel."""
     return _InfoNCE.apply(x, t_norm, log_tau, y, w, precision)
