@@ -43,6 +43,7 @@ PROTOTYPES = {
     "rc_eval_hist": [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "rc_eval_fold": [_vp, _i32, _i32, _vp, _vp, _vp],
     "rc_debug_set_timing_buffer": [_vp],
+    "rc_debug_umma_gemm_2sm": [_vp, _vp, _i32, _i32, _vp, _vp],
     "rc_debug_umma_gemm": [_vp, _vp, _i32, _i32, _i32, _vp, _vp],
 }
 _RESTYPES = {"rc_last_error": C.c_char_p, "rc_launch_count": _i64, "rc_infonce_workspace_bytes": _i64}

@@ -47,6 +47,13 @@ inline int num_sms() {
 // fp32 -> bf16 copy + inverse row norms (defined in infonce_umma.cu, shared with eval_topk_umma.cu)
 int launch_rownorm_f32(const float* x, int B, int D, int64_t HW, __nv_bfloat16* xb, float* inv_norm, cudaStream_t s);
 
+long long* debug_timing_buffer();   // bring-up instrumentation target (rc_debug_set_timing_buffer)
+// CTA-pair (cta_group::2) version of the fused InfoNCE kernel (infonce_umma2.cu)
+bool infonce_pair_supported(int D);
+int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const void* tt_bf16, int B, int D, int64_t HW, int K,
+                        const float* inv_norm, const int32_t* y, const float* w, float inv_tau, const float* grad_scale,
+                        const double* w_sum_in, float* lse, double* loss_sum, double* w_sum, double* dlogtau, cudaStream_t s);
+
 // ---- device helpers ---------------------------------------------------------------------------
 template <typename T> struct ElemIO;
 template <> struct ElemIO<float> {

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 namespace rc {
 
@@ -740,7 +741,7 @@ static int infonce_prepass_impl(const void* x, rc_dtype x_dtype, int B, int D, i
 }
 }  // namespace rc
 
-namespace rc { static long long* g_dbg_buf = nullptr; }
+namespace rc { static long long* g_dbg_buf = nullptr; long long* debug_timing_buffer() { return g_dbg_buf; } }
 extern "C" int rc_debug_set_timing_buffer(int64_t* dev_buf) { rc::g_dbg_buf = (long long*)dev_buf; return RC_OK; }
 
 extern "C" int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, void* workspace,
@@ -773,6 +774,15 @@ extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, in
   if ((rcode = infonce_prepass_impl(x, x_dtype, B, D, HW, workspace, workspace_bytes,
                                     (flags & RC_INFONCE_PREPASS_DONE) ? (cudaStream_t)-1 : s, &inv_norm, &xb))) return rcode;
   const void* xsrc = (x_dtype == RC_F32) ? (const void*)xb : x;
+  {
+    // CTA-pair kernel (cta_group::2) when the channel count allows it; RANGECLIP_B200_INFONCE=1cta forces the
+    // single-CTA kernel (kept for D = 128 / 384 and as the A/B baseline).
+    const char* impl = getenv("RANGECLIP_B200_INFONCE");
+    const bool force_1cta = impl != nullptr && impl[0] == '1';
+    if (!force_1cta && infonce_pair_supported(D))
+      return launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
+                                 loss_sum, w_sum, dlogtau, s);
+  }
   const int Kp = (K + 63) / 64 * 64;
   CUtensorMap m_xs, m_t, m_tt, m_xe, m_dx;
   {
@@ -809,4 +819,84 @@ extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, in
     infonce_umma_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_xe, m_dx, prm);
   }
   return check_launch("rc_infonce_bf16");
+}
+
+// ------------------------------------------------------------------------------------------------
+// bring-up kernel for the CTA-pair (cta_group::2) building blocks: C[256][N] = A[256][Kd] B[N][Kd]^T
+// with A rows split 128/128 over the two CTAs and B rows split N/2 / N/2.
+// ------------------------------------------------------------------------------------------------
+namespace rc {
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+debug_umma_gemm_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int N, int Kd,
+                           float* __restrict__ c) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sa = smem;               // 16 KB: own 128 rows of A, one 64-wide K chunk
+  uint8_t* sbm = smem + 16384;      // <= 16 KB: own N/2 rows of B
+  DebugBars* bars = reinterpret_cast<DebugBars*>(smem + 32768);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    mbar_init(&bars->full, 1);
+    mbar_init(&bars->done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<256>(&bars->tmem_base);
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16(256, N, 0, 0);
+    const int nh = N / 2;
+    for (int ck = 0; ck < Kd / 64; ++ck) {
+      if (rank == 0) mbar_arrive_expect_tx(&bars->full, 2 * (16384 + nh * 128));
+      tma_load_2d_2sm(sa, &map_a, &bars->full, ck * 64, (int)rank * 128);
+      tma_load_2d_2sm(sbm, &map_b, &bars->full, ck * 64, (int)rank * nh);
+      if (rank == 0) {
+        mbar_wait_cluster(&bars->full, ck & 1, 200);
+        tc_fence_after();
+        for (int ks = 0; ks < 4; ++ks)
+          mma_bf16_ss_2sm(tmem, desc_kmajor_sw128(smem_u32(sa) + ks * 32), desc_kmajor_sw128(smem_u32(sbm) + ks * 32), idesc,
+                          (ck | ks) != 0);
+        mma_commit_2sm(&bars->done);
+      }
+      mbar_wait_cluster(&bars->done, ck & 1, 201);   // both CTAs: smem may be refilled, TMEM is current
+    }
+  }
+  __syncthreads();
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int cc = 0; cc < N / 32; ++cc) {
+    uint32_t r[32];
+    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, r);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) c[((int64_t)rank * 128 + row) * N + cc * 32 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_2sm<256>(tmem); }
+}
+
+}  // namespace rc
+
+extern "C" int rc_debug_umma_gemm_2sm(const void* a_bf16, const void* b_bf16, int N, int Kd, float* c, void* stream) {
+  RC_REQUIRE(a_bf16 && b_bf16 && c, "rc_debug_umma_gemm_2sm: null pointer");
+  RC_REQUIRE(N >= 64 && N <= 256 && N % 64 == 0 && Kd >= 64 && Kd % 64 == 0, "rc_debug_umma_gemm_2sm: bad shape N=%d Kd=%d", N, Kd);
+  int rcode = rc::check_sm100("rc_debug_umma_gemm_2sm");
+  if (rcode) return rcode;
+  CUtensorMap ma, mb;
+  {
+    const uint64_t dims[2] = {(uint64_t)Kd, 256}, str[2] = {2, (uint64_t)Kd * 2};
+    const uint32_t box[2] = {64, 128};
+    if ((rcode = rc::make_tmap_bf16(&ma, a_bf16, 2, dims, str, box, "debug2 A"))) return rcode;
+    const uint64_t bdims[2] = {(uint64_t)Kd, (uint64_t)N};
+    const uint32_t bbox[2] = {64, (uint32_t)(N / 2)};
+    if ((rcode = rc::make_tmap_bf16(&mb, b_bf16, 2, bdims, str, bbox, "debug2 B"))) return rcode;
+  }
+  const int smem = 32768 + 64;
+  cudaError_t e = cudaFuncSetAttribute(rc::debug_umma_gemm_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return rc::fail(RC_ERR_CUDA, "rc_debug_umma_gemm_2sm: smem opt-in: %s", cudaGetErrorString(e));
+  rc::debug_umma_gemm_2sm_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(ma, mb, N, Kd, c);
+  return rc::check_launch("rc_debug_umma_gemm_2sm");
 }

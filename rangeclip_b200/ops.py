@@ -440,3 +440,13 @@ def debug_umma_gemm(a: torch.Tensor, b: torch.Tensor, variant: int) -> torch.Ten
     check(_lib.lib().rc_debug_umma_gemm(_p(a.contiguous()), _p(b.contiguous()), N, Kd, variant, _p(c), _stream(a)),
           "rc_debug_umma_gemm")
     return c
+
+
+def debug_umma_gemm_2sm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Bring-up check of the CTA-pair (cta_group::2) path: C[256,N] = A[256,Kd] B[N,Kd]^T."""
+    _need_cuda(a, b)
+    N, Kd = b.shape
+    c = torch.empty(256, N, device=a.device, dtype=torch.float32)
+    check(_lib.lib().rc_debug_umma_gemm_2sm(_p(a.contiguous()), _p(b.contiguous()), N, Kd, _p(c), _stream(a)),
+          "rc_debug_umma_gemm_2sm")
+    return c

@@ -53,6 +53,17 @@ def test_umma_gemm_tile(variant, N, Kd):
     assert maxrel(c, ref) < 1e-5, f"variant {variant}: maxrel {maxrel(c, ref)}"
 
 
+@pytest.mark.parametrize("N,Kd", [(64, 64), (256, 512), (128, 192)])
+def test_umma_gemm_cta_pair(N, Kd):
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(N + Kd)
+    a = torch.randn(256, Kd, generator=g).to(torch.bfloat16)
+    b = torch.randn(N, Kd, generator=g).to(torch.bfloat16)
+    c = ops.debug_umma_gemm_2sm(a.to(dev()), b.to(dev())).cpu()
+    ref = a.float() @ b.float().T
+    assert maxrel(c, ref) < 1e-5, maxrel(c, ref)
+
+
 # ------------------------------------------------------------------------------------------------
 # evaluation histograms (integer, bit-exact)
 # ------------------------------------------------------------------------------------------------
