@@ -1,22 +1,32 @@
-// K1/K2, CTA-pair version: the fused pixel-text InfoNCE forward + backward of infonce_umma.cu on
-// `tcgen05.mma.cta_group::2`.
+// K1/K2, CTA-pair version: the fused pixel-text InfoNCE forward + backward on
+// `tcgen05.mma.cta_group::2`, software-pipelined across tiles.
 //
 // Two CTAs on neighbouring SMs form a cluster and work on two 128-pixel tiles at a time.  Every MMA
 // spans both SMs (M = 256): each CTA stages only ITS half of the streamed operand and the tensor cores
 // read the other half from the peer's shared memory, which halves the shared-memory fill traffic and
-// the operand read traffic per SM -- the two limits the single-CTA kernel runs into
-// (profiles/r1_infonce_umma_ncu.txt):
+// the operand read traffic per SM:
 //   S   = X^T T^T   M = 256 px (128 per CTA, A = own X tile, MN-major), N = Kp text rows, B split: Kp/2 rows per CTA
 //   dX^T = T^T P^T   M = 256 channels (128 per CTA, A = own rows of T^T), N = 128 px (64 of each CTA's tile,
 //                    B = own P rows), four [128 ch x 128 px] accumulators per tile pair per CTA
-// The softmax/CE epilogue is per CTA on its own tile; the dX epilogue of a CTA covers its 128 channels
-// of every 256-channel block for the pixels of BOTH tiles, so the per-pixel row scales are exchanged
-// through distributed shared memory.  Only the leader CTA (cluster rank 0) issues MMAs; completion is
-// multicast to the mbarriers of both CTAs, consumer-release barriers live in the leader and receive
-// remote arrivals from the peer.
+//
+// Pipeline (per tile pair i; TMEM = S 256 columns + two 128-column dX accumulators, all 512 in use):
+//   tensor pipe : S(0) | S(1) dX(0) | S(2) dX(1) | ...      S(i+1) is issued BEFORE dX(i)
+//   softmax     : reads S(i) from TMEM while dX(i-1) runs, keeps P(i) = exp(z - m) as packed bf16 in
+//                 REGISTERS, releases the S columns at once (so S(i+1) can start), and stores P(i) to the
+//                 single shared-memory P buffer as soon as the dX(i-1) MMAs have finished reading P(i-1)
+//   dX epilogue : own 128 channel rows x 64 contiguous pixels per accumulator: x is read straight from
+//                 global memory (L2-resident: the S GEMM just streamed it) with 256-bit loads, prefetched one
+//                 accumulator ahead, and dX goes back with 256-bit stores -- no shared-memory staging.
+// Register budget by role (setmaxnreg; the sum over the five warpgroups must stay within the 5 x 96 the CTA is
+// launched with): control warps 40, softmax warps 120, epilogue warps 96.
+// Only the leader CTA (cluster rank 0) issues MMAs; completion is multicast to the mbarriers of both CTAs,
+// consumer-release barriers live in the leader and receive remote arrivals from the peer.  The per-pixel
+// row scales of a tile are exchanged through distributed shared memory (the dX epilogue of a CTA covers
+// pixels of both tiles).
 #include "common.cuh"
 #include "umma.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 namespace rc {
 using namespace umma;
@@ -24,14 +34,12 @@ using namespace umma;
 namespace pair {
 
 constexpr int kTilePx = 128;
-constexpr int kThreads = 640;          // warps: 0 TMA, 1 MMA (leader CTA only), 2 TMEM alloc, 3 staging DMA, 4-11 softmax, 12-19 dX epilogue
+constexpr int kThreads = 640;          // warps: 0 TMA, 1 MMA (leader CTA only), 2 TMEM alloc, 3 idle, 4-11 softmax, 12-19 dX epilogue
 constexpr int kStages = 4;
 constexpr int kStageBytes = 32 * 1024; // two own X chunks | two text half-chunks [Kp/2][64 d] | own T^T rows [128 d][<=128 k]
 constexpr int kPBytes = 64 * 1024;
-constexpr int kStgBufs = 3;
-constexpr int kStgPx = 32;
-constexpr int kStgBytes = 128 * kStgPx * 2;
 constexpr int kTmemCols = 512;
+constexpr int kRegsCtl = 40, kRegsSoftmax = 120;     // epilogue warps keep the entry allocation (96)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -40,16 +48,14 @@ struct __align__(8) Bars {
   uint64_t s_full, s_empty, p_full, p_empty;
   uint64_t acc_full[2], acc_empty[2];
   uint64_t sc_full[2];
-  uint64_t stg_full[kStgBufs], stg_done[kStgBufs];
   uint32_t tmem_base, pad;
 };
 
 constexpr int kOffP = kStages * kStageBytes;
-constexpr int kOffStg = kOffP + kPBytes;
 constexpr int kScaleBufs = 3;          // the softmax warps run up to two tiles ahead of the dX epilogue warps
-constexpr int kOffScale = kOffStg + kStgBufs * kStgBytes;   // rs, cs: [kScaleBufs tiles][2 owner CTAs][128] floats each
+constexpr int kOffScale = kOffP + kPBytes;                  // {rs, cs}: [kScaleBufs tiles][2 owner CTAs][128 px] float2
 constexpr int kOffXch = kOffScale + 2 * kScaleBufs * 2 * 128 * 4;
-constexpr int kOffBars = kOffXch + 4 * 2 * 128 * 4;
+constexpr int kOffBars = kOffXch + 2 * 4 * 2 * 128 * 4;     // exchange: [2 tile parities][max, sum, sez, sy][2 halves][128]
 constexpr int kSmemBytes = kOffBars + (int)sizeof(Bars);
 static_assert(kSmemBytes <= 232448, "shared-memory budget of one SM (227 KB)");
 
@@ -68,6 +74,10 @@ struct Params {
   int B, D, K, Kp;
   int64_t HW;
   int tiles_per_img, n_tiles, n_pairs;
+  int ablate;               // bring-up only (RANGECLIP_B200_ABLATE): 1 no x loads, 2 no dX stores, 4 no softmax exp
+  int wide;                 // 1: rows of X / dX are 32-byte aligned (256-bit global accesses allowed)
+  const __nv_bfloat16* x;
+  __nv_bfloat16* dx;
   const float* inv_norm;
   const int32_t* y;
   const float* w;
@@ -100,8 +110,47 @@ __device__ __forceinline__ float select32(const uint32_t (&r)[32], int i) {
   return (i & 16) ? a[1] : a[0];
 }
 
+// 16 pixels (32 bytes) of one channel row, straight from / to global memory.  `n8` = number of valid
+// 8-pixel groups (0, 1 or 2); the 256-bit form needs 32-byte alignment (`wide`).
+__device__ __forceinline__ void ldg_px16(const __nv_bfloat16* p, bool wide, int n8, uint32_t* r) {
+  if (wide && n8 == 2) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+  } else {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (g < n8) v = __ldg(reinterpret_cast<const uint4*>(p) + g);
+      r[g * 4] = v.x; r[g * 4 + 1] = v.y; r[g * 4 + 2] = v.z; r[g * 4 + 3] = v.w;
+    }
+  }
+}
+__device__ __forceinline__ void stg_px16(__nv_bfloat16* p, bool wide, int n8, const uint32_t* r) {
+  if (wide && n8 == 2) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+  } else {
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+      if (g < n8) reinterpret_cast<uint4*>(p)[g] = make_uint4(r[g * 4], r[g * 4 + 1], r[g * 4 + 2], r[g * 4 + 3]);
+  }
+}
+
+__device__ __forceinline__ float select16(const uint32_t (&r)[16], int i) {
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = __uint_as_float((i & 1) ? r[2 * j + 1] : r[2 * j]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] = (i & 2) ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) a[j] = (i & 4) ? a[2 * j + 1] : a[2 * j];
+  return (i & 8) ? a[1] : a[0];
+}
+
 // tile -> (image, first pixel); tiles past the end map to image index B, which is out of bounds for every
-// tensor map (TMA loads return zeros, TMA stores write nothing)
+// tensor map (TMA loads return zeros)
 __device__ __forceinline__ void tile_coords(const Params& prm, int tile, int& b, int& px0) {
   if (tile < prm.n_tiles) {
     b = tile / prm.tiles_per_img;
@@ -117,13 +166,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW], box (64 px, 64 d, 1)
                          const __grid_constant__ CUtensorMap map_t,     // T [Kp][D],    box (64 d, Kp/2 rows)
                          const __grid_constant__ CUtensorMap map_tt,    // T^T [D][Kp],  box (64 k, 128 d)
-                         const __grid_constant__ CUtensorMap map_x_e,   // X,            box (32 px, 128 d, 1)
-                         const __grid_constant__ CUtensorMap map_dx,    // dX,           box (32 px, 128 d, 1)
                          const Params prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem + kOffBars);
-  float* rs_s = reinterpret_cast<float*>(smem + kOffScale);   // [kScaleBufs][2][128]
-  float* cs_s = rs_s + kScaleBufs * 2 * 128;
+  float2* sc_s = reinterpret_cast<float2*>(smem + kOffScale);   // {rs, cs}: [kScaleBufs tiles][2 owner CTAs][128 px]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader_cta = rank == 0;
@@ -137,13 +183,12 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x_s); tma_prefetch_desc(&map_t);
-    if (kBwd) { tma_prefetch_desc(&map_tt); tma_prefetch_desc(&map_x_e); tma_prefetch_desc(&map_dx); }
+    if (kBwd) tma_prefetch_desc(&map_tt);
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 512);
     mbar_init(&bars->p_full, 512); mbar_init(&bars->p_empty, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 512); }
-    mbar_init(&bars->sc_full[0], 512); mbar_init(&bars->sc_full[1], 512);
-    for (int i = 0; i < kStgBufs; ++i) { mbar_init(&bars->stg_full[i], 1); mbar_init(&bars->stg_done[i], 256); }
+    mbar_init(&bars->sc_full[0], 129); mbar_init(&bars->sc_full[1], 129);   // 128 local writers + 1 expect_tx (peer: st.async)
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm<kTmemCols>(&bars->tmem_base);
@@ -169,35 +214,39 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     else mbar_arrive_remote(map_to_cta(bar, 0));
   };
 
-  if (warp == 0 && lane == 0) {
-    // =============================== TMA producer (both CTAs) ===============================
-    uint32_t it = 0;
-    for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters) {
-      int b, px0;
-      tile_coords(prm, 2 * pj + (int)rank, b, px0);
-      for (int cp = 0; cp < n_cp; ++cp) {
-        {   // own X chunks 2cp, 2cp+1
-          const int st = it % kStages;
-          RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 1);
-          uint8_t* sb = smem + st * kStageBytes;
-          if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * 4 * 8192);
-          for (int cc = 0; cc < 2; ++cc) {
-            tma_load_3d_2sm(sb + cc * 16384, &map_x_s, &bars->full[st], px0, (2 * cp + cc) * 64, b);
-            tma_load_3d_2sm(sb + cc * 16384 + 8192, &map_x_s, &bars->full[st], px0 + 64, (2 * cp + cc) * 64, b);
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
+    if (warp == 0 && lane == 0) {
+      // =============================== TMA producer (both CTAs) ===============================
+      // ring order == MMA issue order: S(first), then per tile pair [S(next)] [dX(this)]
+      uint32_t it = 0;
+      auto load_s = [&](int pj) {
+        int b, px0;
+        tile_coords(prm, 2 * pj + (int)rank, b, px0);
+        for (int cp = 0; cp < n_cp; ++cp) {
+          {   // own X chunks 2cp, 2cp+1
+            const int st = it % kStages;
+            RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 1);
+            uint8_t* sb = smem + st * kStageBytes;
+            if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * 4 * 8192);
+            for (int cc = 0; cc < 2; ++cc) {
+              tma_load_3d_2sm(sb + cc * 16384, &map_x_s, &bars->full[st], px0, (2 * cp + cc) * 64, b);
+              tma_load_3d_2sm(sb + cc * 16384 + 8192, &map_x_s, &bars->full[st], px0 + 64, (2 * cp + cc) * 64, b);
+            }
+            ++it;
           }
-          ++it;
+          {   // own half (Nh rows) of the text chunks 2cp, 2cp+1
+            const int st = it % kStages;
+            RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 1);
+            uint8_t* sb = smem + st * kStageBytes;
+            if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * 2 * Nh * 128);
+            for (int cc = 0; cc < 2; ++cc)
+              tma_load_2d_2sm(sb + cc * 16384, &map_t, &bars->full[st], (2 * cp + cc) * 64, (int)rank * Nh);
+            ++it;
+          }
         }
-        {   // own half (Nh rows) of the text chunks 2cp, 2cp+1
-          const int st = it % kStages;
-          RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 1);
-          uint8_t* sb = smem + st * kStageBytes;
-          if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * 2 * Nh * 128);
-          for (int cc = 0; cc < 2; ++cc)
-            tma_load_2d_2sm(sb + cc * 16384, &map_t, &bars->full[st], (2 * cp + cc) * 64, (int)rank * Nh);
-          ++it;
-        }
-      }
-      if (kBwd) {
+      };
+      auto load_dx = [&]() {
         for (int blk = 0; blk < n_blk; ++blk)
           for (int u = 0; u < n_units; ++u, ++it) {   // own 128 rows of T^T for this 256-channel block
             const int st = it % kStages;
@@ -208,127 +257,105 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
             for (int jj = 0; jj < nb; ++jj)
               tma_load_2d_2sm(sb + jj * 16384, &map_tt, &bars->full[st], (2 * u + jj) * 64, blk * 256 + (int)rank * 128);
           }
+      };
+      if (cluster_id < prm.n_pairs) load_s(cluster_id);
+      for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters) {
+        if (pj + n_clusters < prm.n_pairs) load_s(pj + n_clusters);
+        if (kBwd) load_dx();
       }
-    }
-  } else if (warp == 1 && lane == 0 && leader_cta) {
-    // =============================== MMA issuer (leader CTA) ================================
-    uint32_t it = 0, lt = 0, uc = 0;
-    for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
-      RC_WAIT(mbar_wait_cluster, &bars->s_empty, (lt & 1) ^ 1, 3);
-      tc_fence_after();
-      for (int cp = 0; cp < n_cp; ++cp, it += 2) {
-        const int sa = it % kStages, sb_ = (it + 1) % kStages;
-        RC_WAIT(mbar_wait_cluster, &bars->full[sa], (it / kStages) & 1, 4);
-        RC_WAIT(mbar_wait_cluster, &bars->full[sb_], ((it + 1) / kStages) & 1, 4);
-        tc_fence_after();
-        const uint32_t xa = smem_u32(smem + sa * kStageBytes);
-        const uint32_t tb = smem_u32(smem + sb_ * kStageBytes);
-        for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t a = desc_mnmajor_sw128(xa + cc * 16384 + ks * 2048, 8192);
-            const uint64_t bdesc = desc_kmajor_sw128(tb + cc * 16384 + ks * 32);
-            mma_bf16_ss_2sm(tmem, a, bdesc, idesc_s, (cp | cc | ks) != 0);
-          }
-        }
-        mma_commit_2sm(&bars->empty[sa]);
-        mma_commit_2sm(&bars->empty[sb_]);
-      }
-      mma_commit_2sm(&bars->s_full);
-      if (kBwd) {
-        RC_WAIT(mbar_wait_cluster, &bars->p_full, lt & 1, 5);
-        tc_fence_after();
-        const uint32_t pb = smem_u32(smem + kOffP);
-        for (int blk = 0; blk < n_blk; ++blk) {
-          for (int u = 0; u < n_units; ++u) {
-            const uint32_t jt = it + u;
-            RC_WAIT(mbar_wait_cluster, &bars->full[jt % kStages], (jt / kStages) & 1, 7);
-          }
+    } else if (warp == 1 && leader_cta) {
+      // =============================== MMA issuer (leader CTA) ================================
+      // The whole warp runs the loop converged, so stage indices, addresses and descriptors live in uniform
+      // registers; one elected lane issues the tcgen05 instructions.
+      uint32_t it = 0, uc = 0;
+      const uint32_t smem_base = smem_u32(smem);
+      // descriptor templates: only the 14-bit start-address field changes (+ bytes/16 per step)
+      const uint64_t dsc_x = desc_mnmajor_sw128(0, 8192);
+      const uint64_t dsc_k = desc_kmajor_sw128(0);
+      auto issue_s = [&]() {
+        for (int cp = 0; cp < n_cp; ++cp, it += 2) {
+          const int sa = it % kStages, sb_ = (it + 1) % kStages;
+          RC_WAIT(mbar_wait_cluster, &bars->full[sa], (it / kStages) & 1, 4);
+          RC_WAIT(mbar_wait_cluster, &bars->full[sb_], ((it + 1) / kStages) & 1, 4);
           tc_fence_after();
-          for (int pxh = 0; pxh < 2; ++pxh, ++uc) {
-            const int ab = uc & 1;
-            RC_WAIT(mbar_wait_cluster, &bars->acc_empty[ab], ((uc >> 1) & 1) ^ 1, 6);
-            tc_fence_after();
-            const uint32_t dcol = tmem + 256 + ab * 128;
-            for (int u = 0; u < n_units; ++u) {
-              const uint32_t sb = smem_u32(smem + ((it + u) % kStages) * kStageBytes);
-              const int nb = min(2, n_kchunks - 2 * u);
-              for (int jj = 0; jj < nb; ++jj) {
+          const uint64_t xa = dsc_x + ((smem_base + sa * kStageBytes) >> 4);
+          const uint64_t tb = dsc_k + ((smem_base + sb_ * kStageBytes) >> 4);
+          if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t a = desc_kmajor_sw128(sb + jj * 16384 + ks * 32);                              // own T^T rows [128 d][64 k]
-                  const uint64_t bdesc = desc_kmajor_sw128(pb + (2 * u + jj) * 16384 + pxh * 8192 + ks * 32);   // own P rows [64 px][64 k]
-                  mma_bf16_ss_2sm(dcol, a, bdesc, idesc_d, (u | jj | ks) != 0);
-                }
-              }
+            for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                mma_bf16_ss_2sm(tmem, xa + ((cc * 16384 + ks * 2048) >> 4), tb + ((cc * 16384 + ks * 32) >> 4), idesc_s,
+                                (cp | cc | ks) != 0);
             }
-            mma_commit_2sm(&bars->acc_full[ab]);
+            mma_commit_2sm(&bars->empty[sa]);
+            mma_commit_2sm(&bars->empty[sb_]);
           }
-          for (int u = 0; u < n_units; ++u) mma_commit_2sm(&bars->empty[(it + u) % kStages]);
-          it += n_units;
+          __syncwarp();
         }
-        mma_commit_2sm(&bars->p_empty);
+        if (elect_one()) mma_commit_2sm(&bars->s_full);
+        __syncwarp();
+      };
+      if (cluster_id < prm.n_pairs) issue_s();
+      uint32_t lt = 0;
+      for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
+        if (pj + n_clusters < prm.n_pairs) {
+          RC_WAIT(mbar_wait_cluster, &bars->s_empty, lt & 1, 3);     // softmax(lt) has read S(lt) out of TMEM
+          tc_fence_after();
+          issue_s();
+        }
+        if (kBwd) {
+          RC_WAIT(mbar_wait_cluster, &bars->p_full, lt & 1, 5);
+          tc_fence_after();
+          const uint64_t pb = dsc_k + ((smem_base + kOffP) >> 4);
+          for (int blk = 0; blk < n_blk; ++blk) {
+            for (int u = 0; u < n_units; ++u) {
+              const uint32_t jt = it + u;
+              RC_WAIT(mbar_wait_cluster, &bars->full[jt % kStages], (jt / kStages) & 1, 7);
+            }
+            tc_fence_after();
+            for (int pxh = 0; pxh < 2; ++pxh, ++uc) {
+              const int ab = uc & 1;
+              RC_WAIT(mbar_wait_cluster, &bars->acc_empty[ab], ((uc >> 1) & 1) ^ 1, 6);
+              tc_fence_after();
+              const uint32_t dcol = tmem + 256 + ab * 128;
+              for (int u = 0; u < n_units; ++u) {
+                const uint64_t sb = dsc_k + ((smem_base + ((it + u) % kStages) * kStageBytes) >> 4);
+                const int nb = min(2, n_kchunks - 2 * u);
+                if (elect_one()) {
+                  for (int jj = 0; jj < nb; ++jj) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)     // A: own T^T rows [128 d][64 k]; B: own P rows [64 px][64 k]
+                      mma_bf16_ss_2sm(dcol, sb + ((jj * 16384 + ks * 32) >> 4),
+                                      pb + (((2 * u + jj) * 16384 + pxh * 8192 + ks * 32) >> 4), idesc_d, (u | jj | ks) != 0);
+                  }
+                }
+                __syncwarp();
+              }
+              if (elect_one()) mma_commit_2sm(&bars->acc_full[ab]);
+              __syncwarp();
+            }
+            if (elect_one())
+              for (int u = 0; u < n_units; ++u) mma_commit_2sm(&bars->empty[(it + u) % kStages]);
+            __syncwarp();
+            it += n_units;
+          }
+          if (elect_one()) mma_commit_2sm(&bars->p_empty);
+          __syncwarp();
+        }
       }
     }
-  } else if (kBwd && warp == 3 && lane == 0) {
-    // ================= staging DMA: X loads for the dX epilogue, dX stores (both CTAs) =================
-    const int steps_per_pair = n_blk * 2 * 4;
-    const int my_pairs = (prm.n_pairs > cluster_id) ? (prm.n_pairs - cluster_id + n_clusters - 1) / n_clusters : 0;
-    const int64_t total_steps = (int64_t)my_pairs * steps_per_pair;
-    struct Cursor { int pj, rem, buf, b[2], px0[2]; };
-    auto load_pair = [&](Cursor& c) {
-      tile_coords(prm, 2 * c.pj, c.b[0], c.px0[0]);
-      tile_coords(prm, 2 * c.pj + 1, c.b[1], c.px0[1]);
-    };
-    auto init = [&](Cursor& c) { c.pj = cluster_id; c.rem = 0; c.buf = 0; load_pair(c); };
-    auto advance = [&](Cursor& c) {
-      c.buf = (c.buf + 1 == kStgBufs) ? 0 : c.buf + 1;
-      if (++c.rem == steps_per_pair) { c.rem = 0; c.pj += n_clusters; load_pair(c); }
-    };
-    // step `rem` = (blk, pxh, h): owner CTA = h >> 1, pixels [pxh*64 + (h&1)*32, +32) of the owner's tile,
-    // channels [blk*256 + rank*128, +128)
-    auto coords = [&](const Cursor& c, int& cx, int& cd, int& cb) {
-      const int h = c.rem & 3, pxh = (c.rem >> 2) & 1, blk = c.rem >> 3, owner = h >> 1;
-      cx = c.px0[owner] + pxh * 64 + (h & 1) * kStgPx;
-      cd = blk * 256 + (int)rank * 128;
-      cb = c.b[owner];
-    };
-    Cursor ld, stc;
-    init(ld); init(stc);
-    auto issue_next_load = [&]() {
-      int cx, cd, cb;
-      coords(ld, cx, cd, cb);
-      mbar_arrive_expect_tx(&bars->stg_full[ld.buf], kStgBytes);
-      tma_load_3d(smem + kOffStg + ld.buf * kStgBytes, &map_x_e, &bars->stg_full[ld.buf], cx, cd, cb);
-      advance(ld);
-    };
-    for (int i = 0; i < kStgBufs - 1; ++i)
-      if (i < total_steps) issue_next_load();
-    uint32_t par = 0;
-    for (int64_t s = 0; s < total_steps; ++s) {
-      RC_WAIT(mbar_wait, &bars->stg_done[stc.buf], par, 13);
-      int cx, cd, cb;
-      coords(stc, cx, cd, cb);
-      tma_store_3d(&map_dx, smem + kOffStg + stc.buf * kStgBytes, cx, cd, cb);
-      tma_store_commit();
-      if (stc.buf + 1 == kStgBufs) par ^= 1;
-      advance(stc);
-      if (s + kStgBufs - 1 < total_steps) {
-        tma_store_wait_read0_keep1();
-        issue_next_load();
-      }
-    }
-    tma_store_wait_all0();
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp < 12) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
     // ======================= softmax / CE warps: own tile (two warps per TMEM lane quarter) =======================
     const int half = warp >= 8 ? 1 : 0;
-    const int row = (warp & 3) * 32 + lane;                 // softmax: pixel of the own tile; epilogue: own channel row
+    const int row = (warp & 3) * 32 + lane;                 // pixel of the own tile == TMEM lane
     const int Kh = prm.Kp >> 1;
     const int cb = half * Kh;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + cb;
     uint8_t* prow = smem + kOffP + row * 128;
     const int sw = row & 7;
-    float* xch = reinterpret_cast<float*>(smem + kOffXch);
+    float* xch_base = reinterpret_cast<float*>(smem + kOffXch);
     float loss_acc = 0.f, w_acc = 0.f, dlt_acc = 0.f;
     float inv_wsum = 0.f, gscale = 1.f;
     if (kBwd) {
@@ -356,7 +383,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     const bool use_bound = prm.inv_tau * (2.02f * kLog2e) < 100.f;
     const float ml_bound = prm.inv_tau * (1.01f * kLog2e);
     // peer copies of the row-scale arrays (same offsets in the other CTA's shared memory)
-    const uint32_t rs_peer = map_to_cta(rs_s, rank ^ 1), cs_peer = map_to_cta(cs_s, rank ^ 1);
+    const uint32_t sc_peer = map_to_cta(sc_s, rank ^ 1);
     const uint32_t sc_peer0 = map_to_cta(&bars->sc_full[0], rank ^ 1), sc_peer1 = map_to_cta(&bars->sc_full[1], rank ^ 1);
     uint32_t lt = 0;
     for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
@@ -372,71 +399,75 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       load_pixel_scalars(pj + n_clusters);
       const float zs = inv_n * prm.inv_tau;
       const float zl = zs * kLog2e;
+      float* xch = xch_base + (lt & 1) * (4 * 2 * 128);      // double-buffered: one named barrier per tile suffices
       RC_WAIT(mbar_wait, &bars->s_full, lt & 1, 8);
       tc_fence_after();
       RC_T0(tsm);
-      float mx = -FLT_MAX;
-      for (int c = 0; !use_bound && c * 32 < Kh; ++c) {
-        const int nvalid = prm.K - (cb + c * 32);
-        if (nvalid <= 0) break;
-        uint32_t r[32];
-        tmem_ld_32x32(trow + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) if (i < nvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
-      }
       float ml = ml_bound;
       if (!use_bound) {
+        float mx = -FLT_MAX;
+        for (int c = 0; c * 32 < Kh; ++c) {
+          const int nvalid = prm.K - (cb + c * 32);
+          if (nvalid <= 0) break;
+          uint32_t r[32];
+          tmem_ld_32x32(trow + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < nvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
         xch[(0 * 2 + half) * 128 + row] = mx;
-        named_bar_sync(2, 256);
+        named_bar_sync(3, 256);
         mx = fmaxf(mx, xch[(0 * 2 + (half ^ 1)) * 128 + row]);
         ml = mx * zl;
       }
-      if (kBwd) RC_WAIT(mbar_wait, &bars->p_empty, (lt & 1) ^ 1, 9);
+      // e = exp(z - m) for this half's columns; P stays in registers as packed bf16 until the P buffer is free
+      uint32_t pk[64];
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, sy = 0.f;
-      for (int c = 0; c * 32 < Kh; ++c) {
-        const int k0 = cb + c * 32;
-        const int nvalid = prm.K - k0;
-        if (nvalid <= 0) break;
-        uint32_t r[32];
-        tmem_ld_32x32(trow + c * 32, r);
-        tmem_ld_wait();
-        const int yrel = yi - k0;
-        if ((unsigned)yrel < 32u) sy = select32(r, yrel);      // target logit: once per row, not per column
-        uint32_t pk[16];
-        if (nvalid >= 32) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float a0 = __uint_as_float(r[i]), a1 = __uint_as_float(r[i + 1]);
-            const float a2 = __uint_as_float(r[i + 2]), a3 = __uint_as_float(r[i + 3]);
-            const float e0 = fast_exp2(fmaf(a0, zl, -ml)), e1 = fast_exp2(fmaf(a1, zl, -ml));
-            const float e2 = fast_exp2(fmaf(a2, zl, -ml)), e3 = fast_exp2(fmaf(a3, zl, -ml));
-            s0 += e0; s1 += e1; s2 += e2; s3 += e3;
-            q0 = fmaf(e0, a0, q0); q1 = fmaf(e1, a1, q1); q2 = fmaf(e2, a2, q2); q3 = fmaf(e3, a3, q3);
-            pk[i >> 1] = pack_bf16x2(e0, e1);
-            pk[(i >> 1) + 1] = pack_bf16x2(e2, e3);
+      for (int c = 0; c < 8; ++c) {       // 16 text columns per step
+        if (c * 16 < Kh) {
+          const int k0 = cb + c * 16;
+          const int nvalid = prm.K - k0;
+          if (nvalid >= 16) {
+            uint32_t r[16];
+            tmem_ld_32x16(trow + c * 16, r);
+            tmem_ld_wait();
+            const int yrel = yi - k0;
+            if ((unsigned)yrel < 16u) sy = select16(r, yrel);      // target logit: once per row, not per column
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float a0 = __uint_as_float(r[i]), a1 = __uint_as_float(r[i + 1]);
+              const float a2 = __uint_as_float(r[i + 2]), a3 = __uint_as_float(r[i + 3]);
+              const float e0 = fast_exp2(fmaf(a0, zl, -ml)), e1 = fast_exp2(fmaf(a1, zl, -ml));
+              const float e2 = fast_exp2(fmaf(a2, zl, -ml)), e3 = fast_exp2(fmaf(a3, zl, -ml));
+              s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+              q0 = fmaf(e0, a0, q0); q1 = fmaf(e1, a1, q1); q2 = fmaf(e2, a2, q2); q3 = fmaf(e3, a3, q3);
+              pk[c * 8 + (i >> 1)] = pack_bf16x2(e0, e1);
+              pk[c * 8 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
+            }
+          } else if (nvalid > 0) {          // the one step that straddles K
+            uint32_t r[16];
+            tmem_ld_32x16(trow + c * 16, r);
+            tmem_ld_wait();
+            const int yrel = yi - k0;
+            if ((unsigned)yrel < 16u) sy = select16(r, yrel);
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float a0 = __uint_as_float(r[i]), a1 = __uint_as_float(r[i + 1]);
+              const float e0 = (i < nvalid) ? fast_exp2(fmaf(a0, zl, -ml)) : 0.f;
+              const float e1 = (i + 1 < nvalid) ? fast_exp2(fmaf(a1, zl, -ml)) : 0.f;
+              s0 += e0; s1 += e1;
+              q0 = fmaf(e0, a0, q0); q1 = fmaf(e1, a1, q1);
+              pk[c * 8 + (i >> 1)] = pack_bf16x2(e0, e1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[c * 8 + i] = 0u;
           }
-        } else {          // the one chunk that straddles K
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float a0 = __uint_as_float(r[i]), a1 = __uint_as_float(r[i + 1]);
-            const float e0 = (i < nvalid) ? fast_exp2(fmaf(a0, zl, -ml)) : 0.f;
-            const float e1 = (i + 1 < nvalid) ? fast_exp2(fmaf(a1, zl, -ml)) : 0.f;
-            s0 += e0; s1 += e1;
-            q0 = fmaf(e0, a0, q0); q1 = fmaf(e1, a1, q1);
-            pk[i >> 1] = pack_bf16x2(e0, e1);
-          }
-        }
-        if (kBwd) {
-          uint8_t* sub = prow + (k0 >> 6) * 16384;
-          const int cbase = (k0 & 32) >> 3;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(sub + (((cbase + g) ^ sw) << 4)) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
         }
       }
       tc_fence_before();
-      arrive_leader(&bars->s_empty);
+      arrive_leader(&bars->s_empty);            // S columns are free: the tensor pipe may start S of the next pair
       float sum = (s0 + s1) + (s2 + s3);
       float sez = (q0 + q1) + (q2 + q3);
       const bool mine_y = yi >= cb && yi < cb + Kh;
@@ -448,41 +479,56 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       sez += xch[(2 * 2 + (half ^ 1)) * 128 + row];
       sy = mine_y ? sy : xch[(3 * 2 + (half ^ 1)) * 128 + row];
       const float zy = sy * zs;
+      float lse = 0.f;
       if (half == 0) {
-        const float lse = (ml + __log2f(sum)) * kLn2;
+        lse = (ml + __log2f(sum)) * kLn2;
         loss_acc += wi * (lse - zy);
         w_acc += wi;
-        if (valid && prm.lse) prm.lse[m] = lse;
       }
+      RC_TACC(1, tsm);
       if (!kBwd) {
-        named_bar_sync(2, 256);     // exchange buffers are rewritten by the next tile
+        if (half == 0 && valid && prm.lse) prm.lse[m] = lse;
         continue;
       }
       {
         const float coef = gscale * wi * inv_wsum;
         const float inv_sum = 1.f / sum;
-        if (mine_y) {
+        if (half == 0) {
+          const float cj = coef * (sez * zs * inv_sum - zy);
+          const float rsv = inv_n * prm.inv_tau * coef * inv_sum, csv = inv_n * inv_n * cj;
+          const int idx = ((lt % kScaleBufs) * 2 + (int)rank) * 128 + row;     // [tile buffer][owner = this CTA][pixel]
+          sc_s[idx] = make_float2(rsv, csv);
+          st_async_remote_v2(sc_peer + idx * 8, rsv, csv, (lt & 1) ? sc_peer1 : sc_peer0);   // peer copy: 8 tx bytes on ITS barrier
+          dlt_acc -= cj;
+          mbar_arrive(&bars->sc_full[lt & 1]);                // own copy
+          if (row == 0) mbar_arrive_expect_tx(&bars->sc_full[lt & 1], 128 * 8);   // the peer's 128 st.async land here
+        }
+        // the dX MMAs of the previous pair have finished reading P: store this pair's P
+        RC_WAIT(mbar_wait, &bars->p_empty, (lt & 1) ^ 1, 9);
+        RC_T0(tst);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c * 32 < Kh) {
+            const int k0 = cb + c * 32;
+            uint8_t* sub = prow + (k0 >> 6) * 16384;
+            const int cbase = (k0 & 32) >> 3;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<uint4*>(sub + (((cbase + g) ^ sw) << 4)) =
+                  make_uint4(pk[c * 16 + g * 4], pk[c * 16 + g * 4 + 1], pk[c * 16 + g * 4 + 2], pk[c * 16 + g * 4 + 3]);
+          }
+        }
+        if (mine_y) {       // P[row][y] = e_y - sum  (softmax - onehot, times sum), subtraction before rounding
           const float ey = fast_exp2(fmaf(sy, zl, -ml));
           const int kk = yi & 63;
           uint8_t* sub = prow + (yi >> 6) * 16384;
           *reinterpret_cast<__nv_bfloat16*>(sub + (((kk >> 3) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(ey - sum);
         }
-        if (half == 0) {
-          const float cj = coef * (sez * zs * inv_sum - zy);
-          const float rsv = inv_n * prm.inv_tau * coef * inv_sum, csv = inv_n * inv_n * cj;
-          const int idx = ((lt % kScaleBufs) * 2 + (int)rank) * 128 + row;     // [tile buffer][owner = this CTA][pixel]
-          rs_s[idx] = rsv; cs_s[idx] = csv;
-          st_remote_f32(rs_peer + idx * 4, rsv);
-          st_remote_f32(cs_peer + idx * 4, csv);
-          dlt_acc -= cj;
-        }
         fence_proxy_async_smem();                 // P is read by the tensor cores (async proxy)
         arrive_leader(&bars->p_full);
-        mbar_arrive(&bars->sc_full[lt & 1]);              // row scales of this tile: visible here ...
-        mbar_arrive_remote((lt & 1) ? sc_peer1 : sc_peer0);   // ... and in the peer CTA
-        named_bar_sync(2, 256);                   // exchange buffers are rewritten by the next tile
+        RC_TACC(2, tst);
+        if (half == 0 && valid && prm.lse) prm.lse[m] = lse;      // after the hand-off: nothing waits behind this store
       }
-      RC_TACC(1, tsm);
     }
     if (half == 0) {
       loss_acc = warp_sum(loss_acc); w_acc = warp_sum(w_acc); dlt_acc = warp_sum(dlt_acc);
@@ -492,64 +538,107 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         if (kBwd && prm.dlogtau) atomicAdd(prm.dlogtau, (double)dlt_acc);
       }
     }
-  } else if (kBwd && warp >= 12) {
-    // ================ dX epilogue warps: own channel rows, pixels of both tiles (two warps per lane quarter) ================
+  } else if (kBwd) {
+    // ================ dX epilogue warps: own channel rows, 64 contiguous pixels per accumulator ================
+    // Warps 12-15 (half 0) take accumulator columns [0,64) = pixels of CTA 0's tile, warps 16-19 (half 1) columns
+    // [64,128) = pixels of CTA 1's tile; accumulator unit (blk, pxh) covers pixels [pxh*64, +64) of both tiles.
     const int half = warp >= 16 ? 1 : 0;
     const int row = (warp & 3) * 32 + lane;
-    const uint32_t trow_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256 + half * 16;
-    int sb = 0;
-    uint32_t sb_par = 0, uc = 0, lt = 0;
+    const uint32_t trow_acc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256 + half * 64;
+    const bool wide = prm.wide != 0;
+    const int units_per_pair = n_blk * 2;
+    // prefetch cursor: x of the NEXT 32-pixel chunk to be consumed from each of the two register buffers
+    int f_pj = cluster_id, f_unit = 0;
+    int64_t f_off = 0;        // element offset of (row, first pixel of the unit) in X / dX
+    int f_n8 = 0;             // valid 8-pixel groups in the 64-pixel span (0..8)
+    auto cursor_set = [&]() {
+      f_n8 = 0; f_off = 0;
+      const int t = 2 * f_pj + half;
+      if (f_pj < prm.n_pairs && t < prm.n_tiles) {
+        const int b = t / prm.tiles_per_img;
+        const int px0 = (t - b * prm.tiles_per_img) * kTilePx + (f_unit & 1) * 64;
+        const int d = (f_unit >> 1) * 256 + (int)rank * 128 + row;
+        f_off = ((int64_t)b * prm.D + d) * prm.HW + px0;
+        const int64_t left = prm.HW - px0;
+        f_n8 = left >= 64 ? 8 : (left > 0 ? (int)(left >> 3) : 0);
+      }
+    };
+    auto cursor_next = [&]() {
+      if (++f_unit == units_per_pair) { f_unit = 0; f_pj += n_clusters; }
+      cursor_set();
+    };
+    // Global accesses are made by lane PAIRS: lanes 2p, 2p+1 own channel rows 2p, 2p+1; access j of a 32-pixel chunk
+    // touches row 2p+j, and lane b = lane & 1 moves the b-th 16-pixel (32-byte) piece -- so one warp instruction
+    // covers 16 rows x 64 contiguous bytes instead of 32 rows x 32 bytes (half the L1 tag work).  A 2x2 exchange
+    // inside the pair (pair_swap) turns "row 2p+j, piece b" into "own row, piece j" and back.
+    const int lb = lane & 1;
+    uint32_t xq[2][16];       // chunk c of the current unit; before pair_swap: [j][8] = (row 2p+j, piece b)
+    auto pair_swap = [&](uint32_t* e) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const uint32_t send = lb ? e[r] : e[8 + r];
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        if (lb) e[r] = recv; else e[8 + r] = recv;
+      }
+    };
+    auto fetch = [&](int c) {
+      int n8 = min(2, max(0, f_n8 - (c * 2 + lb) * 2));      // valid 8-pixel groups of this lane's piece
+      if (prm.ablate & 1) n8 = 0;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        ldg_px16(prm.x + f_off + (int64_t)(j - lb) * prm.HW + c * 32 + lb * 16, wide, n8, &xq[c][j * 8]);
+    };
+    cursor_set();
+    fetch(0); fetch(1);
+    uint32_t uc = 0, lt = 0;
     for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
-      // ------------------------------ dX epilogue: own channels, pixels of both tiles ------------------------------
-      RC_WAIT(mbar_wait_cluster, &bars->sc_full[lt & 1], (lt >> 1) & 1, 10);
-      const float* rs = rs_s + (lt % kScaleBufs) * 256;
-      const float* cs = cs_s + (lt % kScaleBufs) * 256;
-      for (int blk = 0; blk < n_blk; ++blk) {
-        for (int pxh = 0; pxh < 2; ++pxh, ++uc) {
-          const int ab = uc & 1;
-          RC_WAIT(mbar_wait, &bars->acc_full[ab], (uc >> 1) & 1, 11);
-          tc_fence_after();
-          for (int h = 0; h < 4; ++h) {
-            // accumulator columns [h*32, +32) = pixels [pxh*64 + (h&1)*32, +32) of the tile owned by CTA (h >> 1)
-            uint32_t acc[16];
-            tmem_ld_32x16(trow_acc + ab * 128 + h * kStgPx, acc);
-            tmem_ld_wait();
-            if (h == 3) { tc_fence_before(); arrive_leader(&bars->acc_empty[ab]); }
-            RC_WAIT(mbar_wait, &bars->stg_full[sb], sb_par, 12);
-            RC_T0(tep);
-            uint8_t* srow = smem + kOffStg + sb * kStgBytes + row * 64;
-            const int sw64 = (row >> 1) & 3;
-            const int pbase = (h >> 1) * 128 + pxh * 64 + (h & 1) * kStgPx + half * 16;
-            const float* rsp = rs + pbase;
-            const float* csp = cs + pbase;
+      RC_WAIT(mbar_wait, &bars->sc_full[lt & 1], (lt >> 1) & 1, 10);
+      const float2* sc = sc_s + (lt % kScaleBufs) * 256 + half * 128;
+      for (int unit = 0; unit < units_per_pair; ++unit, ++uc) {
+        const int ab = uc & 1;
+        const int pxh = unit & 1;
+        // where this unit's output goes (same cursor arithmetic as the prefetch, one unit behind)
+        const int64_t o_off = f_off;
+        const int o_n8 = f_n8;
+        RC_WAIT(mbar_wait, &bars->acc_full[ab], (uc >> 1) & 1, 11);
+        tc_fence_after();
+        RC_T0(tep);
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              uint4* p = reinterpret_cast<uint4*>(srow + (((half * 2 + g) ^ sw64) << 4));
-              const uint4 xv = *p;
-              const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
-              const float4 r0 = *reinterpret_cast<const float4*>(rsp + g * 8);
-              const float4 r1 = *reinterpret_cast<const float4*>(rsp + g * 8 + 4);
-              const float4 c0 = *reinterpret_cast<const float4*>(csp + g * 8);
-              const float4 c1 = *reinterpret_cast<const float4*>(csp + g * 8 + 4);
-              const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-              const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-              float o[8];
+        for (int c = 0; c < 2; ++c) {
+          uint32_t acc[32];
+          tmem_ld_32x32(trow_acc + ab * 128 + c * 32, acc);
+          tmem_ld_wait();
+          if (c == 1) { tc_fence_before(); arrive_leader(&bars->acc_empty[ab]); }
+          pair_swap(&xq[c][0]);             // -> own row, pixels [c*32, +32) in order
+          const float4* scp = reinterpret_cast<const float4*>(sc + pxh * 64 + c * 32);    // {rs, cs} pairs of 32 pixels
+          uint32_t o[16];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float xval = (i & 1) ? __uint_as_float(xu[i >> 1] & 0xffff0000u) : __uint_as_float(xu[i >> 1] << 16);
-                o[i] = fmaf(rr[i], __uint_as_float(acc[g * 8 + i]), -cc[i] * xval);
-              }
-              uint4 ov;
-              ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
-              ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
-              *p = ov;
+          for (int g = 0; g < 4; ++g) {
+            const float4 s0 = scp[g * 4], s1 = scp[g * 4 + 1], s2 = scp[g * 4 + 2], s3 = scp[g * 4 + 3];
+            const float rr[8] = {s0.x, s0.z, s1.x, s1.z, s2.x, s2.z, s3.x, s3.z};
+            const float cc[8] = {s0.y, s0.w, s1.y, s1.w, s2.y, s2.w, s3.y, s3.w};
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t xu = xq[c][g * 4 + (i >> 1)];
+              const float xval = (i & 1) ? __uint_as_float(xu & 0xffff0000u) : __uint_as_float(xu << 16);
+              v[i] = fmaf(rr[i], __uint_as_float(acc[g * 8 + i]), -cc[i] * xval);
             }
-            fence_proxy_async_smem();
-            mbar_arrive(&bars->stg_done[sb]);
-            RC_TACC(2, tep);
-            if (++sb == kStgBufs) { sb = 0; sb_par ^= 1; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[g * 4 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
           }
+          {
+            pair_swap(&o[0]);               // -> [j][8] = (row 2p+j, piece b)
+            int n8 = min(2, max(0, o_n8 - (c * 2 + lb) * 2));
+            if (prm.ablate & 2) n8 = 0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              stg_px16(prm.dx + o_off + (int64_t)(j - lb) * prm.HW + c * 32 + lb * 16, wide, n8, &o[j * 8]);
+          }
+          if (c == 0) cursor_next();        // both chunks of the next unit are fetched relative to the advanced cursor
+          fetch(c);
         }
+        RC_TACC(2, tep);
       }
     }
   }
@@ -580,15 +669,13 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   using namespace pair;
   const bool bwd = dx != nullptr;
   const int Kp = (K + 63) / 64 * 64;
-  CUtensorMap m_xs, m_t, m_tt, m_xe, m_dx;
+  CUtensorMap m_xs, m_t, m_tt;
   int rcode;
   {
     const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)D, (uint64_t)B};
     const uint64_t str[3] = {2, (uint64_t)HW * 2, (uint64_t)D * HW * 2};
-    const uint32_t box_s[3] = {64, 64, 1}, box_e[3] = {kStgPx, 128, 1};
+    const uint32_t box_s[3] = {64, 64, 1};
     if ((rcode = make_tmap_bf16(&m_xs, xsrc, 3, dims, str, box_s, "pair map_x_s"))) return rcode;
-    if ((rcode = make_tmap_bf16(&m_xe, xsrc, 3, dims, str, box_e, "pair map_x_e"))) return rcode;
-    if ((rcode = make_tmap_bf16(&m_dx, bwd ? dx : xsrc, 3, dims, str, box_e, "pair map_dx"))) return rcode;
     const uint64_t tdims[2] = {(uint64_t)D, (uint64_t)Kp}, tstr[2] = {2, (uint64_t)D * 2};
     const uint32_t tbox[2] = {64, (uint32_t)(Kp / 2)};
     if ((rcode = make_tmap_bf16(&m_t, t_bf16, 2, tdims, tstr, tbox, "pair map_t"))) return rcode;
@@ -604,6 +691,10 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   if ((int64_t)B * prm.tiles_per_img > 0x3fffffff) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: too many tiles");
   prm.n_tiles = B * prm.tiles_per_img;
   prm.n_pairs = (prm.n_tiles + 1) / 2;
+  prm.x = reinterpret_cast<const __nv_bfloat16*>(xsrc);
+  prm.dx = reinterpret_cast<__nv_bfloat16*>(dx);
+  { const char* ab = getenv("RANGECLIP_B200_ABLATE"); prm.ablate = ab ? atoi(ab) : 0; }
+  prm.wide = (HW % 16 == 0) && (reinterpret_cast<uintptr_t>(xsrc) % 32 == 0) && (reinterpret_cast<uintptr_t>(dx) % 32 == 0);
   prm.inv_norm = inv_norm; prm.y = y; prm.w = w; prm.inv_tau = inv_tau; prm.grad_scale = grad_scale;
   prm.w_sum_in = w_sum_in; prm.lse = lse; prm.loss_sum = loss_sum; prm.w_sum = w_sum; prm.dlogtau = dlogtau;
   int n_clusters = num_sms() / 2;
@@ -613,11 +704,11 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   if (bwd) {
     e = cudaFuncSetAttribute(infonce_umma_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_infonce_bf16(pair): smem opt-in: %s", cudaGetErrorString(e));
-    infonce_umma_pair_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_xe, m_dx, prm);
+    infonce_umma_pair_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, prm);
   } else {
     e = cudaFuncSetAttribute(infonce_umma_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_infonce_bf16(pair): smem opt-in: %s", cudaGetErrorString(e));
-    infonce_umma_pair_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_xe, m_dx, prm);
+    infonce_umma_pair_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, prm);
   }
   return check_launch("rc_infonce_bf16(pair)");
 }

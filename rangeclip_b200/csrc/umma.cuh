@@ -195,11 +195,19 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// Remote arrive with the default (release, CTA scope) semantics: a plain SYNCS.ARRIVE over the cluster network.
+// (`.release.cluster` compiles to MEMBAR.ALL.GPU, which drains every global load / store the thread has in
+// flight -- fatal for roles that stream global memory.)  Data published with it must be in the ARRIVING CTA's
+// shared memory (+ fence.proxy.async when the tensor cores read it); data for the peer CTA goes through
+// st_async_remote_v2 below, which carries its own completion.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void st_remote_f32(uint32_t cluster_addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+// 8-byte store into the peer CTA's shared memory; completes 8 transaction bytes on the peer's mbarrier
+__device__ __forceinline__ void st_async_remote_v2(uint32_t cluster_addr, float a, float b, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr),
+               "f"(a), "f"(b), "r"(cluster_mbar)
+               : "memory");
 }
 // wait with cluster-scope acquire (barriers that receive remote arrivals / guard remotely written data)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
