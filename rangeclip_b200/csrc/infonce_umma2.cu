@@ -35,11 +35,11 @@ namespace pair {
 
 constexpr int kTilePx = 128;
 constexpr int kThreads = 640;          // warps: 0 TMA, 1 MMA (leader CTA only), 2 TMEM alloc, 3 idle, 4-11 softmax, 12-19 dX epilogue
-constexpr int kStages = 4;
-constexpr int kStageBytes = 32 * 1024; // two own X chunks | two text half-chunks [Kp/2][64 d] | own T^T rows [128 d][<=128 k]
+constexpr int kStages = 7;
+constexpr int kStageBytes = 16 * 1024; // one own X chunk [64 d][128 px] | one text half-chunk [Kp/2][64 d] | own T^T rows [128 d][64 k]
 constexpr int kPBytes = 64 * 1024;
 constexpr int kTmemCols = 512;
-constexpr int kRegsCtl = 40, kRegsSoftmax = 120;     // epilogue warps keep the entry allocation (96)
+constexpr int kRegsCtl = 40, kRegsSoftmax = 120;     // epilogue warps keep the entry allocation (96); 40 + 2*120 + 2*96 <= 5*96
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -53,9 +53,11 @@ struct __align__(8) Bars {
 
 constexpr int kOffP = kStages * kStageBytes;
 constexpr int kScaleBufs = 3;          // the softmax warps run up to two tiles ahead of the dX epilogue warps
-constexpr int kOffScale = kOffP + kPBytes;                  // {rs, cs}: [kScaleBufs tiles][2 owner CTAs][128 px] float2
+constexpr int kOffScale = kOffP + kPBytes;                  // {rs, -cs} bf16x2 pairs: [kScaleBufs tiles][2 owner CTAs][64 px pairs] uint2
 constexpr int kOffXch = kOffScale + 2 * kScaleBufs * 2 * 128 * 4;
-constexpr int kOffBars = kOffXch + 2 * 4 * 2 * 128 * 4;     // exchange: [2 tile parities][max, sum, sez, sy][2 halves][128]
+constexpr int kOffStg = kOffXch + 2 * 4 * 2 * 128 * 4;      // exchange: [2 tile parities][max, sum, sez, sy][2 halves][128]
+constexpr int kStgBytes = 32 * 32 * 2;                      // dX staging of one epilogue warp: [32 d][32 px] bf16, 64-byte swizzle
+constexpr int kOffBars = kOffStg + 8 * 2 * kStgBytes;       // two staging buffers per epilogue warp
 constexpr int kSmemBytes = kOffBars + (int)sizeof(Bars);
 static_assert(kSmemBytes <= 232448, "shared-memory budget of one SM (227 KB)");
 
@@ -112,8 +114,12 @@ __device__ __forceinline__ float select32(const uint32_t (&r)[32], int i) {
 
 // 16 pixels (32 bytes) of one channel row, straight from / to global memory.  `n8` = number of valid
 // 8-pixel groups (0, 1 or 2); the 256-bit form needs 32-byte alignment (`wide`).
-__device__ __forceinline__ void ldg_px16(const __nv_bfloat16* p, bool wide, int n8, uint32_t* r) {
-  if (wide && n8 == 2) {
+__device__ __forceinline__ void ldg_px16(const __nv_bfloat16* p, bool wide, int n8, uint32_t* r, uint64_t pol = 0) {
+  if (wide && n8 == 2 && pol != 0) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p), "l"(pol));
+  } else if (wide && n8 == 2) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p));
@@ -166,24 +172,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW], box (64 px, 64 d, 1)
                          const __grid_constant__ CUtensorMap map_t,     // T [Kp][D],    box (64 d, Kp/2 rows)
                          const __grid_constant__ CUtensorMap map_tt,    // T^T [D][Kp],  box (64 k, 128 d)
+                         const __grid_constant__ CUtensorMap map_dx,    // dX [B][D][HW], box (32 px, 32 d, 1)
                          const Params prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem + kOffBars);
-  float2* sc_s = reinterpret_cast<float2*>(smem + kOffScale);   // {rs, cs}: [kScaleBufs tiles][2 owner CTAs][128 px]
+  uint2* sc_s = reinterpret_cast<uint2*>(smem + kOffScale);     // {rs, -cs} as bf16x2 of a pixel PAIR: [kScaleBufs tiles][2 owner CTAs][64 pairs]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader_cta = rank == 0;
-  const int n_cp = prm.D / 128;          // X chunk pairs per tile
+  const int n_dchunks = prm.D / 64;      // 64-channel chunks of the S GEMM
   const int n_blk = prm.D / 256;         // 256-channel blocks of the dX GEMM
   const int n_kchunks = prm.Kp / 64;
-  const int n_units = (n_kchunks + 1) / 2;
   const int Nh = prm.Kp / 2;             // text rows staged by each CTA
   const int n_clusters = gridDim.x / 2;
   const int cluster_id = blockIdx.x / 2;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x_s); tma_prefetch_desc(&map_t);
-    if (kBwd) tma_prefetch_desc(&map_tt);
+    if (kBwd) { tma_prefetch_desc(&map_tt); tma_prefetch_desc(&map_dx); }
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 512);
     mbar_init(&bars->p_full, 512); mbar_init(&bars->p_empty, 1);
@@ -223,39 +229,32 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       auto load_s = [&](int pj) {
         int b, px0;
         tile_coords(prm, 2 * pj + (int)rank, b, px0);
-        for (int cp = 0; cp < n_cp; ++cp) {
-          {   // own X chunks 2cp, 2cp+1
+        for (int c = 0; c < n_dchunks; ++c) {
+          {   // own X chunk c: [64 d][128 px] as two 64-pixel boxes
             const int st = it % kStages;
             RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 1);
             uint8_t* sb = smem + st * kStageBytes;
-            if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * 4 * 8192);
-            for (int cc = 0; cc < 2; ++cc) {
-              tma_load_3d_2sm(sb + cc * 16384, &map_x_s, &bars->full[st], px0, (2 * cp + cc) * 64, b);
-              tma_load_3d_2sm(sb + cc * 16384 + 8192, &map_x_s, &bars->full[st], px0 + 64, (2 * cp + cc) * 64, b);
-            }
+            if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * 2 * 8192);
+            tma_load_3d_2sm(sb, &map_x_s, &bars->full[st], px0, c * 64, b);
+            tma_load_3d_2sm(sb + 8192, &map_x_s, &bars->full[st], px0 + 64, c * 64, b);
             ++it;
           }
-          {   // own half (Nh rows) of the text chunks 2cp, 2cp+1
+          {   // own half (Nh rows) of text chunk c
             const int st = it % kStages;
             RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 1);
-            uint8_t* sb = smem + st * kStageBytes;
-            if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * 2 * Nh * 128);
-            for (int cc = 0; cc < 2; ++cc)
-              tma_load_2d_2sm(sb + cc * 16384, &map_t, &bars->full[st], (2 * cp + cc) * 64, (int)rank * Nh);
+            if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * Nh * 128);
+            tma_load_2d_2sm(smem + st * kStageBytes, &map_t, &bars->full[st], c * 64, (int)rank * Nh);
             ++it;
           }
         }
       };
       auto load_dx = [&]() {
         for (int blk = 0; blk < n_blk; ++blk)
-          for (int u = 0; u < n_units; ++u, ++it) {   // own 128 rows of T^T for this 256-channel block
+          for (int kc = 0; kc < n_kchunks; ++kc, ++it) {   // own 128 rows of T^T for this 256-channel block, 64 k at a time
             const int st = it % kStages;
             RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 2);
-            uint8_t* sb = smem + st * kStageBytes;
-            const int nb = min(2, n_kchunks - 2 * u);
-            if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * nb * 16384);
-            for (int jj = 0; jj < nb; ++jj)
-              tma_load_2d_2sm(sb + jj * 16384, &map_tt, &bars->full[st], (2 * u + jj) * 64, blk * 256 + (int)rank * 128);
+            if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * 16384);
+            tma_load_2d_2sm(smem + st * kStageBytes, &map_tt, &bars->full[st], kc * 64, blk * 256 + (int)rank * 128);
           }
       };
       if (cluster_id < prm.n_pairs) load_s(cluster_id);
@@ -273,7 +272,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       const uint64_t dsc_x = desc_mnmajor_sw128(0, 8192);
       const uint64_t dsc_k = desc_kmajor_sw128(0);
       auto issue_s = [&]() {
-        for (int cp = 0; cp < n_cp; ++cp, it += 2) {
+        for (int c = 0; c < n_dchunks; ++c, it += 2) {
           const int sa = it % kStages, sb_ = (it + 1) % kStages;
           RC_WAIT(mbar_wait_cluster, &bars->full[sa], (it / kStages) & 1, 4);
           RC_WAIT(mbar_wait_cluster, &bars->full[sb_], ((it + 1) / kStages) & 1, 4);
@@ -282,12 +281,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           const uint64_t tb = dsc_k + ((smem_base + sb_ * kStageBytes) >> 4);
           if (elect_one()) {
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                mma_bf16_ss_2sm(tmem, xa + ((cc * 16384 + ks * 2048) >> 4), tb + ((cc * 16384 + ks * 32) >> 4), idesc_s,
-                                (cp | cc | ks) != 0);
-            }
+            for (int ks = 0; ks < 4; ++ks)
+              mma_bf16_ss_2sm(tmem, xa + ((ks * 2048) >> 4), tb + ((ks * 32) >> 4), idesc_s, (c | ks) != 0);
             mma_commit_2sm(&bars->empty[sa]);
             mma_commit_2sm(&bars->empty[sb_]);
           }
@@ -309,8 +304,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           tc_fence_after();
           const uint64_t pb = dsc_k + ((smem_base + kOffP) >> 4);
           for (int blk = 0; blk < n_blk; ++blk) {
-            for (int u = 0; u < n_units; ++u) {
-              const uint32_t jt = it + u;
+            for (int kc = 0; kc < n_kchunks; ++kc) {
+              const uint32_t jt = it + kc;
               RC_WAIT(mbar_wait_cluster, &bars->full[jt % kStages], (jt / kStages) & 1, 7);
             }
             tc_fence_after();
@@ -319,16 +314,13 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
               RC_WAIT(mbar_wait_cluster, &bars->acc_empty[ab], ((uc >> 1) & 1) ^ 1, 6);
               tc_fence_after();
               const uint32_t dcol = tmem + 256 + ab * 128;
-              for (int u = 0; u < n_units; ++u) {
-                const uint64_t sb = dsc_k + ((smem_base + ((it + u) % kStages) * kStageBytes) >> 4);
-                const int nb = min(2, n_kchunks - 2 * u);
+              for (int kc = 0; kc < n_kchunks; ++kc) {
+                const uint64_t sb = dsc_k + ((smem_base + ((it + kc) % kStages) * kStageBytes) >> 4);
+                const uint64_t pk_ = pb + ((kc * 16384 + pxh * 8192) >> 4);
                 if (elect_one()) {
-                  for (int jj = 0; jj < nb; ++jj) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)     // A: own T^T rows [128 d][64 k]; B: own P rows [64 px][64 k]
-                      mma_bf16_ss_2sm(dcol, sb + ((jj * 16384 + ks * 32) >> 4),
-                                      pb + (((2 * u + jj) * 16384 + pxh * 8192 + ks * 32) >> 4), idesc_d, (u | jj | ks) != 0);
-                  }
+                  for (int ks = 0; ks < 4; ++ks)     // A: own T^T rows [128 d][64 k]; B: own P rows [64 px][64 k]
+                    mma_bf16_ss_2sm(dcol, sb + ((ks * 32) >> 4), pk_ + ((ks * 32) >> 4), idesc_d, (kc | ks) != 0);
                 }
                 __syncwarp();
               }
@@ -336,9 +328,9 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
               __syncwarp();
             }
             if (elect_one())
-              for (int u = 0; u < n_units; ++u) mma_commit_2sm(&bars->empty[(it + u) % kStages]);
+              for (int kc = 0; kc < n_kchunks; ++kc) mma_commit_2sm(&bars->empty[(it + kc) % kStages]);
             __syncwarp();
-            it += n_units;
+            it += n_kchunks;
           }
           if (elect_one()) mma_commit_2sm(&bars->p_empty);
           __syncwarp();
@@ -423,47 +415,43 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       // e = exp(z - m) for this half's columns; P stays in registers as packed bf16 until the P buffer is free
       uint32_t pk[64];
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, sy = 0.f;
+      // 16 text columns per step
+      auto smx_step = [&](const uint32_t (&r)[16], int c) {
+        const int k0 = cb + c * 16;
+        const int nvalid = prm.K - k0;
+        const int yrel = yi - k0;
+        if ((unsigned)yrel < 16u) sy = select16(r, yrel);      // target logit: once per row, not per column
+        if (nvalid >= 16) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {       // 16 text columns per step
-        if (c * 16 < Kh) {
-          const int k0 = cb + c * 16;
-          const int nvalid = prm.K - k0;
-          if (nvalid >= 16) {
-            uint32_t r[16];
-            tmem_ld_32x16(trow + c * 16, r);
-            tmem_ld_wait();
-            const int yrel = yi - k0;
-            if ((unsigned)yrel < 16u) sy = select16(r, yrel);      // target logit: once per row, not per column
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float a0 = __uint_as_float(r[i]), a1 = __uint_as_float(r[i + 1]);
-              const float a2 = __uint_as_float(r[i + 2]), a3 = __uint_as_float(r[i + 3]);
-              const float e0 = fast_exp2(fmaf(a0, zl, -ml)), e1 = fast_exp2(fmaf(a1, zl, -ml));
-              const float e2 = fast_exp2(fmaf(a2, zl, -ml)), e3 = fast_exp2(fmaf(a3, zl, -ml));
-              s0 += e0; s1 += e1; s2 += e2; s3 += e3;
-              q0 = fmaf(e0, a0, q0); q1 = fmaf(e1, a1, q1); q2 = fmaf(e2, a2, q2); q3 = fmaf(e3, a3, q3);
-              pk[c * 8 + (i >> 1)] = pack_bf16x2(e0, e1);
-              pk[c * 8 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
-            }
-          } else if (nvalid > 0) {          // the one step that straddles K
-            uint32_t r[16];
-            tmem_ld_32x16(trow + c * 16, r);
-            tmem_ld_wait();
-            const int yrel = yi - k0;
-            if ((unsigned)yrel < 16u) sy = select16(r, yrel);
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              const float a0 = __uint_as_float(r[i]), a1 = __uint_as_float(r[i + 1]);
-              const float e0 = (i < nvalid) ? fast_exp2(fmaf(a0, zl, -ml)) : 0.f;
-              const float e1 = (i + 1 < nvalid) ? fast_exp2(fmaf(a1, zl, -ml)) : 0.f;
-              s0 += e0; s1 += e1;
-              q0 = fmaf(e0, a0, q0); q1 = fmaf(e1, a1, q1);
-              pk[c * 8 + (i >> 1)] = pack_bf16x2(e0, e1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pk[c * 8 + i] = 0u;
+          for (int i = 0; i < 16; i += 4) {
+            const float a0 = __uint_as_float(r[i]), a1 = __uint_as_float(r[i + 1]);
+            const float a2 = __uint_as_float(r[i + 2]), a3 = __uint_as_float(r[i + 3]);
+            const float e0 = fast_exp2(fmaf(a0, zl, -ml)), e1 = fast_exp2(fmaf(a1, zl, -ml));
+            const float e2 = fast_exp2(fmaf(a2, zl, -ml)), e3 = fast_exp2(fmaf(a3, zl, -ml));
+            s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+            q0 = fmaf(e0, a0, q0); q1 = fmaf(e1, a1, q1); q2 = fmaf(e2, a2, q2); q3 = fmaf(e3, a3, q3);
+            pk[c * 8 + (i >> 1)] = pack_bf16x2(e0, e1);
+            pk[c * 8 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
           }
+        } else {          // the step that straddles K, or padding columns only
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float a0 = __uint_as_float(r[i]), a1 = __uint_as_float(r[i + 1]);
+            const float e0 = (i < nvalid) ? fast_exp2(fmaf(a0, zl, -ml)) : 0.f;
+            const float e1 = (i + 1 < nvalid) ? fast_exp2(fmaf(a1, zl, -ml)) : 0.f;
+            s0 += e0; s1 += e1;
+            q0 = fmaf(e0, a0, q0); q1 = fmaf(e1, a1, q1);
+            pk[c * 8 + (i >> 1)] = pack_bf16x2(e0, e1);
+          }
+        }
+      };
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c * 16 < Kh) {
+          uint32_t r[16];
+          tmem_ld_32x16(trow + c * 16, r);
+          tmem_ld_wait();
+          smx_step(r, c);
         }
       }
       tc_fence_before();
@@ -496,12 +484,17 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         if (half == 0) {
           const float cj = coef * (sez * zs * inv_sum - zy);
           const float rsv = inv_n * prm.inv_tau * coef * inv_sum, csv = inv_n * inv_n * cj;
-          const int idx = ((lt % kScaleBufs) * 2 + (int)rank) * 128 + row;     // [tile buffer][owner = this CTA][pixel]
-          sc_s[idx] = make_float2(rsv, csv);
-          st_async_remote_v2(sc_peer + idx * 8, rsv, csv, (lt & 1) ? sc_peer1 : sc_peer0);   // peer copy: 8 tx bytes on ITS barrier
+          // the dX epilogue works on packed bf16 pixel pairs: dx = rs * acc + (-cs) * x
+          const float rs_n = __shfl_down_sync(0xffffffffu, rsv, 1), cs_n = __shfl_down_sync(0xffffffffu, csv, 1);
+          if ((lane & 1) == 0) {
+            const uint32_t r2 = pack_bf16x2(rsv, rs_n), c2 = pack_bf16x2(-csv, -cs_n);
+            const int idx = ((lt % kScaleBufs) * 2 + (int)rank) * 64 + (row >> 1);    // [tile buffer][owner = this CTA][pixel pair]
+            sc_s[idx] = make_uint2(r2, c2);
+            st_async_remote_v2(sc_peer + idx * 8, r2, c2, (lt & 1) ? sc_peer1 : sc_peer0);   // peer copy: 8 tx bytes on ITS barrier
+          }
           dlt_acc -= cj;
           mbar_arrive(&bars->sc_full[lt & 1]);                // own copy
-          if (row == 0) mbar_arrive_expect_tx(&bars->sc_full[lt & 1], 128 * 8);   // the peer's 128 st.async land here
+          if (row == 0) mbar_arrive_expect_tx(&bars->sc_full[lt & 1], 64 * 8);   // the peer's 64 st.async land here
         }
         // the dX MMAs of the previous pair have finished reading P: store this pair's P
         RC_WAIT(mbar_wait, &bars->p_empty, (lt & 1) ^ 1, 9);
@@ -549,15 +542,17 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     const int units_per_pair = n_blk * 2;
     // prefetch cursor: x of the NEXT 32-pixel chunk to be consumed from each of the two register buffers
     int f_pj = cluster_id, f_unit = 0;
-    int64_t f_off = 0;        // element offset of (row, first pixel of the unit) in X / dX
+    int64_t f_off = 0;        // element offset of (row, first pixel of the unit) in X
     int f_n8 = 0;             // valid 8-pixel groups in the 64-pixel span (0..8)
+    int f_b = prm.B, f_px = 0, f_d = 0;   // TMA store coordinates of the unit (image index B = out of bounds: nothing is written)
     auto cursor_set = [&]() {
-      f_n8 = 0; f_off = 0;
+      f_n8 = 0; f_off = 0; f_b = prm.B; f_px = 0; f_d = 0;
       const int t = 2 * f_pj + half;
       if (f_pj < prm.n_pairs && t < prm.n_tiles) {
         const int b = t / prm.tiles_per_img;
         const int px0 = (t - b * prm.tiles_per_img) * kTilePx + (f_unit & 1) * 64;
         const int d = (f_unit >> 1) * 256 + (int)rank * 128 + row;
+        f_b = b; f_px = px0; f_d = d - lane;
         f_off = ((int64_t)b * prm.D + d) * prm.HW + px0;
         const int64_t left = prm.HW - px0;
         f_n8 = left >= 64 ? 8 : (left > 0 ? (int)(left >> 3) : 0);
@@ -572,6 +567,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     // covers 16 rows x 64 contiguous bytes instead of 32 rows x 32 bytes (half the L1 tag work).  A 2x2 exchange
     // inside the pair (pair_swap) turns "row 2p+j, piece b" into "own row, piece j" and back.
     const int lb = lane & 1;
+    const uint64_t pol_x = l2_policy_evict_first();     // last use of these X lines in this kernel
     uint32_t xq[2][16];       // chunk c of the current unit; before pair_swap: [j][8] = (row 2p+j, piece b)
     auto pair_swap = [&](uint32_t* e) {
 #pragma unroll
@@ -586,20 +582,22 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       if (prm.ablate & 1) n8 = 0;
 #pragma unroll
       for (int j = 0; j < 2; ++j)
-        ldg_px16(prm.x + f_off + (int64_t)(j - lb) * prm.HW + c * 32 + lb * 16, wide, n8, &xq[c][j * 8]);
+        ldg_px16(prm.x + f_off + (int64_t)(j - lb) * prm.HW + c * 32 + lb * 16, wide, n8, &xq[c][j * 8], pol_x);
     };
+    uint8_t* stg_base = smem + kOffStg + (warp - 12) * 2 * kStgBytes;
+    const uint64_t pol_first = l2_policy_evict_first();  // dX is write-once: keep it from displacing X in L2
+    uint32_t sc_ = 0;         // staging buffer counter
     cursor_set();
     fetch(0); fetch(1);
     uint32_t uc = 0, lt = 0;
     for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
       RC_WAIT(mbar_wait, &bars->sc_full[lt & 1], (lt >> 1) & 1, 10);
-      const float2* sc = sc_s + (lt % kScaleBufs) * 256 + half * 128;
+      const uint2* sc = sc_s + (lt % kScaleBufs) * 128 + half * 64;
       for (int unit = 0; unit < units_per_pair; ++unit, ++uc) {
         const int ab = uc & 1;
         const int pxh = unit & 1;
         // where this unit's output goes (same cursor arithmetic as the prefetch, one unit behind)
-        const int64_t o_off = f_off;
-        const int o_n8 = f_n8;
+        const int o_b = f_b, o_px = f_px, o_d = f_d;
         RC_WAIT(mbar_wait, &bars->acc_full[ab], (uc >> 1) & 1, 11);
         tc_fence_after();
         RC_T0(tep);
@@ -610,30 +608,33 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           tmem_ld_wait();
           if (c == 1) { tc_fence_before(); arrive_leader(&bars->acc_empty[ab]); }
           pair_swap(&xq[c][0]);             // -> own row, pixels [c*32, +32) in order
-          const float4* scp = reinterpret_cast<const float4*>(sc + pxh * 64 + c * 32);    // {rs, cs} pairs of 32 pixels
+          const uint4* scp = reinterpret_cast<const uint4*>(sc + pxh * 32 + c * 16);    // {rs2, -cs2} of 16 pixel pairs
           uint32_t o[16];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 s0 = scp[g * 4], s1 = scp[g * 4 + 1], s2 = scp[g * 4 + 2], s3 = scp[g * 4 + 3];
-            const float rr[8] = {s0.x, s0.z, s1.x, s1.z, s2.x, s2.z, s3.x, s3.z};
-            const float cc[8] = {s0.y, s0.w, s1.y, s1.w, s2.y, s2.w, s3.y, s3.w};
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint32_t xu = xq[c][g * 4 + (i >> 1)];
-              const float xval = (i & 1) ? __uint_as_float(xu & 0xffff0000u) : __uint_as_float(xu << 16);
-              v[i] = fmaf(rr[i], __uint_as_float(acc[g * 8 + i]), -cc[i] * xval);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o[g * 4 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          for (int g = 0; g < 8; ++g) {       // two pixel pairs per step, packed bf16x2 arithmetic
+            const uint4 sv = scp[g];
+            const uint32_t a0 = pack_bf16x2(__uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1]));
+            const uint32_t a1 = pack_bf16x2(__uint_as_float(acc[4 * g + 2]), __uint_as_float(acc[4 * g + 3]));
+            o[2 * g] = bf2_fma(sv.x, a0, bf2_mul(sv.y, xq[c][2 * g]));
+            o[2 * g + 1] = bf2_fma(sv.z, a1, bf2_mul(sv.w, xq[c][2 * g + 1]));
           }
           {
-            pair_swap(&o[0]);               // -> [j][8] = (row 2p+j, piece b)
-            int n8 = min(2, max(0, o_n8 - (c * 2 + lb) * 2));
-            if (prm.ablate & 2) n8 = 0;
+            // own row of the warp's [32 d][32 px] staging tile (64-byte swizzle), then one TMA store per warp
+            uint8_t* stg = stg_base + ((sc_ & 1) ? kStgBytes : 0);
+            if (lane == 0) tma_store_wait_read0_keep1();      // the store issued two chunks ago has read this buffer
+            __syncwarp();
+            uint8_t* srow = stg + lane * 64;
+            const int sw64 = (lane >> 1) & 3;
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              stg_px16(prm.dx + o_off + (int64_t)(j - lb) * prm.HW + c * 32 + lb * 16, wide, n8, &o[j * 8]);
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<uint4*>(srow + ((g ^ sw64) << 4)) = make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(prm.ablate & 2)) {
+              tma_store_3d_hint(&map_dx, stg, o_px + c * 32, o_d, o_b, pol_first);
+              tma_store_commit();
+            }
+            ++sc_;
           }
           if (c == 0) cursor_next();        // both chunks of the next unit are fetched relative to the advanced cursor
           fetch(c);
@@ -641,6 +642,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         RC_TACC(2, tep);
       }
     }
+    if (lane == 0) tma_store_wait_all0();       // shared memory must stay valid until the last bulk store has read it
   }
 #ifdef RC_TIMING
   if (prm.dbg != nullptr && blockIdx.x < 2 && lane == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 12)) {
@@ -669,13 +671,15 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   using namespace pair;
   const bool bwd = dx != nullptr;
   const int Kp = (K + 63) / 64 * 64;
-  CUtensorMap m_xs, m_t, m_tt;
+  CUtensorMap m_xs, m_t, m_tt, m_dx;
   int rcode;
   {
     const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)D, (uint64_t)B};
     const uint64_t str[3] = {2, (uint64_t)HW * 2, (uint64_t)D * HW * 2};
     const uint32_t box_s[3] = {64, 64, 1};
     if ((rcode = make_tmap_bf16(&m_xs, xsrc, 3, dims, str, box_s, "pair map_x_s"))) return rcode;
+    const uint32_t box_o[3] = {32, 32, 1};
+    if ((rcode = make_tmap_bf16(&m_dx, bwd ? dx : xsrc, 3, dims, str, box_o, "pair map_dx"))) return rcode;
     const uint64_t tdims[2] = {(uint64_t)D, (uint64_t)Kp}, tstr[2] = {2, (uint64_t)D * 2};
     const uint32_t tbox[2] = {64, (uint32_t)(Kp / 2)};
     if ((rcode = make_tmap_bf16(&m_t, t_bf16, 2, tdims, tstr, tbox, "pair map_t"))) return rcode;
@@ -704,11 +708,11 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   if (bwd) {
     e = cudaFuncSetAttribute(infonce_umma_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_infonce_bf16(pair): smem opt-in: %s", cudaGetErrorString(e));
-    infonce_umma_pair_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, prm);
+    infonce_umma_pair_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_dx, prm);
   } else {
     e = cudaFuncSetAttribute(infonce_umma_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_infonce_bf16(pair): smem opt-in: %s", cudaGetErrorString(e));
-    infonce_umma_pair_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, prm);
+    infonce_umma_pair_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_dx, prm);
   }
   return check_launch("rc_infonce_bf16(pair)");
 }

@@ -6,7 +6,8 @@ from rangeclip_b200 import _lib, ops
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 dev = torch.device("cuda:0")
-D, H, W, K = 512, 256, 256, 256
+D, K = 512, 256
+H = int(os.environ.get("BENCH_H", 256)); W = int(os.environ.get("BENCH_W", 256))
 HW = H * W
 g = torch.Generator(device=dev).manual_seed(0)
 x = torch.empty(B, D, HW, device=dev, dtype=torch.bfloat16)
@@ -41,4 +42,4 @@ for bwd in (True, False):
     ms = e0.elapsed_time(e1) / reps
     flops = (4 if bwd else 2) * K * D * B * HW
     print(json.dumps({"kernel": "infonce_bf16" + ("_fwd_bwd" if bwd else "_fwd"), "impl": os.environ.get("RANGECLIP_B200_INFONCE", "pair"),
-                      "B": B, "ms": round(ms, 4), "TFLOPs": round(flops / ms / 1e9, 1), "Mpix_s": round(B * HW / ms / 1e3, 1)}), flush=True)
+                      "B": B, "H": H, "W": W, "ms": round(ms, 4), "TFLOPs": round(flops / ms / 1e9, 1), "Mpix_s": round(B * HW / ms / 1e3, 1)}), flush=True)
