@@ -277,7 +277,7 @@ def run_gpu(args):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("infonce_umma_kernel_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "infonce_umma_kernel<true>", "kernel_ms": k_ms,
+                "traffic": traffic, "kernel": "infonce_umma_pair_kernel<true>", "kernel_ms": k_ms,
                 "peak_source": f"{pk['src']} {'sustained' if long_region else 'burst'} cuBLAS bf16",
                 "algorithmic_flops_per_launch": flops}
 
@@ -392,7 +392,7 @@ def run_gpu(args):
             "config": {"workload": "configs[1]: pixel-text InfoNCE fwd+bwd, B=64/GPU, 256x256, D=512, K=256 (63 GT + 193 distractors), "
                                    "0.7 sampling with replacement", "outputs": "loss, lse, dX (bf16), dlogtau",
                        "l2": "inputs (4.3 GB bf16 per step) exceed the 126 MB L2; no flush needed",
-                       "step": "rc_sample_weights + rc_weight_sum + pre-pass (1/|x|) + fused tcgen05 kernel"},
+                       "step": "rc_sample_weights + rc_weight_sum + fused tcgen05 kernel (row norms, S GEMM, softmax/CE, dX GEMM, projection)"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "eval": ev, "loss": loss,
         }

@@ -771,15 +771,18 @@ extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, in
   if (rcode) return rcode;
   cudaStream_t s = (cudaStream_t)stream;
   float* inv_norm; __nv_bfloat16* xb;
-  if ((rcode = infonce_prepass_impl(x, x_dtype, B, D, HW, workspace, workspace_bytes,
-                                    (flags & RC_INFONCE_PREPASS_DONE) ? (cudaStream_t)-1 : s, &inv_norm, &xb))) return rcode;
+  // CTA-pair kernel (cta_group::2) when the channel count allows it; RANGECLIP_B200_INFONCE=1cta forces the
+  // single-CTA kernel (kept for D = 128 / 384 and as the A/B baseline).  The pair kernel computes 1/|x_p| itself
+  // from the operand tiles in shared memory, so a bf16 input needs no pre-pass at all (an fp32 input still needs
+  // its bf16 copy).
+  const char* impl = getenv("RANGECLIP_B200_INFONCE");
+  const bool use_pair = !(impl != nullptr && impl[0] == '1') && infonce_pair_supported(D);
+  const bool skip_prepass = (flags & RC_INFONCE_PREPASS_DONE) || (use_pair && x_dtype == RC_BF16);
+  if ((rcode = infonce_prepass_impl(x, x_dtype, B, D, HW, workspace, workspace_bytes, skip_prepass ? (cudaStream_t)-1 : s,
+                                    &inv_norm, &xb))) return rcode;
   const void* xsrc = (x_dtype == RC_F32) ? (const void*)xb : x;
   {
-    // CTA-pair kernel (cta_group::2) when the channel count allows it; RANGECLIP_B200_INFONCE=1cta forces the
-    // single-CTA kernel (kept for D = 128 / 384 and as the A/B baseline).
-    const char* impl = getenv("RANGECLIP_B200_INFONCE");
-    const bool force_1cta = impl != nullptr && impl[0] == '1';
-    if (!force_1cta && infonce_pair_supported(D))
+    if (use_pair)
       return launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
                                  loss_sum, w_sum, dlogtau, s);
   }

@@ -45,6 +45,7 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 struct __align__(8) Bars {
   uint64_t full[kStages], empty[kStages];
+  uint64_t xf[kStages];         // own X chunk of a ring slot has landed (CTA-local; the norm warps relay it to `full`)
   uint64_t s_full, s_empty, p_full, p_empty;
   uint64_t acc_full[2], acc_empty[2];
   uint64_t sc_full[2];
@@ -57,7 +58,8 @@ constexpr int kOffScale = kOffP + kPBytes;                  // {rs, -cs} bf16x2 
 constexpr int kOffXch = kOffScale + 2 * kScaleBufs * 2 * 128 * 4;
 constexpr int kOffStg = kOffXch + 2 * 4 * 2 * 128 * 4;      // exchange: [2 tile parities][max, sum, sez, sy][2 halves][128]
 constexpr int kStgBytes = 32 * 32 * 2;                      // dX staging of one epilogue warp: [32 d][32 px] bf16, 64-byte swizzle
-constexpr int kOffBars = kOffStg + 8 * 2 * kStgBytes;       // two staging buffers per epilogue warp
+constexpr int kOffPart = kOffStg + 8 * 2 * kStgBytes;       // two staging buffers per epilogue warp
+constexpr int kOffBars = kOffPart + 8 * 128 * 4;            // row-norm partial sums of squares [8 softmax warps][128 px]
 constexpr int kSmemBytes = kOffBars + (int)sizeof(Bars);
 static_assert(kSmemBytes <= 232448, "shared-memory budget of one SM (227 KB)");
 
@@ -190,7 +192,10 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x_s); tma_prefetch_desc(&map_t);
     if (kBwd) { tma_prefetch_desc(&map_tt); tma_prefetch_desc(&map_dx); }
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    // full: 2 arrivals (X slots: the relays of both CTAs; text slots: the leader's expect_tx + the peer producer);
+    // empty: 9 arrivals (MMA commit + the eight softmax warps, which read X slots for the row norms; on text slots
+    // the producer pre-arrives for them)
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 2); mbar_init(&bars->empty[i], 9); mbar_init(&bars->xf[i], 1); }
     mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 512);
     mbar_init(&bars->p_full, 512); mbar_init(&bars->p_empty, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 512); }
@@ -234,16 +239,18 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
             const int st = it % kStages;
             RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 1);
             uint8_t* sb = smem + st * kStageBytes;
-            if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * 2 * 8192);
-            tma_load_3d_2sm(sb, &map_x_s, &bars->full[st], px0, c * 64, b);
-            tma_load_3d_2sm(sb + 8192, &map_x_s, &bars->full[st], px0 + 64, c * 64, b);
+            mbar_arrive_expect_tx(&bars->xf[st], 2 * 8192);          // CTA-local: the norm warps read the chunk too
+            tma_load_3d(sb, &map_x_s, &bars->xf[st], px0, c * 64, b);
+            tma_load_3d(sb + 8192, &map_x_s, &bars->xf[st], px0 + 64, c * 64, b);
             ++it;
           }
           {   // own half (Nh rows) of text chunk c
             const int st = it % kStages;
             RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 1);
             if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * Nh * 128);
+            else mbar_arrive_remote(map_to_cta(&bars->full[st], 0));
             tma_load_2d_2sm(smem + st * kStageBytes, &map_t, &bars->full[st], c * 64, (int)rank * Nh);
+            mbar_arrive_n(&bars->empty[st], 8);                      // no row-norm readers on a text slot
             ++it;
           }
         }
@@ -254,7 +261,9 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
             const int st = it % kStages;
             RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 2);
             if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * 16384);
+            else mbar_arrive_remote(map_to_cta(&bars->full[st], 0));
             tma_load_2d_2sm(smem + st * kStageBytes, &map_tt, &bars->full[st], kc * 64, blk * 256 + (int)rank * 128);
+            mbar_arrive_n(&bars->empty[st], 8);
           }
       };
       if (cluster_id < prm.n_pairs) load_s(cluster_id);
@@ -337,6 +346,23 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         }
       }
     }
+    else if (warp == 2 && lane == 0) {
+      // ========== relay (both CTAs): "own X chunk has landed" (CTA-local xf) -> the leader's full barrier ==========
+      uint32_t it = 0, xf_phase = 0;
+      auto relay_tile = [&]() {
+        for (int c = 0; c < n_dchunks; ++c, it += 2) {
+          const int st = it % kStages;
+          RC_WAIT(mbar_wait, &bars->xf[st], (xf_phase >> st) & 1, 14);      // xf[st] advances only when the slot holds X
+          xf_phase ^= 1u << st;
+          arrive_leader(&bars->full[st]);
+        }
+      };
+      if (cluster_id < prm.n_pairs) relay_tile();
+      for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters) {
+        if (pj + n_clusters < prm.n_pairs) relay_tile();
+        if (kBwd) it += n_blk * n_kchunks;
+      }
+    }
   } else if (warp < 12) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
     // ======================= softmax / CE warps: own tile (two warps per TMEM lane quarter) =======================
@@ -365,13 +391,61 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         const int tpx = (t - tb * prm.tiles_per_img) * kTilePx + row;
         if (tpx < prm.HW) {
           const int64_t tm = (int64_t)tb * prm.HW + tpx;
-          nx_inv_n = __ldg(prm.inv_norm + tm);
+          nx_inv_n = 1.f;        // valid pixel (the value itself comes from the norm warps)
           nx_y = __ldg(prm.y + tm);
           nx_w = __ldg(prm.w + tm);
         }
       }
     };
     load_pixel_scalars(cluster_id);
+    // Row norms 1/|x_p| (model.py:272 F.normalize) of the NEXT tile, computed by these warps while they would
+    // otherwise wait for its S GEMM: the X chunks are read where they sit in the operand ring ([64 d][2 x 64 px],
+    // 128-byte swizzle).  thread = (8-pixel group g, row phase r); sums of squares meet in shared memory.
+    float* part_s = reinterpret_cast<float*>(smem + kOffPart);   // [8 warps][128 px] partial sums of squares
+    const int st_ = threadIdx.x - 128;                           // 0..255
+    const int ng = st_ & 15, nr = st_ >> 4;
+    uint32_t nit = 0, xf_phase = 0;
+    float inv_n_next = 0.f;
+    auto norm_tile = [&]() {
+      float ss[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss[j] = 0.f;
+      for (int c = 0; c < n_dchunks; ++c, nit += 2) {
+        const int st = nit % kStages;
+        RC_WAIT(mbar_wait, &bars->xf[st], (xf_phase >> st) & 1, 15);
+        xf_phase ^= 1u << st;
+        const uint8_t* base = smem + st * kStageBytes + (ng >> 3) * 8192 + nr * 128;
+        const int ch = ng & 7;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int rowd = nr + rr * 16;
+          const uint4 v = *reinterpret_cast<const uint4*>(base + rr * 2048 + ((ch ^ (rowd & 7)) << 4));
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float lo = __uint_as_float(u[j] << 16), hi = __uint_as_float(u[j] & 0xffff0000u);
+            ss[2 * j] = fmaf(lo, lo, ss[2 * j]);
+            ss[2 * j + 1] = fmaf(hi, hi, ss[2 * j + 1]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->empty[st]);
+      }
+      // fixed-order reduction (bit-reproducible): lane pairs, then the eight warps' partials through shared memory
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], 16);     // lanes l and l^16: same pixels, other rows
+      if (lane < 16) {
+        float4* dst = reinterpret_cast<float4*>(part_s + (warp - 4) * 128 + ng * 8);
+        dst[0] = make_float4(ss[0], ss[1], ss[2], ss[3]);
+        dst[1] = make_float4(ss[4], ss[5], ss[6], ss[7]);
+      }
+      named_bar_sync(5, 256);
+      float q = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) q += part_s[wv * 128 + row];
+      inv_n_next = 1.f / fmaxf(sqrtf(q), 1e-12f);
+    };
+    if (cluster_id < prm.n_pairs) norm_tile();
     const bool use_bound = prm.inv_tau * (2.02f * kLog2e) < 100.f;
     const float ml_bound = prm.inv_tau * (1.01f * kLog2e);
     // peer copies of the row-scale arrays (same offsets in the other CTA's shared memory)
@@ -385,13 +459,14 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       const int px = tile_ok ? (tile - b * prm.tiles_per_img) * kTilePx + row : 0;
       const bool valid = tile_ok && px < prm.HW;
       const int64_t m = (int64_t)b * prm.HW + px;
-      const float inv_n = nx_inv_n;
+      const bool px_ok = nx_inv_n != 0.f;
       const int yi = nx_y;
       const float wi = yi >= 0 ? nx_w : 0.f;
       load_pixel_scalars(pj + n_clusters);
+      float* xch = xch_base + (lt & 1) * (4 * 2 * 128);      // double-buffered: one named barrier per tile suffices
+      const float inv_n = px_ok ? inv_n_next : 0.f;
       const float zs = inv_n * prm.inv_tau;
       const float zl = zs * kLog2e;
-      float* xch = xch_base + (lt & 1) * (4 * 2 * 128);      // double-buffered: one named barrier per tile suffices
       RC_WAIT(mbar_wait, &bars->s_full, lt & 1, 8);
       tc_fence_after();
       RC_T0(tsm);
@@ -476,6 +551,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       RC_TACC(1, tsm);
       if (!kBwd) {
         if (half == 0 && valid && prm.lse) prm.lse[m] = lse;
+        if (pj + n_clusters < prm.n_pairs) norm_tile();
         continue;
       }
       {
@@ -521,6 +597,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         arrive_leader(&bars->p_full);
         RC_TACC(2, tst);
         if (half == 0 && valid && prm.lse) prm.lse[m] = lse;      // after the hand-off: nothing waits behind this store
+        if (pj + n_clusters < prm.n_pairs) norm_tile();
+        if (kBwd) nit += n_blk * n_kchunks;
       }
     }
     if (half == 0) {
