@@ -275,7 +275,7 @@ def run_gpu(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("infonce_umma_kernel_bytes_per_launch")
+        traffic = json.load(open(tp)).get("infonce_umma_pair_kernel_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "infonce_umma_pair_kernel<true>", "kernel_ms": k_ms,
                 "peak_source": f"{pk['src']} {'sustained' if long_region else 'burst'} cuBLAS bf16",

@@ -75,10 +75,14 @@ int rc_infonce_f32(const float* x, int B, int D, int64_t HW, int64_t ld_b,
  *   t_bf16   [Kp][D] bf16 normalised rows, Kp = K rounded up to 64, pad rows zero
  *   tt_bf16  [D][Kp] bf16 = transpose of t_bf16 (operand of the dX GEMM)
  *   dx       nullable; same dtype as x; = grad_scale * w_p/sum(w) * d(lse_p - z_py)/dx
- *   dt       nullable [K][D] f32, ADDED to (second kernel, recomputes S slice-wise)
+ *   dt       must be NULL: dText is produced by rc_infonce_f32 (the reference's text embeddings
+ *            are frozen CLIP outputs and never receive a gradient)
  *   workspace from rc_infonce_workspace_bytes; holds bf16 copy of x (f32 input) and 1/|x|.
  *   flags    RC_INFONCE_PREPASS_DONE: the workspace already holds the pre-pass results for this
- *            x (written by rc_infonce_prepass or an earlier call); skip the pre-pass kernel.      */
+ *            x (written by rc_infonce_prepass or an earlier call); skip the pre-pass kernel.
+ * D = 256 / 512 run the CTA-pair kernel, which computes 1/|x_p| itself from the operand tiles in
+ * shared memory: a bf16 x then needs no pre-pass at all.  D = 128 / 384 run the single-CTA kernel
+ * (pre-pass + fused kernel).                                                                      */
 #define RC_INFONCE_PREPASS_DONE 1
 int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
                     const void* t_bf16, const void* tt_bf16, int K,
