@@ -17,7 +17,7 @@ using namespace umma;
 
 namespace topk {
 
-constexpr int kThreads = 256;            // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4-7 top-k scan (one thread per pixel)
+constexpr int kThreads = 384;            // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4-11 top-k scan (two threads per pixel)
 constexpr int kTilePx = 128;
 constexpr int kXBytes = 128 * 1024;      // X tile [D <= 512][128 px] bf16: D/64 chunks of 16 KB
 constexpr int kStages = 3;
@@ -25,16 +25,18 @@ constexpr int kStageBytes = 32 * 1024;   // text block chunk [256 k][64 d]
 constexpr int kNB = 256;                 // text rows per block (MMA N)
 constexpr int kTmemCols = 512;
 constexpr int kMaxK = 8;
+constexpr int kMaxChunks = 8;            // D <= 512
 
 struct __align__(8) Bars {
   uint64_t full[kStages], empty[kStages];
-  uint64_t x_full, x_empty;
+  uint64_t x_full[kMaxChunks], x_empty[kMaxChunks];   // per 64-channel chunk of the resident X tile
   uint64_t s_full[2], s_empty[2];
   uint32_t tmem_base, pad;
 };
 constexpr int kOffRing = kXBytes;
 constexpr int kOffBars = kOffRing + kStages * kStageBytes;
 constexpr int kSmemBytes = kOffBars + (int)sizeof(Bars);
+static_assert(kSmemBytes <= 232448, "shared-memory budget of one SM (227 KB)");
 
 struct Params {
   int B, D, K, k;
@@ -49,6 +51,16 @@ __device__ __forceinline__ void topk_insert(float (&bv)[kMaxK], int (&bi)[kMaxK]
 #pragma unroll
   for (int j = 0; j < kMaxK; ++j) {
     if (j < k && v > bv[j]) {
+      const float tv = bv[j]; const int ti = bi[j];
+      bv[j] = v; bi[j] = id; v = tv; id = ti;
+    }
+  }
+}
+// insertion with an explicit index tie-break (merging lists whose index ranges interleave)
+__device__ __forceinline__ void topk_insert_tie(float (&bv)[kMaxK], int (&bi)[kMaxK], int k, float v, int id) {
+#pragma unroll
+  for (int j = 0; j < kMaxK; ++j) {
+    if (j < k && (v > bv[j] || (v == bv[j] && (unsigned)id < (unsigned)bi[j]))) {
       const float tv = bv[j]; const int ti = bi[j];
       bv[j] = v; bi[j] = id; v = tv; id = ti;
     }
@@ -80,8 +92,8 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_t);
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-    mbar_init(&bars->x_full, 1); mbar_init(&bars->x_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 128); }
+    for (int i = 0; i < kMaxChunks; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 256); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(&bars->tmem_base);
@@ -93,55 +105,68 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
 
   if (warp == 0 && lane == 0) {
     // =============================== TMA producer ===============================
+    // X chunk c of the next tile is refilled as soon as the last text block of this tile has consumed it, so the
+    // tile transition overlaps with the tail of the tensor work.
     uint32_t it = 0, lt = 0;
     for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
       const int b = tile / prm.tiles_per_img;
       const int px0 = (tile - b * prm.tiles_per_img) * kTilePx;
-      mbar_wait(&bars->x_empty, (lt & 1) ^ 1, 1);
-      mbar_arrive_expect_tx(&bars->x_full, n_dchunks * 16384);
-      for (int c = 0; c < n_dchunks; ++c) {
-        tma_load_3d(smem + c * 16384, &map_x, &bars->x_full, px0, c * 64, b);
-        tma_load_3d(smem + c * 16384 + 8192, &map_x, &bars->x_full, px0 + 64, c * 64, b);
-      }
       for (int nb = 0; nb < prm.n_blocks; ++nb)
         for (int c = 0; c < n_dchunks; ++c, ++it) {
+          if (nb == 0) {
+            mbar_wait(&bars->x_empty[c], (lt & 1) ^ 1, 1);
+            mbar_arrive_expect_tx(&bars->x_full[c], 16384);
+            tma_load_3d(smem + c * 16384, &map_x, &bars->x_full[c], px0, c * 64, b);
+            tma_load_3d(smem + c * 16384 + 8192, &map_x, &bars->x_full[c], px0 + 64, c * 64, b);
+          }
           const int st = it % kStages;
           mbar_wait(&bars->empty[st], ((it / kStages) & 1) ^ 1, 2);
           mbar_arrive_expect_tx(&bars->full[st], kStageBytes);
           tma_load_2d(smem + kOffRing + st * kStageBytes, &map_t, &bars->full[st], c * 64, nb * kNB);
         }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // =============================== MMA issuer ================================
+    // whole warp converged (addresses / descriptors in uniform registers), one elected lane issues
     uint32_t it = 0, lt = 0, nbc = 0;
-    const uint32_t xs = smem_u32(smem);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t dsc_x = desc_mnmajor_sw128(0, 8192) + (smem_base >> 4);
+    const uint64_t dsc_t = desc_kmajor_sw128(0) + ((smem_base + kOffRing) >> 4);
     for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
-      mbar_wait(&bars->x_full, lt & 1, 3);
       for (int nb = 0; nb < prm.n_blocks; ++nb, ++nbc) {
         const int sbuf = nbc & 1;
         mbar_wait(&bars->s_empty[sbuf], ((nbc >> 1) & 1) ^ 1, 4);
         tc_fence_after();
+        const bool last = nb + 1 == prm.n_blocks;
         for (int c = 0; c < n_dchunks; ++c, ++it) {
           const int st = it % kStages;
+          if (nb == 0) mbar_wait(&bars->x_full[c], lt & 1, 3);
           mbar_wait(&bars->full[st], (it / kStages) & 1, 5);
           tc_fence_after();
-          const uint32_t tb = smem_u32(smem + kOffRing + st * kStageBytes);
+          const uint64_t xa = dsc_x + ((c * 16384) >> 4);
+          const uint64_t tb = dsc_t + ((st * kStageBytes) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t a = desc_mnmajor_sw128(xs + c * 16384 + ks * 2048, 8192);
-            const uint64_t bdesc = desc_kmajor_sw128(tb + ks * 32);
-            mma_bf16_ss(tmem + sbuf * kNB, a, bdesc, idesc, (c | ks) != 0);
+            for (int ks = 0; ks < 4; ++ks)
+              mma_bf16_ss(tmem + sbuf * kNB, xa + ((ks * 2048) >> 4), tb + ((ks * 32) >> 4), idesc, (c | ks) != 0);
+            mma_commit(&bars->empty[st]);
+            if (last) mma_commit(&bars->x_empty[c]);       // this X chunk has been read for the last time
           }
-          mma_commit(&bars->empty[st]);
+          __syncwarp();
         }
-        mma_commit(&bars->s_full[sbuf]);
+        if (elect_one()) mma_commit(&bars->s_full[sbuf]);
+        __syncwarp();
       }
-      mma_commit(&bars->x_empty);       // all MMAs reading this X tile have completed
     }
   } else if (warp >= 4) {
     // =============================== top-k scan ================================
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    // Two warps per TMEM lane quarter: half 0 (warps 4-7) scans text columns [0,128) of every 256-row block, half 1
+    // (warps 8-11) columns [128,256); each thread keeps a running top-k, the two lists of a pixel are merged at the
+    // end of the tile (half 1 parks its list in its own, already scanned TMEM columns).
+    const int half = warp >= 8 ? 1 : 0;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + half * 128;
     uint32_t nbc = 0;
     for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
       const int b = tile / prm.tiles_per_img;
@@ -156,19 +181,25 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
         mbar_wait(&bars->s_full[sbuf], (nbc >> 1) & 1, 6);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < kNB / 32; ++c) {
-          const int k0 = nb * kNB + c * 32;
+        for (int c = 0; c < kNB / 64; ++c) {
+          const int k0 = nb * kNB + half * 128 + c * 32;
           if (k0 >= prm.K) break;
           uint32_t r[32];
           tmem_ld_32x32(trow + sbuf * kNB + c * 32, r);
           tmem_ld_wait();
           const int nvalid = prm.K - k0;
           // Per thread only ~k ln(K/k) values ever enter the top-k, but with 32 pixels per warp some lane qualifies at
-          // almost every column.  So: a branch-free candidate bitmask first (2 instructions per value), then a short
+          // almost every column.  So: a branch-free candidate bitmask first (four independent chains), then a short
           // per-thread loop over the set bits -- the warp iterates max-over-lanes(#candidates), not once per column.
-          uint32_t mask = 0;
+          uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(r[i]) > kth) ? (1u << i) : 0u;
+          for (int i = 0; i < 8; ++i) {
+            m0 |= (__uint_as_float(r[i]) > kth) ? (1u << i) : 0u;
+            m1 |= (__uint_as_float(r[8 + i]) > kth) ? (1u << (8 + i)) : 0u;
+            m2 |= (__uint_as_float(r[16 + i]) > kth) ? (1u << (16 + i)) : 0u;
+            m3 |= (__uint_as_float(r[24 + i]) > kth) ? (1u << (24 + i)) : 0u;
+          }
+          uint32_t mask = (m0 | m1) | (m2 | m3);
           if (nvalid < 32) mask &= (1u << nvalid) - 1u;
           while (mask) {
             const int i = __ffs(mask) - 1;       // ascending column order: the earlier index wins ties
@@ -182,10 +213,32 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
             }
           }
         }
+        if (nb + 1 == prm.n_blocks) {
+          // merge the two halves' lists through TMEM columns [128,144) of this buffer (half 1's own, scanned range)
+          const uint32_t tpark = tmem + ((uint32_t)(quarter * 32) << 16) + sbuf * kNB + 128;
+          if (half == 1) {
+            uint32_t pkd[16];
+#pragma unroll
+            for (int j = 0; j < kMaxK; ++j) { pkd[j] = __float_as_uint(bv[j]); pkd[8 + j] = (uint32_t)bi[j]; }
+            tmem_st_32x16(tpark, pkd);
+            tmem_st_wait();
+            tc_fence_before();
+            named_bar_sync(4 + quarter, 64);
+          } else {
+            named_bar_sync(4 + quarter, 64);
+            tc_fence_after();
+            uint32_t pkd[16];
+            tmem_ld_32x16(tpark, pkd);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < kMaxK; ++j)
+              if (j < prm.k && (int)pkd[8 + j] >= 0) topk_insert_tie(bv, bi, prm.k, __uint_as_float(pkd[j]), (int)pkd[8 + j]);
+          }
+        }
         tc_fence_before();
         mbar_arrive(&bars->s_empty[sbuf]);
       }
-      if (px < prm.HW) {
+      if (half == 0 && px < prm.HW) {
 #pragma unroll
         for (int j = 0; j < kMaxK; ++j)
           if (j < prm.k) prm.out[((int64_t)b * prm.k + j) * prm.HW + px] = bi[j] >= 0 ? __ldg(prm.index_map + bi[j]) : -1;
