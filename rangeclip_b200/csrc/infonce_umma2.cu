@@ -178,7 +178,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
                          const Params prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem + kOffBars);
-  uint2* sc_s = reinterpret_cast<uint2*>(smem + kOffScale);     // {rs, -cs} as bf16x2 of a pixel PAIR: [kScaleBufs tiles][2 owner CTAs][64 pairs]
+  uint32_t* sc_s = reinterpret_cast<uint32_t*>(smem + kOffScale);   // -cs as bf16x2 of a pixel PAIR: [kScaleBufs tiles][2 owner CTAs][64 pairs]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader_cta = rank == 0;
@@ -557,24 +557,28 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       {
         const float coef = gscale * wi * inv_wsum;
         const float inv_sum = 1.f / sum;
+        // P is stored pre-scaled: G[p][k] = rs_p (e_pk - sum_p [k = y_p]) = d loss / d(xhat_p . that_k) / |x_p|, so the
+        // dX accumulators need no row scale and the same tile is the A operand of the dText GEMM (dT = G^T X).
+        const float rsv = inv_n * prm.inv_tau * coef * inv_sum;
         if (half == 0) {
           const float cj = coef * (sez * zs * inv_sum - zy);
-          const float rsv = inv_n * prm.inv_tau * coef * inv_sum, csv = inv_n * inv_n * cj;
-          // the dX epilogue works on packed bf16 pixel pairs: dx = rs * acc + (-cs) * x
-          const float rs_n = __shfl_down_sync(0xffffffffu, rsv, 1), cs_n = __shfl_down_sync(0xffffffffu, csv, 1);
+          const float csv = inv_n * inv_n * cj;
+          // the dX epilogue works on packed bf16 pixel pairs: dx = acc + (-cs) * x
+          const float cs_n = __shfl_down_sync(0xffffffffu, csv, 1);
           if ((lane & 1) == 0) {
-            const uint32_t r2 = pack_bf16x2(rsv, rs_n), c2 = pack_bf16x2(-csv, -cs_n);
+            const uint32_t c2 = pack_bf16x2(-csv, -cs_n);
             const int idx = ((lt % kScaleBufs) * 2 + (int)rank) * 64 + (row >> 1);    // [tile buffer][owner = this CTA][pixel pair]
-            sc_s[idx] = make_uint2(r2, c2);
-            st_async_remote_v2(sc_peer + idx * 8, r2, c2, (lt & 1) ? sc_peer1 : sc_peer0);   // peer copy: 8 tx bytes on ITS barrier
+            sc_s[idx] = c2;
+            st_async_remote_b32(sc_peer + idx * 4, c2, (lt & 1) ? sc_peer1 : sc_peer0);   // peer copy: 4 tx bytes on ITS barrier
           }
           dlt_acc -= cj;
           mbar_arrive(&bars->sc_full[lt & 1]);                // own copy
-          if (row == 0) mbar_arrive_expect_tx(&bars->sc_full[lt & 1], 64 * 8);   // the peer's 64 st.async land here
+          if (row == 0) mbar_arrive_expect_tx(&bars->sc_full[lt & 1], 64 * 4);   // the peer's 64 st.async land here
         }
         // the dX MMAs of the previous pair have finished reading P: store this pair's P
         RC_WAIT(mbar_wait, &bars->p_empty, (lt & 1) ^ 1, 9);
         RC_T0(tst);
+        const uint32_t rs2 = pack_bf16x2(rsv, rsv);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c * 32 < Kh) {
@@ -584,14 +588,15 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               *reinterpret_cast<uint4*>(sub + (((cbase + g) ^ sw) << 4)) =
-                  make_uint4(pk[c * 16 + g * 4], pk[c * 16 + g * 4 + 1], pk[c * 16 + g * 4 + 2], pk[c * 16 + g * 4 + 3]);
+                  make_uint4(bf2_mul(pk[c * 16 + g * 4], rs2), bf2_mul(pk[c * 16 + g * 4 + 1], rs2),
+                             bf2_mul(pk[c * 16 + g * 4 + 2], rs2), bf2_mul(pk[c * 16 + g * 4 + 3], rs2));
           }
         }
-        if (mine_y) {       // P[row][y] = e_y - sum  (softmax - onehot, times sum), subtraction before rounding
+        if (mine_y) {       // G[row][y] = rs (e_y - sum)  (softmax - onehot), subtraction and scaling before rounding
           const float ey = fast_exp2(fmaf(sy, zl, -ml));
           const int kk = yi & 63;
           uint8_t* sub = prow + (yi >> 6) * 16384;
-          *reinterpret_cast<__nv_bfloat16*>(sub + (((kk >> 3) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(ey - sum);
+          *reinterpret_cast<__nv_bfloat16*>(sub + (((kk >> 3) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn((ey - sum) * rsv);
         }
         fence_proxy_async_smem();                 // P is read by the tensor cores (async proxy)
         arrive_leader(&bars->p_full);
@@ -670,7 +675,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     uint32_t uc = 0, lt = 0;
     for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
       RC_WAIT(mbar_wait, &bars->sc_full[lt & 1], (lt >> 1) & 1, 10);
-      const uint2* sc = sc_s + (lt % kScaleBufs) * 128 + half * 64;
+      const uint32_t* sc = sc_s + (lt % kScaleBufs) * 128 + half * 64;
       for (int unit = 0; unit < units_per_pair; ++unit, ++uc) {
         const int ab = uc & 1;
         const int pxh = unit & 1;
@@ -686,15 +691,18 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           tmem_ld_wait();
           if (c == 1) { tc_fence_before(); arrive_leader(&bars->acc_empty[ab]); }
           pair_swap(&xq[c][0]);             // -> own row, pixels [c*32, +32) in order
-          const uint4* scp = reinterpret_cast<const uint4*>(sc + pxh * 32 + c * 16);    // {rs2, -cs2} of 16 pixel pairs
+          const uint4* scp = reinterpret_cast<const uint4*>(sc + pxh * 32 + c * 16);    // -cs2 of 16 pixel pairs
           uint32_t o[16];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {       // two pixel pairs per step, packed bf16x2 arithmetic
+          for (int g = 0; g < 4; ++g) {       // four pixel pairs per step, packed bf16x2 arithmetic: dx = acc - cs x
             const uint4 sv = scp[g];
-            const uint32_t a0 = pack_bf16x2(__uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1]));
-            const uint32_t a1 = pack_bf16x2(__uint_as_float(acc[4 * g + 2]), __uint_as_float(acc[4 * g + 3]));
-            o[2 * g] = bf2_fma(sv.x, a0, bf2_mul(sv.y, xq[c][2 * g]));
-            o[2 * g + 1] = bf2_fma(sv.z, a1, bf2_mul(sv.w, xq[c][2 * g + 1]));
+            const uint32_t cs4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = 4 * g + j;
+              const uint32_t a = pack_bf16x2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+              o[i] = bf2_fma(cs4[j], xq[c][i], a);
+            }
           }
           {
             // own row of the warp's [32 d][32 px] staging tile (64-byte swizzle), then one TMA store per warp

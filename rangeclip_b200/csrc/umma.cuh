@@ -282,6 +282,12 @@ __device__ __forceinline__ void st_async_remote_v2(uint32_t cluster_addr, uint32
                "r"(a), "r"(b), "r"(cluster_mbar)
                : "memory");
 }
+// 4-byte variant
+__device__ __forceinline__ void st_async_remote_b32(uint32_t cluster_addr, uint32_t a, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(a),
+               "r"(cluster_mbar)
+               : "memory");
+}
 // packed bf16x2 arithmetic on raw 32-bit registers
 __device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
   uint32_t d;
