@@ -59,6 +59,8 @@ int64_t rc_launch_count(void);
 
 /* Workspace bytes rc_infonce_* needs for the given problem (bf16 tensor-core path only). */
 int64_t rc_infonce_workspace_bytes(int B, int D, int64_t HW, int K, rc_dtype x_dtype);
+/* Same, including the bf16 [B][HW][Kp] tensor G the tensor-core dText path needs (rc_infonce_bf16 with dt). */
+int64_t rc_infonce_workspace_bytes_dt(int B, int D, int64_t HW, int K, rc_dtype x_dtype);
 
 /* fp32 CUDA-core path (any K >= 1, D % 8 == 0, D <= 512).  Parity path: 1e-5 relative.
  *   dx (nullable) [B][D][HW] f32 = grad_scale * d(loss)/dx, dt (nullable) [K][D] f32 ADDED to.
@@ -75,8 +77,9 @@ int rc_infonce_f32(const float* x, int B, int D, int64_t HW, int64_t ld_b,
  *   t_bf16   [Kp][D] bf16 normalised rows, Kp = K rounded up to 64, pad rows zero
  *   tt_bf16  [D][Kp] bf16 = transpose of t_bf16 (operand of the dX GEMM)
  *   dx       nullable; same dtype as x; = grad_scale * w_p/sum(w) * d(lse_p - z_py)/dx
- *   dt       must be NULL: dText is produced by rc_infonce_f32 (the reference's text embeddings
- *            are frozen CLIP outputs and never receive a gradient)
+ *   dt       nullable [K][D] f32, ADDED to; needs dx, D = 256 or 512 and a workspace of
+ *            rc_infonce_workspace_bytes_dt: the fused kernel also writes G = rs (P - sum onehot)
+ *            (bf16 [B][HW][Kp]) and a second tensor-core kernel adds G^T X (split-K over pixels)
  *   workspace from rc_infonce_workspace_bytes; holds bf16 copy of x (f32 input) and 1/|x|.
  *   flags    RC_INFONCE_PREPASS_DONE: the workspace already holds the pre-pass results for this
  *            x (written by rc_infonce_prepass or an earlier call); skip the pre-pass kernel.

@@ -24,6 +24,7 @@ PROTOTYPES = {
     "rc_last_error": [],
     "rc_launch_count": [],
     "rc_infonce_workspace_bytes": [_i32, _i32, _i64, _i32, _i32],
+    "rc_infonce_workspace_bytes_dt": [_i32, _i32, _i64, _i32, _i32],
     "rc_infonce_f32": [_vp, _i32, _i32, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp,
                        _vp, _vp, _vp, _vp],
     "rc_infonce_bf16": [_vp, _i32, _i32, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp,
@@ -46,7 +47,8 @@ PROTOTYPES = {
     "rc_debug_umma_gemm_2sm": [_vp, _vp, _i32, _i32, _vp, _vp],
     "rc_debug_umma_gemm": [_vp, _vp, _i32, _i32, _i32, _vp, _vp],
 }
-_RESTYPES = {"rc_last_error": C.c_char_p, "rc_launch_count": _i64, "rc_infonce_workspace_bytes": _i64}
+_RESTYPES = {"rc_last_error": C.c_char_p, "rc_launch_count": _i64, "rc_infonce_workspace_bytes": _i64,
+             "rc_infonce_workspace_bytes_dt": _i64}
 
 _lib = None
 

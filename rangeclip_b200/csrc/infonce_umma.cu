@@ -714,6 +714,12 @@ extern "C" int64_t rc_infonce_workspace_bytes(int B, int D, int64_t HW, int K, r
   return bytes + 256;
 }
 
+extern "C" int64_t rc_infonce_workspace_bytes_dt(int B, int D, int64_t HW, int K, rc_dtype x_dtype) {
+  const int64_t Kp = (K + 63) / 64 * 64;
+  const int64_t base = (rc_infonce_workspace_bytes(B, D, HW, K, x_dtype) + 255) / 256 * 256;
+  return base + (int64_t)B * HW * Kp * 2 + 512;       // + G, bf16 [B][HW][Kp]
+}
+
 namespace rc {
 int launch_rownorm_f32(const float* x, int B, int D, int64_t HW, __nv_bfloat16* xb, float* inv_norm, cudaStream_t s) {
   const int64_t blocks = ((int64_t)B * HW / 8 + 255) / 256;
@@ -764,7 +770,6 @@ extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, in
   RC_REQUIRE((reinterpret_cast<uintptr_t>(t_bf16) & 15) == 0, "rc_infonce_bf16: t must be 16-byte aligned");
   const bool bwd = dx != nullptr;
   if (bwd) RC_REQUIRE(tt_bf16 && w_sum_in && (reinterpret_cast<uintptr_t>(dx) & 15) == 0, "rc_infonce_bf16: backward needs tt_bf16, w_sum_in and aligned dx");
-  if (dt != nullptr) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: dText is produced by rc_infonce_dt_bf16");
   if (dlogtau && !bwd) return fail(RC_ERR_INVALID, "rc_infonce_bf16: dlogtau needs dx");
   if (B == 0 || HW == 0) return RC_OK;
   int rcode = check_sm100("rc_infonce_bf16");
@@ -781,10 +786,23 @@ extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, in
   if ((rcode = infonce_prepass_impl(x, x_dtype, B, D, HW, workspace, workspace_bytes, skip_prepass ? (cudaStream_t)-1 : s,
                                     &inv_norm, &xb))) return rcode;
   const void* xsrc = (x_dtype == RC_F32) ? (const void*)xb : x;
+  if (dt != nullptr) {
+    // dText: the pair kernel also writes G = rs (P - sum onehot) (bf16 [B][HW][Kp]) into the workspace, then one
+    // split-K GEMM over the pixels (infonce_dt_umma.cu) adds G^T X to dt.
+    if (!use_pair || !bwd)
+      return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: dText needs dx and D = 256 or 512 (use rc_infonce_f32 otherwise)");
+    const int64_t base = rc_infonce_workspace_bytes(B, D, HW, K, x_dtype);
+    RC_REQUIRE(workspace_bytes >= rc_infonce_workspace_bytes_dt(B, D, HW, K, x_dtype), "rc_infonce_bf16: workspace too small for dText");
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    void* g = ws + ((base + 255) / 256) * 256;
+    if ((rcode = launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
+                                     loss_sum, w_sum, dlogtau, g, s))) return rcode;
+    return launch_infonce_dt(g, xsrc, B, D, HW, K, dt, s);
+  }
   {
     if (use_pair)
       return launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
-                                 loss_sum, w_sum, dlogtau, s);
+                                 loss_sum, w_sum, dlogtau, nullptr, s);
   }
   const int Kp = (K + 63) / 64 * 64;
   CUtensorMap m_xs, m_t, m_tt, m_xe, m_dx;

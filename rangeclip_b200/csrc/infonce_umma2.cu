@@ -79,6 +79,7 @@ struct Params {
   int64_t HW;
   int tiles_per_img, n_tiles, n_pairs;
   int ablate;               // bring-up only (RANGECLIP_B200_ABLATE): 1 no x loads, 2 no dX stores, 4 no softmax exp
+  int store_g;              // 1: also write G = rs (P - sum onehot) (bf16 [B][HW][Kp]) for the dText GEMM
   int wide;                 // 1: rows of X / dX are 32-byte aligned (256-bit global accesses allowed)
   const __nv_bfloat16* x;
   __nv_bfloat16* dx;
@@ -175,6 +176,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
                          const __grid_constant__ CUtensorMap map_t,     // T [Kp][D],    box (64 d, Kp/2 rows)
                          const __grid_constant__ CUtensorMap map_tt,    // T^T [D][Kp],  box (64 k, 128 d)
                          const __grid_constant__ CUtensorMap map_dx,    // dX [B][D][HW], box (32 px, 32 d, 1)
+                         const __grid_constant__ CUtensorMap map_g,     // G [B][HW][Kp],  box (64 k, 128 px, 1) (dText only)
                          const Params prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem + kOffBars);
@@ -458,6 +460,9 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       const int b = tile_ok ? tile / prm.tiles_per_img : 0;
       const int px = tile_ok ? (tile - b * prm.tiles_per_img) * kTilePx + row : 0;
       const bool valid = tile_ok && px < prm.HW;
+      // dText mode: the bulk store of the previous tile's G must have read the P buffer before anyone rewrites it
+      // (every thread passes the named barrier below before its next P store)
+      if (kBwd && prm.store_g && threadIdx.x == 128) tma_store_wait_read0();
       const int64_t m = (int64_t)b * prm.HW + px;
       const bool px_ok = nx_inv_n != 0.f;
       const int yi = nx_y;
@@ -601,11 +606,20 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         fence_proxy_async_smem();                 // P is read by the tensor cores (async proxy)
         arrive_leader(&bars->p_full);
         RC_TACC(2, tst);
+        if (prm.store_g) {                        // dText: the finished G tile goes to global memory as it sits in smem
+          named_bar_sync(6, 256);
+          if (threadIdx.x == 128 && tile_ok) {
+            const int gpx0 = px - row;
+            for (int j = 0; j < n_kchunks; ++j) tma_store_3d(&map_g, smem + kOffP + j * 16384, j * 64, gpx0, b);
+            tma_store_commit();
+          }
+        }
         if (half == 0 && valid && prm.lse) prm.lse[m] = lse;      // after the hand-off: nothing waits behind this store
         if (pj + n_clusters < prm.n_pairs) norm_tile();
         if (kBwd) nit += n_blk * n_kchunks;
       }
     }
+    if (kBwd && prm.store_g && threadIdx.x == 128) tma_store_wait_all0();
     if (half == 0) {
       loss_acc = warp_sum(loss_acc); w_acc = warp_sum(w_acc); dlt_acc = warp_sum(dlt_acc);
       if (lane == 0) {
@@ -753,11 +767,12 @@ bool infonce_pair_supported(int D) { return D == 256 || D == 512; }
 // launch helper used by rc_infonce_bf16 (infonce_umma.cu owns argument checking, the pre-pass and text maps)
 int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const void* tt_bf16, int B, int D, int64_t HW, int K,
                         const float* inv_norm, const int32_t* y, const float* w, float inv_tau, const float* grad_scale,
-                        const double* w_sum_in, float* lse, double* loss_sum, double* w_sum, double* dlogtau, cudaStream_t s) {
+                        const double* w_sum_in, float* lse, double* loss_sum, double* w_sum, double* dlogtau, void* g_out,
+                        cudaStream_t s) {
   using namespace pair;
   const bool bwd = dx != nullptr;
   const int Kp = (K + 63) / 64 * 64;
-  CUtensorMap m_xs, m_t, m_tt, m_dx;
+  CUtensorMap m_xs, m_t, m_tt, m_dx, m_g;
   int rcode;
   {
     const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)D, (uint64_t)B};
@@ -774,7 +789,19 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
     if ((rcode = make_tmap_bf16(&m_tt, bwd ? tt_bf16 : t_bf16, 2, bwd ? ttdims : tdims, bwd ? ttstr : tstr,
                                 bwd ? ttbox : tbox, "pair map_tt"))) return rcode;
   }
+  {
+    // G [B][HW][Kp] bf16: a tile is stored exactly as it sits in shared memory (four K-major 128B-swizzled sub-tiles)
+    const uint64_t gdims[3] = {(uint64_t)Kp, (uint64_t)HW, (uint64_t)B};
+    const uint64_t gstr[3] = {2, (uint64_t)Kp * 2, (uint64_t)HW * Kp * 2};
+    const uint32_t gbox[3] = {64, 128, 1};
+    if (g_out != nullptr) {
+      if ((rcode = make_tmap_bf16(&m_g, g_out, 3, gdims, gstr, gbox, "pair map_g"))) return rcode;
+    } else {
+      m_g = m_dx;
+    }
+  }
   Params prm;
+  prm.store_g = g_out != nullptr;
   prm.dbg = debug_timing_buffer();
   prm.B = B; prm.D = D; prm.K = K; prm.Kp = Kp; prm.HW = HW;
   prm.tiles_per_img = (int)((HW + kTilePx - 1) / kTilePx);
@@ -794,11 +821,11 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   if (bwd) {
     e = cudaFuncSetAttribute(infonce_umma_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_infonce_bf16(pair): smem opt-in: %s", cudaGetErrorString(e));
-    infonce_umma_pair_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_dx, prm);
+    infonce_umma_pair_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_dx, m_g, prm);
   } else {
     e = cudaFuncSetAttribute(infonce_umma_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_infonce_bf16(pair): smem opt-in: %s", cudaGetErrorString(e));
-    infonce_umma_pair_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_dx, prm);
+    infonce_umma_pair_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_dx, m_g, prm);
   }
   return check_launch("rc_infonce_bf16(pair)");
 }

@@ -119,8 +119,9 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
     w = w.reshape(-1).to(torch.float32).contiguous()
     if y.numel() != M or w.numel() != M:
         raise RuntimeError("infonce: y / w must have one entry per pixel row")
+    dt_on_tc = need_dt and need_dx and D in (256, 512)       # tensor-core dText: pair kernel + split-K GEMM
     if precision == "auto":
-        precision = "bf16" if (bf16_path_supported(D, HW, K) and not need_dt) else "fp32"
+        precision = "bf16" if (bf16_path_supported(D, HW, K) and (not need_dt or dt_on_tc)) else "fp32"
     acc = torch.zeros(4, device=dev, dtype=torch.float64)        # loss_sum, w_sum, dlogtau, w_sum_in
     lse = torch.empty(M, device=dev, dtype=torch.float32)
     need_grad = need_dx or need_dt
@@ -145,18 +146,18 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
     elif precision == "bf16":
         if not bf16_path_supported(D, HW, K):
             raise RuntimeError(f"infonce: bf16 tensor-core path does not cover D={D}, HW={HW}, K={K}")
-        if need_dt:
-            raise RuntimeError("infonce: dText on the bf16 path is not available yet; use precision='fp32'")
+        if need_dt and not dt_on_tc:
+            raise RuntimeError("infonce: dText on the bf16 path needs dx and D in (256, 512); use precision='fp32'")
         if t_bf16 is None:
             t_bf16 = text_to_bf16(t_norm)
         tb, ttb = t_bf16
         xdt = _dt(x)
-        ws_bytes = int(L.rc_infonce_workspace_bytes(B, D, HW, K, xdt))
+        ws_bytes = int((L.rc_infonce_workspace_bytes_dt if need_dt else L.rc_infonce_workspace_bytes)(B, D, HW, K, xdt))
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         dxb = torch.empty(B, D, HW, device=dev, dtype=torch.bfloat16) if need_dx else None
         check(L.rc_infonce_bf16(_p(x), xdt, B, D, HW, _p(tb), _p(ttb), K, _p(y), _p(w), float(inv_tau), _p(lse),
                                 acc[0:].data_ptr(), acc[1:].data_ptr(),
-                                acc[3:].data_ptr() if need_grad else None, _p(gs), _p(dxb), None,
+                                acc[3:].data_ptr() if need_grad else None, _p(gs), _p(dxb), _p(dt),
                                 acc[2:].data_ptr() if need_dx else None, _p(ws), ws_bytes, 0, st), "rc_infonce_bf16")
         dx = None
         if dxb is not None:

@@ -271,6 +271,22 @@ def test_infonce_bf16_tensor_core(B, D, H, W, K, xdtype):
     assert abs(float(r2["loss_sum"] / r2["w_sum"]) - loss) <= 1e-6 * abs(loss)
 
 
+@pytest.mark.parametrize("B,D,H,W,K", [(2, 512, 16, 16, 256), (2, 256, 16, 24, 100), (1, 512, 20, 20, 200), (3, 512, 8, 24, 64)])
+def test_infonce_bf16_dtext_tensor_core(B, D, H, W, K):
+    """dText = G^T X on the tensor cores (pair kernel writes G, split-K GEMM over the pixels) against the oracle."""
+    from rangeclip_b200 import ops
+    x, t, y, w, inv_tau = _infonce_case(B, D, H, W, K, seed=B * 31 + D + K, bf16_exact=True)
+    ref = _oracle_infonce(x, t, y, w, inv_tau)
+    r = ops.infonce_raw(x.to(dev()).to(torch.bfloat16), t.to(dev()), y.to(dev()), w.to(dev()), inv_tau, True, True, "bf16")
+    torch.cuda.synchronize()
+    assert r["precision"] == "bf16"
+    assert maxrel(r["dt"].cpu(), ref["dt"]) < BF16_MAXREL, maxrel(r["dt"].cpu(), ref["dt"])
+    assert maxrel(r["dx"].float().cpu(), ref["dx4"]) < BF16_MAXREL
+    # a second call adds into a fresh dt: same result (split-K reduction order may differ in the last bits only)
+    r2 = ops.infonce_raw(x.to(dev()).to(torch.bfloat16), t.to(dev()), y.to(dev()), w.to(dev()), inv_tau, True, True, "bf16")
+    assert maxrel(r2["dt"].cpu(), r["dt"].cpu()) < 1e-5
+
+
 def test_infonce_bf16_linearity_full_width():
     """Size-independent property at the headline tile shape (D=512, K=256, HW=65536, one image):
     gradients are linear in the upstream scale and rows with w = 0 get exactly zero gradient."""

@@ -43,3 +43,23 @@ for bwd in (True, False):
     flops = (4 if bwd else 2) * K * D * B * HW
     print(json.dumps({"kernel": "infonce_bf16" + ("_fwd_bwd" if bwd else "_fwd"), "impl": os.environ.get("RANGECLIP_B200_INFONCE", "pair"),
                       "B": B, "H": H, "W": W, "ms": round(ms, 4), "TFLOPs": round(flops / ms / 1e9, 1), "Mpix_s": round(B * HW / ms / 1e3, 1)}), flush=True)
+
+# fwd + dX + dText (tensor-core dText: the pair kernel also writes G, then the split-K GEMM)
+ws2_bytes = int(L.rc_infonce_workspace_bytes_dt(B, D, HW, K, _lib.RC_BF16))
+ws2 = torch.empty(ws2_bytes, device=dev, dtype=torch.uint8)
+dt = torch.zeros(K, D, device=dev)
+def run_dt():
+    _lib.check(L.rc_infonce_bf16(x.data_ptr(), _lib.RC_BF16, B, D, HW, tb.data_ptr(), ttb.data_ptr(), K, y.data_ptr(), w.data_ptr(),
+                                 1 / 0.07, lse.data_ptr(), acc[0:].data_ptr(), acc[1:].data_ptr(), acc[3:].data_ptr(), None,
+                                 dx.data_ptr(), dt.data_ptr(), acc[2:].data_ptr(), ws2.data_ptr(), ws2_bytes, 0, st), "infonce+dt")
+for _ in range(3):
+    run_dt()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    run_dt()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print(json.dumps({"kernel": "infonce_bf16_fwd_bwd_dtext", "B": B, "ms": round(ms, 4), "TFLOPs_3units": round(6 * K * D * B * HW / ms / 1e9, 1),
+                  "Mpix_s": round(B * HW / ms / 1e3, 1)}), flush=True)
