@@ -35,8 +35,9 @@ namespace pair {
 
 constexpr int kTilePx = 128;
 constexpr int kThreads = 640;          // warps: 0 TMA, 1 MMA (leader CTA only), 2 TMEM alloc, 3 idle, 4-11 softmax, 12-19 dX epilogue
-constexpr int kStages = 7;
-constexpr int kStageBytes = 16 * 1024; // one own X chunk [64 d][128 px] | one text half-chunk [Kp/2][64 d] | own T^T rows [128 d][64 k]
+constexpr int kXStages = 4;            // X ring: own X chunks [64 d][128 px] (first touch: HBM latency; also read by the row norms)
+constexpr int kTStages = 4;            // text ring: text half-chunks [Kp/2][64 d] for S, own T^T rows [128 d][64 k] for dX (L2 hits)
+constexpr int kStageBytes = 16 * 1024;
 constexpr int kPBytes = 64 * 1024;
 constexpr int kTmemCols = 512;
 constexpr int kRegsCtl = 40, kRegsSoftmax = 120;     // epilogue warps keep the entry allocation (96); 40 + 2*120 + 2*96 <= 5*96
@@ -44,21 +45,23 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 struct __align__(8) Bars {
-  uint64_t full[kStages], empty[kStages];
-  uint64_t xf[kStages];         // own X chunk of a ring slot has landed (CTA-local; the norm warps relay it to `full`)
+  uint64_t xf[kXStages];        // own X chunk has landed (CTA-local; relayed to the leader's xfull)
+  uint64_t xfull[kXStages], xempty[kXStages];
+  uint64_t tfull[kTStages], tempty[kTStages];
   uint64_t s_full, s_empty, p_full, p_empty;
   uint64_t acc_full[2], acc_empty[2];
   uint64_t sc_full[2];
   uint32_t tmem_base, pad;
 };
 
-constexpr int kOffP = kStages * kStageBytes;
+constexpr int kOffT = kXStages * kStageBytes;
+constexpr int kOffP = kOffT + kTStages * kStageBytes;
 constexpr int kScaleBufs = 3;          // the softmax warps run up to two tiles ahead of the dX epilogue warps
 constexpr int kOffScale = kOffP + kPBytes;                  // {rs, -cs} bf16x2 pairs: [kScaleBufs tiles][2 owner CTAs][64 px pairs] uint2
 constexpr int kOffXch = kOffScale + 2 * kScaleBufs * 2 * 128 * 4;
 constexpr int kOffStg = kOffXch + 2 * 4 * 2 * 128 * 4;      // exchange: [2 tile parities][max, sum, sez, sy][2 halves][128]
 constexpr int kStgBytes = 32 * 32 * 2;                      // dX staging of one epilogue warp: [32 d][32 px] bf16, 64-byte swizzle
-constexpr int kOffPart = kOffStg + 8 * 2 * kStgBytes;       // two staging buffers per epilogue warp
+constexpr int kOffPart = kOffStg + 8 * kStgBytes;           // one staging buffer per epilogue warp
 constexpr int kOffBars = kOffPart + 8 * 128 * 4;            // row-norm partial sums of squares [8 softmax warps][128 px]
 constexpr int kSmemBytes = kOffBars + (int)sizeof(Bars);
 static_assert(kSmemBytes <= 232448, "shared-memory budget of one SM (227 KB)");
@@ -194,10 +197,10 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x_s); tma_prefetch_desc(&map_t);
     if (kBwd) { tma_prefetch_desc(&map_tt); tma_prefetch_desc(&map_dx); }
-    // full: 2 arrivals (X slots: the relays of both CTAs; text slots: the leader's expect_tx + the peer producer);
-    // empty: 9 arrivals (MMA commit + the eight softmax warps, which read X slots for the row norms; on text slots
-    // the producer pre-arrives for them)
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 2); mbar_init(&bars->empty[i], 9); mbar_init(&bars->xf[i], 1); }
+    // X ring: xfull = the relays of both CTAs, xempty = MMA commit + the eight softmax warps (row norms);
+    // text ring: tfull = the leader's expect_tx (bytes of both CTAs), tempty = MMA commit
+    for (int i = 0; i < kXStages; ++i) { mbar_init(&bars->xf[i], 1); mbar_init(&bars->xfull[i], 2); mbar_init(&bars->xempty[i], 9); }
+    for (int i = 0; i < kTStages; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 1); }
     mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 512);
     mbar_init(&bars->p_full, 512); mbar_init(&bars->p_empty, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 512); }
@@ -232,70 +235,70 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     if (warp == 0 && lane == 0) {
       // =============================== TMA producer (both CTAs) ===============================
       // ring order == MMA issue order: S(first), then per tile pair [S(next)] [dX(this)]
+      // text ring, in MMA issue order: S(first), then per tile pair [S(next)] [dX(this)]
       uint32_t it = 0;
-      auto load_s = [&](int pj) {
-        int b, px0;
-        tile_coords(prm, 2 * pj + (int)rank, b, px0);
-        for (int c = 0; c < n_dchunks; ++c) {
-          {   // own X chunk c: [64 d][128 px] as two 64-pixel boxes
-            const int st = it % kStages;
-            RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 1);
-            uint8_t* sb = smem + st * kStageBytes;
-            mbar_arrive_expect_tx(&bars->xf[st], 2 * 8192);          // CTA-local: the norm warps read the chunk too
-            tma_load_3d(sb, &map_x_s, &bars->xf[st], px0, c * 64, b);
-            tma_load_3d(sb + 8192, &map_x_s, &bars->xf[st], px0 + 64, c * 64, b);
-            ++it;
-          }
-          {   // own half (Nh rows) of text chunk c
-            const int st = it % kStages;
-            RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 1);
-            if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * Nh * 128);
-            else mbar_arrive_remote(map_to_cta(&bars->full[st], 0));
-            tma_load_2d_2sm(smem + st * kStageBytes, &map_t, &bars->full[st], c * 64, (int)rank * Nh);
-            mbar_arrive_n(&bars->empty[st], 8);                      // no row-norm readers on a text slot
-            ++it;
-          }
+      auto load_s = [&]() {
+        for (int c = 0; c < n_dchunks; ++c, ++it) {   // own half (Nh rows) of text chunk c
+          const int st = it % kTStages;
+          RC_WAIT(mbar_wait, &bars->tempty[st], ((it / kTStages) & 1) ^ 1, 1);
+          if (leader_cta) mbar_arrive_expect_tx(&bars->tfull[st], 2 * Nh * 128);
+          tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_t, &bars->tfull[st], c * 64, (int)rank * Nh);
         }
       };
       auto load_dx = [&]() {
         for (int blk = 0; blk < n_blk; ++blk)
           for (int kc = 0; kc < n_kchunks; ++kc, ++it) {   // own 128 rows of T^T for this 256-channel block, 64 k at a time
-            const int st = it % kStages;
-            RC_WAIT(mbar_wait, &bars->empty[st], ((it / kStages) & 1) ^ 1, 2);
-            if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * 16384);
-            else mbar_arrive_remote(map_to_cta(&bars->full[st], 0));
-            tma_load_2d_2sm(smem + st * kStageBytes, &map_tt, &bars->full[st], kc * 64, blk * 256 + (int)rank * 128);
-            mbar_arrive_n(&bars->empty[st], 8);
+            const int st = it % kTStages;
+            RC_WAIT(mbar_wait, &bars->tempty[st], ((it / kTStages) & 1) ^ 1, 2);
+            if (leader_cta) mbar_arrive_expect_tx(&bars->tfull[st], 2 * 16384);
+            tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_tt, &bars->tfull[st], kc * 64, blk * 256 + (int)rank * 128);
           }
       };
-      if (cluster_id < prm.n_pairs) load_s(cluster_id);
+      if (cluster_id < prm.n_pairs) load_s();
       for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters) {
-        if (pj + n_clusters < prm.n_pairs) load_s(pj + n_clusters);
+        if (pj + n_clusters < prm.n_pairs) load_s();
         if (kBwd) load_dx();
+      }
+    } else if (warp == 3 && lane == 0) {
+      // =============================== X producer (both CTAs) ===============================
+      // own X chunks of every tile, as far ahead as the X ring allows (the next tile's first chunks are in flight
+      // while the dX GEMM of the previous pair runs)
+      uint32_t xit = 0;
+      for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters) {
+        int b, px0;
+        tile_coords(prm, 2 * pj + (int)rank, b, px0);
+        for (int c = 0; c < n_dchunks; ++c, ++xit) {
+          const int st = xit % kXStages;
+          RC_WAIT(mbar_wait, &bars->xempty[st], ((xit / kXStages) & 1) ^ 1, 1);
+          uint8_t* sb = smem + st * kStageBytes;
+          mbar_arrive_expect_tx(&bars->xf[st], 2 * 8192);          // CTA-local: the softmax warps read the chunk too
+          tma_load_3d(sb, &map_x_s, &bars->xf[st], px0, c * 64, b);
+          tma_load_3d(sb + 8192, &map_x_s, &bars->xf[st], px0 + 64, c * 64, b);
+        }
       }
     } else if (warp == 1 && leader_cta) {
       // =============================== MMA issuer (leader CTA) ================================
       // The whole warp runs the loop converged, so stage indices, addresses and descriptors live in uniform
       // registers; one elected lane issues the tcgen05 instructions.
-      uint32_t it = 0, uc = 0;
+      uint32_t it = 0, xit = 0, uc = 0;
       const uint32_t smem_base = smem_u32(smem);
       // descriptor templates: only the 14-bit start-address field changes (+ bytes/16 per step)
       const uint64_t dsc_x = desc_mnmajor_sw128(0, 8192);
       const uint64_t dsc_k = desc_kmajor_sw128(0);
       auto issue_s = [&]() {
-        for (int c = 0; c < n_dchunks; ++c, it += 2) {
-          const int sa = it % kStages, sb_ = (it + 1) % kStages;
-          RC_WAIT(mbar_wait_cluster, &bars->full[sa], (it / kStages) & 1, 4);
-          RC_WAIT(mbar_wait_cluster, &bars->full[sb_], ((it + 1) / kStages) & 1, 4);
+        for (int c = 0; c < n_dchunks; ++c, ++it, ++xit) {
+          const int sa = xit % kXStages, sb_ = it % kTStages;
+          RC_WAIT(mbar_wait_cluster, &bars->xfull[sa], (xit / kXStages) & 1, 4);
+          RC_WAIT(mbar_wait_cluster, &bars->tfull[sb_], (it / kTStages) & 1, 4);
           tc_fence_after();
           const uint64_t xa = dsc_x + ((smem_base + sa * kStageBytes) >> 4);
-          const uint64_t tb = dsc_k + ((smem_base + sb_ * kStageBytes) >> 4);
+          const uint64_t tb = dsc_k + ((smem_base + kOffT + sb_ * kStageBytes) >> 4);
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               mma_bf16_ss_2sm(tmem, xa + ((ks * 2048) >> 4), tb + ((ks * 32) >> 4), idesc_s, (c | ks) != 0);
-            mma_commit_2sm(&bars->empty[sa]);
-            mma_commit_2sm(&bars->empty[sb_]);
+            mma_commit_2sm(&bars->xempty[sa]);
+            mma_commit_2sm(&bars->tempty[sb_]);
           }
           __syncwarp();
         }
@@ -317,7 +320,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           for (int blk = 0; blk < n_blk; ++blk) {
             for (int kc = 0; kc < n_kchunks; ++kc) {
               const uint32_t jt = it + kc;
-              RC_WAIT(mbar_wait_cluster, &bars->full[jt % kStages], (jt / kStages) & 1, 7);
+              RC_WAIT(mbar_wait_cluster, &bars->tfull[jt % kTStages], (jt / kTStages) & 1, 7);
             }
             tc_fence_after();
             for (int pxh = 0; pxh < 2; ++pxh, ++uc) {
@@ -326,21 +329,20 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
               tc_fence_after();
               const uint32_t dcol = tmem + 256 + ab * 128;
               for (int kc = 0; kc < n_kchunks; ++kc) {
-                const uint64_t sb = dsc_k + ((smem_base + ((it + kc) % kStages) * kStageBytes) >> 4);
+                const int st = (it + kc) % kTStages;
+                const uint64_t sb = dsc_k + ((smem_base + kOffT + st * kStageBytes) >> 4);
                 const uint64_t pk_ = pb + ((kc * 16384 + pxh * 8192) >> 4);
                 if (elect_one()) {
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks)     // A: own T^T rows [128 d][64 k]; B: own P rows [64 px][64 k]
                     mma_bf16_ss_2sm(dcol, sb + ((ks * 32) >> 4), pk_ + ((ks * 32) >> 4), idesc_d, (kc | ks) != 0);
+                  if (pxh == 1) mma_commit_2sm(&bars->tempty[st]);     // second (last) reader: the slot refills at once
                 }
                 __syncwarp();
               }
               if (elect_one()) mma_commit_2sm(&bars->acc_full[ab]);
               __syncwarp();
             }
-            if (elect_one())
-              for (int kc = 0; kc < n_kchunks; ++kc) mma_commit_2sm(&bars->empty[(it + kc) % kStages]);
-            __syncwarp();
             it += n_kchunks;
           }
           if (elect_one()) mma_commit_2sm(&bars->p_empty);
@@ -350,20 +352,13 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     }
     else if (warp == 2 && lane == 0) {
       // ========== relay (both CTAs): "own X chunk has landed" (CTA-local xf) -> the leader's full barrier ==========
-      uint32_t it = 0, xf_phase = 0;
-      auto relay_tile = [&]() {
-        for (int c = 0; c < n_dchunks; ++c, it += 2) {
-          const int st = it % kStages;
-          RC_WAIT(mbar_wait, &bars->xf[st], (xf_phase >> st) & 1, 14);      // xf[st] advances only when the slot holds X
-          xf_phase ^= 1u << st;
-          arrive_leader(&bars->full[st]);
+      uint32_t xit = 0;
+      for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters)
+        for (int c = 0; c < n_dchunks; ++c, ++xit) {
+          const int st = xit % kXStages;
+          RC_WAIT(mbar_wait, &bars->xf[st], (xit / kXStages) & 1, 14);
+          arrive_leader(&bars->xfull[st]);
         }
-      };
-      if (cluster_id < prm.n_pairs) relay_tile();
-      for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters) {
-        if (pj + n_clusters < prm.n_pairs) relay_tile();
-        if (kBwd) it += n_blk * n_kchunks;
-      }
     }
   } else if (warp < 12) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
@@ -406,16 +401,15 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     float* part_s = reinterpret_cast<float*>(smem + kOffPart);   // [8 warps][128 px] partial sums of squares
     const int st_ = threadIdx.x - 128;                           // 0..255
     const int ng = st_ & 15, nr = st_ >> 4;
-    uint32_t nit = 0, xf_phase = 0;
+    uint32_t nit = 0;
     float inv_n_next = 0.f;
     auto norm_tile = [&]() {
       float ss[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss[j] = 0.f;
-      for (int c = 0; c < n_dchunks; ++c, nit += 2) {
-        const int st = nit % kStages;
-        RC_WAIT(mbar_wait, &bars->xf[st], (xf_phase >> st) & 1, 15);
-        xf_phase ^= 1u << st;
+      for (int c = 0; c < n_dchunks; ++c, ++nit) {
+        const int st = nit % kXStages;
+        RC_WAIT(mbar_wait, &bars->xf[st], (nit / kXStages) & 1, 15);
         const uint8_t* base = smem + st * kStageBytes + (ng >> 3) * 8192 + nr * 128;
         const int ch = ng & 7;
 #pragma unroll
@@ -431,7 +425,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->empty[st]);
+        if (lane == 0) mbar_arrive(&bars->xempty[st]);
       }
       // fixed-order reduction (bit-reproducible): lane pairs, then the eight warps' partials through shared memory
 #pragma unroll
@@ -616,7 +610,6 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         }
         if (half == 0 && valid && prm.lse) prm.lse[m] = lse;      // after the hand-off: nothing waits behind this store
         if (pj + n_clusters < prm.n_pairs) norm_tile();
-        if (kBwd) nit += n_blk * n_kchunks;
       }
     }
     if (kBwd && prm.store_g && threadIdx.x == 128) tma_store_wait_all0();
@@ -681,9 +674,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       for (int j = 0; j < 2; ++j)
         ldg_px16(prm.x + f_off + (int64_t)(j - lb) * prm.HW + c * 32 + lb * 16, wide, n8, &xq[c][j * 8], pol_x);
     };
-    uint8_t* stg_base = smem + kOffStg + (warp - 12) * 2 * kStgBytes;
+    uint8_t* stg = smem + kOffStg + (warp - 12) * kStgBytes;
     const uint64_t pol_first = l2_policy_evict_first();  // dX is write-once: keep it from displacing X in L2
-    uint32_t sc_ = 0;         // staging buffer counter
     cursor_set();
     fetch(0); fetch(1);
     uint32_t uc = 0, lt = 0;
@@ -720,8 +712,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           }
           {
             // own row of the warp's [32 d][32 px] staging tile (64-byte swizzle), then one TMA store per warp
-            uint8_t* stg = stg_base + ((sc_ & 1) ? kStgBytes : 0);
-            if (lane == 0) tma_store_wait_read0_keep1();      // the store issued two chunks ago has read this buffer
+            if (lane == 0) tma_store_wait_read0();            // the previous store of this warp has read the buffer
             __syncwarp();
             uint8_t* srow = stg + lane * 64;
             const int sw64 = (lane >> 1) & 3;
@@ -734,7 +725,6 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
               tma_store_3d_hint(&map_dx, stg, o_px + c * 32, o_d, o_b, pol_first);
               tma_store_commit();
             }
-            ++sc_;
           }
           if (c == 0) cursor_next();        // both chunks of the next unit are fetched relative to the advanced cursor
           fetch(c);
