@@ -414,6 +414,25 @@ def test_eval_topk_tensor_core(B, D, H, W, K, k, xdtype):
     _tie_aware_equal((out32 - 1) // 3, ref, logits, reduced, 1e-5)
 
 
+def test_eval_topk_ties_go_to_smaller_index():
+    """Exactly equal logits (duplicated text rows placed in different 128-column halves and different 256-row
+    blocks, i.e. in different per-thread lists of the scan) must come out in ascending text index order."""
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, D, H, W, K, k = 1, 256, 16, 16, 600, 5
+    text = unit(torch.randn(K, D, generator=g), 1).to(torch.bfloat16).float()
+    base = text[7].clone()
+    for idx in (7, 130, 259, 400, 599):              # halves 0/1 of block 0, block 1 (both halves), block 2
+        text[idx] = base
+    emb = (base.view(1, D, 1, 1) + 0.05 * torch.randn(B, D, H, W, generator=g)).to(torch.bfloat16).float()
+    out = ops.eval_topk(emb.to(dev()).to(torch.bfloat16), text.to(dev()), torch.arange(K).to(dev()), k, "bf16").cpu()
+    logits = torch.einsum('bdn,cd->bcn', emb.view(B, D, H * W).double(), text.double())
+    dup_is_top = (logits[:, 7] >= logits.max(dim=1).values - 1e-12).view(B, H, W)
+    assert dup_is_top.float().mean() > 0.9               # the duplicated row wins almost everywhere
+    want = torch.tensor([7, 130, 259, 400, 599]).view(1, k, 1, 1).expand(B, k, H, W)
+    assert torch.equal(out[:, :, dup_is_top[0]], want[:, :, dup_is_top[0]])
+
+
 def test_validate_model_golden(golden_dir):
     """Drop-in validate_model against the reference's recorded run (fake model, three batches)."""
     import rangeclip_b200 as R
