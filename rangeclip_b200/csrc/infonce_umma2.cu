@@ -81,7 +81,7 @@ struct Params {
   int B, D, K, Kp;
   int64_t HW;
   int tiles_per_img, n_tiles, n_pairs;
-  int ablate;               // bring-up only (RANGECLIP_B200_ABLATE): 1 no x loads, 2 no dX stores, 4 no softmax exp
+  int ablate;               // bring-up only (RANGECLIP_B200_ABLATE): 1 no epilogue x loads, 2 no dX stores, 64 no row-norm reads, 128 no dX staging
   int store_g;              // 1: also write G = rs (P - sum onehot) (bf16 [B][HW][Kp]) for the dText GEMM
   int wide;                 // 1: rows of X / dX are 32-byte aligned (256-bit global accesses allowed)
   const __nv_bfloat16* x;
@@ -413,7 +413,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         const uint8_t* base = smem + st * kStageBytes + (ng >> 3) * 8192 + nr * 128;
         const int ch = ng & 7;
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
+        for (int rr = 0; rr < ((prm.ablate & 64) ? 0 : 4); ++rr) {
           const int rowd = nr + rr * 16;
           const uint4 v = *reinterpret_cast<const uint4*>(base + rr * 2048 + ((ch ^ (rowd & 7)) << 4));
           const uint32_t u[4] = {v.x, v.y, v.z, v.w};
@@ -717,7 +717,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
             uint8_t* srow = stg + lane * 64;
             const int sw64 = (lane >> 1) & 3;
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
+            for (int g = 0; g < ((prm.ablate & 128) ? 0 : 4); ++g)
               *reinterpret_cast<uint4*>(srow + ((g ^ sw64) << 4)) = make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
             fence_proxy_async_smem();
             __syncwarp();
