@@ -165,6 +165,36 @@ pool_bwd_kernel(const float* __restrict__ g, const int* __restrict__ count, int 
     const int d0 = dg * kPoolDGroup;
     const int d1 = min(D, d0 + kPoolDGroup);
     T* dst = dx + ((int64_t)b * D + d0) * HW + p0;
+    bool uni = true;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) uni &= (slot[j] == slot[0]);
+    if (uni && vec_ok && p0 + 8 <= HW && (D & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+      // the lane's 8 pixels share one slot (the common case away from mask borders): one 16-byte gather of four
+      // channels of that slot's gradient row instead of eight scalar gathers per channel
+      const bool any = slot[0] >= 0;
+      const float4* grow = reinterpret_cast<const float4*>(g + (int64_t)(any ? slot[0] : 0) * D);
+      for (int d = d0; d < d1; d += 4, dst += 4 * HW) {
+        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (any) gv = __ldg(grow + (d >> 2));
+        const float gq[4] = {gv.x * inv[0], gv.y * inv[0], gv.z * inv[0], gv.w * inv[0]};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (d + q >= d1) break;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = gq[q];
+          T* o_ = dst + (int64_t)q * HW;
+          if (accumulate) {
+            float o[8];
+            load8(o_, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += o[j];
+          }
+          store8(o_, v);
+        }
+      }
+      continue;
+    }
     for (int d = d0; d < d1; ++d, dst += HW) {
       float v[8];
 #pragma unroll

@@ -253,6 +253,91 @@ tv_bwd_vec_kernel(const T* __restrict__ x, int64_t planes, int H, int W, int TH,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// bf16 inputs: packed bf16x2 arithmetic.  sign(a - b) of two bf16 values is formed from two packed compares
+// (exact: no subtraction is rounded), the +-1 / 0 counts are exact in bf16, and only the final scale-and-add is
+// rounded -- to the bf16 the gradient is stored in anyway.  ~10 instructions per element instead of ~30, which is
+// what takes the bf16 kernels from instruction-bound to HBM-bound.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf2_sgn_diff(uint32_t a, uint32_t b) {     // sgn(a - b) per half, as bf16x2
+  uint32_t g, l, d;
+  asm("set.gt.bf16x2.bf16x2 %0, %1, %2;" : "=r"(g) : "r"(a), "r"(b));
+  asm("set.lt.bf16x2.bf16x2 %0, %1, %2;" : "=r"(l) : "r"(a), "r"(b));
+  asm("sub.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(g), "r"(l));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_sub(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("sub.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_mul_(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_fma_(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// (x1,x2),(x3,x4),... from pairs (x0,x1),(x2,x3),... and the pair to the right
+__device__ __forceinline__ uint32_t bf2_shl1(uint32_t cur, uint32_t next) { return __byte_perm(cur, next, 0x5432); }
+
+__global__ void __launch_bounds__(kTvThreads)
+tv_bwd_bf16x2_kernel(const __nv_bfloat16* __restrict__ x, int64_t planes, int H, int W, int TH, const float* __restrict__ scale,
+                     __nv_bfloat16* __restrict__ dx, int accumulate, const float* __restrict__ dx_scale) {
+  extern __shared__ __align__(16) unsigned char tv_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(tv_smem);   // [(TH+2)][W], row 0 = h0-1
+  const int tiles_per_plane = (H + TH - 1) / TH;
+  const int64_t n_tiles = planes * tiles_per_plane;
+  const int gpr = W >> 3;
+  const uint32_t sh2 = pack_bf16x2(scale[0], scale[0]), sv2 = pack_bf16x2(scale[1], scale[1]);
+  // the upstream scale of the accumulated gradient is applied as hi + lo bf16 parts (two fmas): 2^-17 relative
+  const float ds = (dx_scale != nullptr) ? dx_scale[0] : 1.f;
+  const float ds_hi = __bfloat162float(__float2bfloat16_rn(ds));
+  const uint32_t dsh2 = pack_bf16x2(ds_hi, ds_hi), dsl2 = pack_bf16x2(ds - ds_hi, ds - ds_hi);
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t pl = t / tiles_per_plane;
+    const int h0 = (int)(t - pl * tiles_per_plane) * TH;
+    const int rows = min(TH, H - h0);
+    __syncthreads();
+    tv_fill_tile(x + pl * (int64_t)H * W, H, W, h0 - 1, rows + 2, tile);
+    __syncthreads();
+    __nv_bfloat16* out = dx + pl * (int64_t)H * W + (int64_t)h0 * W;
+    for (int gi = threadIdx.x; gi < rows * gpr; gi += kTvThreads) {
+      const int r = gi / gpr, c0 = (gi - r * gpr) << 3;
+      const int h = h0 + r;
+      const __nv_bfloat16* p = tile + (r + 1) * W + c0;
+      const uint4 cv = *reinterpret_cast<const uint4*>(p);
+      const uint32_t c[4] = {cv.x, cv.y, cv.z, cv.w};
+      // neighbours outside the plane are replaced by the pixel itself: sgn(0) = 0 drops the term
+      const uint4 av = (h >= 1) ? *reinterpret_cast<const uint4*>(p - W) : cv;
+      const uint4 bv = (h + 1 < H) ? *reinterpret_cast<const uint4*>(p + W) : cv;
+      const uint32_t a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
+      const uint32_t left = (c0 > 0) ? (uint32_t)*reinterpret_cast<const unsigned short*>(p - 1) : (c[0] & 0xffffu);
+      const uint32_t right = (c0 + 8 < W) ? (uint32_t)*reinterpret_cast<const unsigned short*>(p + 8) : (c[3] >> 16);
+      uint32_t g[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t xr = bf2_shl1(c[i], i < 3 ? c[i + 1] : right);                                 // right neighbours
+        const uint32_t xl = (i > 0) ? __byte_perm(c[i - 1], c[i], 0x5432) : __byte_perm(left, c[0], 0x5410);   // left neighbours
+        const uint32_t dh = bf2_sub(bf2_sgn_diff(c[i], xr), bf2_sgn_diff(xl, c[i]));
+        const uint32_t dv = bf2_sub(bf2_sgn_diff(c[i], b[i]), bf2_sgn_diff(a[i], c[i]));
+        g[i] = bf2_fma_(sv2, dv, bf2_mul_(sh2, dh));
+      }
+      uint4* o = reinterpret_cast<uint4*>(out + r * W + c0);
+      if (accumulate) {
+        const uint4 ev = *o;
+        const uint32_t e[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g[i] = bf2_fma_(dsl2, e[i], bf2_fma_(dsh2, e[i], g[i]));
+      }
+      *o = make_uint4(g[0], g[1], g[2], g[3]);
+    }
+  }
+}
+
 static int tv_tile_rows(int H, int W, int halo) {
   int r = kTvSmemFloats / W - halo;
   if (r > 32) r = 32;
@@ -305,8 +390,8 @@ extern "C" int rc_tv_bwd(const void* x, rc_dtype x_dtype, int64_t planes, int H,
     if (x_dtype == RC_F32)
       rc::tv_bwd_vec_kernel<float><<<grid, rc::kTvThreads, vsmem, s>>>((const float*)x, planes, H, W, TH, scale, (float*)dx, accumulate, dx_scale);
     else
-      rc::tv_bwd_vec_kernel<__nv_bfloat16><<<grid, rc::kTvThreads, vsmem, s>>>((const __nv_bfloat16*)x, planes, H, W, TH, scale,
-                                                                                (__nv_bfloat16*)dx, accumulate, dx_scale);
+      rc::tv_bwd_bf16x2_kernel<<<grid, rc::kTvThreads, vsmem, s>>>((const __nv_bfloat16*)x, planes, H, W, TH, scale,
+                                                                   (__nv_bfloat16*)dx, accumulate, dx_scale);
   } else if (x_dtype == RC_F32)
     rc::tv_bwd_kernel<float><<<grid, rc::kTvThreads, smem, s>>>((const float*)x, planes, H, W, TH, scale, (float*)dx, accumulate, dx_scale);
   else
