@@ -18,7 +18,7 @@
 //                 global memory (L2-resident: the S GEMM just streamed it) with 256-bit loads, prefetched one
 //                 accumulator ahead, and dX goes back with 256-bit stores -- no shared-memory staging.
 // Register budget by role (setmaxnreg; the sum over the five warpgroups must stay within the 5 x 96 the CTA is
-// launched with): control warps 40, softmax warps 120, epilogue warps 96.
+// launched with): control warps 48, softmax warps 120, epilogue warps 96.
 // Only the leader CTA (cluster rank 0) issues MMAs; completion is multicast to the mbarriers of both CTAs,
 // consumer-release barriers live in the leader and receive remote arrivals from the peer.  The per-pixel
 // row scales of a tile are exchanged through distributed shared memory (the dX epilogue of a CTA covers
@@ -40,7 +40,7 @@ constexpr int kTStages = 4;            // text ring: text half-chunks [Kp/2][64 
 constexpr int kStageBytes = 16 * 1024;
 constexpr int kPBytes = 64 * 1024;
 constexpr int kTmemCols = 512;
-constexpr int kRegsCtl = 40, kRegsSoftmax = 120;     // epilogue warps keep the entry allocation (96); 40 + 2*120 + 2*96 <= 5*96
+constexpr int kRegsCtl = 48, kRegsSoftmax = 120;     // epilogue warps keep the entry allocation (96); 48 + 2*120 + 2*96 = 5*96
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -70,10 +70,14 @@ static_assert(kSmemBytes <= 232448, "shared-memory budget of one SM (227 KB)");
 #define RC_T0(name) const long long name = clock64()
 #define RC_TACC(idx, name) wt[idx] += clock64() - name
 #define RC_WAIT(fn, bar, par, tag) do { const long long t0_ = clock64(); fn(bar, par, tag); wt[tag] += clock64() - t0_; } while (0)
+// event trace of CTA 0 (tools/timeline_pair.py): clock of event `id` of tile-pair iteration `iter` in [40, 44)
+#define RC_EV(iter, id) do { if (prm.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (iter) >= 40u && (iter) < 44u) \
+    prm.dbg[256 + ((iter) - 40u) * 48 + (id)] = clock64(); } while (0)
 #else
 #define RC_T0(name)
 #define RC_TACC(idx, name)
 #define RC_WAIT(fn, bar, par, tag) fn(bar, par, tag)
+#define RC_EV(iter, id)
 #endif
 
 struct Params {
@@ -190,6 +194,9 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
   const int n_dchunks = prm.D / 64;      // 64-channel chunks of the S GEMM
   const int n_blk = prm.D / 256;         // 256-channel blocks of the dX GEMM
   const int n_kchunks = prm.Kp / 64;
+  // MMA issue order per tile pair: the S GEMM of the next pair is split in two and wrapped around the dX blocks of
+  // this pair, so that the dX epilogue drains accumulators while the tensor pipe works on S
+  const int c_half = n_dchunks / 2, b_half = (n_blk + 1) / 2;
   const int Nh = prm.Kp / 2;             // text rows staged by each CTA
   const int n_clusters = gridDim.x / 2;
   const int cluster_id = blockIdx.x / 2;
@@ -235,18 +242,19 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     if (warp == 0 && lane == 0) {
       // =============================== TMA producer (both CTAs) ===============================
       // ring order == MMA issue order: S(first), then per tile pair [S(next)] [dX(this)]
-      // text ring, in MMA issue order: S(first), then per tile pair [S(next)] [dX(this)]
+      // text ring, in MMA issue order: S(first), then per tile pair
+      //   [S(next) first half] [dX(this) first blocks] [S(next) second half] [dX(this) remaining blocks]
       uint32_t it = 0;
-      auto load_s = [&]() {
-        for (int c = 0; c < n_dchunks; ++c, ++it) {   // own half (Nh rows) of text chunk c
+      auto load_s = [&](int c_begin, int c_end) {
+        for (int c = c_begin; c < c_end; ++c, ++it) {   // own half (Nh rows) of text chunk c
           const int st = it % kTStages;
           RC_WAIT(mbar_wait, &bars->tempty[st], ((it / kTStages) & 1) ^ 1, 1);
           if (leader_cta) mbar_arrive_expect_tx(&bars->tfull[st], 2 * Nh * 128);
           tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_t, &bars->tfull[st], c * 64, (int)rank * Nh);
         }
       };
-      auto load_dx = [&]() {
-        for (int blk = 0; blk < n_blk; ++blk)
+      auto load_dx = [&](int b_begin, int b_end) {
+        for (int blk = b_begin; blk < b_end; ++blk)
           for (int kc = 0; kc < n_kchunks; ++kc, ++it) {   // own 128 rows of T^T for this 256-channel block, 64 k at a time
             const int st = it % kTStages;
             RC_WAIT(mbar_wait, &bars->tempty[st], ((it / kTStages) & 1) ^ 1, 2);
@@ -254,10 +262,13 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
             tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_tt, &bars->tfull[st], kc * 64, blk * 256 + (int)rank * 128);
           }
       };
-      if (cluster_id < prm.n_pairs) load_s();
+      if (cluster_id < prm.n_pairs) load_s(0, n_dchunks);
       for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters) {
-        if (pj + n_clusters < prm.n_pairs) load_s();
-        if (kBwd) load_dx();
+        const bool has_next = pj + n_clusters < prm.n_pairs;
+        if (has_next) load_s(0, c_half);
+        if (kBwd) load_dx(0, b_half);
+        if (has_next) load_s(c_half, n_dchunks);
+        if (kBwd) load_dx(b_half, n_blk);
       }
     } else if (warp == 3 && lane == 0) {
       // =============================== X producer (both CTAs) ===============================
@@ -285,8 +296,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       // descriptor templates: only the 14-bit start-address field changes (+ bytes/16 per step)
       const uint64_t dsc_x = desc_mnmajor_sw128(0, 8192);
       const uint64_t dsc_k = desc_kmajor_sw128(0);
-      auto issue_s = [&]() {
-        for (int c = 0; c < n_dchunks; ++c, ++it, ++xit) {
+      auto issue_s = [&](int c_begin, int c_end) {
+        for (int c = c_begin; c < c_end; ++c, ++it, ++xit) {
           const int sa = xit % kXStages, sb_ = it % kTStages;
           RC_WAIT(mbar_wait_cluster, &bars->xfull[sa], (xit / kXStages) & 1, 4);
           RC_WAIT(mbar_wait_cluster, &bars->tfull[sb_], (it / kTStages) & 1, 4);
@@ -299,54 +310,68 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
               mma_bf16_ss_2sm(tmem, xa + ((ks * 2048) >> 4), tb + ((ks * 32) >> 4), idesc_s, (c | ks) != 0);
             mma_commit_2sm(&bars->xempty[sa]);
             mma_commit_2sm(&bars->tempty[sb_]);
+            if (c + 1 == n_dchunks) mma_commit_2sm(&bars->s_full);
           }
           __syncwarp();
         }
-        if (elect_one()) mma_commit_2sm(&bars->s_full);
-        __syncwarp();
       };
-      if (cluster_id < prm.n_pairs) issue_s();
+      const uint64_t pb = dsc_k + ((smem_base + kOffP) >> 4);
       uint32_t lt = 0;
+      auto issue_dx = [&](int b_begin, int b_end) {
+        for (int blk = b_begin; blk < b_end; ++blk) {
+          for (int kc = 0; kc < n_kchunks; ++kc) {
+            const uint32_t jt = it + kc;
+            RC_WAIT(mbar_wait_cluster, &bars->tfull[jt % kTStages], (jt / kTStages) & 1, 7);
+          }
+          tc_fence_after();
+          for (int pxh = 0; pxh < 2; ++pxh, ++uc) {
+            const int ab = uc & 1;
+            RC_WAIT(mbar_wait_cluster, &bars->acc_empty[ab], ((uc >> 1) & 1) ^ 1, 6);
+            tc_fence_after();
+            RC_EV(lt, 3 + blk * 2 + pxh);     // dX unit issue starts (accumulator free)
+            const uint32_t dcol = tmem + 256 + ab * 128;
+            for (int kc = 0; kc < n_kchunks; ++kc) {
+              const int st = (it + kc) % kTStages;
+              const uint64_t sb = dsc_k + ((smem_base + kOffT + st * kStageBytes) >> 4);
+              const uint64_t pk_ = pb + ((kc * 16384 + pxh * 8192) >> 4);
+              if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)     // A: own T^T rows [128 d][64 k]; B: own P rows [64 px][64 k]
+                  mma_bf16_ss_2sm(dcol, sb + ((ks * 32) >> 4), pk_ + ((ks * 32) >> 4), idesc_d, (kc | ks) != 0);
+                if (pxh == 1) mma_commit_2sm(&bars->tempty[st]);     // second (last) reader: the slot refills at once
+              }
+              __syncwarp();
+            }
+            if (elect_one()) mma_commit_2sm(&bars->acc_full[ab]);
+            __syncwarp();
+          }
+          it += n_kchunks;
+        }
+      };
+      if (cluster_id < prm.n_pairs) issue_s(0, n_dchunks);
       for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
-        if (pj + n_clusters < prm.n_pairs) {
+        const bool has_next = pj + n_clusters < prm.n_pairs;
+        if (has_next) {
           RC_WAIT(mbar_wait_cluster, &bars->s_empty, lt & 1, 3);     // softmax(lt) has read S(lt) out of TMEM
           tc_fence_after();
-          issue_s();
+          RC_EV(lt + 1, 0);        // S(lt+1) issue starts
+          issue_s(0, c_half);
         }
         if (kBwd) {
           RC_WAIT(mbar_wait_cluster, &bars->p_full, lt & 1, 5);
           tc_fence_after();
-          const uint64_t pb = dsc_k + ((smem_base + kOffP) >> 4);
-          for (int blk = 0; blk < n_blk; ++blk) {
-            for (int kc = 0; kc < n_kchunks; ++kc) {
-              const uint32_t jt = it + kc;
-              RC_WAIT(mbar_wait_cluster, &bars->tfull[jt % kTStages], (jt / kTStages) & 1, 7);
-            }
-            tc_fence_after();
-            for (int pxh = 0; pxh < 2; ++pxh, ++uc) {
-              const int ab = uc & 1;
-              RC_WAIT(mbar_wait_cluster, &bars->acc_empty[ab], ((uc >> 1) & 1) ^ 1, 6);
-              tc_fence_after();
-              const uint32_t dcol = tmem + 256 + ab * 128;
-              for (int kc = 0; kc < n_kchunks; ++kc) {
-                const int st = (it + kc) % kTStages;
-                const uint64_t sb = dsc_k + ((smem_base + kOffT + st * kStageBytes) >> 4);
-                const uint64_t pk_ = pb + ((kc * 16384 + pxh * 8192) >> 4);
-                if (elect_one()) {
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)     // A: own T^T rows [128 d][64 k]; B: own P rows [64 px][64 k]
-                    mma_bf16_ss_2sm(dcol, sb + ((ks * 32) >> 4), pk_ + ((ks * 32) >> 4), idesc_d, (kc | ks) != 0);
-                  if (pxh == 1) mma_commit_2sm(&bars->tempty[st]);     // second (last) reader: the slot refills at once
-                }
-                __syncwarp();
-              }
-              if (elect_one()) mma_commit_2sm(&bars->acc_full[ab]);
-              __syncwarp();
-            }
-            it += n_kchunks;
-          }
+          RC_EV(lt, 2);            // dX(lt) issue starts (P(lt) is in shared memory)
+          issue_dx(0, b_half);
+        }
+        if (has_next) {
+          issue_s(c_half, n_dchunks);
+          RC_EV(lt + 1, 1);        // S(lt+1) issued
+        }
+        if (kBwd) {
+          issue_dx(b_half, n_blk);
           if (elect_one()) mma_commit_2sm(&bars->p_empty);
           __syncwarp();
+          RC_EV(lt, 7);            // dX(lt) issued
         }
       }
     }
@@ -468,6 +493,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       const float zl = zs * kLog2e;
       RC_WAIT(mbar_wait, &bars->s_full, lt & 1, 8);
       tc_fence_after();
+      if (warp == 4) RC_EV(lt, 10);    // S(lt) complete (seen by the softmax warps)
       RC_T0(tsm);
       float ml = ml_bound;
       if (!use_bound) {
@@ -529,6 +555,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         }
       }
       tc_fence_before();
+      if (warp == 4) RC_EV(lt, 11);    // exp pass done
       arrive_leader(&bars->s_empty);            // S columns are free: the tensor pipe may start S of the next pair
       float sum = (s0 + s1) + (s2 + s3);
       float sez = (q0 + q1) + (q2 + q3);
@@ -576,6 +603,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         }
         // the dX MMAs of the previous pair have finished reading P: store this pair's P
         RC_WAIT(mbar_wait, &bars->p_empty, (lt & 1) ^ 1, 9);
+        if (warp == 4) RC_EV(lt, 12);  // P buffer free
         RC_T0(tst);
         const uint32_t rs2 = pack_bf16x2(rsv, rsv);
 #pragma unroll
@@ -599,6 +627,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         }
         fence_proxy_async_smem();                 // P is read by the tensor cores (async proxy)
         arrive_leader(&bars->p_full);
+        if (warp == 4) RC_EV(lt, 13);  // P(lt) stored
         RC_TACC(2, tst);
         if (prm.store_g) {                        // dText: the finished G tile goes to global memory as it sits in smem
           named_bar_sync(6, 256);
@@ -610,6 +639,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         }
         if (half == 0 && valid && prm.lse) prm.lse[m] = lse;      // after the hand-off: nothing waits behind this store
         if (pj + n_clusters < prm.n_pairs) norm_tile();
+        if (warp == 4) RC_EV(lt, 14);  // row norms of the next tile done
       }
     }
     if (kBwd && prm.store_g && threadIdx.x == 128) tma_store_wait_all0();
@@ -689,6 +719,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         const int o_b = f_b, o_px = f_px, o_d = f_d;
         RC_WAIT(mbar_wait, &bars->acc_full[ab], (uc >> 1) & 1, 11);
         tc_fence_after();
+        if (warp == 12) RC_EV(lt, 20 + unit * 2);      // accumulator of this unit complete
         RC_T0(tep);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -730,6 +761,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           fetch(c);
         }
         RC_TACC(2, tep);
+        if (warp == 12) RC_EV(lt, 21 + unit * 2);      // unit drained and stored
       }
     }
     if (lane == 0) tma_store_wait_all0();       // shared memory must stay valid until the last bulk store has read it
