@@ -300,7 +300,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         for (int c = c_begin; c < c_end; ++c, ++it, ++xit) {
           const int sa = xit % kXStages, sb_ = it % kTStages;
           RC_WAIT(mbar_wait_cluster, &bars->xfull[sa], (xit / kXStages) & 1, 4);
-          RC_WAIT(mbar_wait_cluster, &bars->tfull[sb_], (it / kTStages) & 1, 4);
+          RC_WAIT(mbar_wait_cluster, &bars->tfull[sb_], (it / kTStages) & 1, 12);
           tc_fence_after();
           const uint64_t xa = dsc_x + ((smem_base + sa * kStageBytes) >> 4);
           const uint64_t tb = dsc_k + ((smem_base + kOffT + sb_ * kStageBytes) >> 4);
