@@ -338,9 +338,72 @@ tv_bwd_bf16x2_kernel(const __nv_bfloat16* __restrict__ x, int64_t planes, int H,
   }
 }
 
-static int tv_tile_rows(int H, int W, int halo) {
-  int r = kTvSmemFloats / W - halo;
-  if (r > 32) r = 32;
+// bf16 forward, column-strip walk: a thread owns one group of 8 pixels and walks down a strip of rows, so every
+// row is unpacked once (the row below becomes the next centre) and there is no per-group index arithmetic --
+// ~5 instructions per element instead of ~14 (the generic kernel above issues at 83 % of the scheduler peak).
+__global__ void __launch_bounds__(kTvThreads)
+tv_fwd_bf16_walk_kernel(const __nv_bfloat16* __restrict__ x, int64_t planes, int H, int W, int TH, double* __restrict__ sums) {
+  extern __shared__ __align__(16) unsigned char tv_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(tv_smem);   // [(TH+1)][W]
+  const int tiles_per_plane = (H + TH - 1) / TH;
+  const int64_t n_tiles = planes * tiles_per_plane;
+  const int gpr = W >> 3;                                  // groups of 8 pixels per row
+  const int strips = max(1, kTvThreads / gpr);             // row strips per tile
+  double acc_h = 0.0, acc_v = 0.0;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t pl = t / tiles_per_plane;
+    const int h0 = (int)(t - pl * tiles_per_plane) * TH;
+    const int rows = min(TH, H - h0);
+    __syncthreads();
+    tv_fill_tile(x + pl * (int64_t)H * W, H, W, h0, rows + 1, tile);
+    __syncthreads();
+    const bool has_below = (h0 + rows) < H;
+    const int rps = (rows + strips - 1) / strips;          // rows per strip
+    float sh[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f};      // four independent accumulation chains each
+    for (int task = threadIdx.x; task < gpr * strips; task += kTvThreads) {
+      const int cg = task % gpr, strip = task / gpr;
+      const int r0 = strip * rps, r1 = min(rows, r0 + rps);
+      if (r0 >= r1) continue;
+      const int c0 = cg << 3;
+      const __nv_bfloat16* p = tile + r0 * W + c0;
+      float v[8];
+      lds8(p, v);
+      for (int r = r0; r < r1; ++r, p += W) {
+        const float right = (c0 + 8 < W) ? lds1(p + 8) : v[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) sh[i & 3] += fabsf(v[i] - v[i + 1]);
+        sh[3] += fabsf(v[7] - right);
+        if (r + 1 < rows || has_below) {
+          float b[8];
+          lds8(p + W, b);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { sv[i & 3] += fabsf(v[i] - b[i]); v[i] = b[i]; }
+        }
+      }
+    }
+    acc_h += (double)((sh[0] + sh[1]) + (sh[2] + sh[3]));
+    acc_v += (double)((sv[0] + sv[1]) + (sv[2] + sv[3]));
+  }
+  acc_h = warp_sum(acc_h);
+  acc_v = warp_sum(acc_v);
+  __shared__ double red[2][kTvThreads / 32];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][wid] = acc_h; red[1][wid] = acc_v; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < kTvThreads / 32; ++i) { a += red[0][i]; b += red[1][i]; }
+    atomicAdd(&sums[0], a);
+    atomicAdd(&sums[1], b);
+  }
+}
+
+// rows per tile: the 48 KB tile budget is in BYTES on the vector paths, so a bf16 tile has twice the rows of an f32
+// tile and a resident block keeps the same number of bytes in flight (what the HBM latency has to be covered with)
+static int tv_tile_rows(int H, int W, int halo, int elt_bytes = 4) {
+  int r = (kTvSmemFloats * 4 / elt_bytes) / W - halo;
+  const int cap = elt_bytes == 2 ? 64 : 32;
+  if (r > cap) r = cap;
   if (r > H) r = H;
   return r;
 }
@@ -351,20 +414,20 @@ extern "C" int rc_tv_fwd(const void* x, rc_dtype x_dtype, int64_t planes, int H,
   RC_REQUIRE(x && sums, "rc_tv_fwd: null pointer");
   RC_REQUIRE(planes >= 0 && H >= 1 && W >= 1, "rc_tv_fwd: bad shape");
   if (planes == 0) return RC_OK;
-  const int TH = rc::tv_tile_rows(H, W, 1);
+  const bool vec = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int TH = rc::tv_tile_rows(H, W, 1, (vec && x_dtype != RC_F32) ? 2 : 4);
   if (TH < 1) return rc::fail(RC_ERR_UNSUPPORTED, "rc_tv_fwd: W=%d too wide for the 48 KB tile", W);
   const int64_t n_tiles = planes * ((H + TH - 1) / TH);
   const int64_t cap = (int64_t)rc::num_sms() * 8;
   const int grid = (int)(n_tiles < cap ? n_tiles : cap);
   const size_t smem = (size_t)(TH + 1) * W * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
-  const bool vec = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   if (vec) {
     const size_t vsmem = (size_t)(TH + 1) * W * (x_dtype == RC_F32 ? 4 : 2);
     if (x_dtype == RC_F32)
       rc::tv_fwd_vec_kernel<float><<<grid, rc::kTvThreads, vsmem, s>>>((const float*)x, planes, H, W, TH, sums);
     else
-      rc::tv_fwd_vec_kernel<__nv_bfloat16><<<grid, rc::kTvThreads, vsmem, s>>>((const __nv_bfloat16*)x, planes, H, W, TH, sums);
+      rc::tv_fwd_bf16_walk_kernel<<<grid, rc::kTvThreads, vsmem, s>>>((const __nv_bfloat16*)x, planes, H, W, TH, sums);
   } else if (x_dtype == RC_F32)
     rc::tv_fwd_kernel<float><<<grid, rc::kTvThreads, smem, s>>>((const float*)x, planes, H, W, TH, sums);
   else
@@ -377,14 +440,14 @@ extern "C" int rc_tv_bwd(const void* x, rc_dtype x_dtype, int64_t planes, int H,
   RC_REQUIRE(x && dx && scale, "rc_tv_bwd: null pointer");
   RC_REQUIRE(planes >= 0 && H >= 1 && W >= 1, "rc_tv_bwd: bad shape");
   if (planes == 0) return RC_OK;
-  const int TH = rc::tv_tile_rows(H, W, 2);
+  const bool vec = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+  const int TH = rc::tv_tile_rows(H, W, 2, (vec && x_dtype != RC_F32) ? 2 : 4);
   if (TH < 1) return rc::fail(RC_ERR_UNSUPPORTED, "rc_tv_bwd: W=%d too wide for the 48 KB tile", W);
   const int64_t n_tiles = planes * ((H + TH - 1) / TH);
   const int64_t cap = (int64_t)rc::num_sms() * 8;
   const int grid = (int)(n_tiles < cap ? n_tiles : cap);
   const size_t smem = (size_t)(TH + 2) * W * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
-  const bool vec = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
   if (vec) {
     const size_t vsmem = (size_t)(TH + 2) * W * (x_dtype == RC_F32 ? 4 : 2);
     if (x_dtype == RC_F32)
