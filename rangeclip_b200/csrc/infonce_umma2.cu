@@ -38,6 +38,7 @@ constexpr int kThreads = 640;          // warps: 0 TMA, 1 MMA (leader CTA only),
 constexpr int kXStages = 4;            // X ring: own X chunks [64 d][128 px] (first touch: HBM latency; also read by the row norms)
 constexpr int kTStages = 4;            // text ring: text half-chunks [Kp/2][64 d] for S, own T^T rows [128 d][64 k] for dX (L2 hits)
 constexpr int kStageBytes = 16 * 1024;
+static_assert(kTStages >= 4, "a dX block keeps Kp/64 <= 4 slots of the text ring at once");
 constexpr int kPBytes = 64 * 1024;
 constexpr int kTmemCols = 512;
 constexpr int kRegsCtl = 48, kRegsSoftmax = 120;     // epilogue warps keep the entry allocation (96); 48 + 2*120 + 2*96 = 5*96
