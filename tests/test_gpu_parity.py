@@ -254,7 +254,8 @@ def test_infonce_fp32(B, D, H, W, K):
 
 @pytest.mark.parametrize("B,D,H,W,K,xdtype", [(1, 128, 16, 8, 64, torch.bfloat16), (2, 512, 16, 16, 256, torch.bfloat16),
                                                (2, 256, 16, 24, 100, torch.bfloat16), (1, 512, 20, 20, 200, torch.float32),
-                                               (3, 384, 8, 40, 7, torch.bfloat16)])
+                                               (3, 384, 8, 40, 7, torch.bfloat16), (2, 256, 5, 8, 33, torch.bfloat16),
+                                               (5, 512, 9, 8, 130, torch.bfloat16)])
 def test_infonce_bf16_tensor_core(B, D, H, W, K, xdtype):
     from rangeclip_b200 import ops
     x, t, y, w, inv_tau = _infonce_case(B, D, H, W, K, seed=B * 77 + D + K, bf16_exact=True)
