@@ -59,7 +59,7 @@ __device__ __forceinline__ RunInfo pool_runs(const int (&slot)[8]) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kPoolThreads)
+__global__ void __launch_bounds__(kPoolThreads, 4)
 pool_fwd_kernel(const T* __restrict__ x, int B, int D, int64_t HW, const int64_t* __restrict__ seg,
                 const int32_t* __restrict__ lut, int64_t lut_ld, int C, float* __restrict__ sum,
                 int* __restrict__ count) {
@@ -90,26 +90,45 @@ pool_fwd_kernel(const T* __restrict__ x, int B, int D, int64_t HW, const int64_t
     const int d1 = min(D, d0 + kPoolDGroup);
     const bool in_range = p0 < HW;   // HW % 8 == 0 on this path, so the lane's 8 px are all in or out
     const T* src = x + ((int64_t)b * D + d0) * HW + p0;
-#pragma unroll 4
-    for (int d = d0; d < d1; ++d, src += HW) {
-      float v[8];
-      if (in_range) load8(src, v);
-      else {
+    constexpr int kBatch = sizeof(T) == 2 ? 8 : 4;      // channels whose loads are issued before any is consumed:
+                                                         // 4 KB in flight per warp for either dtype
+    for (int dbase = d0; dbase < d1; dbase += kBatch, src += (int64_t)kBatch * HW) {
+      // raw 16-byte vectors stay packed until they are consumed (bf16: one per channel, f32: two)
+      constexpr int kVec = sizeof(T) == 2 ? 1 : 2;
+      uint4 raw[kBatch][kVec];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      }
-      float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-      if (ri.mixed) {
+      for (int q = 0; q < kBatch; ++q)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (slot[j] >= 0) atomicAdd(&sum[(int64_t)slot[j] * D + d], v[j]);
-        s = 0.f;
-      }
+        for (int h = 0; h < kVec; ++h)
+          raw[q][h] = (in_range && dbase + q < d1) ? __ldg(reinterpret_cast<const uint4*>(src + (int64_t)q * HW) + h)
+                                                   : make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const float up = __shfl_down_sync(0xffffffffu, s, 1 << i);
-        if (ri.steps & (1u << i)) s += up;
+      for (int q = 0; q < kBatch; ++q) {
+        const int d = dbase + q;
+        if (d >= d1) break;
+        float v[8];
+        if (sizeof(T) == 2) {
+          const uint32_t u[4] = {raw[q][0].x, raw[q][0].y, raw[q][0].z, raw[q][0].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+        } else {
+          const uint4 a = raw[q][0], c = raw[q][kVec - 1];
+          v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+          v[4] = __uint_as_float(c.x); v[5] = __uint_as_float(c.y); v[6] = __uint_as_float(c.z); v[7] = __uint_as_float(c.w);
+        }
+        float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        if (ri.mixed) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (slot[j] >= 0) atomicAdd(&sum[(int64_t)slot[j] * D + d], v[j]);
+          s = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const float up = __shfl_down_sync(0xffffffffu, s, 1 << i);
+          if (ri.steps & (1u << i)) s += up;
+        }
+        if (ri.head) atomicAdd(&sum[(int64_t)ri.key * D + d], s);
       }
-      if (ri.head) atomicAdd(&sum[(int64_t)ri.key * D + d], s);
     }
   }
 }
