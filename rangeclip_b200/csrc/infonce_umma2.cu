@@ -49,7 +49,7 @@ struct __align__(8) Bars {
   uint64_t xf[kXStages];        // own X chunk has landed (CTA-local; relayed to the leader's xfull)
   uint64_t xfull[kXStages], xempty[kXStages];
   uint64_t tfull[kTStages], tempty[kTStages];
-  uint64_t s_full, s_empty, p_full, p_empty;
+  uint64_t s_full[2], s_empty[2], p_full, p_empty;   // S: one TMEM buffer with a backward, two (columns 0 / 256) forward-only
   uint64_t acc_full[2], acc_empty[2];
   uint64_t sc_full[2];
   uint32_t tmem_base, pad;
@@ -209,7 +209,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     // text ring: tfull = the leader's expect_tx (bytes of both CTAs), tempty = MMA commit
     for (int i = 0; i < kXStages; ++i) { mbar_init(&bars->xf[i], 1); mbar_init(&bars->xfull[i], 2); mbar_init(&bars->xempty[i], 9); }
     for (int i = 0; i < kTStages; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 1); }
-    mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 512);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 512); }
     mbar_init(&bars->p_full, 512); mbar_init(&bars->p_empty, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 512); }
     mbar_init(&bars->sc_full[0], 129); mbar_init(&bars->sc_full[1], 129);   // 128 local writers + 1 expect_tx (peer: st.async)
@@ -297,7 +297,15 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       // descriptor templates: only the 14-bit start-address field changes (+ bytes/16 per step)
       const uint64_t dsc_x = desc_mnmajor_sw128(0, 8192);
       const uint64_t dsc_k = desc_kmajor_sw128(0);
-      auto issue_s = [&](int c_begin, int c_end) {
+      // S(n) goes to TMEM columns [0,256); forward-only launches alternate with [256,512) (no dX accumulators there),
+      // so that the S GEMM of the next pair overlaps the softmax of this one
+      auto issue_s = [&](uint32_t n, int c_begin, int c_end) {
+        const uint32_t sidx = kBwd ? 0u : (n & 1u);
+        const uint32_t s_tmem = tmem + sidx * 256;
+        if (c_begin == 0) {
+          RC_WAIT(mbar_wait_cluster, &bars->s_empty[sidx], (((kBwd ? n : (n >> 1)) & 1u) ^ 1u), 3);   // previous user has read it
+          tc_fence_after();
+        }
         for (int c = c_begin; c < c_end; ++c, ++it, ++xit) {
           const int sa = xit % kXStages, sb_ = it % kTStages;
           RC_WAIT(mbar_wait_cluster, &bars->xfull[sa], (xit / kXStages) & 1, 4);
@@ -308,10 +316,10 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              mma_bf16_ss_2sm(tmem, xa + ((ks * 2048) >> 4), tb + ((ks * 32) >> 4), idesc_s, (c | ks) != 0);
+              mma_bf16_ss_2sm(s_tmem, xa + ((ks * 2048) >> 4), tb + ((ks * 32) >> 4), idesc_s, (c | ks) != 0);
             mma_commit_2sm(&bars->xempty[sa]);
             mma_commit_2sm(&bars->tempty[sb_]);
-            if (c + 1 == n_dchunks) mma_commit_2sm(&bars->s_full);
+            if (c + 1 == n_dchunks) mma_commit_2sm(&bars->s_full[sidx]);
           }
           __syncwarp();
         }
@@ -349,14 +357,12 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           it += n_kchunks;
         }
       };
-      if (cluster_id < prm.n_pairs) issue_s(0, n_dchunks);
+      if (cluster_id < prm.n_pairs) issue_s(0, 0, n_dchunks);
       for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
         const bool has_next = pj + n_clusters < prm.n_pairs;
         if (has_next) {
-          RC_WAIT(mbar_wait_cluster, &bars->s_empty, lt & 1, 3);     // softmax(lt) has read S(lt) out of TMEM
-          tc_fence_after();
-          RC_EV(lt + 1, 0);        // S(lt+1) issue starts
-          issue_s(0, c_half);
+          issue_s(lt + 1, 0, c_half);          // waits until the softmax warps have read the previous S out of these columns
+          RC_EV(lt + 1, 0);        // S(lt+1) issue started
         }
         if (kBwd) {
           RC_WAIT(mbar_wait_cluster, &bars->p_full, lt & 1, 5);
@@ -365,7 +371,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           issue_dx(0, b_half);
         }
         if (has_next) {
-          issue_s(c_half, n_dchunks);
+          issue_s(lt + 1, c_half, n_dchunks);
           RC_EV(lt + 1, 1);        // S(lt+1) issued
         }
         if (kBwd) {
@@ -393,7 +399,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     const int row = (warp & 3) * 32 + lane;                 // pixel of the own tile == TMEM lane
     const int Kh = prm.Kp >> 1;
     const int cb = half * Kh;
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + cb;
+    const uint32_t trow0 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + cb;
     uint8_t* prow = smem + kOffP + row * 128;
     const int sw = row & 7;
     float* xch_base = reinterpret_cast<float*>(smem + kOffXch);
@@ -492,7 +498,12 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       const float inv_n = px_ok ? inv_n_next : 0.f;
       const float zs = inv_n * prm.inv_tau;
       const float zl = zs * kLog2e;
-      RC_WAIT(mbar_wait, &bars->s_full, lt & 1, 8);
+      // forward-only: the tensor pipe runs one pair ahead (two S buffers), so the next tile's row norms are taken
+      // first -- its X chunks are already streaming and their ring slots are refilled only after these reads
+      if (!kBwd && pj + n_clusters < prm.n_pairs) norm_tile();
+      const uint32_t sidx = kBwd ? 0u : (lt & 1u);
+      const uint32_t trow = trow0 + sidx * 256;
+      RC_WAIT(mbar_wait, &bars->s_full[sidx], (kBwd ? lt : (lt >> 1)) & 1u, 8);
       tc_fence_after();
       if (warp == 4) RC_EV(lt, 10);    // S(lt) complete (seen by the softmax warps)
       RC_T0(tsm);
@@ -557,7 +568,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       }
       tc_fence_before();
       if (warp == 4) RC_EV(lt, 11);    // exp pass done
-      arrive_leader(&bars->s_empty);            // S columns are free: the tensor pipe may start S of the next pair
+      arrive_leader(&bars->s_empty[sidx]);      // S columns are free: the tensor pipe may start the next S in them
       float sum = (s0 + s1) + (s2 + s3);
       float sez = (q0 + q1) + (q2 + q3);
       const bool mine_y = yi >= cb && yi < cb + Kh;
@@ -578,7 +589,6 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       RC_TACC(1, tsm);
       if (!kBwd) {
         if (half == 0 && valid && prm.lse) prm.lse[m] = lse;
-        if (pj + n_clusters < prm.n_pairs) norm_tile();
         continue;
       }
       {
