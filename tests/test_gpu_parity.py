@@ -288,6 +288,22 @@ def test_infonce_bf16_dtext_tensor_core(B, D, H, W, K):
     assert maxrel(r2["dt"].cpu(), r["dt"].cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("B,D,H,W,K", [(2, 512, 16, 16, 256), (1, 256, 16, 24, 100), (1, 128, 16, 8, 64)])
+def test_infonce_bf16_small_temperature(B, D, H, W, K):
+    """tau = 0.02: the analytic logit bound would overflow the exp2 range, so the kernels take the row-maximum pass."""
+    from rangeclip_b200 import ops
+    x, t, y, w, _ = _infonce_case(B, D, H, W, K, seed=B * 13 + D + K, bf16_exact=True)
+    inv_tau = 1.0 / 0.02
+    ref = _oracle_infonce(x, t, y, w, inv_tau)
+    r = ops.infonce_raw(x.to(dev()).to(torch.bfloat16), t.to(dev()), y.to(dev()), w.to(dev()), inv_tau, True, False, "bf16")
+    torch.cuda.synchronize()
+    loss = float(r["loss_sum"] / r["w_sum"])
+    assert abs(loss - float(ref["loss"])) <= 3e-3 * abs(float(ref["loss"])), (loss, float(ref["loss"]))
+    assert maxrel(r["lse"].cpu(), ref["lse"]) < 3e-3
+    assert maxrel(r["dx"].float().cpu(), ref["dx4"]) < BF16_MAXREL
+    assert abs(float(r["dlogtau"]) - float(ref["dlogtau"])) <= BF16_MAXREL * abs(float(ref["dlogtau"]))
+
+
 def test_infonce_bf16_linearity_full_width():
     """Size-independent property at the headline tile shape (D=512, K=256, HW=65536, one image):
     gradients are linear in the upstream scale and rows with w = 0 get exactly zero gradient."""
