@@ -94,6 +94,23 @@ int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
                     const double* w_sum_in, const float* grad_scale,
                     void* dx, float* dt, double* dlogtau,
                     void* workspace, int64_t workspace_bytes, int flags, void* stream);
+/* Shared-embedding form (decoder.py:113-114): the decoder emits `normalize(nearest_x2(conv))`, so the four
+ * pixels of every 2x2 block share one embedding (quirk Q8).  Here a row of x is that shared embedding (x is the
+ * PRE-upsample tensor [B][D][hw], normalised or not) and carries four targets / multiplicities:
+ *   y4, w4   [B*hw][4] (16-byte aligned), the block's pixels in any fixed order; y = -1 or w = 0: ignored
+ *   loss   = sum_q sum_j w_qj (lse_q - z[q, y_qj]) / sum w        (the reference loss on the upsampled tensor)
+ *   dx     = gradient with respect to the shared row = the sum of the four pixel gradients -- what autograd
+ *            returns below F.interpolate(mode='nearest')
+ *   lse    [B*hw]; w_sum_in = sum of all 4 B hw weights (rc_weight_sum over the flat arrays).
+ * One quarter of the tensor-core work and HBM traffic of rc_infonce_bf16 on the upsampled tensor.  D = 256 or 512
+ * (CTA-pair kernel); everything else as rc_infonce_bf16. */
+int rc_infonce_bf16_rep4(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
+                         const void* t_bf16, const void* tt_bf16, int K,
+                         const int32_t* y4, const float* w4, float inv_tau,
+                         float* lse, double* loss_sum, double* w_sum,
+                         const double* w_sum_in, const float* grad_scale,
+                         void* dx, float* dt, double* dlogtau,
+                         void* workspace, int64_t workspace_bytes, int flags, void* stream);
 /* The pre-pass alone: 1/|x_p| of the bf16-rounded rows (+ bf16 copy of an f32 x) into workspace. */
 int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
                        void* workspace, int64_t workspace_bytes, void* stream);

@@ -300,6 +300,49 @@ def compute_loss(pixel_embeddings, target_indices, candidate_text_embeddings, la
 
 
 # ----------------------------------------------------------------------------
+# (f1) decoder tail + shared-embedding form  --  utils/src/decoder.py:112-116 (quirk Q8)
+# ----------------------------------------------------------------------------
+
+def decoder_tail(output_conv_result: torch.Tensor, target_shape) -> torch.Tensor:
+    """decoder.py:113-114: nearest interpolation to the target shape, then L2 normalisation over
+    the channels.  With target = 2x the input every 2x2 block shares one embedding."""
+    out = F.interpolate(output_conv_result, size=target_shape, mode='nearest')
+    return F.normalize(out, p=2, dim=1)
+
+
+def group_2x2(t: torch.Tensor) -> torch.Tensor:
+    """[B, 2h, 2w] -> [B, h*w, 4]: the four full-resolution entries of every embedding block."""
+    B, H, W = t.shape
+    return t.reshape(B, H // 2, 2, W // 2, 2).permute(0, 1, 3, 2, 4).reshape(B, (H // 2) * (W // 2), 4)
+
+
+def infonce_dense_rep(x_rows: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch.Tensor,
+                      inv_tau: float, dtype=torch.float64):
+    """Weighted InfoNCE where row q carries R targets (y, w are [M, R]): the reference loss
+    (model.py:272-291) on the nearest-upsampled tensor, written on the distinct rows:
+    loss = sum_q sum_j w_qj (lse_q - z[q, y_qj]) / sum w; dx = gradient w.r.t. the shared row."""
+    x = x_rows.to(dtype)
+    t = t_norm.to(dtype)
+    w = w.to(dtype) * (y >= 0).to(dtype)
+    yy = y.clamp(min=0).long()
+    nrm = x.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    xh = x / nrm
+    z = (xh @ t.T) * inv_tau
+    lse = torch.logsumexp(z, dim=1)
+    wsum = w.sum()
+    wrow = w.sum(1)
+    loss = ((wrow * lse).sum() - (w * z.gather(1, yy)).sum()) / wsum
+    dz = torch.softmax(z, dim=1) * wrow[:, None]
+    dz.scatter_add_(1, yy, -w)
+    dz = dz / wsum
+    dxh = (dz @ t) * inv_tau
+    dx = (dxh - xh * (xh * dxh).sum(1, keepdim=True)) / nrm
+    dt = (dz.T @ xh) * inv_tau
+    dlogtau = -(dz * z).sum()
+    return dict(loss=loss, lse=lse, dx=dx, dt=dt, dlogtau=dlogtau, wsum=wsum)
+
+
+# ----------------------------------------------------------------------------
 # (a9) predict tail  --  model.py:144-173
 # ----------------------------------------------------------------------------
 

@@ -758,10 +758,12 @@ extern "C" int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D,
   return rc::infonce_prepass_impl(x, x_dtype, B, D, HW, workspace, workspace_bytes, (cudaStream_t)stream, &inv_norm, &xb);
 }
 
-extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16,
-                               const void* tt_bf16, int K, const int32_t* y, const float* w, float inv_tau, float* lse,
-                               double* loss_sum, double* w_sum, const double* w_sum_in, const float* grad_scale, void* dx,
-                               float* dt, double* dlogtau, void* workspace, int64_t workspace_bytes, int flags, void* stream) {
+// rep = 1: rc_infonce_bf16; rep = 4: rc_infonce_bf16_rep4 (y, w are [B*HW][4])
+static int infonce_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16,
+                             const void* tt_bf16, int K, const int32_t* y, const float* w, float inv_tau, float* lse,
+                             double* loss_sum, double* w_sum, const double* w_sum_in, const float* grad_scale, void* dx,
+                             float* dt, double* dlogtau, void* workspace, int64_t workspace_bytes, int flags, int rep,
+                             void* stream) {
   using namespace rc;
   RC_REQUIRE(x && t_bf16 && y && w && workspace, "rc_infonce_bf16: null pointer");
   RC_REQUIRE(B >= 0 && HW >= 0, "rc_infonce_bf16: bad shape");
@@ -781,7 +783,12 @@ extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, in
   // from the operand tiles in shared memory, so a bf16 input needs no pre-pass at all (an fp32 input still needs
   // its bf16 copy).
   const char* impl = getenv("RANGECLIP_B200_INFONCE");
-  const bool use_pair = !(impl != nullptr && impl[0] == '1') && infonce_pair_supported(D);
+  const bool use_pair = (rep != 1 || !(impl != nullptr && impl[0] == '1')) && infonce_pair_supported(D);
+  if (rep != 1) {
+    if (!use_pair) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16_rep4: D=%d must be 256 or 512", D);
+    RC_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+               "rc_infonce_bf16_rep4: y and w must be 16-byte aligned");
+  }
   const bool skip_prepass = (flags & RC_INFONCE_PREPASS_DONE) || (use_pair && x_dtype == RC_BF16);
   if ((rcode = infonce_prepass_impl(x, x_dtype, B, D, HW, workspace, workspace_bytes, skip_prepass ? (cudaStream_t)-1 : s,
                                     &inv_norm, &xb))) return rcode;
@@ -796,13 +803,13 @@ extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, in
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
     void* g = ws + ((base + 255) / 256) * 256;
     if ((rcode = launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
-                                     loss_sum, w_sum, dlogtau, g, s))) return rcode;
+                                     loss_sum, w_sum, dlogtau, g, rep, s))) return rcode;
     return launch_infonce_dt(g, xsrc, B, D, HW, K, dt, s);
   }
   {
     if (use_pair)
       return launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
-                                 loss_sum, w_sum, dlogtau, nullptr, s);
+                                 loss_sum, w_sum, dlogtau, nullptr, rep, s);
   }
   const int Kp = (K + 63) / 64 * 64;
   CUtensorMap m_xs, m_t, m_tt, m_xe, m_dx;
@@ -840,6 +847,23 @@ extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, in
     infonce_umma_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_xe, m_dx, prm);
   }
   return check_launch("rc_infonce_bf16");
+}
+
+extern "C" int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16,
+                               const void* tt_bf16, int K, const int32_t* y, const float* w, float inv_tau, float* lse,
+                               double* loss_sum, double* w_sum, const double* w_sum_in, const float* grad_scale, void* dx,
+                               float* dt, double* dlogtau, void* workspace, int64_t workspace_bytes, int flags, void* stream) {
+  return infonce_bf16_impl(x, x_dtype, B, D, HW, t_bf16, tt_bf16, K, y, w, inv_tau, lse, loss_sum, w_sum, w_sum_in, grad_scale,
+                           dx, dt, dlogtau, workspace, workspace_bytes, flags, 1, stream);
+}
+
+extern "C" int rc_infonce_bf16_rep4(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16,
+                                    const void* tt_bf16, int K, const int32_t* y4, const float* w4, float inv_tau, float* lse,
+                                    double* loss_sum, double* w_sum, const double* w_sum_in, const float* grad_scale,
+                                    void* dx, float* dt, double* dlogtau, void* workspace, int64_t workspace_bytes,
+                                    int flags, void* stream) {
+  return infonce_bf16_impl(x, x_dtype, B, D, HW, t_bf16, tt_bf16, K, y4, w4, inv_tau, lse, loss_sum, w_sum, w_sum_in,
+                           grad_scale, dx, dt, dlogtau, workspace, workspace_bytes, flags, 4, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -178,7 +178,10 @@ __device__ __forceinline__ void tile_coords(const Params& prm, int tile, int& b,
   }
 }
 
-template <bool kBwd>
+// R = targets per embedding row: 1 = one pixel per row (y, w are [B*HW]); 4 = every row stands for the four pixels of a
+// 2x2 block that share one embedding (decoder.py:113 nearest x2): y, w are [B*HW][4], the loss of the row is
+// sum_j w_j (lse - z[y_j]) and dX is the gradient with respect to the shared embedding (the sum over the block).
+template <bool kBwd, int R>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW], box (64 px, 64 d, 1)
                          const __grid_constant__ CUtensorMap map_t,     // T [Kp][D],    box (64 d, Kp/2 rows)
@@ -421,8 +424,13 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         if (tpx < prm.HW) {
           const int64_t tm = (int64_t)tb * prm.HW + tpx;
           nx_inv_n = 1.f;        // valid pixel (the value itself comes from the norm warps)
-          nx_y = __ldg(prm.y + tm);
-          nx_w = __ldg(prm.w + tm);
+          if (R == 1) {
+            nx_y = __ldg(prm.y + tm);
+            nx_w = __ldg(prm.w + tm);
+          } else {               // four targets, 8 bits each (K <= 256); ignored targets are sorted out when w is read
+            const int4 y4 = __ldg(reinterpret_cast<const int4*>(prm.y) + tm);
+            nx_y = (y4.x & 255) | ((y4.y & 255) << 8) | ((y4.z & 255) << 16) | ((y4.w & 255) << 24);
+          }
         }
       }
     };
@@ -492,7 +500,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       const int64_t m = (int64_t)b * prm.HW + px;
       const bool px_ok = nx_inv_n != 0.f;
       const int yi = nx_y;
-      const float wi = yi >= 0 ? nx_w : 0.f;
+      const float wi = (R == 1 && yi >= 0) ? nx_w : 0.f;
       load_pixel_scalars(pj + n_clusters);
       float* xch = xch_base + (lt & 1) * (4 * 2 * 128);      // double-buffered: one named barrier per tile suffices
       const float inv_n = px_ok ? inv_n_next : 0.f;
@@ -526,13 +534,19 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       }
       // e = exp(z - m) for this half's columns; P stays in registers as packed bf16 until the P buffer is free
       uint32_t pk[64];
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, sy = 0.f;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+      float sy[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) sy[j] = 0.f;
       // 16 text columns per step
       auto smx_step = [&](const uint32_t (&r)[16], int c) {
         const int k0 = cb + c * 16;
         const int nvalid = prm.K - k0;
-        const int yrel = yi - k0;
-        if ((unsigned)yrel < 16u) sy = select16(r, yrel);      // target logit: once per row, not per column
+#pragma unroll
+        for (int j = 0; j < R; ++j) {                          // target logit(s): once per row, not per column
+          const int yrel = (R == 1 ? yi : (int)(((uint32_t)yi >> (8 * j)) & 255u)) - k0;
+          if ((unsigned)yrel < 16u) sy[j] = select16(r, yrel);
+        }
         if (nvalid >= 16) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
@@ -571,20 +585,43 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       arrive_leader(&bars->s_empty[sidx]);      // S columns are free: the tensor pipe may start the next S in them
       float sum = (s0 + s1) + (s2 + s3);
       float sez = (q0 + q1) + (q2 + q3);
-      const bool mine_y = yi >= cb && yi < cb + Kh;
+      // targets of this row: y_j, w_j (w_j = 0: ignored); tz = sum_j w_j s[y_j] over the targets in this half's columns
+      int yj[R];
+      float wj[R];
+      if (R == 1) {
+        yj[0] = yi; wj[0] = wi;
+      } else {
+        int4 y4 = make_int4(-1, -1, -1, -1);
+        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (px_ok) {
+          y4 = __ldg(reinterpret_cast<const int4*>(prm.y) + m);
+          w4 = __ldg(reinterpret_cast<const float4*>(prm.w) + m);
+        }
+        const int ya[4] = {y4.x, y4.y, y4.z, y4.w};
+        const float wa[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int j = 0; j < R; ++j) { yj[j] = ya[j]; wj[j] = ya[j] >= 0 ? wa[j] : 0.f; }
+      }
+      float wtot = 0.f, tz = 0.f;
+      bool mine[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        mine[j] = yj[j] >= cb && yj[j] < cb + Kh;
+        wtot += wj[j];
+        tz += mine[j] ? wj[j] * sy[j] : 0.f;
+      }
       xch[(1 * 2 + half) * 128 + row] = sum;
       xch[(2 * 2 + half) * 128 + row] = sez;
-      xch[(3 * 2 + half) * 128 + row] = mine_y ? sy : 0.f;
+      xch[(3 * 2 + half) * 128 + row] = tz;
       named_bar_sync(2, 256);
       sum += xch[(1 * 2 + (half ^ 1)) * 128 + row];
       sez += xch[(2 * 2 + (half ^ 1)) * 128 + row];
-      sy = mine_y ? sy : xch[(3 * 2 + (half ^ 1)) * 128 + row];
-      const float zy = sy * zs;
+      tz += xch[(3 * 2 + (half ^ 1)) * 128 + row];
       float lse = 0.f;
       if (half == 0) {
         lse = (ml + __log2f(sum)) * kLn2;
-        loss_acc += wi * (lse - zy);
-        w_acc += wi;
+        loss_acc += wtot * lse - tz * zs;
+        w_acc += wtot;
       }
       RC_TACC(1, tsm);
       if (!kBwd) {
@@ -592,13 +629,14 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         continue;
       }
       {
-        const float coef = gscale * wi * inv_wsum;
+        const float coefb = gscale * inv_wsum;
+        const float coef = coefb * wtot;
         const float inv_sum = 1.f / sum;
         // P is stored pre-scaled: G[p][k] = rs_p (e_pk - sum_p [k = y_p]) = d loss / d(xhat_p . that_k) / |x_p|, so the
         // dX accumulators need no row scale and the same tile is the A operand of the dText GEMM (dT = G^T X).
         const float rsv = inv_n * prm.inv_tau * coef * inv_sum;
         if (half == 0) {
-          const float cj = coef * (sez * zs * inv_sum - zy);
+          const float cj = coef * sez * zs * inv_sum - coefb * tz * zs;
           const float csv = inv_n * inv_n * cj;
           // the dX epilogue works on packed bf16 pixel pairs: dx = acc + (-cs) * x
           const float cs_n = __shfl_down_sync(0xffffffffu, csv, 1);
@@ -630,11 +668,24 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
                              bf2_mul(pk[c * 16 + g * 4 + 2], rs2), bf2_mul(pk[c * 16 + g * 4 + 3], rs2));
           }
         }
-        if (mine_y) {       // G[row][y] = rs (e_y - sum)  (softmax - onehot), subtraction and scaling before rounding
-          const float ey = fast_exp2(fmaf(sy, zl, -ml));
-          const int kk = yi & 63;
-          uint8_t* sub = prow + (yi >> 6) * 16384;
-          *reinterpret_cast<__nv_bfloat16*>(sub + (((kk >> 3) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn((ey - sum) * rsv);
+        // G[row][y_j] = rs (e_y - sum * (weight of target y_j) / (weight of the row))  (softmax - onehot), formed before rounding
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          if (mine[j]) {
+            const float ey = fast_exp2(fmaf(sy[j], zl, -ml));
+            float gv;
+            if (R == 1) {
+              gv = (ey - sum) * rsv;
+            } else {
+              float wk = 0.f;                 // targets of the block that name the same text row
+#pragma unroll
+              for (int i = 0; i < R; ++i) wk += (yj[i] == yj[j]) ? wj[i] : 0.f;
+              gv = (ey - sum * (wtot > 0.f ? wk / wtot : 0.f)) * rsv;      // rs = rsv carries the block's total weight
+            }
+            const int kk = yj[j] & 63;
+            uint8_t* sub = prow + (yj[j] >> 6) * 16384;
+            *reinterpret_cast<__nv_bfloat16*>(sub + (((kk >> 3) ^ sw) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(gv);
+          }
         }
         fence_proxy_async_smem();                 // P is read by the tensor cores (async proxy)
         arrive_leader(&bars->p_full);
@@ -801,7 +852,7 @@ bool infonce_pair_supported(int D) { return D == 256 || D == 512; }
 int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const void* tt_bf16, int B, int D, int64_t HW, int K,
                         const float* inv_norm, const int32_t* y, const float* w, float inv_tau, const float* grad_scale,
                         const double* w_sum_in, float* lse, double* loss_sum, double* w_sum, double* dlogtau, void* g_out,
-                        cudaStream_t s) {
+                        int rep, cudaStream_t s) {
   using namespace pair;
   const bool bwd = dx != nullptr;
   const int Kp = (K + 63) / 64 * 64;
@@ -850,17 +901,14 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   int n_clusters = num_sms() / 2;
   if (n_clusters > prm.n_pairs) n_clusters = prm.n_pairs;
   const int grid = 2 * n_clusters;
-  cudaError_t e;
-  if (bwd) {
-    e = cudaFuncSetAttribute(infonce_umma_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  auto launch = [&](auto kernel) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_infonce_bf16(pair): smem opt-in: %s", cudaGetErrorString(e));
-    infonce_umma_pair_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_dx, m_g, prm);
-  } else {
-    e = cudaFuncSetAttribute(infonce_umma_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_infonce_bf16(pair): smem opt-in: %s", cudaGetErrorString(e));
-    infonce_umma_pair_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_dx, m_g, prm);
-  }
-  return check_launch("rc_infonce_bf16(pair)");
+    kernel<<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_dx, m_g, prm);
+    return check_launch("rc_infonce_bf16(pair)");
+  };
+  if (rep == 4) return bwd ? launch(infonce_umma_pair_kernel<true, 4>) : launch(infonce_umma_pair_kernel<false, 4>);
+  return bwd ? launch(infonce_umma_pair_kernel<true, 1>) : launch(infonce_umma_pair_kernel<false, 1>);
 }
 
 }  // namespace rc

@@ -54,14 +54,26 @@ def build_contrast_indices(unique_labels: torch.Tensor, C: int, label_similarity
 
 def text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embeddings, label_similarity_sets,
                           log_temperature_text, percent_image_sampling=0.7, k_distractors=50, pct_medium=0.0,
-                          pct_hard=0.75, pct_rand=0.25, precision="auto", return_aux=False, with_smoothness=False):
+                          pct_hard=0.75, pct_rand=0.25, precision="auto", return_aux=False, with_smoothness=False,
+                          shared2x2=False):
     """Pixel-text InfoNCE of model.py:199-301 on the fused kernels.
 
     The reference gathers ``int(0.7*HW)`` pixel rows per image WITH replacement and drops label 0
     (model.py:220-228); here the same ``torch.randint`` draw becomes a per-pixel multiplicity weight
-    and the [B,D,H,W] tensor is read in place (no gather, no [N,K] logits)."""
+    and the [B,D,H,W] tensor is read in place (no gather, no [N,K] logits).
+
+    ``shared2x2``: ``pixel_embeddings`` is the decoder's PRE-upsample output [B,D,H/2,W/2] (normalised
+    or not) while ``target_indices`` stays [B,H,W]; every embedding row then carries the four targets /
+    multiplicities of its 2x2 block (decoder.py:113-114, quirk Q8) and the same loss and gradient come
+    out of a quarter of the tensor-core work."""
     assert abs(pct_medium + pct_hard + pct_rand - 1.0) < 1e-4, "Sum of text percentages must be 1."
     B, D, H, W = pixel_embeddings.shape
+    if shared2x2:
+        H, W = 2 * H, 2 * W
+        if with_smoothness:
+            raise RuntimeError("text_contrastive_loss: with_smoothness is not available with shared2x2")
+        if tuple(target_indices.shape[-2:]) != (H, W):
+            raise RuntimeError(f"text_contrastive_loss(shared2x2): targets must be {H}x{W}, got {tuple(target_indices.shape)}")
     C = candidate_text_embeddings.shape[0]
     device = pixel_embeddings.device
     zero = lambda: torch.tensor(0.0, device=device)
@@ -97,8 +109,18 @@ def text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embed
         loss, smooth = ops.pixel_losses(pixel_embeddings, t_norm, log_temperature_text, y, w, precision)
         aux["smoothness"] = smooth
         return loss, aux
-    loss = ops.infonce(pixel_embeddings, t_norm, log_temperature_text, y, w, precision)
+    if shared2x2:
+        y, w = group_2x2(y.view(B, H, W)), group_2x2(w.view(B, H, W))
+        loss = ops.infonce(pixel_embeddings, t_norm, log_temperature_text, y, w, precision, rep=4)
+    else:
+        loss = ops.infonce(pixel_embeddings, t_norm, log_temperature_text, y, w, precision)
     return (loss, aux) if return_aux else loss
+
+
+def group_2x2(t: torch.Tensor) -> torch.Tensor:
+    """[B, 2h, 2w] -> [B, h*w, 4]: the four full-resolution entries of every shared-embedding block."""
+    B, H, W = t.shape
+    return t.reshape(B, H // 2, 2, W // 2, 2).permute(0, 1, 3, 2, 4).reshape(B, (H // 2) * (W // 2), 4).contiguous()
 
 
 def image_contrastive_loss(area_embeddings, image_embeddings, log_temperature_image, precision="fp32"):
@@ -121,6 +143,37 @@ def compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddin
                  percent_image_sampling=0.7, k_distractors=50, pct_medium=0.0, pct_hard=0.75, pct_rand=0.25,
                  precision="auto"):
     """Hybrid contrastive loss: pixel-text + area-image + smoothness (model.py:178-355)."""
+    return _compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddings, label_similarity_sets,
+                         area_embeddings, image_embeddings, W_text, W_image, W_smooth, percent_image_sampling,
+                         k_distractors, pct_medium, pct_hard, pct_rand, precision, shared2x2=False)
+
+
+def compute_loss_shared2x2(self, decoder_output, target_indices, candidate_text_embeddings, label_similarity_sets,
+                           area_embeddings, image_embeddings, W_text=1.0, W_image=0.5, W_smooth=2e2,
+                           percent_image_sampling=0.7, k_distractors=50, pct_medium=0.0, pct_hard=0.75,
+                           pct_rand=0.25, precision="auto"):
+    """``compute_loss`` of the tensor the decoder WOULD emit, taken before its tail.
+
+    The reference decoder ends in ``output_conv -> F.interpolate(nearest, x2) -> F.normalize``
+    (utils/src/decoder.py:112-116), so ``compute_loss`` always sees 2x2 blocks of identical embeddings
+    (quirk Q8).  Given ``decoder_output`` = the ``output_conv`` result [B,D,H/2,W/2] (what the decoder holds
+    before line 113) and the full-resolution ``target_indices`` [B,H,W], this returns the same
+    ``(total_loss, loss_info)`` as ``compute_loss(decoder_tail(decoder_output), ...)`` and back-propagates the
+    same gradient into ``decoder_output`` -- without materialising the upsampled tensor:
+      * text term: one embedding row per block with its four targets (rc_infonce_bf16_rep4): 1/4 of the GEMM
+        work and HBM traffic, row norms taken inside the kernel;
+      * smoothness: differences inside a block are exactly 0 and every low-resolution difference appears
+        twice, so sum_hi = 2 sum_lo over the normalised low-resolution rows, divided by the full-resolution
+        element counts of model.py:332-333.
+    Same RNG streams as the reference (the pixel draw is over the full-resolution H*W)."""
+    return _compute_loss(self, decoder_output, target_indices, candidate_text_embeddings, label_similarity_sets,
+                         area_embeddings, image_embeddings, W_text, W_image, W_smooth, percent_image_sampling,
+                         k_distractors, pct_medium, pct_hard, pct_rand, precision, shared2x2=True)
+
+
+def _compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddings, label_similarity_sets,
+                  area_embeddings, image_embeddings, W_text, W_image, W_smooth, percent_image_sampling, k_distractors,
+                  pct_medium, pct_hard, pct_rand, precision, shared2x2):
     device = pixel_embeddings.device
     log_tau_text = self.log_temperature_text
     log_tau_image = self.log_temperature_image
@@ -128,11 +181,11 @@ def compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddin
     text_loss = torch.tensor(0.0, device=device)
     fused_smooth = None
     if W_text > 0:
-        fuse = W_smooth > 0 and pixel_embeddings.requires_grad
+        fuse = W_smooth > 0 and pixel_embeddings.requires_grad and not shared2x2
         out = text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embeddings,
                                     label_similarity_sets, log_tau_text, percent_image_sampling,
                                     k_distractors, pct_medium, pct_hard, pct_rand, precision, return_aux=True,
-                                    with_smoothness=fuse)
+                                    with_smoothness=fuse, shared2x2=shared2x2)
         text_loss = out[0]
         fused_smooth = out[1].get("smoothness")
 
@@ -144,7 +197,12 @@ def compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddin
         image_loss = dummy * torch.exp(log_tau_image) * 0.0
 
     smooth_loss = torch.tensor(0.0, device=device)
-    if W_smooth > 0:
+    if W_smooth > 0 and shared2x2:
+        B, D, h, w = pixel_embeddings.shape
+        H, W = 2 * h, 2 * w
+        rows = torch.nn.functional.normalize(pixel_embeddings.float(), p=2, dim=1)       # decoder.py:114
+        smooth_loss = ops.smoothness(rows, denominators=(B * D * H * (W - 1) / 2.0, B * D * (H - 1) * W / 2.0))
+    elif W_smooth > 0:
         smooth_loss = fused_smooth if fused_smooth is not None else ops.smoothness(pixel_embeddings)
 
     total = W_text * text_loss + W_image * image_loss + W_smooth * smooth_loss
@@ -171,3 +229,4 @@ class DepthCLIPLossMixin:
     """Mixin giving a model with ``log_temperature_text`` / ``log_temperature_image`` parameters the
     reference's ``compute_loss`` on the B200 kernels."""
     compute_loss = compute_loss
+    compute_loss_shared2x2 = compute_loss_shared2x2

@@ -107,9 +107,11 @@ def sample_weights(seg: torch.Tensor, rand_idx: Optional[torch.Tensor], label_ma
 
 def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch.Tensor, inv_tau: float,
                 need_dx: bool, need_dt: bool, precision: str = "auto",
-                grad_scale: Optional[torch.Tensor] = None, t_bf16=None):
+                grad_scale: Optional[torch.Tensor] = None, t_bf16=None, rep: int = 1):
     """One fused pass: returns dict(loss_sum, w_sum (double[1] tensors), lse, dx, dt, dlogtau).
-    loss = loss_sum / w_sum; dx/dt/dlogtau are gradients of that mean loss times grad_scale."""
+    loss = loss_sum / w_sum; dx/dt/dlogtau are gradients of that mean loss times grad_scale.
+    rep = 4: every row of x is the embedding shared by a 2x2 block of pixels (decoder.py:113, Q8);
+    y / w are [rows, 4] and dx is the gradient w.r.t. the shared row (tensor-core path only)."""
     _need_cuda(x, t_norm, y, w)
     x, B, D, HW = _emb3(x)
     K = t_norm.shape[0]
@@ -117,8 +119,15 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
     M = B * HW
     y = y.reshape(-1).to(torch.int32).contiguous()
     w = w.reshape(-1).to(torch.float32).contiguous()
-    if y.numel() != M or w.numel() != M:
-        raise RuntimeError("infonce: y / w must have one entry per pixel row")
+    if rep not in (1, 4):
+        raise RuntimeError("infonce: rep must be 1 or 4")
+    if y.numel() != M * rep or w.numel() != M * rep:
+        raise RuntimeError("infonce: y / w must have `rep` entries per embedding row")
+    if rep == 4:
+        if precision == "fp32" or need_dt and not need_dx or D not in (256, 512) or not bf16_path_supported(D, HW, K):
+            raise RuntimeError(f"infonce(rep=4): needs the tensor-core path (D in (256, 512), K <= 256, HW % 8 == 0); "
+                               f"got D={D}, HW={HW}, K={K}, precision={precision!r}")
+        precision = "bf16"
     dt_on_tc = need_dt and need_dx and D in (256, 512)       # tensor-core dText: pair kernel + split-K GEMM
     if precision == "auto":
         precision = "bf16" if (bf16_path_supported(D, HW, K) and (not need_dt or dt_on_tc)) else "fp32"
@@ -128,7 +137,7 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
     L = _lib.lib()
     st = _stream(x)
     if need_grad:
-        check(L.rc_weight_sum(_p(w), _p(y), M, acc[3:].data_ptr(), st), "rc_weight_sum")
+        check(L.rc_weight_sum(_p(w), _p(y), M * rep, acc[3:].data_ptr(), st), "rc_weight_sum")
     gs = None
     if grad_scale is not None:
         gs = grad_scale.detach().reshape(1).to(device=dev, dtype=torch.float32)
@@ -155,10 +164,12 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
         ws_bytes = int((L.rc_infonce_workspace_bytes_dt if need_dt else L.rc_infonce_workspace_bytes)(B, D, HW, K, xdt))
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         dxb = torch.empty(B, D, HW, device=dev, dtype=torch.bfloat16) if need_dx else None
-        check(L.rc_infonce_bf16(_p(x), xdt, B, D, HW, _p(tb), _p(ttb), K, _p(y), _p(w), float(inv_tau), _p(lse),
-                                acc[0:].data_ptr(), acc[1:].data_ptr(),
-                                acc[3:].data_ptr() if need_grad else None, _p(gs), _p(dxb), _p(dt),
-                                acc[2:].data_ptr() if need_dx else None, _p(ws), ws_bytes, 0, st), "rc_infonce_bf16")
+        entry = L.rc_infonce_bf16 if rep == 1 else L.rc_infonce_bf16_rep4
+        check(entry(_p(x), xdt, B, D, HW, _p(tb), _p(ttb), K, _p(y), _p(w), float(inv_tau), _p(lse),
+                    acc[0:].data_ptr(), acc[1:].data_ptr(),
+                    acc[3:].data_ptr() if need_grad else None, _p(gs), _p(dxb), _p(dt),
+                    acc[2:].data_ptr() if need_dx else None, _p(ws), ws_bytes, 0, st),
+              "rc_infonce_bf16" if rep == 1 else "rc_infonce_bf16_rep4")
         dx = None
         if dxb is not None:
             dx = dxb.view(x.shape) if x.dtype == torch.bfloat16 else dxb.view(x.shape).to(x.dtype)
@@ -172,12 +183,12 @@ class _InfoNCE(torch.autograd.Function):
     produced by the same fused kernel launch as the loss (single pass over X)."""
 
     @staticmethod
-    def forward(ctx, x, t_norm, log_tau, y, w, precision):
+    def forward(ctx, x, t_norm, log_tau, y, w, precision, rep=1):
         need_dx = x.requires_grad
         need_dt = t_norm.requires_grad
         need_tau = log_tau.requires_grad
         inv_tau = float(torch.exp(-log_tau.detach().float()))          # one scalar sync, as .item() in the reference
-        r = infonce_raw(x.detach(), t_norm.detach(), y, w, inv_tau, need_dx or need_tau, need_dt, precision)
+        r = infonce_raw(x.detach(), t_norm.detach(), y, w, inv_tau, need_dx or need_tau, need_dt, precision, rep=rep)
         wsum = r["w_sum"]
         loss = torch.where(wsum > 0, r["loss_sum"] / wsum.clamp_min(1e-300), torch.zeros_like(wsum)).float()
         ctx.save_for_backward(r["dx"] if need_dx else None, r["dt"], r["dlogtau"].float())
@@ -198,7 +209,7 @@ class _InfoNCE(torch.autograd.Function):
             gt = dt * g
         if need_tau:
             gl = (dlt * g).reshape(())
-        return gx, gt, gl, None, None, None
+        return gx, gt, gl, None, None, None, None
 
 
 class _PixelLosses(torch.autograd.Function):
@@ -246,9 +257,10 @@ def pixel_losses(x, t_norm, log_tau, y, w, precision="auto"):
     return _PixelLosses.apply(x, t_norm, log_tau, y, w, precision)
 
 
-def infonce(x, t_norm, log_tau, y, w, precision="auto"):
-    """Autograd-aware fused InfoNCE; x [B,D,H,W], t_norm [K,D] normalised, y/w per pixel."""
-    return _InfoNCE.apply(x, t_norm, log_tau, y, w, precision)
+def infonce(x, t_norm, log_tau, y, w, precision="auto", rep=1):
+    """Autograd-aware fused InfoNCE; x [B,D,H,W], t_norm [K,D] normalised, y/w per pixel
+    (rep = 4: x holds the embeddings shared by 2x2 pixel blocks, y/w are [B*H*W, 4])."""
+    return _InfoNCE.apply(x, t_norm, log_tau, y, w, precision, rep)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -288,9 +300,10 @@ def tv_backward(x: torch.Tensor, scale: torch.Tensor, dx: Optional[torch.Tensor]
 
 class _Smoothness(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, denominators=None):
         sums = tv_sums(x.detach())
-        dh, dv = tv_denominators(x.shape)
+        dh, dv = tv_denominators(x.shape) if denominators is None else denominators
+        ctx.den = (dh, dv)
         ctx.save_for_backward(x)
         # l1_loss over an empty slice is NaN in the reference (W == 1 or H == 1); keep that
         th = sums[0] / dh if dh > 0 else torch.full((), float("nan"), device=x.device, dtype=torch.float64)
@@ -300,13 +313,15 @@ class _Smoothness(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
-        dh, dv = tv_denominators(x.shape)
+        dh, dv = ctx.den
         scale = torch.stack([g.float() / dh if dh > 0 else g.float() * 0, g.float() / dv if dv > 0 else g.float() * 0])
-        return tv_backward(x.detach(), scale)
+        return tv_backward(x.detach(), scale), None
 
 
-def smoothness(x: torch.Tensor) -> torch.Tensor:
-    return _Smoothness.apply(x)
+def smoothness(x: torch.Tensor, denominators=None) -> torch.Tensor:
+    """sum_h / dh + sum_v / dv; the denominators default to the element counts of x's own slices
+    (model.py:332-333) and can be overridden when x stands for a larger tensor (shared 2x2 blocks)."""
+    return _Smoothness.apply(x, denominators)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,148 @@
+"""GPU parity of the shared-embedding (2x2 block) path, SURVEY 8(f)-1: `rc_infonce_bf16_rep4` and
+`compute_loss_shared2x2` against the oracle, against the fixtures produced by the reference decoder tail +
+`compute_loss` (tests/golden/make_golden_up2.py), and against the full-resolution kernel on the upsampled
+tensor.  bf16 tensor-core path: 2e-2 max-relative on gradients, 2e-3 on loss / lse (BASELINE.json)."""
+import os
+import random
+from unittest import mock
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rangeclip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF16_MAXREL = 2e-2
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def maxrel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _rep4_case(B, D, h, w, K, seed, tau=0.07):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(B, D, h, w, generator=g) * (0.5 + torch.rand(B, 1, h, w, generator=g))).to(torch.bfloat16).float()
+    t = torch.nn.functional.normalize(torch.randn(K, D, generator=g), dim=1).to(torch.bfloat16).float()
+    M = B * h * w
+    base = torch.randint(0, K, (M, 1), generator=g, dtype=torch.int32)
+    y4 = base.repeat(1, 4)                                   # mostly one label per block ...
+    mixed = torch.rand(M, 4, generator=g) < 0.3              # ... with mixed blocks, duplicates and ignored pixels
+    y4 = torch.where(mixed, torch.randint(0, K, (M, 4), generator=g, dtype=torch.int32), y4)
+    y4[torch.rand(M, 4, generator=g) < 0.15] = -1
+    y4[torch.rand(M, generator=g) < 0.05] = -1               # blocks without any target
+    w4 = torch.randint(0, 4, (M, 4), generator=g).float()
+    return x, t, y4, w4, 1.0 / tau
+
+
+def _oracle_rep4(x, t, y4, w4, inv_tau):
+    B, D, h, w = x.shape
+    r = O.infonce_dense_rep(x.permute(0, 2, 3, 1).reshape(-1, D), t, y4, w4, inv_tau)
+    r["dx4"] = r["dx"].reshape(B, h, w, D).permute(0, 3, 1, 2)
+    return r
+
+
+@pytest.mark.parametrize("B,D,h,w,K,xdtype,tau", [
+    (2, 512, 16, 16, 256, torch.bfloat16, 0.07), (2, 256, 16, 24, 100, torch.bfloat16, 0.07),
+    (1, 512, 20, 20, 200, torch.float32, 0.07), (5, 512, 9, 8, 130, torch.bfloat16, 0.07),
+    (2, 256, 5, 8, 33, torch.bfloat16, 0.07), (2, 512, 16, 16, 256, torch.bfloat16, 0.02),
+    (1, 512, 8, 8, 2, torch.bfloat16, 0.07)])
+def test_infonce_rep4_tensor_core(B, D, h, w, K, xdtype, tau):
+    from rangeclip_b200 import ops
+    x, t, y4, w4, inv_tau = _rep4_case(B, D, h, w, K, seed=B * 91 + D + K + h, tau=tau)
+    ref = _oracle_rep4(x, t, y4, w4, inv_tau)
+    r = ops.infonce_raw(x.to(dev()).to(xdtype), t.to(dev()), y4.to(dev()), w4.to(dev()), inv_tau, True, False, "bf16", rep=4)
+    torch.cuda.synchronize()
+    loss = float(r["loss_sum"] / r["w_sum"])
+    tol = 3e-3 if tau < 0.029 else 2e-3
+    assert float(r["w_sum"]) == float(ref["wsum"])
+    assert abs(loss - float(ref["loss"])) <= tol * abs(float(ref["loss"])) + 1e-6, (loss, float(ref["loss"]))
+    assert maxrel(r["lse"].cpu(), ref["lse"]) < tol
+    assert maxrel(r["dx"].float().cpu(), ref["dx4"]) < BF16_MAXREL, maxrel(r["dx"].float().cpu(), ref["dx4"])
+    assert abs(float(r["dlogtau"]) - float(ref["dlogtau"])) <= BF16_MAXREL * abs(float(ref["dlogtau"])) + 1e-7
+    # forward-only launch gives the same loss
+    r2 = ops.infonce_raw(x.to(dev()).to(xdtype), t.to(dev()), y4.to(dev()), w4.to(dev()), inv_tau, False, False, "bf16", rep=4)
+    assert abs(float(r2["loss_sum"] / r2["w_sum"]) - loss) <= 1e-6 * abs(loss) + 1e-9
+
+
+def test_infonce_rep4_dtext():
+    from rangeclip_b200 import ops
+    x, t, y4, w4, inv_tau = _rep4_case(2, 512, 16, 16, 200, seed=77)
+    ref = _oracle_rep4(x, t, y4, w4, inv_tau)
+    r = ops.infonce_raw(x.to(dev()).to(torch.bfloat16), t.to(dev()), y4.to(dev()), w4.to(dev()), inv_tau, True, True, "bf16", rep=4)
+    assert maxrel(r["dt"].cpu(), ref["dt"]) < BF16_MAXREL
+    assert maxrel(r["dx"].float().cpu(), ref["dx4"]) < BF16_MAXREL
+
+
+def test_rep4_equals_full_resolution_kernel():
+    """Size-independent property at 128 x 128 shared rows (= one 256 x 256 map): the four-target launch on the
+    distinct rows agrees with the one-target launch on the nearest-upsampled tensor -- same loss, and the row
+    gradient is the sum of the block's four pixel gradients."""
+    from rangeclip_b200 import ops
+    from rangeclip_b200.losses import group_2x2
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, D, h, w, K = 1, 512, 128, 128, 256
+    H, W = 2 * h, 2 * w
+    e = torch.randn(B, D, h, w, device=dev(), generator=g).to(torch.bfloat16)
+    t = torch.nn.functional.normalize(torch.randn(K, D, device=dev(), generator=g), dim=1)
+    seg = torch.randint(0, K, (B, H // 8, W // 8), device=dev(), generator=g).repeat_interleave(8, 1).repeat_interleave(8, 2)
+    seg = torch.roll(seg, (3, 5), (1, 2)).to(torch.int32)            # label borders cut through embedding blocks
+    wt = torch.randint(0, 3, (B, H, W), device=dev(), generator=g).float()
+    x_hi = e.repeat_interleave(2, 2).repeat_interleave(2, 3).contiguous()
+    r_hi = ops.infonce_raw(x_hi, t, seg.reshape(B, -1), wt.reshape(B, -1), 1 / 0.07, True, False, "bf16")
+    r_lo = ops.infonce_raw(e, t, group_2x2(seg), group_2x2(wt), 1 / 0.07, True, False, "bf16", rep=4)
+    assert float(r_hi["w_sum"]) == float(r_lo["w_sum"])
+    l_hi, l_lo = float(r_hi["loss_sum"] / r_hi["w_sum"]), float(r_lo["loss_sum"] / r_lo["w_sum"])
+    assert abs(l_hi - l_lo) <= 1e-5 * abs(l_hi)
+    dsum = r_hi["dx"].float().view(B, D, h, 2, w, 2).sum(dim=(3, 5))
+    assert maxrel(r_lo["dx"].float().cpu(), dsum.cpu()) < BF16_MAXREL
+    assert abs(float(r_hi["dlogtau"]) - float(r_lo["dlogtau"])) <= 1e-3 * abs(float(r_hi["dlogtau"]))
+
+
+class _Model(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.log_temperature_text = torch.nn.Parameter(torch.log(torch.tensor(0.07)))
+        self.log_temperature_image = torch.nn.Parameter(torch.log(torch.tensor(0.1)))
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_compute_loss_shared2x2_golden(golden_dir, case):
+    """Reference: decoder tail (decoder.py:112-116) + DepthUNet.compute_loss, gradient w.r.t. the decoder output."""
+    import rangeclip_b200 as R
+    g = np.load(os.path.join(golden_dir, f"up2_{case}.npz"))
+    model = _Model().to(dev())
+    E = torch.tensor(g["E"]).to(dev()).requires_grad_(True)
+    C = g["text"].shape[0]
+    sets = {"medium": {i: [int(v) for v in g["medium"][i]] for i in range(C)},
+            "hard": {i: [int(v) for v in g["hard"][i]] for i in range(C)}}
+    rand_idx = torch.tensor(g["rand_idx"]).to(dev())
+    seed = int(g["seed"])
+    np.random.seed(seed); torch.manual_seed(seed); random.seed(seed)
+    with mock.patch("torch.randint", lambda *a, **k: rand_idx):
+        total, info = R.compute_loss_shared2x2(model, E, torch.tensor(g["seg"]).to(dev()), torch.tensor(g["text"]).to(dev()),
+                                               sets, None, None, W_smooth=float(g["W_smooth"]),
+                                               percent_image_sampling=float(g["pct_sampling"]),
+                                               k_distractors=int(g["k_distractors"]))
+    total.backward()
+    assert abs(info["text_contrastive_loss"] - float(g["text_loss"])) <= 2e-3 * abs(float(g["text_loss"]))
+    assert abs(info["smoothness_loss"] - float(g["smooth_loss"])) <= 1e-5 * abs(float(g["smooth_loss"])) + 1e-12
+    assert abs(float(total) - float(g["total"])) <= 2e-3 * abs(float(g["total"]))
+    assert maxrel(E.grad.cpu(), g["dE"]) < BF16_MAXREL, maxrel(E.grad.cpu(), g["dE"])
+    assert abs(float(model.log_temperature_text.grad) - float(g["dlogtau_text"])) <= BF16_MAXREL * abs(float(g["dlogtau_text"]))
+
+
+def test_rep4_rejects_unsupported_shapes():
+    from rangeclip_b200 import ops
+    x = torch.zeros(1, 128, 8, 8, device=dev(), dtype=torch.bfloat16)
+    t = torch.nn.functional.normalize(torch.randn(4, 128, device=dev()), dim=1)
+    y4 = torch.zeros(64, 4, device=dev(), dtype=torch.int32)
+    with pytest.raises(RuntimeError):
+        ops.infonce_raw(x, t, y4, y4.float(), 10.0, True, False, "bf16", rep=4)

@@ -160,3 +160,67 @@ def test_segclip_restatement_agrees_when_transitive():
     a1, m1, ak, mk = O.topk_metrics_numpy(gt, topk, eq)
     assert np.isclose(a1, fin["pixel_accuracy_t1"]) and np.isclose(ak, fin["pixel_accuracy_tk"])
     assert np.isclose(m1, fin["mIoU_t1"])
+
+
+# ---------------------------------------------------------------------------------------------
+# shared-embedding (2x2 block) form, SURVEY 8(f)-1: fixtures from the reference decoder tail +
+# compute_loss (tests/golden/make_golden_up2.py)
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_decoder_tail_and_loss_match_reference(golden_dir, case):
+    g = _load(golden_dir, f"up2_{case}.npz")
+    E = torch.tensor(g["E"], requires_grad=True)
+    seg = torch.tensor(g["seg"])
+    lt = torch.log(torch.tensor(0.07)).requires_grad_(True)
+    li = torch.log(torch.tensor(0.1)).requires_grad_(True)
+    C = g["text"].shape[0]
+    sets = {"medium": {i: [int(v) for v in g["medium"][i]] for i in range(C)},
+            "hard": {i: [int(v) for v in g["hard"][i]] for i in range(C)}}
+    seed = int(g["seed"])
+    np.random.seed(seed); torch.manual_seed(seed); random.seed(seed)
+    X = O.decoder_tail(E, seg.shape[1:])
+    total, info, contrast = O.compute_loss(X, seg, torch.tensor(g["text"]), sets, None, None, lt, li,
+                                           W_smooth=float(g["W_smooth"]), percent_image_sampling=float(g["pct_sampling"]),
+                                           k_distractors=int(g["k_distractors"]), rand_indices=torch.tensor(g["rand_idx"]))
+    assert np.array_equal(contrast.numpy(), g["contrast"])
+    total.backward()
+    assert np.allclose(total.detach().numpy(), g["total"], rtol=1e-6)
+    assert np.allclose(E.grad.numpy(), g["dE"], rtol=1e-5, atol=1e-9)
+    assert np.allclose(lt.grad.numpy(), g["dlogtau_text"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_shared_embedding_form_equals_reference(golden_dir, case):
+    """Quirk Q8: the loss on the nearest-upsampled tensor equals the four-target form on the distinct
+    low-resolution rows, and the gradient w.r.t. the decoder output is that form's row gradient plus
+    the smoothness term taken at low resolution (each low-res difference appears twice)."""
+    g = _load(golden_dir, f"up2_{case}.npz")
+    E = torch.tensor(g["E"]).double()
+    seg = torch.tensor(g["seg"]); text = torch.tensor(g["text"])
+    B, D, h, w_ = E.shape
+    H, W = 2 * h, 2 * w_
+    assert int(g["n_mixed_blocks"]) > 0          # blocks with several different targets are exercised
+    contrast = torch.tensor(g["contrast"])
+    wt = O.sampling_weights(seg, torch.tensor(g["rand_idx"]))
+    mapping = torch.full((text.shape[0],), -1, dtype=torch.long)
+    mapping[contrast] = torch.arange(len(contrast))
+    y = torch.where(seg > 0, mapping[seg], torch.full_like(seg, -1))
+    y4 = O.group_2x2(y).reshape(-1, 4)
+    w4 = O.group_2x2(wt.reshape(B, H, W)).reshape(-1, 4)
+    rows = E.permute(0, 2, 3, 1).reshape(-1, D)
+    t = torch.nn.functional.normalize(text[contrast].double(), dim=1)
+    r = O.infonce_dense_rep(rows, t, y4, w4, 1.0 / 0.07)
+    assert np.isclose(float(r["loss"]), float(g["text_loss"]), rtol=2e-6)
+    assert np.isclose(float(r["dlogtau"]), float(g["dlogtau_text"]), rtol=1e-5)
+    dE = r["dx"].reshape(B, h, w_, D).permute(0, 3, 1, 2)
+    Ws = float(g["W_smooth"])
+    if Ws > 0:
+        El = E.clone().requires_grad_(True)
+        N = torch.nn.functional.normalize(El, dim=1)
+        sm = 2 * (N[..., :, :-1] - N[..., :, 1:]).abs().sum() / (B * D * H * (W - 1)) \
+            + 2 * (N[..., :-1, :] - N[..., 1:, :]).abs().sum() / (B * D * (H - 1) * W)
+        assert np.isclose(float(sm.detach()), float(g["smooth_loss"]), rtol=1e-6)
+        (Ws * sm).backward()
+        dE = dE + El.grad
+    assert np.allclose(dE.numpy(), g["dE"], rtol=2e-4, atol=2e-7)
