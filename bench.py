@@ -373,6 +373,47 @@ def run_gpu(args):
                       "tcgen05 top-5 + histogram kernels per batch, one int64 all-reduce at the end"}
         assert fin["total_pixels"] == tot_pix
 
+    # ---- the same loss when X comes out of the reference decoder (nearest x2 of a 128x128 map, quirk Q8):
+    #      one embedding row per 2x2 block with its four targets -- informational, not the headline (configs[1] is
+    #      defined on independent per-pixel embeddings)
+    shared = None
+    if not args.no_shared:
+        from rangeclip_b200.losses import group_2x2
+        xl = x[:, :, ::2, ::2].contiguous()                  # [B, D, 128, 128]: the tensor before decoder.py:113
+        hw = xl.shape[2] * xl.shape[3]
+        dxl = torch.empty(B, D, hw, device=device, dtype=torch.bfloat16)
+        lsel = torch.empty(B * hw, device=device, dtype=torch.float32)
+        wsl_bytes = int(L.rc_infonce_workspace_bytes(B, D, hw, K, _lib.RC_BF16))
+        wsl = torch.empty(wsl_bytes, device=device, dtype=torch.uint8)
+
+        def shared_step():
+            w, y = ops.sample_weights(seg.view(B, HW), wl["rand_idx"], label_map)
+            acc.zero_()
+            _lib.check(L.rc_weight_sum(w.data_ptr(), y.data_ptr(), M, acc[3:].data_ptr(), st), "rc_weight_sum")
+            y4, w4 = group_2x2(y.view(B, H, W)), group_2x2(w.view(B, H, W))
+            _lib.check(L.rc_infonce_bf16_rep4(xl.data_ptr(), _lib.RC_BF16, B, D, hw, tb.data_ptr(), ttb.data_ptr(), K,
+                                              y4.data_ptr(), w4.data_ptr(), inv_tau, lsel.data_ptr(), acc[0:].data_ptr(),
+                                              acc[1:].data_ptr(), acc[3:].data_ptr(), None, dxl.data_ptr(), None,
+                                              acc[2:].data_ptr(), wsl.data_ptr(), wsl_bytes, 0, st), "rc_infonce_bf16_rep4")
+
+        for _ in range(3):
+            shared_step()
+        barrier()
+        es = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        es[0].record()
+        for _ in range(args.steps):
+            shared_step()
+        es[1].record()
+        barrier()
+        ts = torch.tensor([es[0].elapsed_time(es[1])], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        shared = {"value": world * M * args.steps / (float(ts) * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": float(ts) / args.steps,
+                  "loss": float(acc[0] / acc[1]),
+                  "note": "full-resolution pixels per second when X = nearest_x2 of a 128x128 decoder output: "
+                          "rc_infonce_bf16_rep4 on the 128x128 distinct rows (sampling weights + 2x2 grouping inside the step)"}
+        del xl, dxl, lsel, wsl
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, t, cores = time_cpu(2, 3, 1)
@@ -390,7 +431,7 @@ def run_gpu(args):
                        "l2": "inputs (4.3 GB bf16 per step) exceed the 126 MB L2; no flush needed",
                        "step": "rc_sample_weights + rc_weight_sum + fused tcgen05 kernel (row norms, S GEMM, softmax/CE, dX GEMM, projection)"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "eval": ev, "loss": loss,
+            "eval": ev, "shared2x2": shared, "loss": loss,
         }
         print(json.dumps(line))
     if world > 1:
@@ -406,6 +447,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-shared", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
