@@ -331,11 +331,6 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       uint32_t lt = 0;
       auto issue_dx = [&](int b_begin, int b_end) {
         for (int blk = b_begin; blk < b_end; ++blk) {
-          for (int kc = 0; kc < n_kchunks; ++kc) {
-            const uint32_t jt = it + kc;
-            RC_WAIT(mbar_wait_cluster, &bars->tfull[jt % kTStages], (jt / kTStages) & 1, 7);
-          }
-          tc_fence_after();
           for (int pxh = 0; pxh < 2; ++pxh, ++uc) {
             const int ab = uc & 1;
             RC_WAIT(mbar_wait_cluster, &bars->acc_empty[ab], ((uc >> 1) & 1) ^ 1, 6);
@@ -344,6 +339,10 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
             const uint32_t dcol = tmem + 256 + ab * 128;
             for (int kc = 0; kc < n_kchunks; ++kc) {
               const int st = (it + kc) % kTStages;
+              if (pxh == 0) {          // the block's last text slot was requested only when the preceding S chunk retired:
+                RC_WAIT(mbar_wait_cluster, &bars->tfull[st], ((it + kc) / kTStages) & 1, 7);     // wait per slot, not up front
+                tc_fence_after();
+              }
               const uint64_t sb = dsc_k + ((smem_base + kOffT + st * kStageBytes) >> 4);
               const uint64_t pk_ = pb + ((kc * 16384 + pxh * 8192) >> 4);
               if (elect_one()) {
