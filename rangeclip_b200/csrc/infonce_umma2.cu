@@ -27,6 +27,7 @@
 #include "umma.cuh"
 #include <float.h>
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace rc {
 using namespace umma;
@@ -68,12 +69,17 @@ constexpr int kSmemBytes = kOffBars + (int)sizeof(Bars);
 static_assert(kSmemBytes <= 232448, "shared-memory budget of one SM (227 KB)");
 
 #ifdef RC_TIMING
+__device__ __forceinline__ unsigned long long globaltimer_ns() {     // one clock for both CTAs of the pair
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #define RC_T0(name) const long long name = clock64()
 #define RC_TACC(idx, name) wt[idx] += clock64() - name
 #define RC_WAIT(fn, bar, par, tag) do { const long long t0_ = clock64(); fn(bar, par, tag); wt[tag] += clock64() - t0_; } while (0)
 // event trace of CTA 0 (tools/timeline_pair.py): clock of event `id` of tile-pair iteration `iter` in [40, 44)
-#define RC_EV(iter, id) do { if (prm.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (iter) >= 40u && (iter) < 44u) \
-    prm.dbg[256 + ((iter) - 40u) * 48 + (id)] = clock64(); } while (0)
+#define RC_EV(iter, id) do { if (prm.dbg != nullptr && blockIdx.x < 2 && lane == 0 && (iter) >= 40u && (iter) < 44u) \
+    prm.dbg[256 + blockIdx.x * 192 + ((iter) - 40u) * 48 + (id)] = (long long)globaltimer_ns(); } while (0)
 #else
 #define RC_T0(name)
 #define RC_TACC(idx, name)
@@ -89,6 +95,7 @@ struct Params {
   int ablate;               // bring-up only (RANGECLIP_B200_ABLATE): 1 no epilogue x loads, 2 no dX stores, 64 no row-norm reads, 128 no dX staging
   int store_g;              // 1: also write G = rs (P - sum onehot) (bf16 [B][HW][Kp]) for the dText GEMM
   int wide;                 // 1: rows of X / dX are 32-byte aligned (256-bit global accesses allowed)
+  int split_c, split_b;     // bring-up (RANGECLIP_B200_SPLIT="c,b"): S chunks / dX blocks issued in the first half of an iteration; -1 = default
   const __nv_bfloat16* x;
   __nv_bfloat16* dx;
   const float* inv_norm;
@@ -200,7 +207,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
   const int n_kchunks = prm.Kp / 64;
   // MMA issue order per tile pair: the S GEMM of the next pair is split in two and wrapped around the dX blocks of
   // this pair, so that the dX epilogue drains accumulators while the tensor pipe works on S
-  const int c_half = n_dchunks / 2, b_half = (n_blk + 1) / 2;
+  const int c_half = prm.split_c >= 0 ? min(prm.split_c, n_dchunks) : n_dchunks / 2;
+  const int b_half = prm.split_b >= 0 ? min(prm.split_b, n_blk) : (n_blk + 1) / 2;
   const int Nh = prm.Kp / 2;             // text rows staged by each CTA
   const int n_clusters = gridDim.x / 2;
   const int cluster_id = blockIdx.x / 2;
@@ -212,10 +220,13 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     // text ring: tfull = the leader's expect_tx (bytes of both CTAs), tempty = MMA commit
     for (int i = 0; i < kXStages; ++i) { mbar_init(&bars->xf[i], 1); mbar_init(&bars->xfull[i], 2); mbar_init(&bars->xempty[i], 9); }
     for (int i = 0; i < kTStages; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 512); }
-    mbar_init(&bars->p_full, 512); mbar_init(&bars->p_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 512); }
-    mbar_init(&bars->sc_full[0], 129); mbar_init(&bars->sc_full[1], 129);   // 128 local writers + 1 expect_tx (peer: st.async)
+    // consumer releases are ONE arrival per warp (after __syncwarp), not one per thread: an mbarrier arrive is a
+    // shared-memory atomic, and 512 of them per hand-off (half of them remote) cost the leader's shared-memory pipe
+    // more wavefronts than the P stores
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 16); }
+    mbar_init(&bars->p_full, 16); mbar_init(&bars->p_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 16); }
+    mbar_init(&bars->sc_full[0], 5); mbar_init(&bars->sc_full[1], 5);   // 4 local writer warps + 1 expect_tx (peer: st.async)
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm<kTmemCols>(&bars->tmem_base);
@@ -239,6 +250,11 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
   auto arrive_leader = [&](uint64_t* bar) {
     if (leader_cta) mbar_arrive(bar);
     else mbar_arrive_remote(map_to_cta(bar, 0));
+  };
+  // one arrival for the whole warp: every lane has fenced its own accesses, __syncwarp orders them before lane 0's arrive
+  auto arrive_leader_warp = [&](uint64_t* bar) {
+    __syncwarp();
+    if (lane == 0) arrive_leader(bar);
   };
 
   if (warp < 4) {
@@ -581,7 +597,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       }
       tc_fence_before();
       if (warp == 4) RC_EV(lt, 11);    // exp pass done
-      arrive_leader(&bars->s_empty[sidx]);      // S columns are free: the tensor pipe may start the next S in them
+      if (warp == 11) RC_EV(lt, 15);   // exp pass done (last softmax warp)
+      arrive_leader_warp(&bars->s_empty[sidx]);      // S columns are free: the tensor pipe may start the next S in them
       float sum = (s0 + s1) + (s2 + s3);
       float sez = (q0 + q1) + (q2 + q3);
       // targets of this row: y_j, w_j (w_j = 0: ignored); tz = sum_j w_j s[y_j] over the targets in this half's columns
@@ -646,7 +663,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
             st_async_remote_b32(sc_peer + idx * 4, c2, (lt & 1) ? sc_peer1 : sc_peer0);   // peer copy: 4 tx bytes on ITS barrier
           }
           dlt_acc -= cj;
-          mbar_arrive(&bars->sc_full[lt & 1]);                // own copy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->sc_full[lt & 1]);                // own copy (one arrival per writer warp)
           if (row == 0) mbar_arrive_expect_tx(&bars->sc_full[lt & 1], 64 * 4);   // the peer's 64 st.async land here
         }
         // the dX MMAs of the previous pair have finished reading P: store this pair's P
@@ -687,8 +705,9 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           }
         }
         fence_proxy_async_smem();                 // P is read by the tensor cores (async proxy)
-        arrive_leader(&bars->p_full);
+        arrive_leader_warp(&bars->p_full);
         if (warp == 4) RC_EV(lt, 13);  // P(lt) stored
+        if (warp == 11) RC_EV(lt, 16); // P(lt) stored (last softmax warp)
         RC_TACC(2, tst);
         if (prm.store_g) {                        // dText: the finished G tile goes to global memory as it sits in smem
           named_bar_sync(6, 256);
@@ -787,7 +806,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           uint32_t acc[32];
           tmem_ld_32x32(trow_acc + ab * 128 + c * 32, acc);
           tmem_ld_wait();
-          if (c == 1) { tc_fence_before(); arrive_leader(&bars->acc_empty[ab]); }
+          if (c == 1) { tc_fence_before(); arrive_leader_warp(&bars->acc_empty[ab]); }
           pair_swap(&xq[c][0]);             // -> own row, pixels [c*32, +32) in order
           const uint4* scp = reinterpret_cast<const uint4*>(sc + pxh * 32 + c * 16);    // -cs2 of 16 pixel pairs
           uint32_t o[16];
@@ -894,6 +913,8 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   prm.x = reinterpret_cast<const __nv_bfloat16*>(xsrc);
   prm.dx = reinterpret_cast<__nv_bfloat16*>(dx);
   { const char* ab = getenv("RANGECLIP_B200_ABLATE"); prm.ablate = ab ? atoi(ab) : 0; }
+  prm.split_c = prm.split_b = -1;
+  if (const char* sp = getenv("RANGECLIP_B200_SPLIT")) sscanf(sp, "%d,%d", &prm.split_c, &prm.split_b);
   prm.wide = (HW % 16 == 0) && (reinterpret_cast<uintptr_t>(xsrc) % 32 == 0) && (reinterpret_cast<uintptr_t>(dx) % 32 == 0);
   prm.inv_norm = inv_norm; prm.y = y; prm.w = w; prm.inv_tau = inv_tau; prm.grad_scale = grad_scale;
   prm.w_sum_in = w_sum_in; prm.lse = lse; prm.loss_sum = loss_sum; prm.w_sum = w_sum; prm.dlogtau = dlogtau;

@@ -18,17 +18,18 @@ for rep in range(2):
     ops.infonce_raw(x, t, y, w, 1 / 0.07, True, False, "bf16")
     torch.cuda.synchronize()
 _lib.lib().rc_debug_set_timing_buffer(None)
-ev = buf[256:256 + 4 * 48].view(4, 48).tolist()
+ev = buf[256:256 + 2 * 4 * 48].view(2, 4, 48).tolist()
 names = {0: "mma  S issue start", 1: "mma  S issued", 2: "mma  dX start (P ready)", 3: "mma  dX unit0 start", 4: "mma  dX unit1 start",
          5: "mma  dX unit2 start", 6: "mma  dX unit3 start", 7: "mma  dX issued", 10: "smx  S complete", 11: "smx  exp pass done",
          12: "smx  P buffer free", 13: "smx  P stored", 14: "smx  norms(next) done", 20: "epi  unit0 acc full", 21: "epi  unit0 done",
          22: "epi  unit1 acc full", 23: "epi  unit1 done", 24: "epi  unit2 acc full", 25: "epi  unit2 done", 26: "epi  unit3 acc full",
-         27: "epi  unit3 done"}
-t0 = min(v for row in ev for v in row if v)
+         27: "epi  unit3 done", 15: "smx  exp pass done (warp 11)", 16: "smx  P stored (warp 11)"}
+t0 = min(v for cta in ev for row in cta for v in row if v)
 rows = []
-for it, row in enumerate(ev):
-    for i, v in enumerate(row):
-        if v:
-            rows.append((v - t0, 40 + it, names.get(i, str(i))))
-for tt, it, nm in sorted(rows):
-    print(f"{tt:8d}  iter {it}  {nm}")
+for cta in range(2):
+    for it, row in enumerate(ev[cta]):
+        for i, v in enumerate(row):
+            if v:
+                rows.append((v - t0, cta, 40 + it, names.get(i, str(i))))
+for tt, cta, it, nm in sorted(rows):        # %globaltimer nanoseconds (one clock for both CTAs of the pair)
+    print(f"{tt:8d} ns  cta{cta}  iter {it}  {nm}")
