@@ -42,7 +42,16 @@ constexpr int kStageBytes = 16 * 1024;
 static_assert(kTStages >= 4, "a dX block keeps Kp/64 <= 4 slots of the text ring at once");
 constexpr int kPBytes = 64 * 1024;
 constexpr int kTmemCols = 512;
+// Measured, not adopted: TMEM load of softmax step c+1 in flight while step c is computed (needs 128 softmax registers,
+// taken from the control warps): 2.62 ms against 2.49 ms -- the extra spills cost more than the hidden latency.
+#ifndef RC_SMX_DOUBLE_BUFFER
+#define RC_SMX_DOUBLE_BUFFER 0
+#endif
+#if RC_SMX_DOUBLE_BUFFER
+constexpr int kRegsCtl = 32, kRegsSoftmax = 128;     // epilogue warps keep the entry allocation (96); 32 + 2*128 + 2*96 = 5*96
+#else
 constexpr int kRegsCtl = 48, kRegsSoftmax = 120;     // epilogue warps keep the entry allocation (96); 48 + 2*120 + 2*96 = 5*96
+#endif
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -586,6 +595,25 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           }
         }
       };
+#if RC_SMX_DOUBLE_BUFFER
+      {   // the TMEM load of step c+1 is in flight while step c is computed (two 16-column register buffers)
+        uint32_t ra[16], rb[16];
+        tmem_ld_32x16(trow, ra);
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          if (c * 16 < Kh) {
+            tmem_ld_wait16(ra);
+            if ((c + 1) * 16 < Kh) tmem_ld_32x16(trow + (c + 1) * 16, rb);
+            smx_step(ra, c);
+          }
+          if ((c + 1) * 16 < Kh) {
+            tmem_ld_wait16(rb);
+            if ((c + 2) * 16 < Kh) tmem_ld_32x16(trow + (c + 2) * 16, ra);
+            smx_step(rb, c + 1);
+          }
+        }
+      }
+#else
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         if (c * 16 < Kh) {
@@ -595,6 +623,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           smx_step(r, c);
         }
       }
+#endif
       tc_fence_before();
       if (warp == 4) RC_EV(lt, 11);    // exp pass done
       if (warp == 11) RC_EV(lt, 15);   // exp pass done (last softmax warp)
