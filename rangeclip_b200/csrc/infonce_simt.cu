@@ -315,11 +315,23 @@ __global__ void sample_map_kernel(const int64_t* __restrict__ seg, int64_t n, co
   }
 }
 
+// x *= s[0] in place, 16 bytes per thread per step; a scale of exactly one (W_text = 1, the reference default,
+// model.py:337) leaves after reading the scalar, so the late upstream scaling of dX costs no pass over HBM
 template <typename T>
-__global__ void scale_kernel(T* __restrict__ x, int64_t n, const float* __restrict__ s) {
+__global__ void __launch_bounds__(256) scale_kernel(T* __restrict__ x, int64_t n, const float* __restrict__ s, int vec_ok) {
   const float f = s[0];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    ElemIO<T>::st(x + i, ElemIO<T>::ld(x + i) * f);
+  if (f == 1.0f) return;
+  constexpr int V = 16 / (int)sizeof(T);
+  const int64_t nv = vec_ok ? n / V : 0;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < nv; i += nt) {
+    uint4 v = reinterpret_cast<uint4*>(x)[i];
+    T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) e[j] = static_cast<T>(static_cast<float>(e[j]) * f);     // registers: plain conversions
+    reinterpret_cast<uint4*>(x)[i] = v;
+  }
+  for (int64_t i = nv * V + tid; i < n; i += nt) ElemIO<T>::st(x + i, ElemIO<T>::ld(x + i) * f);
 }
 
 template <template <int> class Launcher, typename... Args>
@@ -425,11 +437,13 @@ extern "C" int rc_sample_weights(const int64_t* seg, const int64_t* rand_idx, in
 }
 
 extern "C" int rc_scale(void* x, rc_dtype dtype, int64_t n, const float* sc, void* stream) {
-  RC_REQUIRE(x && sc && n >= 0, "rc_scale: bad argument");
-  if (n == 0) return RC_OK;
+  RC_REQUIRE(n >= 0, "rc_scale: bad argument");
+  if (n == 0) return RC_OK;                       // an empty tensor has no storage to point at
+  RC_REQUIRE(x && sc, "rc_scale: null pointer");
   const int64_t blocks = (n + 255) / 256;
   const int grid = (int)(blocks < rc::num_sms() * 8 ? blocks : rc::num_sms() * 8);
-  if (dtype == RC_F32) rc::scale_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, n, sc);
-  else rc::scale_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, n, sc);
+  const int vec_ok = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (dtype == RC_F32) rc::scale_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, n, sc, vec_ok);
+  else rc::scale_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, n, sc, vec_ok);
   return rc::check_launch("rc_scale");
 }

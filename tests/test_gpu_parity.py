@@ -485,3 +485,22 @@ def test_missing_gpu_paths_fail_loudly():
     from rangeclip_b200 import ops
     with pytest.raises(RuntimeError):
         ops.tv_sums(torch.zeros(1, 1, 4, 4))          # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("dtype,n,offset", [(torch.bfloat16, 8 * 1000 + 3, 0), (torch.float32, 4099, 0), (torch.bfloat16, 5000, 1),
+                                            (torch.float32, 64, 3), (torch.bfloat16, 0, 0)])
+@pytest.mark.parametrize("scale", [1.0, -2.5])
+def test_scale_in_place(dtype, n, offset, scale):
+    """rc_scale (late upstream gradient of dX): vector body + scalar tail, unaligned base pointers, and the
+    early exit at a scale of exactly one (bit-identical output)."""
+    from rangeclip_b200 import _lib
+    from rangeclip_b200.ops import _dt
+    g = torch.Generator().manual_seed(n + offset)
+    base = torch.randn(n + offset + 8, generator=g).to(dtype).to(dev())
+    pristine = base.clone()
+    x = base[offset:offset + n]
+    ref = (x.float() * scale).to(dtype)
+    s = torch.tensor([scale], device=dev())
+    _lib.check(_lib.lib().rc_scale(x.data_ptr(), _dt(x), n, s.data_ptr(), torch.cuda.current_stream().cuda_stream), "rc_scale")
+    assert torch.equal(x, ref)
+    assert torch.equal(base[offset + n:], pristine[offset + n:]) and torch.equal(base[:offset], pristine[:offset])
