@@ -328,36 +328,47 @@ def smoothness(x: torch.Tensor, denominators=None) -> torch.Tensor:
 # masked pooling
 # ----------------------------------------------------------------------------------------------
 
-def pool_forward(x: torch.Tensor, seg: torch.Tensor, lut: torch.Tensor, lut_per_image: bool, n_slots: int):
-    """sum/count per slot then mean; lut [B,C] (per image) or [C] (batch-wide) int32, -1 = none."""
-    _need_cuda(x, seg, lut)
+def _seg_views(seg: torch.Tensor, B: int):
+    """One label map per pass: a tensor, or a list of tensors that label the SAME embedding rows (shared 2x2
+    blocks: the four full-resolution label sub-grids of a half-resolution embedding map)."""
+    segs = list(seg) if isinstance(seg, (list, tuple)) else [seg]
+    return [s_.reshape(B, -1).to(torch.int64).contiguous() for s_ in segs]
+
+
+def pool_forward(x: torch.Tensor, seg, lut: torch.Tensor, lut_per_image: bool, n_slots: int):
+    """sum/count per slot then mean; lut [B,C] (per image) or [C] (batch-wide) int32, -1 = none.
+    ``seg`` may be a list of label maps over the same rows: every pass adds into the same sums and counts."""
+    _need_cuda(x, lut)
     x, B, D, HW = _emb3(x)
-    seg = seg.reshape(B, -1).to(torch.int64).contiguous()
+    segs = _seg_views(seg, B)
     lut = lut.to(torch.int32).contiguous()
     C = lut.shape[-1]
     out = torch.zeros(n_slots, D, device=x.device, dtype=torch.float32)
     cnt = torch.zeros(max(n_slots, 1), device=x.device, dtype=torch.int32)
     L = _lib.lib()
-    check(L.rc_pool_fwd(_p(x), _dt(x), B, D, HW, _p(seg), _p(lut), C if lut_per_image else 0, C, n_slots,
-                        _p(out), _p(cnt), _stream(x)), "rc_pool_fwd")
+    for sg in segs:
+        _need_cuda(sg)
+        check(L.rc_pool_fwd(_p(x), _dt(x), B, D, HW, _p(sg), _p(lut), C if lut_per_image else 0, C, n_slots,
+                            _p(out), _p(cnt), _stream(x)), "rc_pool_fwd")
     check(L.rc_pool_finish(_p(out), _p(cnt), n_slots, D, _stream(x)), "rc_pool_finish")
     return out, cnt
 
 
-def pool_backward(g: torch.Tensor, cnt: torch.Tensor, seg: torch.Tensor, lut: torch.Tensor, lut_per_image: bool,
+def pool_backward(g: torch.Tensor, cnt: torch.Tensor, seg, lut: torch.Tensor, lut_per_image: bool,
                   shape, dtype) -> torch.Tensor:
     B, D = shape[0], shape[1]
     HW = 1
     for s in shape[2:]:
         HW *= s
-    seg = seg.reshape(B, -1).to(torch.int64).contiguous()
+    segs = _seg_views(seg, B)
     lut = lut.to(torch.int32).contiguous()
     C = lut.shape[-1]
     g = g.float().contiguous()
     dx = torch.empty(shape, device=g.device, dtype=dtype)
-    check(_lib.lib().rc_pool_bwd(_p(g), _p(cnt), B, D, HW, _p(seg), _p(lut), C if lut_per_image else 0, C,
-                                 g.shape[0], _p(dx), RC_F32 if dtype == torch.float32 else RC_BF16, 0,
-                                 _stream(g)), "rc_pool_bwd")
+    for i, sg in enumerate(segs):          # later passes accumulate: a row's gradient is the sum over its label maps
+        check(_lib.lib().rc_pool_bwd(_p(g), _p(cnt), B, D, HW, _p(sg), _p(lut), C if lut_per_image else 0, C,
+                                     g.shape[0], _p(dx), RC_F32 if dtype == torch.float32 else RC_BF16, 1 if i else 0,
+                                     _stream(g)), "rc_pool_bwd")
     return dx
 
 
@@ -365,15 +376,16 @@ class _MaskedPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, seg, lut, lut_per_image, n_slots):
         out, cnt = pool_forward(x.detach(), seg, lut, lut_per_image, n_slots)
-        ctx.save_for_backward(cnt, seg, lut)
+        segs = list(seg) if isinstance(seg, (list, tuple)) else [seg]
+        ctx.save_for_backward(cnt, lut, *segs)
         ctx.meta = (lut_per_image, tuple(x.shape), x.dtype)
         return out.to(x.dtype) if x.dtype != torch.float32 else out
 
     @staticmethod
     def backward(ctx, g):
-        cnt, seg, lut = ctx.saved_tensors
+        cnt, lut, *segs = ctx.saved_tensors
         lut_per_image, shape, dtype = ctx.meta
-        return pool_backward(g, cnt, seg, lut, lut_per_image, shape, dtype), None, None, None, None
+        return pool_backward(g, cnt, segs, lut, lut_per_image, shape, dtype), None, None, None, None
 
 
 def masked_pool(x, seg, lut, lut_per_image, n_slots):

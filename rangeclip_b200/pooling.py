@@ -28,9 +28,21 @@ def masked_average_pooling(pixel_embeddings, segmentation_map, object_indices):
     return pooled[inverse]
 
 
-def pool_objects_per_image(pixel_embeddings, segmentation, image_index, labels, differentiable=False):
+def _subgrids_2x2(seg):
+    """The four full-resolution label sub-grids [B, H/2, W/2] that sit on one half-resolution embedding map."""
+    return [seg[:, a::2, b::2] for a in (0, 1) for b in (0, 1)]
+
+
+def pool_objects_per_image(pixel_embeddings, segmentation, image_index, labels, differentiable=False, shared2x2=False):
     """area[i] = mean of pixel_embeddings[image_index[i]] over segmentation == labels[i]
-    (dataloader.py:286-304); zeros where the mask is empty.  All objects in one kernel launch."""
+    (dataloader.py:286-304); zeros where the mask is empty.  All objects in one kernel launch.
+
+    ``shared2x2``: ``pixel_embeddings`` is the decoder's ``output_conv`` result [B,D,H/2,W/2] and the
+    segmentation is full resolution: the mean over the nearest-upsampled, normalised tensor
+    (decoder.py:113-114) is the count-weighted mean of the normalised half-resolution rows -- four
+    accumulating passes over the small tensor, one per label sub-grid, instead of one over the large one."""
+    if shared2x2:
+        pixel_embeddings = torch.nn.functional.normalize(pixel_embeddings.float(), p=2, dim=1)     # decoder.py:114
     B, D = pixel_embeddings.shape[0], pixel_embeddings.shape[1]
     device = pixel_embeddings.device
     image_index = torch.as_tensor(image_index, device=device, dtype=torch.long).reshape(-1)
@@ -48,6 +60,10 @@ def pool_objects_per_image(pixel_embeddings, segmentation, image_index, labels, 
     lut[uniq] = torch.arange(uniq.numel(), device=device, dtype=torch.int32)
     neg = labels < 0
     x = pixel_embeddings if differentiable else pixel_embeddings.detach()
+    if shared2x2:
+        if tuple(seg.shape[-2:]) != (2 * x.shape[2], 2 * x.shape[3]):
+            raise RuntimeError(f"pool_objects_per_image(shared2x2): segmentation must be {2 * x.shape[2]}x{2 * x.shape[3]}")
+        seg = _subgrids_2x2(seg)
     pooled = ops.masked_pool(x, seg, lut.view(B, C), True, int(uniq.numel()))[inverse]
     if bool(neg.any()):
         pooled = pooled.masked_fill(neg[:, None], 0)
@@ -56,11 +72,12 @@ def pool_objects_per_image(pixel_embeddings, segmentation, image_index, labels, 
 
 @torch.no_grad()
 def prepare_image_contrast_data(image_processed_batch, object_bbox_batch, object_label_batch, segmentation_batch,
-                                pixel_embeddings_batch, clip_image_encoder, clip_processor, device):
+                                pixel_embeddings_batch, clip_image_encoder, clip_processor, device, shared2x2=False):
     """Area embeddings + CLIP crop embeddings for the image contrastive loss (dataloader.py:205-305).
     Validation, cropping and the CLIP call are the reference's host logic; the per-object masked
     means (dataloader.py:286-304) run as one pooling kernel.  ``@torch.no_grad`` as in the
-    reference: the area embeddings are detached."""
+    reference: the area embeddings are detached.  ``shared2x2``: ``pixel_embeddings_batch`` is the
+    decoder's half-resolution ``output_conv`` result (see ``pool_objects_per_image``)."""
     if not isinstance(image_processed_batch, torch.Tensor) or image_processed_batch.dim() != 4:
         print("Warning: 'image_processed_batch' is not a 4D tensor.")
         return None, None
@@ -99,5 +116,5 @@ def prepare_image_contrast_data(image_processed_batch, object_bbox_batch, object
         image_embeddings = clip_image_encoder.get_image_features(pixel_values=image_inputs['pixel_values'])
     except Exception as e:
         raise TypeError(f"CLIP image encoder failed: {e}. Ensure it's a compatible model.") from e
-    area = pool_objects_per_image(pixel_embeddings_batch, segmentation_batch, keep, keep_labels)
+    area = pool_objects_per_image(pixel_embeddings_batch, segmentation_batch, keep, keep_labels, shared2x2=shared2x2)
     return area.to(image_embeddings.dtype), image_embeddings

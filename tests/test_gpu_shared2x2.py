@@ -146,3 +146,32 @@ def test_rep4_rejects_unsupported_shapes():
     y4 = torch.zeros(64, 4, device=dev(), dtype=torch.int32)
     with pytest.raises(RuntimeError):
         ops.infonce_raw(x, t, y4, y4.float(), 10.0, True, False, "bf16", rep=4)
+
+
+def test_area_pooling_shared2x2():
+    """dataloader.py:286-304 on the decoder-tail output (decoder.py:113-114) against four accumulating pooling passes
+    over the half-resolution rows, forward and gradient w.r.t. the decoder output."""
+    import rangeclip_b200 as R
+    g = torch.Generator().manual_seed(21)
+    B, D, h, w = 3, 64, 12, 10
+    H, W = 2 * h, 2 * w
+    E = torch.randn(B, D, h, w, generator=g) * (0.5 + torch.rand(B, 1, h, w, generator=g))
+    seg = torch.randint(0, 7, (B, H // 3 + 1, W // 3 + 1), generator=g).repeat_interleave(3, 1).repeat_interleave(3, 2)[:, :H, :W].contiguous()
+    items, labels = [], []
+    for b in range(B):
+        for lab in torch.unique(seg[b]).tolist():
+            items.append(b); labels.append(lab)
+    items += [0, 1]; labels += [labels[0], 99]            # a duplicate and an absent label
+    Er = E.double().requires_grad_(True)
+    ref = O.area_pool_per_image(O.decoder_tail(Er, (H, W)), seg, items, labels)
+    up = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (ref * up).sum().backward()
+    Eg = E.to(dev()).requires_grad_(True)
+    out = R.pool_objects_per_image(Eg, seg.to(dev()), items, labels, differentiable=True, shared2x2=True)
+    (out * up.float().to(dev())).sum().backward()
+    assert maxrel(out.detach().cpu(), ref.detach()) < 1e-5
+    assert float(out[-1].abs().sum()) == 0.0
+    assert maxrel(Eg.grad.cpu(), Er.grad) < 1e-5
+    # the no-grad drop-in form returns the same values
+    out2 = R.pool_objects_per_image(E.to(dev()), seg.to(dev()), items, labels, shared2x2=True)
+    assert torch.equal(out2, out.detach())
