@@ -43,7 +43,8 @@ static_assert(kTStages >= 4, "a dX block keeps Kp/64 <= 4 slots of the text ring
 constexpr int kPBytes = 64 * 1024;
 constexpr int kTmemCols = 512;
 // Measured, not adopted: TMEM load of softmax step c+1 in flight while step c is computed (needs 128 softmax registers,
-// taken from the control warps): 2.62 ms against 2.49 ms -- the extra spills cost more than the hidden latency.
+// taken from the control warps): 2.62 ms against 2.49 ms; forward-only launches, which have the registers without
+// spilling, also lose (1.61 ms against 1.47 ms) -- the exposed TMEM latency is not what bounds the exp pass.
 #ifndef RC_SMX_DOUBLE_BUFFER
 #define RC_SMX_DOUBLE_BUFFER 0
 #endif
@@ -595,8 +596,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           }
         }
       };
-#if RC_SMX_DOUBLE_BUFFER
-      {   // the TMEM load of step c+1 is in flight while step c is computed (two 16-column register buffers)
+      if (RC_SMX_DOUBLE_BUFFER) {
+        // the TMEM load of step c+1 is in flight while step c is computed (two 16-column register buffers)
         uint32_t ra[16], rb[16];
         tmem_ld_32x16(trow, ra);
 #pragma unroll
@@ -612,18 +613,17 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
             smx_step(rb, c + 1);
           }
         }
-      }
-#else
+      } else {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (c * 16 < Kh) {
-          uint32_t r[16];
-          tmem_ld_32x16(trow + c * 16, r);
-          tmem_ld_wait();
-          smx_step(r, c);
+        for (int c = 0; c < 8; ++c) {
+          if (c * 16 < Kh) {
+            uint32_t r[16];
+            tmem_ld_32x16(trow + c * 16, r);
+            tmem_ld_wait();
+            smx_step(r, c);
+          }
         }
       }
-#endif
       tc_fence_before();
       if (warp == 4) RC_EV(lt, 11);    // exp pass done
       if (warp == 11) RC_EV(lt, 15);   // exp pass done (last softmax warp)
