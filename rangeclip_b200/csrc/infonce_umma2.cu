@@ -97,6 +97,25 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {     // one cloc
 #define RC_EV(iter, id)
 #endif
 
+// Measured, not adopted (RC_ROLE_WAIT): a whole role (eight warps) waits for one mbarrier phase with ONE polling warp and
+// the others blocked in a named barrier.  A polling warp spends ~12 issue slots per probe and the epilogue's probes are
+// a quarter of all instructions the SM issues (ncu source view), yet coupling the epilogue warps costs more than the
+// probes (2.65 ms against 2.52 ms) and coupling the softmax warps is within noise (2.49 against 2.52 ms).
+#ifndef RC_ROLE_WAIT
+#define RC_ROLE_WAIT 0      // bit 0: epilogue warps, bit 1: softmax warps
+#endif
+#define ROLE_WAIT_ON(poller, bar, par, tag, bar_id) do { if (poller) RC_WAIT(mbar_wait, bar, par, tag); named_bar_sync(bar_id, 256); } while (0)
+#if RC_ROLE_WAIT & 1
+#define ROLE_WAIT_EPI ROLE_WAIT_ON
+#else
+#define ROLE_WAIT_EPI(poller, bar, par, tag, bar_id) RC_WAIT(mbar_wait, bar, par, tag)
+#endif
+#if RC_ROLE_WAIT & 2
+#define ROLE_WAIT_SMX ROLE_WAIT_ON
+#else
+#define ROLE_WAIT_SMX(poller, bar, par, tag, bar_id) RC_WAIT(mbar_wait, bar, par, tag)
+#endif
+
 struct Params {
   long long* dbg;
   int B, D, K, Kp;
@@ -474,7 +493,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       for (int j = 0; j < 8; ++j) ss[j] = 0.f;
       for (int c = 0; c < n_dchunks; ++c, ++nit) {
         const int st = nit % kXStages;
-        RC_WAIT(mbar_wait, &bars->xf[st], (nit / kXStages) & 1, 15);
+        ROLE_WAIT_SMX(warp == 4, &bars->xf[st], (nit / kXStages) & 1, 15, 8);
         const uint8_t* base = smem + st * kStageBytes + (ng >> 3) * 8192 + nr * 128;
         const int ch = ng & 7;
 #pragma unroll
@@ -536,7 +555,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       if (!kBwd && pj + n_clusters < prm.n_pairs) norm_tile();
       const uint32_t sidx = kBwd ? 0u : (lt & 1u);
       const uint32_t trow = trow0 + sidx * 256;
-      RC_WAIT(mbar_wait, &bars->s_full[sidx], (kBwd ? lt : (lt >> 1)) & 1u, 8);
+      ROLE_WAIT_SMX(warp == 4, &bars->s_full[sidx], (kBwd ? lt : (lt >> 1)) & 1u, 8, 8);
       tc_fence_after();
       if (warp == 4) RC_EV(lt, 10);    // S(lt) complete (seen by the softmax warps)
       RC_T0(tsm);
@@ -697,7 +716,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           if (row == 0) mbar_arrive_expect_tx(&bars->sc_full[lt & 1], 64 * 4);   // the peer's 64 st.async land here
         }
         // the dX MMAs of the previous pair have finished reading P: store this pair's P
-        RC_WAIT(mbar_wait, &bars->p_empty, (lt & 1) ^ 1, 9);
+        ROLE_WAIT_SMX(warp == 4, &bars->p_empty, (lt & 1) ^ 1, 9, 8);
         if (warp == 4) RC_EV(lt, 12);  // P buffer free
         RC_T0(tst);
         const uint32_t rs2 = pack_bf16x2(rsv, rsv);
@@ -819,14 +838,14 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     fetch(0); fetch(1);
     uint32_t uc = 0, lt = 0;
     for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
-      RC_WAIT(mbar_wait, &bars->sc_full[lt & 1], (lt >> 1) & 1, 10);
+      ROLE_WAIT_EPI(warp == 12, &bars->sc_full[lt & 1], (lt >> 1) & 1, 10, 7);
       const uint32_t* sc = sc_s + (lt % kScaleBufs) * 128 + half * 64;
       for (int unit = 0; unit < units_per_pair; ++unit, ++uc) {
         const int ab = uc & 1;
         const int pxh = unit & 1;
         // where this unit's output goes (same cursor arithmetic as the prefetch, one unit behind)
         const int o_b = f_b, o_px = f_px, o_d = f_d;
-        RC_WAIT(mbar_wait, &bars->acc_full[ab], (uc >> 1) & 1, 11);
+        ROLE_WAIT_EPI(warp == 12, &bars->acc_full[ab], (uc >> 1) & 1, 11, 7);
         tc_fence_after();
         if (warp == 12) RC_EV(lt, 20 + unit * 2);      // accumulator of this unit complete
         RC_T0(tep);
