@@ -191,6 +191,10 @@ int rc_debug_set_timing_buffer(int64_t* dev_buf);
 int rc_debug_umma_gemm(const void* a_bf16, const void* b_bf16, int N, int Kd, int variant,
                        float* c, void* stream);
 
+/* Bring-up query: number of clusters of `cluster_size` CTAs (block size and dynamic shared memory as given) the device
+ * keeps resident at once (cudaOccupancyMaxActiveClusters); negative = rc_status. */
+int rc_debug_max_active_clusters(int cluster_size, int threads, int smem_bytes);
+
 /* CTA-pair (cta_group::2) variant of the bring-up GEMM: C[256][N] = A[256][Kd] B[N][Kd]^T, both K-major. */
 int rc_debug_umma_gemm_2sm(const void* a_bf16, const void* b_bf16, int N, int Kd, float* c, void* stream);
 

@@ -46,6 +46,7 @@ PROTOTYPES = {
     "rc_eval_hist": [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "rc_eval_fold": [_vp, _i32, _i32, _vp, _vp, _vp],
     "rc_debug_set_timing_buffer": [_vp],
+    "rc_debug_max_active_clusters": [_i32, _i32, _i32],
     "rc_debug_umma_gemm_2sm": [_vp, _vp, _i32, _i32, _vp, _vp],
     "rc_debug_umma_gemm": [_vp, _vp, _i32, _i32, _i32, _vp, _vp],
 }

@@ -852,10 +852,14 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t acc[32];
+          RC_T0(t3);
           tmem_ld_32x32(trow_acc + ab * 128 + c * 32, acc);
           tmem_ld_wait();
+          RC_TACC(3, t3);
           if (c == 1) { tc_fence_before(); arrive_leader_warp(&bars->acc_empty[ab]); }
+          RC_T0(t4);
           pair_swap(&xq[c][0]);             // -> own row, pixels [c*32, +32) in order
+          RC_TACC(4, t4);                   // first use of the prefetched x: exposed global-load latency shows here
           const uint4* scp = reinterpret_cast<const uint4*>(sc + pxh * 32 + c * 16);    // -cs2 of 16 pixel pairs
           uint32_t o[16];
 #pragma unroll
@@ -871,8 +875,10 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           }
           {
             // own row of the warp's [32 d][32 px] staging tile (64-byte swizzle), then one TMA store per warp
+            RC_T0(t5);
             if (lane == 0) tma_store_wait_read0();            // the previous store of this warp has read the buffer
             __syncwarp();
+            RC_TACC(5, t5);
             uint8_t* srow = stg + lane * 64;
             const int sw64 = (lane >> 1) & 3;
 #pragma unroll
@@ -885,8 +891,10 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
               tma_store_commit();
             }
           }
+          RC_T0(t6);
           if (c == 0) cursor_next();        // both chunks of the next unit are fetched relative to the advanced cursor
           fetch(c);
+          RC_TACC(6, t6);
         }
         RC_TACC(2, tep);
         if (warp == 12) RC_EV(lt, 21 + unit * 2);      // unit drained and stored

@@ -13,7 +13,7 @@ y = torch.randint(0, K, (B, H * W), device=dev, generator=g, dtype=torch.int32)
 w = torch.ones(B, H * W, device=dev)
 buf = torch.zeros(2, 128, device=dev, dtype=torch.int64)
 names = {0: {1: "empty(S)", 2: "empty(dX)"}, 1: {3: "s_empty", 4: "xfull(S)", 12: "tfull(S)", 5: "p_full", 6: "acc_empty", 7: "tfull(dX)"},
-         2: {8: "s_full", 9: "p_empty", 1: "softmax", 2: "p_store"}, 3: {10: "sc_full", 11: "acc_full", 2: "epi_compute", 3: "tmem_ld", 4: "x_wait", 5: "math+store", 6: "fetch_issue"}}
+         2: {8: "s_full", 9: "p_empty", 1: "softmax", 2: "p_store"}, 3: {10: "sc_full", 11: "acc_full", 2: "epi_compute", 3: "tmem_ld", 4: "x_wait+swap", 5: "store_buf_wait", 6: "cursor+fetch"}}
 roles = ["producer", "mma", "softmax", "epilogue"]
 for rep in range(2):
     _lib.lib().rc_debug_set_timing_buffer(buf[rep].data_ptr())
