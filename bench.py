@@ -197,6 +197,10 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner / debug output on stderr
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     c = CFG
     B, D, H, W, K = c["B"], c["D"], c["H"], c["W"], c["K"]
