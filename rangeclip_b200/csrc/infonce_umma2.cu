@@ -121,6 +121,7 @@ struct Params {
   int B, D, K, Kp;
   int64_t HW;
   int tiles_per_img, n_tiles, n_pairs;
+  uint32_t tpi_magic;       // floor(2^32 / tiles_per_img): tile / tiles_per_img as a multiply-high + one correction
   int ablate;               // bring-up only (RANGECLIP_B200_ABLATE): 1 no epilogue x loads, 2 no dX stores, 64 no row-norm reads, 128 no dX staging
   int store_g;              // 1: also write G = rs (P - sum onehot) (bf16 [B][HW][Kp]) for the dText GEMM
   int wide;                 // 1: rows of X / dX are 32-byte aligned (256-bit global accesses allowed)
@@ -138,6 +139,13 @@ struct Params {
   double* w_sum;
   double* dlogtau;
 };
+
+// tile / tiles_per_img without the ~20-instruction runtime division (exact for tile < 2^32: the estimate is low by at most 1)
+__device__ __forceinline__ int div_tiles(const Params& prm, int tile) {
+  int q = (int)__umulhi((uint32_t)tile, prm.tpi_magic);
+  if (tile - q * prm.tiles_per_img >= prm.tiles_per_img) ++q;
+  return q;
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -206,7 +214,7 @@ __device__ __forceinline__ float select16(const uint32_t (&r)[16], int i) {
 // tensor map (TMA loads return zeros)
 __device__ __forceinline__ void tile_coords(const Params& prm, int tile, int& b, int& px0) {
   if (tile < prm.n_tiles) {
-    b = tile / prm.tiles_per_img;
+    b = div_tiles(prm, tile);
     px0 = (tile - b * prm.tiles_per_img) * kTilePx;
   } else {
     b = prm.B;
@@ -463,7 +471,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       nx_inv_n = 0.f; nx_w = 0.f; nx_y = -1;
       const int t = 2 * pj + (int)rank;
       if (pj < prm.n_pairs && t < prm.n_tiles) {
-        const int tb = t / prm.tiles_per_img;
+        const int tb = div_tiles(prm, t);
         const int tpx = (t - tb * prm.tiles_per_img) * kTilePx + row;
         if (tpx < prm.HW) {
           const int64_t tm = (int64_t)tb * prm.HW + tpx;
@@ -535,7 +543,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
       const int tile = 2 * pj + (int)rank;
       const bool tile_ok = tile < prm.n_tiles;
-      const int b = tile_ok ? tile / prm.tiles_per_img : 0;
+      const int b = tile_ok ? div_tiles(prm, tile) : 0;
       const int px = tile_ok ? (tile - b * prm.tiles_per_img) * kTilePx + row : 0;
       const bool valid = tile_ok && px < prm.HW;
       // dText mode: the bulk store of the previous tile's G must have read the P buffer before anyone rewrites it
@@ -797,7 +805,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       f_n8 = 0; f_off = 0; f_b = prm.B; f_px = 0; f_d = 0;
       const int t = 2 * f_pj + half;
       if (f_pj < prm.n_pairs && t < prm.n_tiles) {
-        const int b = t / prm.tiles_per_img;
+        const int b = div_tiles(prm, t);
         const int px0 = (t - b * prm.tiles_per_img) * kTilePx + (f_unit & 1) * 64;
         const int d = (f_unit >> 1) * 256 + (int)rank * 128 + row;
         f_b = b; f_px = px0; f_d = d - lane;
@@ -965,6 +973,7 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   prm.tiles_per_img = (int)((HW + kTilePx - 1) / kTilePx);
   if ((int64_t)B * prm.tiles_per_img > 0x3fffffff) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: too many tiles");
   prm.n_tiles = B * prm.tiles_per_img;
+  prm.tpi_magic = prm.tiles_per_img == 1 ? 0xffffffffu : (uint32_t)(0x100000000ull / (uint64_t)prm.tiles_per_img);
   prm.n_pairs = (prm.n_tiles + 1) / 2;
   prm.x = reinterpret_cast<const __nv_bfloat16*>(xsrc);
   prm.dx = reinterpret_cast<__nv_bfloat16*>(dx);
