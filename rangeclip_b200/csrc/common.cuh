@@ -70,6 +70,30 @@ template <> struct ElemIO<__nv_bfloat16> {
   static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
+// Mixed-precision scalar arithmetic on the halves of a packed bf16x2 word (PTX fma/add .f32.bf16, SASS FHFMA.BF16 /
+// FHADD.BF16 with .H0/.H1 operand selectors): the bf16 operand is widened inside the instruction, so there is no unpack
+// instruction, and the result is the correctly rounded fp32 value -- bit-identical to unpack + FFMA / FADD.
+__device__ __forceinline__ float sqacc_bf16x2_lo(float acc, uint32_t u) {      // acc + lo(u)^2
+  float r;
+  asm("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %1; fma.rn.f32.bf16 %0, lo, lo, %2;}" : "=f"(r) : "r"(u), "f"(acc));
+  return r;
+}
+__device__ __forceinline__ float sqacc_bf16x2_hi(float acc, uint32_t u) {      // acc + hi(u)^2
+  float r;
+  asm("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %1; fma.rn.f32.bf16 %0, hi, hi, %2;}" : "=f"(r) : "r"(u), "f"(acc));
+  return r;
+}
+__device__ __forceinline__ float addacc_bf16x2_lo(float acc, uint32_t u) {     // acc + lo(u)
+  float r;
+  asm("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %1; add.rn.f32.bf16 %0, lo, %2;}" : "=f"(r) : "r"(u), "f"(acc));
+  return r;
+}
+__device__ __forceinline__ float addacc_bf16x2_hi(float acc, uint32_t u) {     // acc + hi(u)
+  float r;
+  asm("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %1; add.rn.f32.bf16 %0, hi, %2;}" : "=f"(r) : "r"(u), "f"(acc));
+  return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

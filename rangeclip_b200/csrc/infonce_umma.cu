@@ -77,6 +77,18 @@ rownorm_kernel(const T* __restrict__ x, int B, int D, int64_t HW, __nv_bfloat16*
     float ss[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) ss[j] = 0.f;
+    if (sizeof(T) == 2) {          // bf16 rows: nothing to round or copy, squares straight from the packed words
+#pragma unroll 8
+      for (int d = 0; d < D; ++d) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)d * HW));
+        const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ss[2 * j] = sqacc_bf16x2_lo(ss[2 * j], u[j]);
+          ss[2 * j + 1] = sqacc_bf16x2_hi(ss[2 * j + 1], u[j]);
+        }
+      }
+    } else
 #pragma unroll 4
     for (int d = 0; d < D; ++d) {
       float v[8];

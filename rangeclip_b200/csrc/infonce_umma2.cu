@@ -510,10 +510,9 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           const uint4 v = *reinterpret_cast<const uint4*>(base + rr * 2048 + ((ch ^ (rowd & 7)) << 4));
           const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float lo = __uint_as_float(u[j] << 16), hi = __uint_as_float(u[j] & 0xffff0000u);
-            ss[2 * j] = fmaf(lo, lo, ss[2 * j]);
-            ss[2 * j + 1] = fmaf(hi, hi, ss[2 * j + 1]);
+          for (int j = 0; j < 4; ++j) {       // FHFMA.BF16 on the word's halves: no unpack instructions
+            ss[2 * j] = sqacc_bf16x2_lo(ss[2 * j], u[j]);
+            ss[2 * j + 1] = sqacc_bf16x2_hi(ss[2 * j + 1], u[j]);
           }
         }
         __syncwarp();

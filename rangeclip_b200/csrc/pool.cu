@@ -109,6 +109,19 @@ pool_fwd_kernel(const T* __restrict__ x, int B, int D, int64_t HW, const int64_t
         float v[8];
         if (sizeof(T) == 2) {
           const uint32_t u[4] = {raw[q][0].x, raw[q][0].y, raw[q][0].z, raw[q][0].w};
+          if (!ri.mixed) {          // uniform lane: only the sum is needed -- two FHADD.BF16 chains on the packed words, no unpack
+            float sa = addacc_bf16x2_lo(0.f, u[0]), sb = addacc_bf16x2_hi(0.f, u[0]);
+#pragma unroll
+            for (int i = 1; i < 4; ++i) { sa = addacc_bf16x2_lo(sa, u[i]); sb = addacc_bf16x2_hi(sb, u[i]); }
+            float s = sa + sb;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              const float up = __shfl_down_sync(0xffffffffu, s, 1 << i);
+              if (ri.steps & (1u << i)) s += up;
+            }
+            if (ri.head) atomicAdd(&sum[(int64_t)ri.key * D + d], s);
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
         } else {
