@@ -583,7 +583,9 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         mx = fmaxf(mx, xch[(0 * 2 + (half ^ 1)) * 128 + row]);
         ml = mx * zl;
       }
-      // e = exp(z - m) for this half's columns; P stays in registers as packed bf16 until the P buffer is free
+      // e = exp(z - m) for this half's columns; P stays in registers as packed bf16 until the P buffer is free.
+      // (Measured, not adopted: the scale / sum / e*s arithmetic as packed fp32x2 -- FFMA2 / FADD2, 6 instead of 9
+      // issued instructions per two columns -- is 2.7 % slower, 2.57 against 2.50 ms.)
       uint32_t pk[64];
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
       float sy[R];
