@@ -6,6 +6,7 @@
 // a 16-byte coalesced load per lane, a lane-local sum and a warp-shuffle segmented reduction;
 // only run heads issue a (no-return) atomic add.
 #include "common.cuh"
+#include <type_traits>
 
 namespace rc {
 
@@ -58,6 +59,11 @@ __device__ __forceinline__ RunInfo pool_runs(const int (&slot)[8]) {
   return r;
 }
 
+// A warp task is TWO consecutive 256-pixel chunks of one image x 64 channels.  When both chunks carry the same slot
+// in every pixel position (consecutive image rows inside object masks: the common case) they are summed lane-locally
+// first and share ONE segmented reduction and ONE set of atomics per channel -- half the shuffles and half the
+// atomics per byte read, which is what bounded the bf16 kernel (8 atomics per 512 bytes).  Otherwise the two chunks
+// are processed one after the other.
 template <typename T>
 __global__ void __launch_bounds__(kPoolThreads, 4)
 pool_fwd_kernel(const T* __restrict__ x, int B, int D, int64_t HW, const int64_t* __restrict__ seg,
@@ -66,82 +72,119 @@ pool_fwd_kernel(const T* __restrict__ x, int B, int D, int64_t HW, const int64_t
   const int lane = threadIdx.x & 31;
   const int warps_per_block = kPoolThreads / 32;
   const int64_t chunks = (HW + kPoolPx - 1) / kPoolPx;
+  const int64_t cpairs = (chunks + 1) / 2;
   const int dgroups = (D + kPoolDGroup - 1) / kPoolDGroup;
-  const int64_t n_tasks = (int64_t)B * chunks * dgroups;
+  const int64_t n_tasks = (int64_t)B * cpairs * dgroups;
+  constexpr int kVec = sizeof(T) == 2 ? 1 : 2;          // 16-byte vectors per lane per channel (8 pixels)
+  constexpr int kLoads = sizeof(T) == 2 ? 8 : 4;        // (channel, chunk) rows whose loads are issued before any is consumed:
+                                                         // 4 KB in flight per warp for either dtype
   for (int64_t task = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < n_tasks;
        task += (int64_t)gridDim.x * warps_per_block) {
     const int dg = (int)(task % dgroups);
     const int64_t rest = task / dgroups;
-    const int64_t ch = rest % chunks;
-    const int b = (int)(rest / chunks);
-    const int64_t p0 = ch * kPoolPx + lane * 8;
-    int slot[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) slot[j] = pool_slot(seg + (int64_t)b * HW, lut, (int64_t)b * lut_ld, C, p0 + j, HW);
-    const RunInfo ri = pool_runs(slot);
-    if (dg == 0) {
-      if (ri.head) atomicAdd(&count[ri.key], ri.run_px);
-      if (ri.mixed) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (slot[j] >= 0) atomicAdd(&count[slot[j]], 1);
-      }
-    }
+    const int64_t cp = rest % cpairs;
+    const int b = (int)(rest / cpairs);
+    const int64_t pA = (2 * cp) * kPoolPx + lane * 8;
+    const int64_t pB = pA + kPoolPx;
+    const bool hasB = (2 * cp + 1) < chunks;
+    const int64_t* segb = seg + (int64_t)b * HW;
     const int d0 = dg * kPoolDGroup;
     const int d1 = min(D, d0 + kPoolDGroup);
-    const bool in_range = p0 < HW;   // HW % 8 == 0 on this path, so the lane's 8 px are all in or out
-    const T* src = x + ((int64_t)b * D + d0) * HW + p0;
-    constexpr int kBatch = sizeof(T) == 2 ? 8 : 4;      // channels whose loads are issued before any is consumed:
-                                                         // 4 KB in flight per warp for either dtype
-    for (int dbase = d0; dbase < d1; dbase += kBatch, src += (int64_t)kBatch * HW) {
-      // raw 16-byte vectors stay packed until they are consumed (bf16: one per channel, f32: two)
-      constexpr int kVec = sizeof(T) == 2 ? 1 : 2;
-      uint4 raw[kBatch][kVec];
+    // the lane's 8 pixels of one channel row as floats (raw 16-byte vectors stay packed until here)
+    auto unpack8 = [&](const uint4 (&raw)[kVec], float (&v)[8]) {
+      if (sizeof(T) == 2) {
+        const uint32_t u[4] = {raw[0].x, raw[0].y, raw[0].z, raw[0].w};
 #pragma unroll
-      for (int q = 0; q < kBatch; ++q)
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+      } else {
+        const uint4 a = raw[0], c = raw[kVec - 1];
+        v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+        v[4] = __uint_as_float(c.x); v[5] = __uint_as_float(c.y); v[6] = __uint_as_float(c.z); v[7] = __uint_as_float(c.w);
+      }
+    };
+    // their sum: bf16 words are added with two FHADD.BF16 chains, no unpack
+    auto lane_sum = [&](const uint4 (&raw)[kVec]) -> float {
+      if (sizeof(T) == 2) {
+        const uint32_t u[4] = {raw[0].x, raw[0].y, raw[0].z, raw[0].w};
+        float sa = addacc_bf16x2_lo(0.f, u[0]), sb = addacc_bf16x2_hi(0.f, u[0]);
 #pragma unroll
-        for (int h = 0; h < kVec; ++h)
-          raw[q][h] = (in_range && dbase + q < d1) ? __ldg(reinterpret_cast<const uint4*>(src + (int64_t)q * HW) + h)
-                                                   : make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int q = 0; q < kBatch; ++q) {
-        const int d = dbase + q;
-        if (d >= d1) break;
-        float v[8];
-        if (sizeof(T) == 2) {
-          const uint32_t u[4] = {raw[q][0].x, raw[q][0].y, raw[q][0].z, raw[q][0].w};
-          if (!ri.mixed) {          // uniform lane: only the sum is needed -- two FHADD.BF16 chains on the packed words, no unpack
-            float sa = addacc_bf16x2_lo(0.f, u[0]), sb = addacc_bf16x2_hi(0.f, u[0]);
-#pragma unroll
-            for (int i = 1; i < 4; ++i) { sa = addacc_bf16x2_lo(sa, u[i]); sb = addacc_bf16x2_hi(sb, u[i]); }
-            float s = sa + sb;
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              const float up = __shfl_down_sync(0xffffffffu, s, 1 << i);
-              if (ri.steps & (1u << i)) s += up;
-            }
-            if (ri.head) atomicAdd(&sum[(int64_t)ri.key * D + d], s);
-            continue;
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
-        } else {
-          const uint4 a = raw[q][0], c = raw[q][kVec - 1];
-          v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
-          v[4] = __uint_as_float(c.x); v[5] = __uint_as_float(c.y); v[6] = __uint_as_float(c.z); v[7] = __uint_as_float(c.w);
-        }
-        float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        for (int i = 1; i < 4; ++i) { sa = addacc_bf16x2_lo(sa, u[i]); sb = addacc_bf16x2_hi(sb, u[i]); }
+        return sa + sb;
+      }
+      float v[8];
+      unpack8(raw, v);
+      return ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    };
+    // one pass over the channel group for `rows` (1 or 2) chunks starting at pixel p0 that share `slot` / `ri`
+    auto process = [&](const int (&slot)[8], const RunInfo& ri, int64_t p0, auto rows_c) {
+      constexpr int rows = decltype(rows_c)::value;
+      if (dg == 0) {
+        if (ri.head) atomicAdd(&count[ri.key], ri.run_px * rows);
         if (ri.mixed) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) if (slot[j] >= 0) atomicAdd(&sum[(int64_t)slot[j] * D + d], v[j]);
-          s = 0.f;
+          for (int j = 0; j < 8; ++j) if (slot[j] >= 0) atomicAdd(&count[slot[j]], rows);
+        }
+      }
+      const bool in_range = p0 < HW;   // HW % 8 == 0 on this path, so the lane's 8 px are all in or out
+      const T* src = x + ((int64_t)b * D + d0) * HW + p0;
+      constexpr int cpb = kLoads / rows;   // channels per batch of loads
+      for (int dbase = d0; dbase < d1; dbase += cpb, src += (int64_t)cpb * HW) {
+        uint4 raw[kLoads][kVec];
+#pragma unroll
+        for (int q = 0; q < kLoads; ++q) {
+          const int dq = rows == 2 ? (q >> 1) : q;                  // channel of load slot q
+          const int64_t off = (int64_t)dq * HW + ((rows == 2 && (q & 1)) ? kPoolPx : 0);
+#pragma unroll
+          for (int h = 0; h < kVec; ++h)
+            raw[q][h] = (in_range && dbase + dq < d1 && p0 + (off - (int64_t)dq * HW) < HW)      // second chunk may end early
+                            ? __ldg(reinterpret_cast<const uint4*>(src + off) + h) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          const float up = __shfl_down_sync(0xffffffffu, s, 1 << i);
-          if (ri.steps & (1u << i)) s += up;
+        for (int q = 0; q < kLoads; ++q) {
+          if (rows == 2 && (q & 1)) continue;                       // consumed together with its even partner
+          const int d = dbase + (rows == 2 ? (q >> 1) : q);
+          if (d >= d1) break;
+          float sl = 0.f;
+          if (!ri.mixed) {
+            sl = lane_sum(raw[q]);
+            if (rows == 2) sl += lane_sum(raw[q | 1]);
+          } else {             // lane with several slots among its 8 pixels (mask borders): per-pixel atomics
+#pragma unroll
+            for (int rr = 0; rr < rows; ++rr) {
+              float v[8];
+              unpack8(raw[q | rr], v);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) if (slot[j] >= 0) atomicAdd(&sum[(int64_t)slot[j] * D + d], v[j]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const float up = __shfl_down_sync(0xffffffffu, sl, 1 << i);
+            if (ri.steps & (1u << i)) sl += up;
+          }
+          if (ri.head) atomicAdd(&sum[(int64_t)ri.key * D + d], sl);
         }
-        if (ri.head) atomicAdd(&sum[(int64_t)ri.key * D + d], s);
       }
+    };
+    int slot[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) slot[j] = pool_slot(segb, lut, (int64_t)b * lut_ld, C, pA + j, HW);
+    bool same = hasB;
+    if (hasB) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) same &= (pool_slot(segb, lut, (int64_t)b * lut_ld, C, pB + j, HW) == slot[j]);
+    }
+    const bool merged = __all_sync(0xffffffffu, same) != 0;
+    {
+      const RunInfo ri = pool_runs(slot);
+      if (merged) process(slot, ri, pA, std::integral_constant<int, 2>{});
+      else process(slot, ri, pA, std::integral_constant<int, 1>{});
+    }
+    if (hasB && !merged) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) slot[j] = pool_slot(segb, lut, (int64_t)b * lut_ld, C, pB + j, HW);
+      const RunInfo ri = pool_runs(slot);
+      process(slot, ri, pB, std::integral_constant<int, 1>{});
     }
   }
 }
@@ -262,7 +305,8 @@ extern "C" int rc_pool_fwd(const void* x, rc_dtype x_dtype, int B, int D, int64_
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = (HW % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   if (vec) {
-    const int64_t tasks = (int64_t)B * ((HW + rc::kPoolPx - 1) / rc::kPoolPx) * ((D + rc::kPoolDGroup - 1) / rc::kPoolDGroup);
+    const int64_t chunk_pairs = ((HW + rc::kPoolPx - 1) / rc::kPoolPx + 1) / 2;      // a warp task = two 256-pixel chunks
+    const int64_t tasks = (int64_t)B * chunk_pairs * ((D + rc::kPoolDGroup - 1) / rc::kPoolDGroup);
     const int64_t blocks = (tasks + 7) / 8;
     const int64_t cap = (int64_t)rc::num_sms() * 8;
     const int grid = (int)(blocks < cap ? blocks : cap);

@@ -211,6 +211,33 @@ def test_pooling_all_blocks(B, D, H, W, blk, dtype):
     assert float(out[-1].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("H,W,kind,dtype", [(3, 200, "rows", torch.bfloat16), (3, 200, "noise", torch.float32),
+                                            (5, 256, "rows", torch.float32), (4, 256, "unmapped", torch.bfloat16),
+                                            (2, 512, "halves", torch.bfloat16)])
+def test_pooling_chunk_pairs(H, W, kind, dtype):
+    """The forward kernel sums two consecutive 256-pixel chunks before the segmented reduction when their slots agree:
+    identical rows (merged), per-pixel noise (never merged), an odd / partial last chunk, unmapped labels next to the
+    end of the image (the second chunk must not be read past the tensor), two different halves of one wide row."""
+    import rangeclip_b200 as R
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    B, D = 2, 64
+    x = torch.randn(B, D, H, W, generator=g).to(dtype).float()
+    if kind == "rows":          # every image row has the same label pattern
+        seg = torch.randint(1, 5, (B, 1, W // 8), generator=g).repeat_interleave(8, 2).repeat(1, H, 1)
+    elif kind == "noise":
+        seg = torch.randint(1, 5, (B, H, W), generator=g)
+    elif kind == "unmapped":    # labels >= 7 have no slot: whole chunks of -1 at the end of the image
+        seg = torch.full((B, H, W), 9)
+        seg[:, :1] = torch.randint(1, 5, (B, 1, W), generator=g)
+    else:                       # left and right half of a 512-pixel row differ
+        seg = torch.cat([torch.full((B, H, W // 2), 1), torch.full((B, H, W // 2), 2)], dim=2)
+    items = [b for b in range(B) for _ in range(1, 5)]
+    labels = [lab for _ in range(B) for lab in range(1, 5)]
+    ref = O.area_pool_per_image(x.double(), seg, items, labels)
+    out = R.pool_objects_per_image(x.to(dev()).to(dtype), seg.to(dev()), items, labels)
+    assert maxrel(out.float().cpu(), ref) < (2e-6 if dtype == torch.float32 else 5e-3)
+
+
 # ------------------------------------------------------------------------------------------------
 # InfoNCE
 # ------------------------------------------------------------------------------------------------
