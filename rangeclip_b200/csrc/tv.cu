@@ -401,6 +401,45 @@ tv_fwd_bf16_walk_kernel(const __nv_bfloat16* __restrict__ x, int64_t planes, int
   }
 }
 
+// Rows too wide for a shared-memory tile (W > ~6000 f32 / ~12000 bf16 pixels): one thread per element, neighbours
+// straight from global memory (L1 / L2 provide the reuse).  Same arithmetic and sign(0) = 0 as the tiled kernels.
+template <typename T>
+__global__ void __launch_bounds__(kTvThreads)
+tv_fwd_direct_kernel(const T* __restrict__ x, int64_t planes, int H, int W, double* __restrict__ sums) {
+  const int64_t n = planes * (int64_t)H * W;
+  float sh = 0.f, sv = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % W);
+    const int h = (int)((i / W) % H);
+    const float a = ElemIO<T>::ld(x + i);
+    if (c + 1 < W) sh += fabsf(a - ElemIO<T>::ld(x + i + 1));
+    if (h + 1 < H) sv += fabsf(a - ElemIO<T>::ld(x + i + W));
+  }
+  double acc_h = warp_sum((double)sh), acc_v = warp_sum((double)sv);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sums[0], acc_h); atomicAdd(&sums[1], acc_v); }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTvThreads)
+tv_bwd_direct_kernel(const T* __restrict__ x, int64_t planes, int H, int W, const float* __restrict__ scale,
+                     T* __restrict__ dx, int accumulate, const float* __restrict__ dx_scale) {
+  const int64_t n = planes * (int64_t)H * W;
+  const float sh = scale[0], sv = scale[1];
+  const float ds = (dx_scale != nullptr) ? dx_scale[0] : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % W);
+    const int h = (int)((i / W) % H);
+    const float a = ElemIO<T>::ld(x + i);
+    float g = 0.f;
+    if (c + 1 < W) g += sh * sgnf(a - ElemIO<T>::ld(x + i + 1));
+    if (c >= 1) g -= sh * sgnf(ElemIO<T>::ld(x + i - 1) - a);
+    if (h + 1 < H) g += sv * sgnf(a - ElemIO<T>::ld(x + i + W));
+    if (h >= 1) g -= sv * sgnf(ElemIO<T>::ld(x + i - W) - a);
+    if (accumulate) g += ds * ElemIO<T>::ld(dx + i);
+    ElemIO<T>::st(dx + i, g);
+  }
+}
+
 // rows per tile: the 48 KB tile budget is in BYTES on the vector paths, so a bf16 tile has twice the rows of an f32
 // tile and a resident block keeps the same number of bytes in flight (what the HBM latency has to be covered with)
 static int tv_tile_rows(int H, int W, int halo, int elt_bytes = 4) {
@@ -419,7 +458,14 @@ extern "C" int rc_tv_fwd(const void* x, rc_dtype x_dtype, int64_t planes, int H,
   if (planes == 0) return RC_OK;
   const bool vec = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const int TH = rc::tv_tile_rows(H, W, 1, (vec && x_dtype != RC_F32) ? 2 : 4);
-  if (TH < 1) return rc::fail(RC_ERR_UNSUPPORTED, "rc_tv_fwd: W=%d too wide for the 48 KB tile", W);
+  if (TH < 1) {          // wider than a shared-memory tile: element-wise kernel
+    const int64_t n = planes * (int64_t)H * W;
+    const int64_t nb = (n + rc::kTvThreads - 1) / rc::kTvThreads, capd = (int64_t)rc::num_sms() * 16;
+    const int gridd = (int)(nb < capd ? nb : capd);
+    if (x_dtype == RC_F32) rc::tv_fwd_direct_kernel<float><<<gridd, rc::kTvThreads, 0, (cudaStream_t)stream>>>((const float*)x, planes, H, W, sums);
+    else rc::tv_fwd_direct_kernel<__nv_bfloat16><<<gridd, rc::kTvThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, planes, H, W, sums);
+    return rc::check_launch("rc_tv_fwd(direct)");
+  }
   const int64_t n_tiles = planes * ((H + TH - 1) / TH);
   const int64_t cap = (int64_t)rc::num_sms() * 8;
   const int grid = (int)(n_tiles < cap ? n_tiles : cap);
@@ -445,7 +491,17 @@ extern "C" int rc_tv_bwd(const void* x, rc_dtype x_dtype, int64_t planes, int H,
   if (planes == 0) return RC_OK;
   const bool vec = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
   const int TH = rc::tv_tile_rows(H, W, 2, (vec && x_dtype != RC_F32) ? 2 : 4);
-  if (TH < 1) return rc::fail(RC_ERR_UNSUPPORTED, "rc_tv_bwd: W=%d too wide for the 48 KB tile", W);
+  if (TH < 1) {          // wider than a shared-memory tile: element-wise kernel
+    const int64_t n = planes * (int64_t)H * W;
+    const int64_t nb = (n + rc::kTvThreads - 1) / rc::kTvThreads, capd = (int64_t)rc::num_sms() * 16;
+    const int gridd = (int)(nb < capd ? nb : capd);
+    if (x_dtype == RC_F32)
+      rc::tv_bwd_direct_kernel<float><<<gridd, rc::kTvThreads, 0, (cudaStream_t)stream>>>((const float*)x, planes, H, W, scale, (float*)dx, accumulate, dx_scale);
+    else
+      rc::tv_bwd_direct_kernel<__nv_bfloat16><<<gridd, rc::kTvThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, planes, H, W, scale,
+                                                                                                  (__nv_bfloat16*)dx, accumulate, dx_scale);
+    return rc::check_launch("rc_tv_bwd(direct)");
+  }
   const int64_t n_tiles = planes * ((H + TH - 1) / TH);
   const int64_t cap = (int64_t)rc::num_sms() * 8;
   const int grid = (int)(n_tiles < cap ? n_tiles : cap);

@@ -154,7 +154,8 @@ def test_eval_hist_full_size_properties():
 @pytest.mark.parametrize("shape,dtype", [((2, 8, 16, 16), torch.float32), ((1, 3, 37, 50), torch.float32),
                                           ((2, 16, 64, 256), torch.bfloat16), ((1, 4, 5, 8), torch.float32),
                                           ((3, 2, 130, 24), torch.float32), ((1, 3, 64, 1024), torch.bfloat16),
-                                          ((1, 2, 40, 512), torch.float32)])
+                                          ((1, 2, 40, 512), torch.float32), ((1, 1, 3, 6000), torch.float32),
+                                          ((1, 2, 2, 16384), torch.bfloat16)])
 def test_smoothness_fwd_bwd(shape, dtype):
     from rangeclip_b200 import ops
     g = torch.Generator().manual_seed(7)
