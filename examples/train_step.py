@@ -51,8 +51,10 @@ def main():
             emb, _, _ = net(depth, skip_tail=args.shared2x2)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        # W_image keeps the reference default: without area embeddings the image term is `dummy * exp(log_tau_image) * 0`
+        # (model.py:325-326), which still gives log_temperature_image a (zero) gradient -- DDP wants one for every parameter
         loss_fn = R.compute_loss_shared2x2 if args.shared2x2 else R.compute_loss
-        loss, info = loss_fn(model, emb, seg, text, sets, None, None, W_text=1.0, W_image=0.0, W_smooth=2e2, k_distractors=192,
+        loss, info = loss_fn(model, emb, seg, text, sets, None, None, W_text=1.0, W_image=0.5, W_smooth=2e2, k_distractors=192,
                              pct_medium=0.0, pct_hard=0.75, pct_rand=0.25)
         torch.cuda.synchronize()
         t2 = time.perf_counter()
