@@ -192,6 +192,34 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
           tmem_ld_32x32(trow + sbuf * kNB + c * 32, r);
           tmem_ld_wait();
           const int nvalid = prm.K - k0;
+          if (KT == 1) {
+            // arg-max: a branch-free running maximum with static register indices (3 instructions per column) is
+            // cheaper than the bitmask + candidate loop at every position of the scan
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = __uint_as_float(r[i]);
+              const bool better = (i < nvalid) && (v > bv[0]);       // strict: the smaller index wins ties
+              bv[0] = better ? v : bv[0];
+              bi[0] = better ? k0 + i : bi[0];
+            }
+            continue;
+          }
+          if (nb == 0 && c == 0) {
+            // The first 32 columns of a tile all beat the empty list: the candidate loop below would run 32 rounds of
+            // dynamic register selection (a third of all its rounds in a K = 1024 scan).  Insert them with static
+            // register indices instead: no bit scan, no select tree, no branch.
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) topk_insert<KT>(bv, bi, prm.k, __uint_as_float(r[i]), k0 + i);
+            if (KT > 0) {
+              kth = bv[KT - 1];
+            } else {
+              kth = bv[0];
+#pragma unroll
+              for (int j = 1; j < kMaxK; ++j) if (j < prm.k) kth = bv[j];
+            }
+            continue;
+          }
           // Per thread only ~k ln(K/k) values ever enter the top-k, but with 32 pixels per warp some lane qualifies at
           // almost every column.  So: a branch-free candidate bitmask first (four independent chains), then a short
           // per-thread loop over the set bits -- the warp iterates max-over-lanes(#candidates), not once per column.
