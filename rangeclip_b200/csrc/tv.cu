@@ -4,6 +4,7 @@
 // forward and one read of X (+ one read-modify-write of dX) for the backward.  sign(0) = 0 as
 // torch.sgn (the nearest-upsampled decoder makes half of all differences exactly 0).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace rc {
 
@@ -440,14 +441,37 @@ tv_bwd_direct_kernel(const T* __restrict__ x, int64_t planes, int H, int W, cons
   }
 }
 
-// rows per tile: the 48 KB tile budget is in BYTES on the vector paths, so a bf16 tile has twice the rows of an f32
-// tile and a resident block keeps the same number of bytes in flight (what the HBM latency has to be covered with)
-static int tv_tile_rows(int H, int W, int halo, int elt_bytes = 4) {
-  int r = (kTvSmemFloats * 4 / elt_bytes) / W - halo;
-  const int cap = elt_bytes == 2 ? 64 : 32;
+// Rows per tile.  The tile budget is in BYTES on the vector paths.  f32: 32-row tiles (33 KB, six resident blocks).  bf16
+// is instruction-heavier per byte and does better with FEWER, LARGER tiles (each tile costs two block-wide barriers and
+// a drained load pipeline): measured at 256 x 256 planes, forward 0.77 -> 0.87 of HBM with 128-row tiles (66 KB, opt-in
+// shared memory, three resident blocks), backward 0.82 -> 0.85 and fused backward 0.85 -> 0.865 with 86-row tiles
+// (48 KB); 64 KB+ tiles lose again on the backward.  Rows are balanced over the tiles of a plane (a plane is never
+// split into two large tiles and a sliver).  RANGECLIP_B200_TV_ROWS / _TV_SMEM_KB override cap and budget (bring-up).
+static int tv_tile_budget_bytes(bool vec, int dflt) {
+  int bytes = dflt;
+  if (vec) if (const char* e = getenv("RANGECLIP_B200_TV_SMEM_KB")) { const int v = atoi(e); if (v >= 8 && v <= 224) bytes = v * 1024; }
+  return bytes;
+}
+static int tv_tile_rows(int H, int W, int halo, int elt_bytes, bool vec, bool fwd) {
+  const bool big = vec && elt_bytes == 2;
+  const int budget = tv_tile_budget_bytes(vec, (big && fwd) ? 66 * 1024 + 512 : kTvSmemFloats * 4);
+  int r = (budget / elt_bytes) / W - halo;
+  int cap = big ? (fwd ? 128 : 94) : 32;
+  if (const char* e = getenv("RANGECLIP_B200_TV_ROWS")) { const int v = atoi(e); if (v > 0) cap = v; }
   if (r > cap) r = cap;
   if (r > H) r = H;
+  if (r >= 1) {                        // balance: same number of tiles, equal heights
+    const int n = (H + r - 1) / r;
+    r = (H + n - 1) / n;
+  }
   return r;
+}
+template <typename K>
+static int tv_allow_smem(K kernel, size_t bytes, const char* what) {
+  if (bytes <= 48 * 1024) return RC_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return fail(RC_ERR_CUDA, "%s: smem opt-in: %s", what, cudaGetErrorString(e));
+  return RC_OK;
 }
 
 }  // namespace rc
@@ -457,7 +481,7 @@ extern "C" int rc_tv_fwd(const void* x, rc_dtype x_dtype, int64_t planes, int H,
   RC_REQUIRE(planes >= 0 && H >= 1 && W >= 1, "rc_tv_fwd: bad shape");
   if (planes == 0) return RC_OK;
   const bool vec = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  const int TH = rc::tv_tile_rows(H, W, 1, (vec && x_dtype != RC_F32) ? 2 : 4);
+  const int TH = rc::tv_tile_rows(H, W, 1, (vec && x_dtype != RC_F32) ? 2 : 4, vec, true);
   if (TH < 1) {          // wider than a shared-memory tile: element-wise kernel
     const int64_t n = planes * (int64_t)H * W;
     const int64_t nb = (n + rc::kTvThreads - 1) / rc::kTvThreads, capd = (int64_t)rc::num_sms() * 16;
@@ -473,6 +497,8 @@ extern "C" int rc_tv_fwd(const void* x, rc_dtype x_dtype, int64_t planes, int H,
   cudaStream_t s = (cudaStream_t)stream;
   if (vec) {
     const size_t vsmem = (size_t)(TH + 1) * W * (x_dtype == RC_F32 ? 4 : 2);
+    int rcode = x_dtype == RC_F32 ? rc::tv_allow_smem(rc::tv_fwd_vec_kernel<float>, vsmem, "rc_tv_fwd") : rc::tv_allow_smem(rc::tv_fwd_bf16_walk_kernel, vsmem, "rc_tv_fwd");
+    if (rcode) return rcode;
     if (x_dtype == RC_F32)
       rc::tv_fwd_vec_kernel<float><<<grid, rc::kTvThreads, vsmem, s>>>((const float*)x, planes, H, W, TH, sums);
     else
@@ -490,7 +516,7 @@ extern "C" int rc_tv_bwd(const void* x, rc_dtype x_dtype, int64_t planes, int H,
   RC_REQUIRE(planes >= 0 && H >= 1 && W >= 1, "rc_tv_bwd: bad shape");
   if (planes == 0) return RC_OK;
   const bool vec = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
-  const int TH = rc::tv_tile_rows(H, W, 2, (vec && x_dtype != RC_F32) ? 2 : 4);
+  const int TH = rc::tv_tile_rows(H, W, 2, (vec && x_dtype != RC_F32) ? 2 : 4, vec, false);
   if (TH < 1) {          // wider than a shared-memory tile: element-wise kernel
     const int64_t n = planes * (int64_t)H * W;
     const int64_t nb = (n + rc::kTvThreads - 1) / rc::kTvThreads, capd = (int64_t)rc::num_sms() * 16;
@@ -509,6 +535,8 @@ extern "C" int rc_tv_bwd(const void* x, rc_dtype x_dtype, int64_t planes, int H,
   cudaStream_t s = (cudaStream_t)stream;
   if (vec) {
     const size_t vsmem = (size_t)(TH + 2) * W * (x_dtype == RC_F32 ? 4 : 2);
+    int rcode = x_dtype == RC_F32 ? rc::tv_allow_smem(rc::tv_bwd_vec_kernel<float>, vsmem, "rc_tv_bwd") : rc::tv_allow_smem(rc::tv_bwd_bf16x2_kernel, vsmem, "rc_tv_bwd");
+    if (rcode) return rcode;
     if (x_dtype == RC_F32)
       rc::tv_bwd_vec_kernel<float><<<grid, rc::kTvThreads, vsmem, s>>>((const float*)x, planes, H, W, TH, scale, (float*)dx, accumulate, dx_scale);
     else
