@@ -351,8 +351,9 @@ def run_gpu(args):
 
         def eval_batch(gb):
             nb_ = B if gb < n_batches - 1 else 8
-            topk = ops.eval_topk(x[:nb_], text_e, idx_map, 5, "bf16", t_bf16=tbe)
-            acc_m.update(torch.roll(seg_e[:nb_], gb, dims=2), topk, batch_index=gb)
+            # one fused kernel per batch: top-5 on the tensor cores, ids -> class histograms in registers (no id tensor)
+            acc_m.update_from_embeddings(x[:nb_], text_e, idx_map, torch.roll(seg_e[:nb_], gb, dims=2), 5, batch_index=gb,
+                                         t_bf16=tbe, want_ids=False)
             return nb_ * HW
 
         eval_batch(0); acc_m = MetricAccumulator(E, cmap, device=device)
@@ -374,7 +375,7 @@ def run_gpu(args):
               "total_pixels_counted": fin["total_pixels"], "pixel_accuracy_t1": fin["pixel_accuracy_t1"],
               "tensor_tflops": 2.0 * Ce * D * tot_pix / (float(tm) * 1e-3) / 1e12,
               "note": "78x64+8 synthetic maps (one resident embedding batch re-used with rolled label maps), "
-                      "tcgen05 top-5 + histogram kernels per batch, one int64 all-reduce at the end"}
+                      "fused tcgen05 top-5 + equivalence-aware histograms (one kernel per batch) + fold, one int64 all-reduce at the end"}
         assert fin["total_pixels"] == tot_pix
 
     # ---- the same loss when X comes out of the reference decoder (nearest x2 of a 128x128 map, quirk Q8):

@@ -172,6 +172,14 @@ int rc_eval_topk_f32(const float* x, int B, int D, int64_t HW, int64_t ld_b, con
 int rc_eval_topk_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
                       const void* t_bf16, int K, const int64_t* index_map, int k, int64_t* out,
                       void* workspace, int64_t workspace_bytes, void* stream);
+/* Fused form: the top-k ids of a pixel go from the scan registers straight into the five class histograms and the
+ * three counters of rc_eval_hist (same per-pixel function, warp-aggregated atomics); `out` is optional (NULL when only
+ * the metrics are wanted).  hist / counters are ADDED to. */
+int rc_eval_topk_hist_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
+                           const void* t_bf16, int K, const int64_t* index_map, int k, int64_t* out /*nullable*/,
+                           const int64_t* gt /*[B*HW]*/, const uint8_t* E, const int64_t* cmap, int C,
+                           int64_t* hist /*[5][C]*/, int64_t* counters /*[3]*/,
+                           void* workspace, int64_t workspace_bytes, void* stream);
 int rc_eval_hist(const int64_t* gt, const int64_t* topk, int B, int64_t HW, int k,
                  const uint8_t* E, const int64_t* cmap, int C,
                  int64_t* hist /*[5][C]*/, int64_t* counters /*[3]*/, void* stream);

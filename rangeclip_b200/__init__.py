@@ -14,7 +14,7 @@ The CUDA code lives in ``csrc/`` and is reached through the C ABI in ``include/r
 from .losses import (DepthCLIPLossMixin, build_contrast_indices, compute_loss, compute_loss_shared2x2,
                      image_contrastive_loss, text_contrastive_loss)
 from .pooling import masked_average_pooling, pool_objects_per_image, prepare_image_contrast_data
-from .evaluation import (MetricAccumulator, build_reduced_candidates, finalize_metrics, predict,
+from .evaluation import (MetricAccumulator, build_reduced_candidates, finalize_metrics, predict, predict_and_accumulate,
                          predict_from_embeddings, validate_model)
 from . import ops
 
@@ -22,5 +22,5 @@ __all__ = [
     "DepthCLIPLossMixin", "build_contrast_indices", "compute_loss", "compute_loss_shared2x2", "image_contrastive_loss",
     "text_contrastive_loss", "masked_average_pooling", "pool_objects_per_image",
     "prepare_image_contrast_data", "MetricAccumulator", "build_reduced_candidates", "predict",
-    "predict_from_embeddings", "finalize_metrics", "validate_model", "ops",
+    "predict_from_embeddings", "predict_and_accumulate", "finalize_metrics", "validate_model", "ops",
 ]

@@ -3,18 +3,9 @@
 // (and the top-1 accuracy lines of evaluation.py:94-104) with one pass over (gt, top-k) that
 // builds five per-class histograms with warp-aggregated atomics.  Integer only -> bit-exact.
 #include "common.cuh"
+#include "eval_metrics.cuh"
 
 namespace rc {
-
-// one atomic per distinct bin per warp (labels are spatially coherent, so usually 1-2 per warp)
-template <typename CounterT>
-__device__ __forceinline__ void warp_agg_add(CounterT* bins, int bin, bool pred) {
-  const unsigned active = __ballot_sync(0xffffffffu, pred);
-  if (!pred) return;
-  const unsigned peers = __match_any_sync(active, bin);
-  const int leader = __ffs(peers) - 1;
-  if ((int)(threadIdx.x & 31) == leader) atomicAdd(&bins[bin], (CounterT)__popc(peers));
-}
 
 template <bool kSmem>
 __global__ void __launch_bounds__(256)
@@ -37,29 +28,14 @@ eval_hist_kernel(const int64_t* __restrict__ gt, const int64_t* __restrict__ top
     bool top1_same = false, orc_same = false;
     if (ok) {
       const int64_t b = i / HW, p = i - b * HW;
-      const int64_t g = gt[i];
       const int64_t* tk = topk + (b * k) * HW + p;
-      const int64_t t1 = tk[0];
-      ok = (uint64_t)g < (uint64_t)C && (uint64_t)t1 < (uint64_t)C;
+      const PixelMetric m = pixel_metric(gt[i], k, [&](int j) { return tk[(int64_t)j * HW]; }, E, cmap, C);
+      ok = m.ok;
       if (ok) {
-        ge = (int)cmap[g];
-        p1 = (int)cmap[t1];
-        const uint8_t* Erow = E + (int64_t)g * C;
-        bool any_eq = Erow[t1] != 0;
-        bool hit = (p1 == ge);
-        c1 += any_eq ? 1u : 0u;
-        for (int j = 1; j < k; ++j) {
-          const int64_t tj = tk[(int64_t)j * HW];
-          if ((uint64_t)tj < (uint64_t)C) {
-            any_eq |= Erow[tj] != 0;
-            hit |= ((int)cmap[tj] == ge);
-          }
-        }
-        ck += any_eq ? 1u : 0u;
+        ge = m.ge; p1 = m.p1; orc = m.orc; top1_same = m.top1_same; orc_same = m.orc_same;
+        c1 += m.any_eq1 ? 1u : 0u;
+        ck += m.any_eqk ? 1u : 0u;
         tot += 1u;
-        orc = hit ? ge : (int)t1;   // validate.py:122 -- oracle_pred starts from RAW top-1 ids
-        top1_same = (p1 == ge);
-        orc_same = (orc == ge);
       }
     }
     if (kSmem) {

@@ -9,6 +9,7 @@
 // positive constant), so no normalisation pass over X is needed; ties go to the smaller text index.
 #include "common.cuh"
 #include "umma.cuh"
+#include "eval_metrics.cuh"
 #include <float.h>
 
 namespace rc {
@@ -43,7 +44,14 @@ struct Params {
   int64_t HW;
   int tiles_per_img, n_tiles, n_blocks;
   const int64_t* index_map;
-  int64_t* out;
+  int64_t* out;                          // nullable when only the metrics are wanted
+  // fused metrics (validate.py:88-139), all nullable together: the histograms of this batch are added to `hist`
+  const int64_t* gt;                     // [B*HW] ground-truth ids
+  const uint8_t* E;                      // [C][C] equivalence matrix
+  const int64_t* cmap;                   // [C] id -> equivalence class
+  int C;
+  unsigned long long* hist;              // [5][C]
+  unsigned long long* counters;          // [3]
 };
 
 // KT > 0: compile-time k (the insertion network has exactly k stages); KT == 0: run-time k <= kMaxK
@@ -172,6 +180,7 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
     const int row = quarter * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + half * 128;
     uint32_t nbc = 0;
+    unsigned int m_c1 = 0, m_ck = 0, m_tot = 0;      // fused metrics: per-thread counters
     for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
       const int b = tile / prm.tiles_per_img;
       const int px = (tile - b * prm.tiles_per_img) * kTilePx + row;
@@ -274,10 +283,48 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
         tc_fence_before();
         mbar_arrive(&bars->s_empty[sbuf]);
       }
-      if (half == 0 && px < prm.HW) {
+      if (half == 0) {               // warps 4-7: lane = pixel, 32 consecutive pixels of one image per warp
+        const bool inb = px < prm.HW;
+        int64_t ids[kMaxK];
 #pragma unroll
-        for (int j = 0; j < kMaxK; ++j)
-          if (j < prm.k) prm.out[((int64_t)b * prm.k + j) * prm.HW + px] = bi[j] >= 0 ? __ldg(prm.index_map + bi[j]) : -1;
+        for (int j = 0; j < kMaxK; ++j) ids[j] = (inb && j < prm.k && bi[j] >= 0) ? __ldg(prm.index_map + bi[j]) : -1;
+        if (inb && prm.out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < kMaxK; ++j)
+            if (j < prm.k) prm.out[((int64_t)b * prm.k + j) * prm.HW + px] = ids[j];
+        }
+        if (prm.hist != nullptr) {
+          // Fused metrics: the pixel's top-k ids never leave the registers on their way into the five class histograms
+          // (warp-aggregated atomics: one per distinct class per warp); same per-pixel function as rc_eval_hist.
+          PixelMetric m;
+          m.ok = false; m.ge = 0; m.p1 = 0; m.orc = 0; m.top1_same = false; m.orc_same = false; m.any_eq1 = false; m.any_eqk = false;
+          if (inb) {
+            m = pixel_metric(__ldg(prm.gt + (int64_t)b * prm.HW + px), prm.k, [&](int j) {
+              int64_t v = ids[0];
+#pragma unroll
+              for (int q = 1; q < kMaxK; ++q) v = (j == q) ? ids[q] : v;
+              return v;
+            }, prm.E, prm.cmap, prm.C);
+          }
+          if (m.ok) { m_c1 += m.any_eq1 ? 1u : 0u; m_ck += m.any_eqk ? 1u : 0u; m_tot += 1u; }
+          warp_agg_add(prm.hist + 0 * (int64_t)prm.C, m.ge, m.ok);
+          warp_agg_add(prm.hist + 1 * (int64_t)prm.C, m.p1, m.ok);
+          warp_agg_add(prm.hist + 2 * (int64_t)prm.C, m.ge, m.ok && m.top1_same);
+          warp_agg_add(prm.hist + 3 * (int64_t)prm.C, m.orc, m.ok);
+          warp_agg_add(prm.hist + 4 * (int64_t)prm.C, m.ge, m.ok && m.orc_same);
+        }
+      }
+    }
+    if (half == 0 && prm.hist != nullptr) {
+      for (int o = 16; o > 0; o >>= 1) {
+        m_c1 += __shfl_xor_sync(0xffffffffu, m_c1, o);
+        m_ck += __shfl_xor_sync(0xffffffffu, m_ck, o);
+        m_tot += __shfl_xor_sync(0xffffffffu, m_tot, o);
+      }
+      if (lane == 0) {
+        if (m_c1) atomicAdd(&prm.counters[0], (unsigned long long)m_c1);
+        if (m_ck) atomicAdd(&prm.counters[1], (unsigned long long)m_ck);
+        if (m_tot) atomicAdd(&prm.counters[2], (unsigned long long)m_tot);
       }
     }
   }
@@ -289,27 +336,29 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
 }  // namespace topk
 }  // namespace rc
 
-extern "C" int rc_eval_topk_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16, int K,
-                                 const int64_t* index_map, int k, int64_t* out, void* workspace, int64_t workspace_bytes,
-                                 void* stream) {
+static int eval_topk_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16, int K,
+                               const int64_t* index_map, int k, int64_t* out, const int64_t* gt, const uint8_t* E,
+                               const int64_t* cmap, int C, int64_t* hist, int64_t* counters, void* workspace,
+                               int64_t workspace_bytes, void* stream, const char* who) {
   using namespace rc;
-  RC_REQUIRE(x && t_bf16 && index_map && out, "rc_eval_topk_bf16: null pointer");
-  RC_REQUIRE(B >= 0 && HW >= 0 && K >= 1 && k >= 1 && k <= topk::kMaxK && k <= K, "rc_eval_topk_bf16: bad shape (k=%d K=%d)", k, K);
-  if (D < 64 || D > 512 || D % 64 != 0) return fail(RC_ERR_UNSUPPORTED, "rc_eval_topk_bf16: D=%d must be a multiple of 64 and <= 512", D);
-  if (HW % 8 != 0) return fail(RC_ERR_UNSUPPORTED, "rc_eval_topk_bf16: HW=%lld must be a multiple of 8", (long long)HW);
+  RC_REQUIRE(x && t_bf16 && index_map && (out || hist), "%s: null pointer", who);
+  RC_REQUIRE(B >= 0 && HW >= 0 && K >= 1 && k >= 1 && k <= topk::kMaxK && k <= K, "%s: bad shape (k=%d K=%d)", who, k, K);
+  if (hist != nullptr) RC_REQUIRE(gt && E && cmap && counters && C >= 1, "%s: the fused metrics need gt, E, cmap, counters and C >= 1", who);
+  if (D < 64 || D > 512 || D % 64 != 0) return fail(RC_ERR_UNSUPPORTED, "%s: D=%d must be a multiple of 64 and <= 512", who, D);
+  if (HW % 8 != 0) return fail(RC_ERR_UNSUPPORTED, "%s: HW=%lld must be a multiple of 8", who, (long long)HW);
   RC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(t_bf16) & 15) == 0,
-             "rc_eval_topk_bf16: x and t must be 16-byte aligned");
+             "%s: x and t must be 16-byte aligned", who);
   if (B == 0 || HW == 0) return RC_OK;
   int dev = 0, major = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-  if (major != 10) return fail(RC_ERR_NO_DEVICE, "rc_eval_topk_bf16: needs an sm_100 device");
+  if (major != 10) return fail(RC_ERR_NO_DEVICE, "%s: needs an sm_100 device", who);
   cudaStream_t s = (cudaStream_t)stream;
   const void* xsrc = x;
   int rcode;
   if (x_dtype == RC_F32) {
     const int64_t M = (int64_t)B * HW;
-    RC_REQUIRE(workspace && workspace_bytes >= rc_infonce_workspace_bytes(B, D, HW, K, RC_F32), "rc_eval_topk_bf16: workspace too small for the bf16 copy");
+    RC_REQUIRE(workspace && workspace_bytes >= rc_infonce_workspace_bytes(B, D, HW, K, RC_F32), "%s: workspace too small for the bf16 copy", who);
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
     float* inv_norm = reinterpret_cast<float*>(ws);
     __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws + ((M * 4 + 255) / 256) * 256);
@@ -330,19 +379,38 @@ extern "C" int rc_eval_topk_bf16(const void* x, rc_dtype x_dtype, int B, int D, 
   topk::Params prm;
   prm.B = B; prm.D = D; prm.K = K; prm.k = k; prm.HW = HW;
   prm.tiles_per_img = (int)((HW + topk::kTilePx - 1) / topk::kTilePx);
-  if ((int64_t)B * prm.tiles_per_img > 0x7fffffff) return fail(RC_ERR_UNSUPPORTED, "rc_eval_topk_bf16: too many tiles");
+  if ((int64_t)B * prm.tiles_per_img > 0x7fffffff) return fail(RC_ERR_UNSUPPORTED, "%s: too many tiles", who);
   prm.n_tiles = B * prm.tiles_per_img;
   prm.n_blocks = (K + topk::kNB - 1) / topk::kNB;
   prm.index_map = index_map; prm.out = out;
+  prm.gt = gt; prm.E = E; prm.cmap = cmap; prm.C = C;
+  prm.hist = reinterpret_cast<unsigned long long*>(hist); prm.counters = reinterpret_cast<unsigned long long*>(counters);
   const int grid = prm.n_tiles < num_sms() ? prm.n_tiles : num_sms();
   auto launch = [&](auto kernel) -> int {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, topk::kSmemBytes);
-    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_eval_topk_bf16: smem opt-in: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "%s: smem opt-in: %s", who, cudaGetErrorString(e));
     kernel<<<grid, topk::kThreads, topk::kSmemBytes, s>>>(m_x, m_t, prm);
-    return check_launch("rc_eval_topk_bf16");
+    return check_launch(who);
   };
   // the two k the reference evaluates with (validate.py: top-1 and top-5) get fixed-size insertion networks
   if (k == 1) return launch(topk::eval_topk_umma_kernel<1>);
   if (k == 5) return launch(topk::eval_topk_umma_kernel<5>);
   return launch(topk::eval_topk_umma_kernel<0>);
+}
+
+extern "C" int rc_eval_topk_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16, int K,
+                                 const int64_t* index_map, int k, int64_t* out, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  RC_REQUIRE(out, "rc_eval_topk_bf16: null pointer");
+  return eval_topk_bf16_impl(x, x_dtype, B, D, HW, t_bf16, K, index_map, k, out, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
+                             workspace, workspace_bytes, stream, "rc_eval_topk_bf16");
+}
+
+extern "C" int rc_eval_topk_hist_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16, int K,
+                                      const int64_t* index_map, int k, int64_t* out, const int64_t* gt, const uint8_t* E,
+                                      const int64_t* cmap, int C, int64_t* hist, int64_t* counters, void* workspace,
+                                      int64_t workspace_bytes, void* stream) {
+  RC_REQUIRE(hist, "rc_eval_topk_hist_bf16: null pointer");
+  return eval_topk_bf16_impl(x, x_dtype, B, D, HW, t_bf16, K, index_map, k, out, gt, E, cmap, C, hist, counters, workspace,
+                             workspace_bytes, stream, "rc_eval_topk_hist_bf16");
 }

@@ -40,6 +40,20 @@ def predict_from_embeddings(pixel_embeddings, candidate_text_embeddings, segment
     return topk, F.normalize(pixel_embeddings, dim=1)
 
 
+def predict_and_accumulate(pixel_embeddings, candidate_text_embeddings, segmentation, accumulator, num_negatives=300, top_k=5,
+                           batch_index=None, want_ids=True):
+    """``predict_from_embeddings`` + ``MetricAccumulator.update`` as one fused kernel per batch: same reduced candidate
+    set (same ``random.sample`` draw, Q6), same ids, same histograms -- the ids never make the round trip through HBM
+    between the two steps.  Returns (topk ids or None, L2-normalised embeddings)."""
+    total = candidate_text_embeddings.shape[0]
+    reduced = build_reduced_candidates(segmentation, total, num_negatives)
+    index_tensor = torch.tensor(reduced, device=pixel_embeddings.device)
+    t_norm, _, _ = ops.text_prepare(candidate_text_embeddings, index_tensor, want_f32=True)
+    ids = accumulator.update_from_embeddings(pixel_embeddings, t_norm, index_tensor, segmentation, min(top_k, len(reduced)),
+                                             batch_index=batch_index, want_ids=want_ids)
+    return ids, F.normalize(pixel_embeddings, dim=1)
+
+
 def predict(self, depth_maps, candidate_text_embeddings, segmentation, num_negatives=300, top_k=5):
     """Drop-in for ``DepthUNet.predict`` (model.py:119-175): backbone in PyTorch, tail on the kernels."""
     self.eval()
@@ -73,6 +87,18 @@ class MetricAccumulator:
         ops.eval_hist(segmentation, pred_topk, self.E, self.cmap, self._hist, self.counters)
         ops.eval_fold(self._hist, self.n_batches if batch_index is None else batch_index, self.acc, self.first_seen)
         self.n_batches += 1
+
+    def update_from_embeddings(self, pixel_embeddings: torch.Tensor, t_norm: torch.Tensor, index_tensor: torch.Tensor,
+                               segmentation: torch.Tensor, top_k: int = 5, batch_index: Optional[int] = None,
+                               t_bf16=None, want_ids: bool = True):
+        """One validation batch straight from the pixel embeddings: ONE kernel does the top-k over the text rows and the
+        metric histograms (rc_eval_topk_hist_bf16); the ids are returned only if ``want_ids``."""
+        self._hist.zero_()
+        ids = ops.eval_topk_hist(pixel_embeddings, t_norm, index_tensor, top_k, segmentation, self.E, self.cmap, self._hist,
+                                 self.counters, t_bf16=t_bf16, want_ids=want_ids)
+        ops.eval_fold(self._hist, self.n_batches if batch_index is None else batch_index, self.acc, self.first_seen)
+        self.n_batches += 1
+        return ids
 
     def state(self) -> Dict[str, torch.Tensor]:
         return dict(acc=self.acc, counters=self.counters, first_seen=self.first_seen)

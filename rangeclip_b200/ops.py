@@ -434,6 +434,40 @@ def eval_topk(x: torch.Tensor, t_norm: torch.Tensor, index_map: torch.Tensor, k:
     return out
 
 
+def eval_topk_hist(x: torch.Tensor, t_norm: torch.Tensor, index_map: torch.Tensor, k: int, gt: torch.Tensor,
+                   E_u8: torch.Tensor, cmap: torch.Tensor, hist: torch.Tensor, counters: torch.Tensor, t_bf16=None,
+                   want_ids: bool = True):
+    """Fused evaluation batch (model.py:164-173 + validate.py:88-139): top-k on the tensor cores with the five class
+    histograms and three counters built from the ids while they are still in registers (added to ``hist`` /
+    ``counters``, int64).  Returns the ids [B,k,H,W] when ``want_ids`` (the drop-in ``predict`` needs them), else None.
+    Tensor-core path only (D % 64 == 0, D <= 512, HW % 8 == 0)."""
+    _need_cuda(x, t_norm, index_map, gt, E_u8, cmap, hist, counters)
+    x, B, D, HW = _emb3(x)
+    if not topk_bf16_supported(D, HW):
+        raise RuntimeError(f"eval_topk_hist: the fused kernel does not cover D={D}, HW={HW}; use eval_topk + eval_hist")
+    K = t_norm.shape[0]
+    k = min(k, K)
+    C = cmap.numel()
+    gt = gt.reshape(-1).to(torch.int64).contiguous()
+    if gt.numel() != B * HW:
+        raise RuntimeError("eval_topk_hist: gt must have one entry per pixel")
+    if hist.dtype != torch.int64 or counters.dtype != torch.int64 or tuple(hist.shape) != (5, C) or counters.numel() != 3:
+        raise RuntimeError("eval_topk_hist: hist must be int64 [5, C] and counters int64 [3]")
+    out = torch.empty((B, k) + tuple(x.shape[2:]), device=x.device, dtype=torch.int64) if want_ids else None
+    index_map = index_map.to(torch.int64).contiguous()
+    tb = t_bf16 if t_bf16 is not None else text_to_bf16(t_norm)[0]
+    L = _lib.lib()
+    xdt = _dt(x)
+    ws, ws_bytes = None, 0
+    if xdt == RC_F32:
+        ws_bytes = int(L.rc_infonce_workspace_bytes(B, D, HW, K, xdt))
+        ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+    check(L.rc_eval_topk_hist_bf16(_p(x), xdt, B, D, HW, _p(tb), K, _p(index_map), k, _p(out), _p(gt), _p(E_u8.contiguous()),
+                                   _p(cmap.to(torch.int64).contiguous()), C, _p(hist), _p(counters), _p(ws), ws_bytes,
+                                   _stream(x)), "rc_eval_topk_hist_bf16")
+    return out
+
+
 def eval_hist(gt: torch.Tensor, topk: torch.Tensor, E_u8: torch.Tensor, cmap: torch.Tensor,
               hist: Optional[torch.Tensor] = None, counters: Optional[torch.Tensor] = None):
     """One batch of validate.py:88-139 as five class histograms + three counters (int64, added to)."""

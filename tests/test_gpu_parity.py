@@ -533,3 +533,41 @@ def test_scale_in_place(dtype, n, offset, scale):
     _lib.check(_lib.lib().rc_scale(x.data_ptr(), _dt(x), n, s.data_ptr(), torch.cuda.current_stream().cuda_stream), "rc_scale")
     assert torch.equal(x, ref)
     assert torch.equal(base[offset + n:], pristine[offset + n:]) and torch.equal(base[:offset], pristine[:offset])
+
+
+@pytest.mark.parametrize("B,D,H,W,C,k,xdtype", [(2, 512, 16, 16, 1024, 5, torch.bfloat16), (3, 128, 8, 24, 300, 5, torch.bfloat16),
+                                                 (1, 256, 20, 20, 64, 1, torch.float32), (2, 64, 5, 8, 33, 3, torch.bfloat16)])
+def test_fused_topk_histograms_bit_exact(B, D, H, W, C, k, xdtype):
+    """rc_eval_topk_hist_bf16 (ids -> histograms inside the top-k kernel) against the two-kernel path on the same inputs:
+    ids, five class histograms and three counters are identical; the accumulator built from either gives the same
+    finalised metrics.  Non-transitive equivalences (a~b, b~c, a!~c) and ids outside the reduced candidate set included."""
+    import rangeclip_b200 as R
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(B * 7 + D + C + k)
+    eq = {i: {i} for i in range(C)}
+    for a, b in [(3, 7), (7, 11), (11, 2), (20, 21), (21, 22), (5, 30), (0, 9), (31, 1)]:
+        eq[a].add(b); eq[b].add(a)
+    E = torch.tensor(O.build_equivalence_tensor(eq, C)); cmap = torch.tensor(O.build_equivalence_class_map(E.numpy()))
+    text = torch.nn.functional.normalize(torch.randn(C, D, generator=g), dim=1)
+    seg = torch.randint(0, C, (B, H // 4 + 1, W // 4 + 1), generator=g).repeat_interleave(4, 1).repeat_interleave(4, 2)[:, :H, :W].contiguous()
+    x = (text[seg].permute(0, 3, 1, 2) + 0.4 * torch.randn(B, D, H, W, generator=g)).to(xdtype)
+    reduced = torch.arange(0, C, 2) if C > 64 else torch.arange(C)          # half of the vocabulary: some gt ids are not candidates
+    t_red = text[reduced]
+    xd, sd, td, rd = x.to(dev()), seg.to(dev()), t_red.to(dev()), reduced.to(dev())
+    ids = ops.eval_topk(xd, td, rd, k, "bf16")
+    hist2 = torch.zeros(5, C, device=dev(), dtype=torch.int64); cnt2 = torch.zeros(3, device=dev(), dtype=torch.int64)
+    ops.eval_hist(sd, ids, E.to(dev()).to(torch.uint8), cmap.to(dev()), hist2, cnt2)
+    hist1 = torch.zeros_like(hist2); cnt1 = torch.zeros_like(cnt2)
+    ids1 = ops.eval_topk_hist(xd, td, rd, k, sd, E.to(dev()).to(torch.uint8), cmap.to(dev()), hist1, cnt1)
+    assert torch.equal(ids1, ids)
+    assert torch.equal(hist1, hist2) and torch.equal(cnt1, cnt2)
+    assert int(cnt1[2]) == B * H * W
+    hist0 = torch.zeros_like(hist2); cnt0 = torch.zeros_like(cnt2)
+    assert ops.eval_topk_hist(xd, td, rd, k, sd, E.to(dev()).to(torch.uint8), cmap.to(dev()), hist0, cnt0, want_ids=False) is None
+    assert torch.equal(hist0, hist2) and torch.equal(cnt0, cnt2)
+    a1 = R.MetricAccumulator(E, cmap, device=dev()); a2 = R.MetricAccumulator(E, cmap, device=dev())
+    a1.update_from_embeddings(xd, td, rd, sd, k)
+    a2.update(sd, ids)
+    f1, f2 = a1.finalize(sd), a2.finalize(sd)
+    for key in ("mIoU_t1", "mIoU_tk", "pixel_accuracy_t1", "pixel_accuracy_tk", "intersection_top1", "union_topk"):
+        assert f1[key] == f2[key], key
