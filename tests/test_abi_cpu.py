@@ -44,6 +44,33 @@ def test_ops_refuse_cpu_tensors():
                       torch.eye(3, dtype=torch.uint8), torch.arange(3))
 
 
+def test_shared_embedding_and_fused_eval_entry_points_validate_on_cpu():
+    """The round's added entry points fail loudly without a GPU and reject malformed arguments before any launch."""
+    import rangeclip_b200 as R
+    from rangeclip_b200 import _lib, ops
+    L = _lib.lib()
+    assert L.rc_infonce_bf16_rep4(None, _lib.RC_BF16, 1, 512, 64, None, None, 4, None, None, 1.0, None, None, None, None, None,
+                                  None, None, None, None, 0, 0, None) == -1
+    assert L.rc_eval_topk_hist_bf16(None, _lib.RC_BF16, 1, 512, 64, None, 4, None, 1, None, None, None, None, 4, None, None,
+                                    None, 0, None) == -1
+    assert L.rc_debug_max_active_clusters(0, 640, 1024) == -1            # bad cluster size
+    with pytest.raises(RuntimeError):                                      # CPU tensors
+        ops.infonce_raw(torch.zeros(1, 256, 2, 4), torch.zeros(3, 256), torch.zeros(8, 4, dtype=torch.int32), torch.zeros(8, 4),
+                        10.0, True, False, "bf16", rep=4)
+    with pytest.raises(RuntimeError):
+        ops.eval_topk_hist(torch.zeros(1, 64, 2, 4), torch.zeros(3, 64), torch.arange(3), 1, torch.zeros(1, 2, 4, dtype=torch.long),
+                           torch.eye(3, dtype=torch.uint8), torch.arange(3), torch.zeros(5, 3, dtype=torch.long),
+                           torch.zeros(3, dtype=torch.long))
+
+    class M:
+        log_temperature_text = torch.tensor(0.0)
+        log_temperature_image = torch.tensor(0.0)
+    with pytest.raises(RuntimeError):                                      # targets must be twice the embedding resolution
+        R.compute_loss_shared2x2(M(), torch.zeros(1, 256, 4, 4), torch.zeros(1, 9, 8, dtype=torch.long), torch.zeros(5, 256),
+                                 {"medium": {}, "hard": {}}, None, None)
+    assert R.losses.group_2x2(torch.arange(16).view(1, 4, 4)).tolist() == [[[0, 1, 4, 5], [2, 3, 6, 7], [8, 9, 12, 13], [10, 11, 14, 15]]]
+
+
 @pytest.mark.parametrize("case", ["dict", "list", "noimg", "medium"])
 def test_contrast_set_builder_matches_reference(golden_dir, case):
     from rangeclip_b200 import build_contrast_indices
