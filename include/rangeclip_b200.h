@@ -87,6 +87,15 @@ int rc_infonce_f32(const float* x, int B, int D, int64_t HW, int64_t ld_b,
  * shared memory: a bf16 x then needs no pre-pass at all.  D = 128 / 384 run the single-CTA kernel
  * (pre-pass + fused kernel).                                                                      */
 #define RC_INFONCE_PREPASS_DONE 1
+/* More than 256 candidates (e.g. the area-image loss at thousands of objects): split the candidate rows into launches of
+ * <= 256 (D = 256 / 512, no dt).  y is then the target index RELATIVE to the launch's first row and may fall outside
+ * [0, K); ignored rows are encoded by w = 0 only.
+ *   RC_INFONCE_KEEP_WEIGHT  a row whose target is outside this launch keeps its weight (its one-hot term is dropped);
+ *                           round 1 = forward launches with this flag: lse per block, loss_sum = sum w lse_blk - sum_{y in blk} w z_y
+ *   RC_INFONCE_LSE_GIVEN    `lse` is an INPUT: the row's logsumexp over all candidates (logsumexp of the per-block values);
+ *                           round 2 = backward launches with both flags: dx and dlogtau of each block add up to the full gradient */
+#define RC_INFONCE_KEEP_WEIGHT 2
+#define RC_INFONCE_LSE_GIVEN 4
 int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
                     const void* t_bf16, const void* tt_bf16, int K,
                     const int32_t* y, const float* w, float inv_tau,

@@ -796,6 +796,13 @@ static int infonce_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, int6
   // its bf16 copy).
   const char* impl = getenv("RANGECLIP_B200_INFONCE");
   const bool use_pair = (rep != 1 || !(impl != nullptr && impl[0] == '1')) && infonce_pair_supported(D);
+  const int keep_w = (flags & RC_INFONCE_KEEP_WEIGHT) ? 1 : 0;
+  const float* lse_in = (flags & RC_INFONCE_LSE_GIVEN) ? lse : nullptr;
+  if (keep_w || lse_in) {
+    if (!use_pair || rep != 1 || dt != nullptr)
+      return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: the K-blocked flags need D = 256 or 512, one target per row and no dText");
+    RC_REQUIRE(!(flags & RC_INFONCE_LSE_GIVEN) || lse != nullptr, "rc_infonce_bf16: RC_INFONCE_LSE_GIVEN needs lse");
+  }
   if (rep != 1) {
     if (!use_pair) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16_rep4: D=%d must be 256 or 512", D);
     RC_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
@@ -815,13 +822,13 @@ static int infonce_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, int6
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
     void* g = ws + ((base + 255) / 256) * 256;
     if ((rcode = launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
-                                     loss_sum, w_sum, dlogtau, g, rep, s))) return rcode;
+                                     loss_sum, w_sum, dlogtau, g, rep, 0, nullptr, s))) return rcode;
     return launch_infonce_dt(g, xsrc, B, D, HW, K, dt, s);
   }
   {
     if (use_pair)
       return launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
-                                 loss_sum, w_sum, dlogtau, nullptr, rep, s);
+                                 loss_sum, w_sum, dlogtau, nullptr, rep, keep_w, lse_in, s);
   }
   const int Kp = (K + 63) / 64 * 64;
   CUtensorMap m_xs, m_t, m_tt, m_xe, m_dx;

@@ -129,6 +129,12 @@ struct Params {
   const __nv_bfloat16* x;
   __nv_bfloat16* dx;
   const float* inv_norm;
+  // K-blocked use (more than 256 candidates, e.g. the area-image loss at thousands of objects): the candidates are split
+  // into launches of <= 256 rows.  keep_w: a target outside this launch's rows keeps its weight (only the one-hot term is
+  // dropped).  lse_in: the row's logsumexp over ALL candidates, from a first round of forward launches; the softmax of
+  // this block is then exp(z - lse_in) instead of exp(z - m) / (block sum).
+  int keep_w;
+  const float* lse_in;
   const int32_t* y;
   const float* w;
   float inv_tau;
@@ -225,7 +231,8 @@ __device__ __forceinline__ void tile_coords(const Params& prm, int tile, int& b,
 // R = targets per embedding row: 1 = one pixel per row (y, w are [B*HW]); 4 = every row stands for the four pixels of a
 // 2x2 block that share one embedding (decoder.py:113 nearest x2): y, w are [B*HW][4], the loss of the row is
 // sum_j w_j (lse - z[y_j]) and dX is the gradient with respect to the shared embedding (the sum over the block).
-template <bool kBwd, int R>
+// kKB: K-blocked launches (Params::keep_w / lse_in); a template flag so that the headline instantiation carries none of it
+template <bool kBwd, int R, bool kKB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW], box (64 px, 64 d, 1)
                          const __grid_constant__ CUtensorMap map_t,     // T [Kp][D],    box (64 d, Kp/2 rows)
@@ -551,7 +558,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       const int64_t m = (int64_t)b * prm.HW + px;
       const bool px_ok = nx_inv_n != 0.f;
       const int yi = nx_y;
-      const float wi = (R == 1 && yi >= 0) ? nx_w : 0.f;
+      const float wi = (R == 1 && (yi >= 0 || (kKB && prm.keep_w))) ? nx_w : 0.f;
       load_pixel_scalars(pj + n_clusters);
       float* xch = xch_base + (lt & 1) * (4 * 2 * 128);      // double-buffered: one named barrier per tile suffices
       const float inv_n = px_ok ? inv_n_next : 0.f;
@@ -690,6 +697,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       sum += xch[(1 * 2 + (half ^ 1)) * 128 + row];
       sez += xch[(2 * 2 + (half ^ 1)) * 128 + row];
       tz += xch[(3 * 2 + (half ^ 1)) * 128 + row];
+      if (kKB && prm.lse_in != nullptr && valid) sum = fast_exp2(fmaf(__ldg(prm.lse_in + m), kLog2e, -ml));   // 1 / sum = exp(m - lse)
       float lse = 0.f;
       if (half == 0) {
         lse = (ml + __log2f(sum)) * kLn2;
@@ -774,7 +782,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
             tma_store_commit();
           }
         }
-        if (half == 0 && valid && prm.lse) prm.lse[m] = lse;      // after the hand-off: nothing waits behind this store
+        if (half == 0 && valid && prm.lse && !(kKB && prm.lse_in != nullptr)) prm.lse[m] = lse;      // after the hand-off: nothing waits behind this store
         if (pj + n_clusters < prm.n_pairs) norm_tile();
         if (warp == 4) RC_EV(lt, 14);  // row norms of the next tile done
       }
@@ -935,7 +943,7 @@ bool infonce_pair_supported(int D) { return D == 256 || D == 512; }
 int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const void* tt_bf16, int B, int D, int64_t HW, int K,
                         const float* inv_norm, const int32_t* y, const float* w, float inv_tau, const float* grad_scale,
                         const double* w_sum_in, float* lse, double* loss_sum, double* w_sum, double* dlogtau, void* g_out,
-                        int rep, cudaStream_t s) {
+                        int rep, int keep_w, const float* lse_in, cudaStream_t s) {
   using namespace pair;
   const bool bwd = dx != nullptr;
   const int Kp = (K + 63) / 64 * 64;
@@ -984,6 +992,7 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   prm.wide = (HW % 16 == 0) && (reinterpret_cast<uintptr_t>(xsrc) % 32 == 0) && (reinterpret_cast<uintptr_t>(dx) % 32 == 0);
   prm.inv_norm = inv_norm; prm.y = y; prm.w = w; prm.inv_tau = inv_tau; prm.grad_scale = grad_scale;
   prm.w_sum_in = w_sum_in; prm.lse = lse; prm.loss_sum = loss_sum; prm.w_sum = w_sum; prm.dlogtau = dlogtau;
+  prm.keep_w = keep_w; prm.lse_in = lse_in;
   int n_clusters = num_sms() / 2;
   if (n_clusters > prm.n_pairs) n_clusters = prm.n_pairs;
   const int grid = 2 * n_clusters;
@@ -993,8 +1002,9 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
     kernel<<<grid, kThreads, kSmemBytes, s>>>(m_xs, m_t, m_tt, m_dx, m_g, prm);
     return check_launch("rc_infonce_bf16(pair)");
   };
-  if (rep == 4) return bwd ? launch(infonce_umma_pair_kernel<true, 4>) : launch(infonce_umma_pair_kernel<false, 4>);
-  return bwd ? launch(infonce_umma_pair_kernel<true, 1>) : launch(infonce_umma_pair_kernel<false, 1>);
+  if (rep == 4) return bwd ? launch(infonce_umma_pair_kernel<true, 4, false>) : launch(infonce_umma_pair_kernel<false, 4, false>);
+  if (keep_w || lse_in != nullptr) return bwd ? launch(infonce_umma_pair_kernel<true, 1, true>) : launch(infonce_umma_pair_kernel<false, 1, true>);
+  return bwd ? launch(infonce_umma_pair_kernel<true, 1, false>) : launch(infonce_umma_pair_kernel<false, 1, false>);
 }
 
 }  // namespace rc

@@ -123,11 +123,28 @@ def group_2x2(t: torch.Tensor) -> torch.Tensor:
     return t.reshape(B, H // 2, 2, W // 2, 2).permute(0, 1, 3, 2, 4).reshape(B, (H // 2) * (W // 2), 4).contiguous()
 
 
-def image_contrastive_loss(area_embeddings, image_embeddings, log_temperature_image, precision="fp32"):
+def image_contrastive_loss(area_embeddings, image_embeddings, log_temperature_image, precision="auto"):
     """Area-image InfoNCE of model.py:304-321: rows = pooled area embeddings, candidates = CLIP
     crop embeddings, positives on the diagonal.  n is at most a few thousand, so the rows are
-    transposed to the kernels' [D][n] layout first (n*D elements; plumbing)."""
+    transposed to the kernels' [D][n] layout first (n*D elements; plumbing).
+
+    ``precision``: "fp32" = CUDA-core kernel (1e-5 path; what the reference's n <= batch size needs -- the call is
+    launch-bound there); "bf16" = tensor cores with the candidates in blocks of 256 (``ops.infonce_kblocked``; the
+    fp32 kernel takes 9 ms at n = 4096); "auto" = bf16 from n = 512 when the shape allows it (D in (256, 512), n % 8 == 0,
+    frozen image embeddings)."""
     n, D = area_embeddings.shape
+    blocked_ok = ops.kblocked_supported(D, n) and not image_embeddings.requires_grad
+    if precision == "auto":
+        precision = "bf16" if (blocked_ok and n >= 512) else "fp32"
+    if precision == "bf16":
+        if not blocked_ok:
+            raise RuntimeError(f"image_contrastive_loss: the tensor-core path needs D in (256, 512), n % 8 == 0 and frozen "
+                               f"image embeddings; got n={n}, D={D}")
+        x = area_embeddings.float().t().contiguous().view(1, D, n, 1)
+        t_norm, _, _ = ops.text_prepare(image_embeddings, None, want_f32=True)
+        y = torch.arange(n, device=x.device, dtype=torch.int32)
+        w = torch.ones(n, device=x.device, dtype=torch.float32)
+        return ops.infonce_kblocked(x, t_norm, log_temperature_image, y, w)
     x = area_embeddings.float().t().contiguous().view(1, D, n, 1)
     if image_embeddings.requires_grad:
         t_norm = torch.nn.functional.normalize(image_embeddings.float(), dim=1)

@@ -252,6 +252,92 @@ class _PixelLosses(torch.autograd.Function):
         return gx, gt, gl, None, None, None
 
 
+RC_INFONCE_KEEP_WEIGHT, RC_INFONCE_LSE_GIVEN = 2, 4
+
+
+def kblocked_supported(D: int, HW: int) -> bool:
+    return D in (256, 512) and HW % 8 == 0 and HW > 0
+
+
+def infonce_kblocked_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch.Tensor, inv_tau: float,
+                         need_dx: bool, block: int = 256):
+    """InfoNCE against MORE than 256 candidates on the tensor cores (model.py:304-321 at thousands of objects): the
+    candidate rows are split into launches of <= 256.  Round 1: forward launches give the per-block logsumexp; their
+    logsumexp is the row's lse over all candidates.  Round 2: fwd+bwd launches with that lse given produce per-block dx /
+    dlogtau that add up to the full gradient.  Returns dict(loss, lse, dx, dlogtau, w_sum); bf16 operands, fp32 sums."""
+    _need_cuda(x, t_norm, y, w)
+    x, B, D, HW = _emb3(x)
+    if not kblocked_supported(D, HW):
+        raise RuntimeError(f"infonce_kblocked: needs D in (256, 512) and HW % 8 == 0; got D={D}, HW={HW}")
+    K = t_norm.shape[0]
+    M = B * HW
+    dev = x.device
+    y = y.reshape(-1).to(torch.int32)
+    w = (w.reshape(-1).to(torch.float32) * (y >= 0)).contiguous()        # ignored rows: weight 0 (targets may leave the block)
+    L = _lib.lib()
+    st = _stream(x)
+    xdt = _dt(x)
+    ws_bytes = int(L.rc_infonce_workspace_bytes(B, D, HW, block, xdt))
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    check(L.rc_infonce_prepass(_p(x), xdt, B, D, HW, _p(ws), ws_bytes, st), "rc_infonce_prepass")    # once for all launches
+    starts = list(range(0, K, block))
+    nb = len(starts)
+    texts = [text_to_bf16(t_norm[s0:s0 + block]) for s0 in starts]
+    ys = [(y - s0).contiguous() for s0 in starts]
+    lse_blk = torch.empty(nb, M, device=dev, dtype=torch.float32)
+    acc = torch.zeros(nb, 4, device=dev, dtype=torch.float64)             # per block: loss_sum, w_sum, dlogtau, w_sum_in
+    wsum = w.double().sum()
+    acc[:, 3] = wsum
+    for i, s0 in enumerate(starts):
+        Kb = min(block, K - s0)
+        check(L.rc_infonce_bf16(_p(x), xdt, B, D, HW, _p(texts[i][0]), _p(texts[i][1]), Kb, _p(ys[i]), _p(w), float(inv_tau),
+                                lse_blk[i].data_ptr(), acc[i, 0:].data_ptr(), acc[i, 1:].data_ptr(), None, None, None, None, None,
+                                _p(ws), ws_bytes, 1 | RC_INFONCE_KEEP_WEIGHT, st), "rc_infonce_bf16(K block, forward)")
+    lse = torch.logsumexp(lse_blk, dim=0)
+    # sum_p w z[p, y_p] from the blocks that own the targets: loss_sum_b = sum_p w lse_b - sum_{y in b} w z_y
+    wz = ((lse_blk.double() * w.double()).sum(dim=1) - acc[:, 0]).sum()
+    loss = torch.where(wsum > 0, ((lse.double() * w.double()).sum() - wz) / wsum.clamp_min(1e-300), torch.zeros_like(wsum))
+    dx = dlogtau = None
+    if need_dx:
+        dxb = torch.empty(B, D, HW, device=dev, dtype=torch.bfloat16)     # the tensor-core kernel always writes bf16
+        dx = torch.zeros(B, D, HW, device=dev, dtype=torch.float32)
+        acc2 = torch.zeros(nb, 4, device=dev, dtype=torch.float64)
+        acc2[:, 3] = wsum
+        for i, s0 in enumerate(starts):
+            Kb = min(block, K - s0)
+            check(L.rc_infonce_bf16(_p(x), xdt, B, D, HW, _p(texts[i][0]), _p(texts[i][1]), Kb, _p(ys[i]), _p(w), float(inv_tau),
+                                    _p(lse), acc2[i, 0:].data_ptr(), acc2[i, 1:].data_ptr(), acc2[i, 3:].data_ptr(), None, _p(dxb),
+                                    None, acc2[i, 2:].data_ptr(), _p(ws), ws_bytes,
+                                    1 | RC_INFONCE_KEEP_WEIGHT | RC_INFONCE_LSE_GIVEN, st), "rc_infonce_bf16(K block, backward)")
+            dx += dxb
+        dlogtau = acc2[:, 2].sum()
+        dx = dx.view(x.shape).to(x.dtype)
+    return dict(loss=loss, lse=lse, dx=dx, dlogtau=dlogtau, w_sum=wsum)
+
+
+class _InfoNCEKBlocked(torch.autograd.Function):
+    """Autograd wrapper of ``infonce_kblocked_raw`` (gradients for x and log_tau; the candidate rows are constants)."""
+
+    @staticmethod
+    def forward(ctx, x, t_norm, log_tau, y, w):
+        need = x.requires_grad or log_tau.requires_grad
+        inv_tau = float(torch.exp(-log_tau.detach().float()))
+        r = infonce_kblocked_raw(x.detach(), t_norm.detach(), y, w, inv_tau, need)
+        ctx.save_for_backward(r["dx"], r["dlogtau"].float() if need else None)
+        ctx.flags = (x.requires_grad, log_tau.requires_grad)
+        return r["loss"].float()
+
+    @staticmethod
+    def backward(ctx, g):
+        dx, dlt = ctx.saved_tensors
+        need_dx, need_tau = ctx.flags
+        return (dx * g.to(dx.dtype)) if need_dx else None, None, (dlt * g).reshape(()) if need_tau else None, None, None
+
+
+def infonce_kblocked(x, t_norm, log_tau, y, w):
+    return _InfoNCEKBlocked.apply(x, t_norm, log_tau, y, w)
+
+
 def pixel_losses(x, t_norm, log_tau, y, w, precision="auto"):
     """(text InfoNCE, smoothness) with a fused single-pass backward."""
     return _PixelLosses.apply(x, t_norm, log_tau, y, w, precision)

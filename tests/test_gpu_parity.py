@@ -571,3 +571,43 @@ def test_fused_topk_histograms_bit_exact(B, D, H, W, C, k, xdtype):
     f1, f2 = a1.finalize(sd), a2.finalize(sd)
     for key in ("mIoU_t1", "mIoU_tk", "pixel_accuracy_t1", "pixel_accuracy_tk", "intersection_top1", "union_topk"):
         assert f1[key] == f2[key], key
+
+
+@pytest.mark.parametrize("n,K,D,diag", [(512, 512, 512, True), (1000, 1000, 256, True), (264, 300, 512, False), (136, 700, 256, False)])
+def test_infonce_kblocked_tensor_core(n, K, D, diag):
+    """More than 256 candidates on the tensor cores (the area-image loss at hundreds / thousands of objects): candidate
+    rows in launches of 256, per-block logsumexp combined, per-block gradients summed -- against the oracle."""
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(n + K + D)
+    x = (torch.randn(1, D, n, 1, generator=g) * (0.5 + torch.rand(1, 1, n, 1, generator=g))).to(torch.bfloat16).float()
+    t = unit(torch.randn(K, D, generator=g), 1).to(torch.bfloat16).float()
+    if diag:
+        y = torch.arange(n, dtype=torch.int32); w = torch.ones(n)
+    else:
+        y = torch.randint(0, K, (n,), generator=g, dtype=torch.int32); y[torch.rand(n, generator=g) < 0.2] = -1
+        w = torch.randint(0, 3, (n,), generator=g).float()
+    ref = O.infonce_dense(x[0, :, :, 0].t(), t, y, w, 1 / 0.1)
+    r = ops.infonce_kblocked_raw(x.to(dev()), t.to(dev()), y.to(dev()), w.to(dev()), 1 / 0.1, True)
+    torch.cuda.synchronize()
+    assert abs(float(r["loss"]) - float(ref["loss"])) <= 2e-3 * abs(float(ref["loss"])), (float(r["loss"]), float(ref["loss"]))
+    assert maxrel(r["lse"].cpu(), ref["lse"]) < 2e-3
+    assert maxrel(r["dx"][0, :, :, 0].t().float().cpu(), ref["dx"]) < BF16_MAXREL
+    assert abs(float(r["dlogtau"]) - float(ref["dlogtau"])) <= BF16_MAXREL * abs(float(ref["dlogtau"]))
+
+
+def test_image_contrastive_loss_large_n_uses_tensor_cores():
+    import rangeclip_b200 as R
+    g = torch.Generator().manual_seed(3)
+    n, D = 768, 512
+    area = torch.randn(n, D, generator=g).to(torch.bfloat16).float()
+    img = torch.randn(n, D, generator=g)
+    lt = torch.log(torch.tensor(0.1))
+    a_ref = area.clone().double().requires_grad_(True); lt_ref = lt.clone().double().requires_grad_(True)
+    loss_ref = O.image_infonce(a_ref, img.double(), lt_ref)
+    loss_ref.backward()
+    a = area.to(dev()).requires_grad_(True); ltd = lt.to(dev()).requires_grad_(True)
+    loss = R.image_contrastive_loss(a, img.to(dev()), ltd)          # "auto": n >= 512 -> K-blocked tensor-core path
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 2e-3 * abs(float(loss_ref.detach()))
+    assert maxrel(a.grad.cpu(), a_ref.grad) < BF16_MAXREL
+    assert abs(float(ltd.grad) - float(lt_ref.grad)) <= BF16_MAXREL * abs(float(lt_ref.grad))
