@@ -282,7 +282,14 @@ def infonce_kblocked_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor,
     check(L.rc_infonce_prepass(_p(x), xdt, B, D, HW, _p(ws), ws_bytes, st), "rc_infonce_prepass")    # once for all launches
     starts = list(range(0, K, block))
     nb = len(starts)
-    texts = [text_to_bf16(t_norm[s0:s0 + block]) for s0 in starts]
+    # bf16 operand copies of the candidate blocks: all full blocks with two tensor ops, a shorter last block on its own
+    n_full = K // block if block % 64 == 0 else 0
+    texts = []
+    if n_full:
+        tb_full = t_norm[:n_full * block].detach().to(torch.bfloat16).contiguous()
+        ttb_full = tb_full.view(n_full, block, D).transpose(1, 2).contiguous()
+        texts = [(tb_full[i * block:(i + 1) * block], ttb_full[i]) for i in range(n_full)]
+    texts += [text_to_bf16(t_norm[s0:s0 + block]) for s0 in starts[n_full:]]
     ys = [(y - s0).contiguous() for s0 in starts]
     lse_blk = torch.empty(nb, M, device=dev, dtype=torch.float32)
     acc = torch.zeros(nb, 4, device=dev, dtype=torch.float64)             # per block: loss_sum, w_sum, dlogtau, w_sum_in
