@@ -128,6 +128,18 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
             raise RuntimeError(f"infonce(rep=4): needs the tensor-core path (D in (256, 512), K <= 256, HW % 8 == 0); "
                                f"got D={D}, HW={HW}, K={K}, precision={precision!r}")
         precision = "bf16"
+    if precision == "auto" and rep == 1 and K > 256 and not need_dt and kblocked_supported(D, HW):
+        # more candidates than one launch takes: tensor cores over blocks of 256 candidate rows instead of the CUDA-core
+        # kernel (which needs ~100x longer at full size)
+        r = infonce_kblocked_raw(x, t_norm, y, w, inv_tau, need_dx)
+        dx = r["dx"]
+        if dx is not None and grad_scale is not None:
+            dx = dx * grad_scale.detach().reshape(1).to(device=dev, dtype=dx.dtype)
+        dlt = r["dlogtau"] if r["dlogtau"] is not None else torch.zeros((), device=dev, dtype=torch.float64)
+        if grad_scale is not None:
+            dlt = dlt * grad_scale.detach().reshape(()).to(device=dev, dtype=torch.float64)
+        return dict(loss_sum=r["loss"] * r["w_sum"], w_sum=r["w_sum"], dlogtau=dlt, lse=r["lse"], dx=dx, dt=None,
+                    precision="bf16-kblocked")
     dt_on_tc = need_dt and need_dx and D in (256, 512)       # tensor-core dText: pair kernel + split-K GEMM
     if precision == "auto":
         precision = "bf16" if (bf16_path_supported(D, HW, K) and (not need_dt or dt_on_tc)) else "fp32"

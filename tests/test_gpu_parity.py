@@ -611,3 +611,24 @@ def test_image_contrastive_loss_large_n_uses_tensor_cores():
     assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 2e-3 * abs(float(loss_ref.detach()))
     assert maxrel(a.grad.cpu(), a_ref.grad) < BF16_MAXREL
     assert abs(float(ltd.grad) - float(lt_ref.grad)) <= BF16_MAXREL * abs(float(lt_ref.grad))
+
+
+def test_infonce_auto_takes_tensor_cores_beyond_256_candidates():
+    """K = 300 contrast rows (more distractors than one launch takes): `precision="auto"` runs the K-blocked tensor-core
+    path, not the CUDA-core kernel, and the autograd op returns the oracle's loss and gradients."""
+    from rangeclip_b200 import ops
+    B, D, H, W, K = 2, 256, 16, 16, 300
+    x, t, y, w, inv_tau = _infonce_case(B, D, H, W, K, seed=5, bf16_exact=True)
+    ref = _oracle_infonce(x, t, y, w, inv_tau)
+    r = ops.infonce_raw(x.to(dev()).to(torch.bfloat16), t.to(dev()), y.to(dev()), w.to(dev()), inv_tau, True, False, "auto")
+    assert r["precision"] == "bf16-kblocked"
+    loss = float(r["loss_sum"] / r["w_sum"])
+    assert abs(loss - float(ref["loss"])) <= 2e-3 * abs(float(ref["loss"]))
+    assert maxrel(r["dx"].float().cpu(), ref["dx4"]) < BF16_MAXREL
+    assert abs(float(r["dlogtau"]) - float(ref["dlogtau"])) <= BF16_MAXREL * abs(float(ref["dlogtau"]))
+    xg = x.to(dev()).to(torch.bfloat16).requires_grad_(True)
+    lt = torch.log(torch.tensor(1.0 / inv_tau, device=dev())).requires_grad_(True)
+    l = ops.infonce(xg, t.to(dev()), lt, y.to(dev()), w.to(dev()))
+    (2.0 * l).backward()
+    assert maxrel(xg.grad.float().cpu(), 2.0 * ref["dx4"]) < BF16_MAXREL
+    assert abs(float(lt.grad) - 2.0 * float(ref["dlogtau"])) <= BF16_MAXREL * abs(2.0 * float(ref["dlogtau"]))
