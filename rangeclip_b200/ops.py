@@ -319,7 +319,7 @@ def infonce_kblocked_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor,
     dx = dlogtau = None
     if need_dx:
         dxb = torch.empty(B, D, HW, device=dev, dtype=torch.bfloat16)     # the tensor-core kernel always writes bf16
-        dx = torch.zeros(B, D, HW, device=dev, dtype=torch.float32)
+        dx = None                                                          # fp32 sum of the per-block gradients
         acc2 = torch.zeros(nb, 4, device=dev, dtype=torch.float64)
         acc2[:, 3] = wsum
         for i, s0 in enumerate(starts):
@@ -328,7 +328,7 @@ def infonce_kblocked_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor,
                                     _p(lse), acc2[i, 0:].data_ptr(), acc2[i, 1:].data_ptr(), acc2[i, 3:].data_ptr(), None, _p(dxb),
                                     None, acc2[i, 2:].data_ptr(), _p(ws), ws_bytes,
                                     1 | RC_INFONCE_KEEP_WEIGHT | RC_INFONCE_LSE_GIVEN, st), "rc_infonce_bf16(K block, backward)")
-            dx += dxb
+            dx = dxb.float() if dx is None else dx.add_(dxb)
         dlogtau = acc2[:, 2].sum()
         dx = dx.view(x.shape).to(x.dtype)
     return dict(loss=loss, lse=lse, dx=dx, dlogtau=dlogtau, w_sum=wsum)
