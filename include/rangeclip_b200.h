@@ -120,6 +120,19 @@ int rc_infonce_bf16_rep4(const void* x, rc_dtype x_dtype, int B, int D, int64_t 
                          const double* w_sum_in, const float* grad_scale,
                          void* dx, float* dt, double* dlogtau,
                          void* workspace, int64_t workspace_bytes, int flags, void* stream);
+/* All candidate blocks of the K-blocked scheme in ONE launch (K > 256 candidates against ONE image of rows, HW % 256 == 0,
+ * D = 256 / 512): the kernel's image index runs over the n_blocks = ceil(K / 256) blocks of candidate rows.
+ *   t_bf16_all [n_blocks*256][D], tt_bf16_all [D][n_blocks*256] (zero pad rows / columns past K)
+ *   y_rel, w_rep [n_blocks][HW]: target index relative to the block's first row (any value outside [0,256) when the
+ *       target lives in another block), the row weight repeated per block (0 = ignored row)
+ *   round 1 (dx_blocks = NULL): lse [n_blocks][HW] OUT per-block logsumexp; loss_sum += sum_b (sum_p w lse_b - sum_{y in b} w z_y)
+ *   round 2 (flags has RC_INFONCE_LSE_GIVEN): lse [HW] IN = logsumexp over the blocks; dx_blocks [n_blocks][D][HW] bf16 OUT,
+ *       their sum over the blocks is dx; dlogtau += the full gradient. */
+int rc_infonce_bf16_kblocks(const void* x, rc_dtype x_dtype, int D, int64_t HW,
+                            const void* t_bf16_all, const void* tt_bf16_all, int K, int n_blocks,
+                            const int32_t* y_rel, const float* w_rep, float inv_tau,
+                            float* lse, double* loss_sum, double* w_sum, const double* w_sum_in, const float* grad_scale,
+                            void* dx_blocks, double* dlogtau, void* workspace, int64_t workspace_bytes, int flags, void* stream);
 /* The pre-pass alone: 1/|x_p| of the bf16-rounded rows (+ bf16 copy of an f32 x) into workspace. */
 int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
                        void* workspace, int64_t workspace_bytes, void* stream);

@@ -822,13 +822,13 @@ static int infonce_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, int6
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
     void* g = ws + ((base + 255) / 256) * 256;
     if ((rcode = launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
-                                     loss_sum, w_sum, dlogtau, g, rep, 0, nullptr, s))) return rcode;
+                                     loss_sum, w_sum, dlogtau, g, rep, 0, nullptr, 0, s))) return rcode;
     return launch_infonce_dt(g, xsrc, B, D, HW, K, dt, s);
   }
   {
     if (use_pair)
       return launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
-                                 loss_sum, w_sum, dlogtau, nullptr, rep, keep_w, lse_in, s);
+                                 loss_sum, w_sum, dlogtau, nullptr, rep, keep_w, lse_in, 0, s);
   }
   const int Kp = (K + 63) / 64 * 64;
   CUtensorMap m_xs, m_t, m_tt, m_xe, m_dx;
@@ -883,6 +883,32 @@ extern "C" int rc_infonce_bf16_rep4(const void* x, rc_dtype x_dtype, int B, int 
                                     int flags, void* stream) {
   return infonce_bf16_impl(x, x_dtype, B, D, HW, t_bf16, tt_bf16, K, y4, w4, inv_tau, lse, loss_sum, w_sum, w_sum_in,
                            grad_scale, dx, dt, dlogtau, workspace, workspace_bytes, flags, 4, stream);
+}
+
+extern "C" int rc_infonce_bf16_kblocks(const void* x, rc_dtype x_dtype, int D, int64_t HW, const void* t_bf16_all,
+                                       const void* tt_bf16_all, int K, int n_blocks, const int32_t* y_rel, const float* w_rep,
+                                       float inv_tau, float* lse, double* loss_sum, double* w_sum, const double* w_sum_in,
+                                       const float* grad_scale, void* dx_blocks, double* dlogtau, void* workspace,
+                                       int64_t workspace_bytes, int flags, void* stream) {
+  using namespace rc;
+  RC_REQUIRE(x && t_bf16_all && y_rel && w_rep && workspace && lse, "rc_infonce_bf16_kblocks: null pointer");
+  RC_REQUIRE(HW >= 0 && K >= 1 && n_blocks >= 1 && n_blocks == (K + 255) / 256, "rc_infonce_bf16_kblocks: n_blocks must be ceil(K / 256)");
+  if (!infonce_pair_supported(D)) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16_kblocks: D=%d must be 256 or 512", D);
+  if (HW % 256 != 0) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16_kblocks: HW=%lld must be a multiple of 256", (long long)HW);
+  RC_REQUIRE((reinterpret_cast<uintptr_t>(t_bf16_all) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "rc_infonce_bf16_kblocks: alignment");
+  const bool bwd = dx_blocks != nullptr;
+  if (bwd) RC_REQUIRE(tt_bf16_all && w_sum_in && (flags & RC_INFONCE_LSE_GIVEN), "rc_infonce_bf16_kblocks: the backward needs tt_bf16_all, w_sum_in and RC_INFONCE_LSE_GIVEN");
+  if (HW == 0) return RC_OK;
+  int rcode = check_sm100("rc_infonce_bf16_kblocks");
+  if (rcode) return rcode;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* inv_norm; __nv_bfloat16* xb;
+  const bool skip_prepass = (flags & RC_INFONCE_PREPASS_DONE) || x_dtype == RC_BF16;
+  if ((rcode = infonce_prepass_impl(x, x_dtype, 1, D, HW, workspace, workspace_bytes, skip_prepass ? (cudaStream_t)-1 : s, &inv_norm, &xb))) return rcode;
+  const void* xsrc = (x_dtype == RC_F32) ? (const void*)xb : x;
+  const float* lse_in = (flags & RC_INFONCE_LSE_GIVEN) ? lse : nullptr;
+  return launch_infonce_pair(xsrc, dx_blocks, t_bf16_all, tt_bf16_all, n_blocks, D, HW, K, inv_norm, y_rel, w_rep, inv_tau, grad_scale,
+                             w_sum_in, lse, loss_sum, w_sum, dlogtau, nullptr, 1, 1, lse_in, n_blocks, s);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -135,6 +135,10 @@ struct Params {
   // this block is then exp(z - lse_in) instead of exp(z - m) / (block sum).
   int keep_w;
   const float* lse_in;
+  // kb > 0: ALL candidate blocks in one launch.  The "images" of the tile index are the kb blocks of 256 candidate rows:
+  // X (one image) is read with image coordinate 0, everything else (y, w, lse, dX, text rows) is indexed by the block.
+  // K is then the total number of candidates; lse_in is indexed by the pixel alone.
+  int kb;
   const int32_t* y;
   const float* w;
   float inv_tau;
@@ -309,30 +313,33 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       // text ring, in MMA issue order: S(first), then per tile pair
       //   [S(next) first half] [dX(this) first blocks] [S(next) second half] [dX(this) remaining blocks]
       uint32_t it = 0;
-      auto load_s = [&](int c_begin, int c_end) {
+      // first candidate row of the pair's block (kb mode: both tiles of a pair lie in one block, tiles_per_img is even)
+      auto koff_of = [&](int pj) -> int { return (kKB && prm.kb > 0) ? div_tiles(prm, 2 * pj) * 256 : 0; };
+      auto load_s = [&](int c_begin, int c_end, int koff) {
         for (int c = c_begin; c < c_end; ++c, ++it) {   // own half (Nh rows) of text chunk c
           const int st = it % kTStages;
           RC_WAIT(mbar_wait, &bars->tempty[st], ((it / kTStages) & 1) ^ 1, 1);
           if (leader_cta) mbar_arrive_expect_tx(&bars->tfull[st], 2 * Nh * 128);
-          tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_t, &bars->tfull[st], c * 64, (int)rank * Nh);
+          tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_t, &bars->tfull[st], c * 64, koff + (int)rank * Nh);
         }
       };
-      auto load_dx = [&](int b_begin, int b_end) {
+      auto load_dx = [&](int b_begin, int b_end, int koff) {
         for (int blk = b_begin; blk < b_end; ++blk)
           for (int kc = 0; kc < n_kchunks; ++kc, ++it) {   // own 128 rows of T^T for this 256-channel block, 64 k at a time
             const int st = it % kTStages;
             RC_WAIT(mbar_wait, &bars->tempty[st], ((it / kTStages) & 1) ^ 1, 2);
             if (leader_cta) mbar_arrive_expect_tx(&bars->tfull[st], 2 * 16384);
-            tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_tt, &bars->tfull[st], kc * 64, blk * 256 + (int)rank * 128);
+            tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_tt, &bars->tfull[st], koff + kc * 64, blk * 256 + (int)rank * 128);
           }
       };
-      if (cluster_id < prm.n_pairs) load_s(0, n_dchunks);
+      if (cluster_id < prm.n_pairs) load_s(0, n_dchunks, koff_of(cluster_id));
       for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters) {
         const bool has_next = pj + n_clusters < prm.n_pairs;
-        if (has_next) load_s(0, c_half);
-        if (kBwd) load_dx(0, b_half);
-        if (has_next) load_s(c_half, n_dchunks);
-        if (kBwd) load_dx(b_half, n_blk);
+        const int k_this = koff_of(pj), k_next = has_next ? koff_of(pj + n_clusters) : 0;
+        if (has_next) load_s(0, c_half, k_next);
+        if (kBwd) load_dx(0, b_half, k_this);
+        if (has_next) load_s(c_half, n_dchunks, k_next);
+        if (kBwd) load_dx(b_half, n_blk, k_this);
       }
     } else if (warp == 3 && lane == 0) {
       // =============================== X producer (both CTAs) ===============================
@@ -347,8 +354,9 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           RC_WAIT(mbar_wait, &bars->xempty[st], ((xit / kXStages) & 1) ^ 1, 1);
           uint8_t* sb = smem + st * kStageBytes;
           mbar_arrive_expect_tx(&bars->xf[st], 2 * 8192);          // CTA-local: the softmax warps read the chunk too
-          tma_load_3d(sb, &map_x_s, &bars->xf[st], px0, c * 64, b);
-          tma_load_3d(sb + 8192, &map_x_s, &bars->xf[st], px0 + 64, c * 64, b);
+          const int bx = (kKB && prm.kb > 0) ? (b < prm.B ? 0 : 1) : b;      // kb mode: the one image of X (1 = out of bounds)
+          tma_load_3d(sb, &map_x_s, &bars->xf[st], px0, c * 64, bx);
+          tma_load_3d(sb + 8192, &map_x_s, &bars->xf[st], px0 + 64, c * 64, bx);
         }
       }
     } else if (warp == 1 && leader_cta) {
@@ -556,6 +564,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       // (every thread passes the named barrier below before its next P store)
       if (kBwd && prm.store_g && threadIdx.x == 128) tma_store_wait_read0();
       const int64_t m = (int64_t)b * prm.HW + px;
+      // candidates in this tile's block (kb mode: the last block may be short; its zero pad rows are masked like any pad)
+      const int Kt = (kKB && prm.kb > 0) ? min(256, prm.K - 256 * b) : prm.K;
       const bool px_ok = nx_inv_n != 0.f;
       const int yi = nx_y;
       const float wi = (R == 1 && (yi >= 0 || (kKB && prm.keep_w))) ? nx_w : 0.f;
@@ -577,7 +587,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       if (!use_bound) {
         float mx = -FLT_MAX;
         for (int c = 0; c * 32 < Kh; ++c) {
-          const int nvalid = prm.K - (cb + c * 32);
+          const int nvalid = Kt - (cb + c * 32);
           if (nvalid <= 0) break;
           uint32_t r[32];
           tmem_ld_32x32(trow + c * 32, r);
@@ -601,7 +611,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       // 16 text columns per step
       auto smx_step = [&](const uint32_t (&r)[16], int c) {
         const int k0 = cb + c * 16;
-        const int nvalid = prm.K - k0;
+        const int nvalid = Kt - k0;
 #pragma unroll
         for (int j = 0; j < R; ++j) {                          // target logit(s): once per row, not per column
           const int yrel = (R == 1 ? yi : (int)(((uint32_t)yi >> (8 * j)) & 255u)) - k0;
@@ -697,7 +707,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       sum += xch[(1 * 2 + (half ^ 1)) * 128 + row];
       sez += xch[(2 * 2 + (half ^ 1)) * 128 + row];
       tz += xch[(3 * 2 + (half ^ 1)) * 128 + row];
-      if (kKB && prm.lse_in != nullptr && valid) sum = fast_exp2(fmaf(__ldg(prm.lse_in + m), kLog2e, -ml));   // 1 / sum = exp(m - lse)
+      if (kKB && prm.lse_in != nullptr && valid) sum = fast_exp2(fmaf(__ldg(prm.lse_in + (prm.kb > 0 ? (int64_t)px : m)), kLog2e, -ml));   // 1 / sum = exp(m - lse)
       float lse = 0.f;
       if (half == 0) {
         lse = (ml + __log2f(sum)) * kLn2;
@@ -818,7 +828,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         const int px0 = (t - b * prm.tiles_per_img) * kTilePx + (f_unit & 1) * 64;
         const int d = (f_unit >> 1) * 256 + (int)rank * 128 + row;
         f_b = b; f_px = px0; f_d = d - lane;
-        f_off = ((int64_t)b * prm.D + d) * prm.HW + px0;
+        f_off = ((int64_t)((kKB && prm.kb > 0) ? 0 : b) * prm.D + d) * prm.HW + px0;      // kb mode: X has one image
         const int64_t left = prm.HW - px0;
         f_n8 = left >= 64 ? 8 : (left > 0 ? (int)(left >> 3) : 0);
       }
@@ -943,23 +953,27 @@ bool infonce_pair_supported(int D) { return D == 256 || D == 512; }
 int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const void* tt_bf16, int B, int D, int64_t HW, int K,
                         const float* inv_norm, const int32_t* y, const float* w, float inv_tau, const float* grad_scale,
                         const double* w_sum_in, float* lse, double* loss_sum, double* w_sum, double* dlogtau, void* g_out,
-                        int rep, int keep_w, const float* lse_in, cudaStream_t s) {
+                        int rep, int keep_w, const float* lse_in, int kb, cudaStream_t s) {
   using namespace pair;
   const bool bwd = dx != nullptr;
-  const int Kp = (K + 63) / 64 * 64;
+  // kb > 0: all kb blocks of 256 candidate rows in one launch -- B counts the blocks (virtual images), X has ONE image,
+  // the text maps span all blocks (row offset = block * 256), dX has one [D][HW] slab per block
+  const int Kp = kb > 0 ? 256 : (K + 63) / 64 * 64;
+  const int Kall = kb > 0 ? kb * 256 : Kp;          // rows of the text matrices
   CUtensorMap m_xs, m_t, m_tt, m_dx, m_g;
   int rcode;
   {
     const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)D, (uint64_t)B};
+    const uint64_t xdims[3] = {(uint64_t)HW, (uint64_t)D, (uint64_t)(kb > 0 ? 1 : B)};
     const uint64_t str[3] = {2, (uint64_t)HW * 2, (uint64_t)D * HW * 2};
     const uint32_t box_s[3] = {64, 64, 1};
-    if ((rcode = make_tmap_bf16(&m_xs, xsrc, 3, dims, str, box_s, "pair map_x_s"))) return rcode;
+    if ((rcode = make_tmap_bf16(&m_xs, xsrc, 3, xdims, str, box_s, "pair map_x_s"))) return rcode;
     const uint32_t box_o[3] = {32, 32, 1};
-    if ((rcode = make_tmap_bf16(&m_dx, bwd ? dx : xsrc, 3, dims, str, box_o, "pair map_dx"))) return rcode;
-    const uint64_t tdims[2] = {(uint64_t)D, (uint64_t)Kp}, tstr[2] = {2, (uint64_t)D * 2};
+    if ((rcode = make_tmap_bf16(&m_dx, bwd ? dx : xsrc, 3, bwd ? dims : xdims, str, box_o, "pair map_dx"))) return rcode;
+    const uint64_t tdims[2] = {(uint64_t)D, (uint64_t)Kall}, tstr[2] = {2, (uint64_t)D * 2};
     const uint32_t tbox[2] = {64, (uint32_t)(Kp / 2)};
     if ((rcode = make_tmap_bf16(&m_t, t_bf16, 2, tdims, tstr, tbox, "pair map_t"))) return rcode;
-    const uint64_t ttdims[2] = {(uint64_t)Kp, (uint64_t)D}, ttstr[2] = {2, (uint64_t)Kp * 2};
+    const uint64_t ttdims[2] = {(uint64_t)Kall, (uint64_t)D}, ttstr[2] = {2, (uint64_t)Kall * 2};
     const uint32_t ttbox[2] = {64, 128};
     if ((rcode = make_tmap_bf16(&m_tt, bwd ? tt_bf16 : t_bf16, 2, bwd ? ttdims : tdims, bwd ? ttstr : tstr,
                                 bwd ? ttbox : tbox, "pair map_tt"))) return rcode;
@@ -992,7 +1006,8 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   prm.wide = (HW % 16 == 0) && (reinterpret_cast<uintptr_t>(xsrc) % 32 == 0) && (reinterpret_cast<uintptr_t>(dx) % 32 == 0);
   prm.inv_norm = inv_norm; prm.y = y; prm.w = w; prm.inv_tau = inv_tau; prm.grad_scale = grad_scale;
   prm.w_sum_in = w_sum_in; prm.lse = lse; prm.loss_sum = loss_sum; prm.w_sum = w_sum; prm.dlogtau = dlogtau;
-  prm.keep_w = keep_w; prm.lse_in = lse_in;
+  prm.keep_w = keep_w; prm.lse_in = lse_in; prm.kb = kb;
+  if (kb > 0 && (prm.tiles_per_img & 1)) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16_kblocks: HW must be a multiple of 256");
   int n_clusters = num_sms() / 2;
   if (n_clusters > prm.n_pairs) n_clusters = prm.n_pairs;
   const int grid = 2 * n_clusters;
@@ -1003,7 +1018,7 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
     return check_launch("rc_infonce_bf16(pair)");
   };
   if (rep == 4) return bwd ? launch(infonce_umma_pair_kernel<true, 4, false>) : launch(infonce_umma_pair_kernel<false, 4, false>);
-  if (keep_w || lse_in != nullptr) return bwd ? launch(infonce_umma_pair_kernel<true, 1, true>) : launch(infonce_umma_pair_kernel<false, 1, true>);
+  if (keep_w || lse_in != nullptr || kb > 0) return bwd ? launch(infonce_umma_pair_kernel<true, 1, true>) : launch(infonce_umma_pair_kernel<false, 1, true>);
   return bwd ? launch(infonce_umma_pair_kernel<true, 1, false>) : launch(infonce_umma_pair_kernel<false, 1, false>);
 }
 

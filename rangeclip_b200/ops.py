@@ -294,6 +294,36 @@ def infonce_kblocked_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor,
     check(L.rc_infonce_prepass(_p(x), xdt, B, D, HW, _p(ws), ws_bytes, st), "rc_infonce_prepass")    # once for all launches
     starts = list(range(0, K, block))
     nb = len(starts)
+    if B == 1 and HW % 256 == 0 and block == 256:
+        # one image of rows (the area-image loss): every candidate block in ONE launch per round -- the kernel's image
+        # index runs over the blocks (rc_infonce_bf16_kblocks)
+        tb_all = torch.zeros(nb * 256, D, device=dev, dtype=torch.bfloat16)
+        tb_all[:K] = t_norm.detach().to(torch.bfloat16)
+        ttb_all = tb_all.t().contiguous()
+        y_rel = (y[None, :] - 256 * torch.arange(nb, device=dev, dtype=torch.int32)[:, None]).contiguous()
+        w_rep = w[None, :].expand(nb, M).contiguous()
+        wsum = w.double().sum()
+        acc = torch.zeros(4, device=dev, dtype=torch.float64)
+        acc[3] = wsum * nb                       # (unused by the forward round)
+        lse_blk = torch.empty(nb, M, device=dev, dtype=torch.float32)
+        check(L.rc_infonce_bf16_kblocks(_p(x), xdt, D, HW, _p(tb_all), _p(ttb_all), K, nb, _p(y_rel), _p(w_rep), float(inv_tau),
+                                        _p(lse_blk), acc[0:].data_ptr(), acc[1:].data_ptr(), None, None, None, None, _p(ws),
+                                        ws_bytes, 1, st), "rc_infonce_bf16_kblocks(forward)")
+        lse = torch.logsumexp(lse_blk, dim=0)
+        wz = (lse_blk.double() * w.double()[None, :]).sum() - acc[0]
+        loss = torch.where(wsum > 0, ((lse.double() * w.double()).sum() - wz) / wsum.clamp_min(1e-300), torch.zeros_like(wsum))
+        dx = dlogtau = None
+        if need_dx:
+            dxb = torch.empty(nb, D, HW, device=dev, dtype=torch.bfloat16)
+            acc2 = torch.zeros(4, device=dev, dtype=torch.float64)
+            acc2[3] = wsum
+            check(L.rc_infonce_bf16_kblocks(_p(x), xdt, D, HW, _p(tb_all), _p(ttb_all), K, nb, _p(y_rel), _p(w_rep), float(inv_tau),
+                                            _p(lse), acc2[0:].data_ptr(), acc2[1:].data_ptr(), acc2[3:].data_ptr(), None, _p(dxb),
+                                            acc2[2:].data_ptr(), _p(ws), ws_bytes, 1 | RC_INFONCE_LSE_GIVEN, st),
+                  "rc_infonce_bf16_kblocks(backward)")
+            dx = dxb.float().sum(dim=0).view(x.shape).to(x.dtype)
+            dlogtau = acc2[2].clone()
+        return dict(loss=loss, lse=lse, dx=dx, dlogtau=dlogtau, w_sum=wsum)
     # bf16 operand copies of the candidate blocks: all full blocks with two tensor ops, a shorter last block on its own
     n_full = K // block if block % 64 == 0 else 0
     texts = []

@@ -573,10 +573,13 @@ def test_fused_topk_histograms_bit_exact(B, D, H, W, C, k, xdtype):
         assert f1[key] == f2[key], key
 
 
-@pytest.mark.parametrize("n,K,D,diag", [(512, 512, 512, True), (1000, 1000, 256, True), (264, 300, 512, False), (136, 700, 256, False)])
+@pytest.mark.parametrize("n,K,D,diag", [(512, 512, 512, True), (1000, 1000, 256, True), (264, 300, 512, False), (136, 700, 256, False),
+                                        (512, 700, 256, False), (768, 600, 512, False), (256, 257, 512, False)])
 def test_infonce_kblocked_tensor_core(n, K, D, diag):
     """More than 256 candidates on the tensor cores (the area-image loss at hundreds / thousands of objects): candidate
-    rows in launches of 256, per-block logsumexp combined, per-block gradients summed -- against the oracle."""
+    rows in blocks of 256, per-block logsumexp combined, per-block gradients summed -- against the oracle.  n % 256 == 0
+    takes the single-launch form (rc_infonce_bf16_kblocks: the blocks are the kernel's image index, incl. a short last
+    block), other n one launch per block."""
     from rangeclip_b200 import ops
     g = torch.Generator().manual_seed(n + K + D)
     x = (torch.randn(1, D, n, 1, generator=g) * (0.5 + torch.rand(1, 1, n, 1, generator=g))).to(torch.bfloat16).float()
