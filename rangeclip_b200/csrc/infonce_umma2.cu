@@ -302,7 +302,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
   // one arrival for the whole warp: every lane has fenced its own accesses, __syncwarp orders them before lane 0's arrive
   auto arrive_leader_warp = [&](uint64_t* bar) {
     __syncwarp();
-    if (lane == 0) arrive_leader(bar);
+    if (elect_one()) arrive_leader(bar);
   };
 
   if (warp < 4) {
@@ -531,7 +531,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->xempty[st]);
+        if (elect_one()) mbar_arrive(&bars->xempty[st]);     // (elect.sync: no lane id to re-materialise in this hot loop)
       }
       // fixed-order reduction (bit-reproducible): lane pairs, then the eight warps' partials through shared memory
 #pragma unroll
