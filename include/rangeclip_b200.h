@@ -96,6 +96,10 @@ int rc_infonce_f32(const float* x, int B, int D, int64_t HW, int64_t ld_b,
  *                           round 2 = backward launches with both flags: dx and dlogtau of each block add up to the full gradient */
 #define RC_INFONCE_KEEP_WEIGHT 2
 #define RC_INFONCE_LSE_GIVEN 4
+/* Backward launches (dx given, no dt) of D = 256 / 512 run the kernel whose softmax tile is a tensor-memory operand of the dX
+ * GEMM (TS-mode tcgen05.mma, csrc/infonce_ts.cu).  RC_INFONCE_SS_KERNEL selects the earlier kernel with both operands in
+ * shared memory instead (csrc/infonce_umma2.cu; same results within bf16 rounding) -- kept for A/B timing. */
+#define RC_INFONCE_SS_KERNEL 8
 int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
                     const void* t_bf16, const void* tt_bf16, int K,
                     const int32_t* y, const float* w, float inv_tau,
@@ -138,19 +142,24 @@ int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW
                        void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Helpers used by both paths.
- * rc_text_prepare: rows of `text[idx[k]]` (idx nullable = identity) are L2-normalised
+ * rc_text_prepare: rows of `text[idx[k]]` (idx nullable = identity; `text` has n_rows rows, an index outside [0, n_rows)
+ *   yields a row of NaN instead of an out-of-bounds read -- the reference raises an index error there) are L2-normalised
  *   (F.normalize, eps 1e-12; model.py:272) and written as f32 [K][D] (nullable), bf16 [Kp][D]
  *   (nullable) and transposed bf16 [D][Kp] (nullable), Kp = round_up(K, 64), pads zeroed.
  * rc_weight_sum: w_sum[0] += sum_p w_p * (y_p >= 0)  (double).
  * rc_sample_weights: w[b][p] = multiplicity of p in rand_idx[b][:] * (seg[b][p] > 0), and
  *   y[b][p] = map[seg[b][p]] (or -1 where seg == 0) -- the dense form of model.py:220-228,276-278.
  * rc_scale: in-place x *= s[0] (device scalar) for a late upstream gradient. */
-int rc_text_prepare(const float* text, int64_t ld_text, const int64_t* idx, int K, int D,
+int rc_text_prepare(const float* text, int64_t ld_text, int64_t n_rows, const int64_t* idx, int K, int D,
                     float* t_f32, void* t_bf16, void* tt_bf16, void* stream);
 int rc_weight_sum(const float* w, const int32_t* y, int64_t n, double* w_sum, void* stream);
 int rc_sample_weights(const int64_t* seg, const int64_t* rand_idx, int B, int64_t HW, int64_t n_samples,
                       const int32_t* map, int C, float* w, int32_t* y, void* stream);
 int rc_scale(void* x, rc_dtype dtype, int64_t n, const float* s, void* stream);
+/* out[i] = s[0] * x[i] (s nullable = 1) into a separate buffer, converting x_dtype -> out_dtype: the late upstream scaling of a
+ * saved gradient (autograd may run a backward twice; the saved tensor must stay intact) and the bf16 -> f32 widening of the
+ * tensor-core gradient in one pass. */
+int rc_scale_to(const void* x, rc_dtype x_dtype, void* out, rc_dtype out_dtype, int64_t n, const float* s, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Segment-masked average pooling  (replaces dataloader.py:286-304 and model.py:36-54)
@@ -177,6 +186,11 @@ int rc_pool_bwd(const float* g, const int32_t* count, int B, int D, int64_t HW,
 int rc_tv_fwd(const void* x, rc_dtype x_dtype, int64_t planes, int H, int W, double* sums, void* stream);
 int rc_tv_bwd(const void* x, rc_dtype x_dtype, int64_t planes, int H, int W, const float* scale,
               void* dx, int accumulate, const float* dx_scale, void* stream);
+/* Out-of-place / mixed-dtype form: dx_out (x_dtype) = dx_scale[0] * dx_in + scale_h d(sum_h)/dx + scale_v d(sum_v)/dx.
+ * dx_in may be bf16 under an f32 x (the tensor-core InfoNCE gradient): the fused text + smoothness backward of an f32
+ * embedding tensor then reads x once, dx_in once and writes dx once.  dx_in == dx_out (same dtype) is allowed. */
+int rc_tv_bwd_from(const void* x, rc_dtype x_dtype, int64_t planes, int H, int W, const float* scale,
+                   const void* dx_in, rc_dtype dx_in_dtype, const float* dx_scale, void* dx_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Evaluation  (replaces model.py:164-173 and validate.py:88-139)
@@ -227,6 +241,8 @@ int rc_debug_max_active_clusters(int cluster_size, int threads, int smem_bytes);
 
 /* CTA-pair (cta_group::2) variant of the bring-up GEMM: C[256][N] = A[256][Kd] B[N][Kd]^T, both K-major. */
 int rc_debug_umma_gemm_2sm(const void* a_bf16, const void* b_bf16, int N, int Kd, float* c, void* stream);
+/* Same GEMM with A as a tensor-memory operand (TS mode): the threads write A [256][Kd] (Kd <= 256) to TMEM with tcgen05.st. */
+int rc_debug_umma_gemm_ts_2sm(const void* a_bf16, const void* b_bf16, int N, int Kd, float* c, void* stream);
 
 #ifdef __cplusplus
 }

@@ -34,15 +34,17 @@ PROTOTYPES = {
     "rc_infonce_bf16_kblocks": [_vp, _i32, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _i64, _i32, _vp],
     "rc_infonce_prepass": [_vp, _i32, _i32, _i32, _i64, _vp, _i64, _vp],
-    "rc_text_prepare": [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
+    "rc_text_prepare": [_vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "rc_weight_sum": [_vp, _vp, _i64, _vp, _vp],
     "rc_sample_weights": [_vp, _vp, _i32, _i64, _i64, _vp, _i32, _vp, _vp, _vp],
     "rc_scale": [_vp, _i32, _i64, _vp, _vp],
+    "rc_scale_to": [_vp, _i32, _vp, _i32, _i64, _vp, _vp],
     "rc_pool_fwd": [_vp, _i32, _i32, _i32, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp],
     "rc_pool_finish": [_vp, _vp, _i32, _i32, _vp],
     "rc_pool_bwd": [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp],
     "rc_tv_fwd": [_vp, _i32, _i64, _i32, _i32, _vp, _vp],
     "rc_tv_bwd": [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp],
+    "rc_tv_bwd_from": [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "rc_eval_topk_f32": [_vp, _i32, _i32, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _vp],
     "rc_eval_topk_bf16": [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _vp],
     "rc_eval_topk_hist_bf16": [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp,
@@ -52,6 +54,7 @@ PROTOTYPES = {
     "rc_debug_set_timing_buffer": [_vp],
     "rc_debug_max_active_clusters": [_i32, _i32, _i32],
     "rc_debug_umma_gemm_2sm": [_vp, _vp, _i32, _i32, _vp, _vp],
+    "rc_debug_umma_gemm_ts_2sm": [_vp, _vp, _i32, _i32, _vp, _vp],
     "rc_debug_umma_gemm": [_vp, _vp, _i32, _i32, _i32, _vp, _vp],
 }
 _RESTYPES = {"rc_last_error": C.c_char_p, "rc_launch_count": _i64, "rc_infonce_workspace_bytes": _i64,

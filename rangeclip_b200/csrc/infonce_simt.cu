@@ -251,7 +251,7 @@ eval_topk_f32_kernel(const float* __restrict__ x, int B, int D, int64_t HW, int6
 // ---- small helpers ---------------------------------------------------------------------------
 
 // one warp per text row: F.normalize (model.py:272 / :161), write f32 / bf16 / transposed bf16
-__global__ void text_prepare_kernel(const float* __restrict__ text, int64_t ld_text, const int64_t* __restrict__ idx,
+__global__ void text_prepare_kernel(const float* __restrict__ text, int64_t ld_text, int64_t n_rows, const int64_t* __restrict__ idx,
                                     int K, int Kp, int D, float* __restrict__ t_f32, __nv_bfloat16* __restrict__ t_bf16,
                                     __nv_bfloat16* __restrict__ tt_bf16) {
   const int lane = threadIdx.x & 31;
@@ -264,7 +264,17 @@ __global__ void text_prepare_kernel(const float* __restrict__ text, int64_t ld_t
     }
     return;
   }
-  const float* row = text + (idx ? idx[k] : (int64_t)k) * ld_text;
+  const int64_t src = idx ? idx[k] : (int64_t)k;
+  if (src < 0 || src >= n_rows) {      // the reference raises an index error here (text[index_tensor]); a kernel cannot, and must not read out of bounds
+    const float nan = __int_as_float(0x7fc00000);
+    for (int d = lane; d < D; d += 32) {
+      if (t_f32) t_f32[(int64_t)k * D + d] = nan;
+      if (t_bf16) t_bf16[(int64_t)k * D + d] = __float2bfloat16_rn(nan);
+      if (tt_bf16) tt_bf16[(int64_t)d * Kp + k] = __float2bfloat16_rn(nan);
+    }
+    return;
+  }
+  const float* row = text + src * ld_text;
   float ss = 0.f;
   for (int d = lane; d < D; d += 32) { const float v = row[d]; ss = fmaf(v, v, ss); }
   ss = warp_sum(ss);
@@ -334,6 +344,24 @@ __global__ void __launch_bounds__(256) scale_kernel(T* __restrict__ x, int64_t n
   for (int64_t i = nv * V + tid; i < n; i += nt) ElemIO<T>::st(x + i, ElemIO<T>::ld(x + i) * f);
 }
 
+// out = s[0] * x with a dtype conversion on the way (8 elements per thread per step): the late upstream scaling of a saved
+// gradient into a FRESH buffer of the caller's dtype -- the saved tensor stays intact for a second backward
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) scale_to_kernel(const TI* __restrict__ x, TO* __restrict__ out, int64_t n,
+                                                        const float* __restrict__ s, int vec_ok) {
+  const float f = s ? s[0] : 1.f;
+  const int64_t nv = vec_ok ? n / 8 : 0;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < nv; i += nt) {
+    float v[8];
+    load8(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= f;
+    store8(out + i * 8, v);
+  }
+  for (int64_t i = nv * 8 + tid; i < n; i += nt) ElemIO<TO>::st(out + i, ElemIO<TI>::ld(x + i) * f);
+}
+
 template <template <int> class Launcher, typename... Args>
 static int dispatch_dpt(int D, Args... args) {
   if (D <= 64) return Launcher<8>::run(args...);
@@ -394,13 +422,14 @@ extern "C" int rc_eval_topk_f32(const float* x, int B, int D, int64_t HW, int64_
   return rc::check_launch("rc_eval_topk_f32");
 }
 
-extern "C" int rc_text_prepare(const float* text, int64_t ld_text, const int64_t* idx, int K, int D, float* t_f32,
+extern "C" int rc_text_prepare(const float* text, int64_t ld_text, int64_t n_rows, const int64_t* idx, int K, int D, float* t_f32,
                                void* t_bf16, void* tt_bf16, void* stream) {
-  RC_REQUIRE(text && K >= 1 && D >= 1, "rc_text_prepare: bad argument");
+  RC_REQUIRE(text && K >= 1 && D >= 1 && n_rows >= 1, "rc_text_prepare: bad argument");
+  RC_REQUIRE(idx != nullptr || K <= n_rows, "rc_text_prepare: K=%d rows requested from a table of %lld", K, (long long)n_rows);
   const int Kp = (K + 63) / 64 * 64;
   const int rows = (t_bf16 || tt_bf16) ? Kp : K;
   rc::text_prepare_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
-      text, ld_text, idx, K, rows, D, t_f32, (__nv_bfloat16*)t_bf16, (__nv_bfloat16*)tt_bf16);
+      text, ld_text, n_rows, idx, K, rows, D, t_f32, (__nv_bfloat16*)t_bf16, (__nv_bfloat16*)tt_bf16);
   return rc::check_launch("rc_text_prepare");
 }
 
@@ -446,4 +475,20 @@ extern "C" int rc_scale(void* x, rc_dtype dtype, int64_t n, const float* sc, voi
   if (dtype == RC_F32) rc::scale_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, n, sc, vec_ok);
   else rc::scale_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, n, sc, vec_ok);
   return rc::check_launch("rc_scale");
+}
+
+extern "C" int rc_scale_to(const void* x, rc_dtype x_dtype, void* out, rc_dtype out_dtype, int64_t n, const float* sc, void* stream) {
+  using bf16 = __nv_bfloat16;
+  RC_REQUIRE(n >= 0, "rc_scale_to: bad argument");
+  if (n == 0) return RC_OK;
+  RC_REQUIRE(x && out && x != out, "rc_scale_to: null pointer or in-place call (use rc_scale)");
+  const int64_t blocks = (n / 8 + 255) / 256 + 1;
+  const int grid = (int)(blocks < rc::num_sms() * 8 ? blocks : rc::num_sms() * 8);
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (x_dtype == RC_BF16 && out_dtype == RC_BF16) rc::scale_to_kernel<bf16, bf16><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)out, n, sc, vec_ok);
+  else if (x_dtype == RC_BF16) rc::scale_to_kernel<bf16, float><<<grid, 256, 0, s>>>((const bf16*)x, (float*)out, n, sc, vec_ok);
+  else if (out_dtype == RC_BF16) rc::scale_to_kernel<float, bf16><<<grid, 256, 0, s>>>((const float*)x, (bf16*)out, n, sc, vec_ok);
+  else rc::scale_to_kernel<float, float><<<grid, 256, 0, s>>>((const float*)x, (float*)out, n, sc, vec_ok);
+  return rc::check_launch("rc_scale_to");
 }

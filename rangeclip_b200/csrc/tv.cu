@@ -75,10 +75,12 @@ tv_fwd_kernel(const T* __restrict__ x, int64_t planes, int H, int W, int TH, dou
 
 __device__ __forceinline__ float sgnf(float v) { return (float)((v > 0.f) - (v < 0.f)); }
 
-template <typename T>
+// dx_in (nullable): the gradient to accumulate onto, dx = dx_scale * dx_in + TV'; it may be dx itself (in place) and
+// may have another element type than dx (a bf16 InfoNCE gradient under an fp32 x)
+template <typename T, typename TI>
 __global__ void __launch_bounds__(kTvThreads)
 tv_bwd_kernel(const T* __restrict__ x, int64_t planes, int H, int W, int TH, const float* __restrict__ scale,
-              T* __restrict__ dx, int accumulate, const float* __restrict__ dx_scale) {
+              T* dx, const TI* dx_in, const float* __restrict__ dx_scale) {
   extern __shared__ float tile[];  // [(TH+2)][W], row 0 = h0-1
   const int tiles_per_plane = (H + TH - 1) / TH;
   const int64_t n_tiles = planes * tiles_per_plane;
@@ -93,6 +95,7 @@ tv_bwd_kernel(const T* __restrict__ x, int64_t planes, int H, int W, int TH, con
     tv_load_rows(x + pl * (int64_t)H * W, H, W, h0 - 1, rows + 2, tile, vec_ok);
     __syncthreads();
     T* out = dx + pl * (int64_t)H * W + (int64_t)h0 * W;
+    const TI* in = dx_in ? dx_in + pl * (int64_t)H * W + (int64_t)h0 * W : nullptr;
     const float* ctr = tile + W;
     for (int i = threadIdx.x; i < rows * W; i += kTvThreads) {
       const int r = i / W, c = i - r * W;
@@ -103,7 +106,7 @@ tv_bwd_kernel(const T* __restrict__ x, int64_t planes, int H, int W, int TH, con
       if (c >= 1) g -= sh * sgnf(ctr[i - 1] - a);
       if (h + 1 < H) g += sv * sgnf(a - ctr[i + W]);
       if (h >= 1) g -= sv * sgnf(ctr[i - W] - a);
-      if (accumulate) g += ds * ElemIO<T>::ld(out + i);
+      if (in) g += ds * ElemIO<TI>::ld(in + i);
       ElemIO<T>::st(out + i, g);
     }
   }
@@ -195,10 +198,10 @@ tv_fwd_vec_kernel(const T* __restrict__ x, int64_t planes, int H, int W, int TH,
   }
 }
 
-template <typename T>
+template <typename T, typename TI>
 __global__ void __launch_bounds__(kTvThreads)
 tv_bwd_vec_kernel(const T* __restrict__ x, int64_t planes, int H, int W, int TH, const float* __restrict__ scale,
-                  T* __restrict__ dx, int accumulate, const float* __restrict__ dx_scale) {
+                  T* dx, const TI* dx_in, const float* __restrict__ dx_scale) {
   extern __shared__ __align__(16) unsigned char tv_smem[];
   T* tile = reinterpret_cast<T*>(tv_smem);   // [(TH+2)][W], row 0 = h0-1
   const int tiles_per_plane = (H + TH - 1) / TH;
@@ -214,6 +217,7 @@ tv_bwd_vec_kernel(const T* __restrict__ x, int64_t planes, int H, int W, int TH,
     tv_fill_tile(x + pl * (int64_t)H * W, H, W, h0 - 1, rows + 2, tile);
     __syncthreads();
     T* out = dx + pl * (int64_t)H * W + (int64_t)h0 * W;
+    const TI* in = dx_in ? dx_in + pl * (int64_t)H * W + (int64_t)h0 * W : nullptr;
     for (int gi = threadIdx.x; gi < rows * gpr; gi += kTvThreads) {
       const int r = gi / gpr, c0 = (gi - r * gpr) << 3;
       const int h = h0 + r;
@@ -243,9 +247,9 @@ tv_bwd_vec_kernel(const T* __restrict__ x, int64_t planes, int H, int W, int TH,
         for (int i = 0; i < 8; ++i) g[i] -= sv * sgnf(a[i] - v[i]);
       }
       T* o = out + r * W + c0;
-      if (accumulate) {
+      if (in) {
         float e[8];
-        load8(o, e);
+        load8(in + r * W + c0, e);
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = fmaf(ds, e[i], g[i]);
       }
@@ -287,7 +291,7 @@ __device__ __forceinline__ uint32_t bf2_shl1(uint32_t cur, uint32_t next) { retu
 
 __global__ void __launch_bounds__(kTvThreads)
 tv_bwd_bf16x2_kernel(const __nv_bfloat16* __restrict__ x, int64_t planes, int H, int W, int TH, const float* __restrict__ scale,
-                     __nv_bfloat16* __restrict__ dx, int accumulate, const float* __restrict__ dx_scale) {
+                     __nv_bfloat16* dx, const __nv_bfloat16* dx_in, const float* __restrict__ dx_scale) {
   extern __shared__ __align__(16) unsigned char tv_smem[];
   __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(tv_smem);   // [(TH+2)][W], row 0 = h0-1
   const int tiles_per_plane = (H + TH - 1) / TH;
@@ -306,6 +310,7 @@ tv_bwd_bf16x2_kernel(const __nv_bfloat16* __restrict__ x, int64_t planes, int H,
     tv_fill_tile(x + pl * (int64_t)H * W, H, W, h0 - 1, rows + 2, tile);
     __syncthreads();
     __nv_bfloat16* out = dx + pl * (int64_t)H * W + (int64_t)h0 * W;
+    const __nv_bfloat16* in = dx_in ? dx_in + pl * (int64_t)H * W + (int64_t)h0 * W : nullptr;
     for (int gi = threadIdx.x; gi < rows * gpr; gi += kTvThreads) {
       const int r = gi / gpr, c0 = (gi - r * gpr) << 3;
       const int h = h0 + r;
@@ -328,8 +333,8 @@ tv_bwd_bf16x2_kernel(const __nv_bfloat16* __restrict__ x, int64_t planes, int H,
         g[i] = bf2_fma_(sv2, dv, bf2_mul_(sh2, dh));
       }
       uint4* o = reinterpret_cast<uint4*>(out + r * W + c0);
-      if (accumulate) {
-        const uint4 ev = *o;
+      if (in) {
+        const uint4 ev = *reinterpret_cast<const uint4*>(in + r * W + c0);
         const uint32_t e[4] = {ev.x, ev.y, ev.z, ev.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) g[i] = bf2_fma_(dsl2, e[i], bf2_fma_(dsh2, e[i], g[i]));
@@ -420,10 +425,10 @@ tv_fwd_direct_kernel(const T* __restrict__ x, int64_t planes, int H, int W, doub
   if ((threadIdx.x & 31) == 0) { atomicAdd(&sums[0], acc_h); atomicAdd(&sums[1], acc_v); }
 }
 
-template <typename T>
+template <typename T, typename TI>
 __global__ void __launch_bounds__(kTvThreads)
 tv_bwd_direct_kernel(const T* __restrict__ x, int64_t planes, int H, int W, const float* __restrict__ scale,
-                     T* __restrict__ dx, int accumulate, const float* __restrict__ dx_scale) {
+                     T* dx, const TI* dx_in, const float* __restrict__ dx_scale) {
   const int64_t n = planes * (int64_t)H * W;
   const float sh = scale[0], sv = scale[1];
   const float ds = (dx_scale != nullptr) ? dx_scale[0] : 1.f;
@@ -436,7 +441,7 @@ tv_bwd_direct_kernel(const T* __restrict__ x, int64_t planes, int H, int W, cons
     if (c >= 1) g -= sh * sgnf(ElemIO<T>::ld(x + i - 1) - a);
     if (h + 1 < H) g += sv * sgnf(a - ElemIO<T>::ld(x + i + W));
     if (h >= 1) g -= sv * sgnf(ElemIO<T>::ld(x + i - W) - a);
-    if (accumulate) g += ds * ElemIO<T>::ld(dx + i);
+    if (dx_in) g += ds * ElemIO<TI>::ld(dx_in + i);
     ElemIO<T>::st(dx + i, g);
   }
 }
@@ -510,42 +515,64 @@ extern "C" int rc_tv_fwd(const void* x, rc_dtype x_dtype, int64_t planes, int H,
   return rc::check_launch("rc_tv_fwd");
 }
 
-extern "C" int rc_tv_bwd(const void* x, rc_dtype x_dtype, int64_t planes, int H, int W, const float* scale,
-                         void* dx, int accumulate, const float* dx_scale, void* stream) {
-  RC_REQUIRE(x && dx && scale, "rc_tv_bwd: null pointer");
-  RC_REQUIRE(planes >= 0 && H >= 1 && W >= 1, "rc_tv_bwd: bad shape");
+// dx (x_dtype) = dx_scale * dx_in + scale_h d(sum_h)/dx + scale_v d(sum_v)/dx; dx_in nullable, any supported dtype pairing
+static int tv_bwd_impl(const void* x, rc_dtype x_dtype, int64_t planes, int H, int W, const float* scale, void* dx,
+                       const void* dx_in, rc_dtype in_dtype, const float* dx_scale, void* stream, const char* what) {
+  using bf16 = __nv_bfloat16;
+  RC_REQUIRE(x && dx && scale, "%s: null pointer", what);
+  RC_REQUIRE(planes >= 0 && H >= 1 && W >= 1, "%s: bad shape", what);
+  if (dx_in != nullptr && x_dtype == RC_BF16 && in_dtype != RC_BF16)
+    return rc::fail(RC_ERR_UNSUPPORTED, "%s: an f32 dx_in needs an f32 x / dx", what);
   if (planes == 0) return RC_OK;
-  const bool vec = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+  const bool in_bf = dx_in != nullptr && in_dtype == RC_BF16;
+  const bool vec = (W % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dx_in) & 15) == 0);
   const int TH = rc::tv_tile_rows(H, W, 2, (vec && x_dtype != RC_F32) ? 2 : 4, vec, false);
+  cudaStream_t s = (cudaStream_t)stream;
   if (TH < 1) {          // wider than a shared-memory tile: element-wise kernel
     const int64_t n = planes * (int64_t)H * W;
     const int64_t nb = (n + rc::kTvThreads - 1) / rc::kTvThreads, capd = (int64_t)rc::num_sms() * 16;
     const int gridd = (int)(nb < capd ? nb : capd);
-    if (x_dtype == RC_F32)
-      rc::tv_bwd_direct_kernel<float><<<gridd, rc::kTvThreads, 0, (cudaStream_t)stream>>>((const float*)x, planes, H, W, scale, (float*)dx, accumulate, dx_scale);
+    if (x_dtype == RC_F32 && in_bf)
+      rc::tv_bwd_direct_kernel<float, bf16><<<gridd, rc::kTvThreads, 0, s>>>((const float*)x, planes, H, W, scale, (float*)dx, (const bf16*)dx_in, dx_scale);
+    else if (x_dtype == RC_F32)
+      rc::tv_bwd_direct_kernel<float, float><<<gridd, rc::kTvThreads, 0, s>>>((const float*)x, planes, H, W, scale, (float*)dx, (const float*)dx_in, dx_scale);
     else
-      rc::tv_bwd_direct_kernel<__nv_bfloat16><<<gridd, rc::kTvThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, planes, H, W, scale,
-                                                                                                  (__nv_bfloat16*)dx, accumulate, dx_scale);
-    return rc::check_launch("rc_tv_bwd(direct)");
+      rc::tv_bwd_direct_kernel<bf16, bf16><<<gridd, rc::kTvThreads, 0, s>>>((const bf16*)x, planes, H, W, scale, (bf16*)dx, (const bf16*)dx_in, dx_scale);
+    return rc::check_launch(what);
   }
   const int64_t n_tiles = planes * ((H + TH - 1) / TH);
   const int64_t cap = (int64_t)rc::num_sms() * 8;
   const int grid = (int)(n_tiles < cap ? n_tiles : cap);
   const size_t smem = (size_t)(TH + 2) * W * sizeof(float);
-  cudaStream_t s = (cudaStream_t)stream;
   if (vec) {
     const size_t vsmem = (size_t)(TH + 2) * W * (x_dtype == RC_F32 ? 4 : 2);
-    int rcode = x_dtype == RC_F32 ? rc::tv_allow_smem(rc::tv_bwd_vec_kernel<float>, vsmem, "rc_tv_bwd") : rc::tv_allow_smem(rc::tv_bwd_bf16x2_kernel, vsmem, "rc_tv_bwd");
+    int rcode = x_dtype != RC_F32 ? rc::tv_allow_smem(rc::tv_bwd_bf16x2_kernel, vsmem, what)
+                : in_bf        ? rc::tv_allow_smem(rc::tv_bwd_vec_kernel<float, bf16>, vsmem, what)
+                               : rc::tv_allow_smem(rc::tv_bwd_vec_kernel<float, float>, vsmem, what);
     if (rcode) return rcode;
-    if (x_dtype == RC_F32)
-      rc::tv_bwd_vec_kernel<float><<<grid, rc::kTvThreads, vsmem, s>>>((const float*)x, planes, H, W, TH, scale, (float*)dx, accumulate, dx_scale);
+    if (x_dtype != RC_F32)
+      rc::tv_bwd_bf16x2_kernel<<<grid, rc::kTvThreads, vsmem, s>>>((const bf16*)x, planes, H, W, TH, scale, (bf16*)dx, (const bf16*)dx_in, dx_scale);
+    else if (in_bf)
+      rc::tv_bwd_vec_kernel<float, bf16><<<grid, rc::kTvThreads, vsmem, s>>>((const float*)x, planes, H, W, TH, scale, (float*)dx, (const bf16*)dx_in, dx_scale);
     else
-      rc::tv_bwd_bf16x2_kernel<<<grid, rc::kTvThreads, vsmem, s>>>((const __nv_bfloat16*)x, planes, H, W, TH, scale,
-                                                                   (__nv_bfloat16*)dx, accumulate, dx_scale);
-  } else if (x_dtype == RC_F32)
-    rc::tv_bwd_kernel<float><<<grid, rc::kTvThreads, smem, s>>>((const float*)x, planes, H, W, TH, scale, (float*)dx, accumulate, dx_scale);
+      rc::tv_bwd_vec_kernel<float, float><<<grid, rc::kTvThreads, vsmem, s>>>((const float*)x, planes, H, W, TH, scale, (float*)dx, (const float*)dx_in, dx_scale);
+  } else if (x_dtype == RC_F32 && in_bf)
+    rc::tv_bwd_kernel<float, bf16><<<grid, rc::kTvThreads, smem, s>>>((const float*)x, planes, H, W, TH, scale, (float*)dx, (const bf16*)dx_in, dx_scale);
+  else if (x_dtype == RC_F32)
+    rc::tv_bwd_kernel<float, float><<<grid, rc::kTvThreads, smem, s>>>((const float*)x, planes, H, W, TH, scale, (float*)dx, (const float*)dx_in, dx_scale);
   else
-    rc::tv_bwd_kernel<__nv_bfloat16><<<grid, rc::kTvThreads, smem, s>>>((const __nv_bfloat16*)x, planes, H, W, TH, scale,
-                                                                         (__nv_bfloat16*)dx, accumulate, dx_scale);
-  return rc::check_launch("rc_tv_bwd");
+    rc::tv_bwd_kernel<bf16, bf16><<<grid, rc::kTvThreads, smem, s>>>((const bf16*)x, planes, H, W, TH, scale, (bf16*)dx, (const bf16*)dx_in, dx_scale);
+  return rc::check_launch(what);
+}
+
+extern "C" int rc_tv_bwd(const void* x, rc_dtype x_dtype, int64_t planes, int H, int W, const float* scale,
+                         void* dx, int accumulate, const float* dx_scale, void* stream) {
+  return tv_bwd_impl(x, x_dtype, planes, H, W, scale, dx, accumulate ? dx : nullptr, x_dtype, dx_scale, stream, "rc_tv_bwd");
+}
+
+extern "C" int rc_tv_bwd_from(const void* x, rc_dtype x_dtype, int64_t planes, int H, int W, const float* scale,
+                              const void* dx_in, rc_dtype dx_in_dtype, const float* dx_scale, void* dx_out, void* stream) {
+  RC_REQUIRE(dx_in != nullptr, "rc_tv_bwd_from: null dx_in");
+  return tv_bwd_impl(x, x_dtype, planes, H, W, scale, dx_out, dx_in, dx_in_dtype, dx_scale, stream, "rc_tv_bwd_from");
 }

@@ -359,6 +359,17 @@ __device__ __forceinline__ void mma_bf16_ss_2sm(uint32_t d_tmem, uint64_t a_desc
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// TS mode: D[tmem, both CTAs] (+)= A[TMEM of each CTA: its 128 rows, packed bf16 pairs, 8 columns per 16 k] *
+// B[smem, N split: N/2 rows per CTA].  A must be K-major (operands in tensor memory cannot be transposed).
+__device__ __forceinline__ void mma_bf16_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive (once all prior MMAs of this thread completed) on the mbarrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void mma_commit_2sm(uint64_t* bar) {
   asm volatile(

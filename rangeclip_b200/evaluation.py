@@ -103,10 +103,19 @@ class MetricAccumulator:
     def state(self) -> Dict[str, torch.Tensor]:
         return dict(acc=self.acc, counters=self.counters, first_seen=self.first_seen)
 
-    def finalize(self, last_segmentation: torch.Tensor) -> Dict[str, object]:
+    def valid_mask(self, last_segmentation: Optional[torch.Tensor]) -> torch.Tensor:
+        """uint8 [C]: classes present in a batch's ground truth -- the label filter of validate.py:206-210 (Q11)."""
+        mask = torch.zeros(self.C, device=self.cmap.device, dtype=torch.uint8)
+        if last_segmentation is not None:
+            mask[self.cmap[last_segmentation.reshape(-1).to(self.cmap.device)]] = 1
+        return mask
+
+    def finalize(self, last_segmentation: Optional[torch.Tensor] = None, valid_mask: Optional[torch.Tensor] = None) -> Dict[str, object]:
         """validate.py:194-214: mIoU over labels present in the LAST batch's GT (Q11), averaged in the
-        reference's dict insertion order (batch of first appearance, then label id); accuracies."""
-        valid = set(self.cmap[last_segmentation.reshape(-1).to(self.cmap.device)].tolist())
+        reference's dict insertion order (batch of first appearance, then label id); accuracies.  ``valid_mask``
+        (uint8 [C]) replaces ``last_segmentation`` when the globally last batch lives on another rank."""
+        mask = valid_mask if valid_mask is not None else self.valid_mask(last_segmentation)
+        valid = set(torch.nonzero(mask).reshape(-1).tolist())
         return finalize_metrics(self.acc, self.counters, self.first_seen, valid)
 
 
@@ -159,7 +168,11 @@ def validate_model(model, clip_model, clip_processor, candidate_text_embeddings,
     """Drop-in for ``validate_model`` (validate.py:34-266).  Same arguments, same ``best_results`` keys and log
     lines; the per-batch metric loops (validate.py:88-139) run as two kernels per batch with no host sync, and the
     finalisation (validate.py:194-214) reads the integer state back once.  ``all_reduce=True`` (an addition) sums
-    the state over the default process group first, so that every rank may validate its own shard."""
+    the state over the default process group first, so that every rank may validate its own shard of the batches:
+    ``dataloader`` then yields the batches ``distributed.shard_batches`` assigns to this rank (round robin: the i-th
+    local batch is global batch rank + i * world_size), the per-label first-appearance order is kept in GLOBAL batch
+    indices, and the class filter of the final mean (the LAST batch's ground truth, Q11) comes from the rank that owns
+    the globally last batch -- every rank then returns the single-process result bit for bit."""
     from .losses import compute_loss as _compute_loss
     from .pooling import prepare_image_contrast_data as _prepare
 
@@ -170,6 +183,11 @@ def validate_model(model, clip_model, clip_processor, candidate_text_embeddings,
     segmentation = None
     temperature_text = None
     core = _unwrap(model)
+    rank, world = 0, 1
+    if all_reduce:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
     with torch.no_grad():
         for batch in dataloader:
             depth = batch['depth'].to(device, non_blocking=True)
@@ -180,7 +198,7 @@ def validate_model(model, clip_model, clip_processor, candidate_text_embeddings,
             pred_topk, pixel_embeddings, temperature_text = core.predict(
                 depth_maps=depth, candidate_text_embeddings=candidate_text_embeddings, segmentation=segmentation,
                 num_negatives=50, top_k=5)
-            acc.update(segmentation, pred_topk)
+            acc.update(segmentation, pred_topk, batch_index=rank + n_batches * world)
             area_embeddings, image_embeddings = _prepare(
                 image_processed_batch=image_processed, object_bbox_batch=object_bbox, object_label_batch=object_label,
                 segmentation_batch=segmentation, pixel_embeddings_batch=pixel_embeddings, clip_image_encoder=clip_model,
@@ -197,10 +215,16 @@ def validate_model(model, clip_model, clip_processor, candidate_text_embeddings,
             totals[2] += loss_info.get('image_contrastive_loss', 0)
             totals[3] += loss_info.get('smoothness_loss', 0)
             n_batches += 1
+    valid_mask = acc.valid_mask(segmentation)
     if all_reduce:
-        from .distributed import all_reduce_metrics
+        from .distributed import all_reduce_metrics, global_last_batch_mask
         all_reduce_metrics(acc)
-    fin = acc.finalize(segmentation) if segmentation is not None else finalize_metrics(acc.acc, acc.counters, acc.first_seen, set())
+        valid_mask = global_last_batch_mask(valid_mask, rank + (n_batches - 1) * world if n_batches else -1)
+        tot = torch.tensor(totals + [float(n_batches)], device=acc.acc.device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot)                  # the logged losses are averages over all batches of all ranks
+        totals, n_batches = tot[:4].tolist(), int(tot[4])
+    fin = acc.finalize(valid_mask=valid_mask)
     miou_top1, miou_topk = fin["mIoU_t1"], fin["mIoU_tk"]
     pixel_acc_top1, pixel_acc_topk = fin["pixel_accuracy_t1"], fin["pixel_accuracy_tk"]
     avg = [t / max(n_batches, 1) for t in totals]

@@ -100,20 +100,30 @@ def text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embed
         return (zero(), aux) if return_aux else zero()
     label_map = torch.full((C,), -1, dtype=torch.int32, device=device)
     label_map[contrast] = torch.arange(contrast.shape[0], device=device, dtype=torch.int32)
-    w, y = ops.sample_weights(target_flat, rand_indices, label_map)
+    w, y = torch.ops.rangeclip.sample_weights(target_flat, rand_indices, label_map)
+    t_bf16 = None
     if candidate_text_embeddings.requires_grad:
         t_norm = torch.nn.functional.normalize(candidate_text_embeddings[contrast].float(), dim=1)
-    else:
-        t_norm, _, _ = ops.text_prepare(candidate_text_embeddings, contrast, want_f32=True)
+    else:       # one launch: normalised rows as f32 and as the two bf16 operand layouts of the tensor-core kernels
+        t_norm, tb, ttb = torch.ops.rangeclip.text_prepare(candidate_text_embeddings, contrast)
+        t_bf16 = (tb, ttb)
     if with_smoothness:      # one autograd node for both terms -> one fused backward pass over X / dX
-        loss, smooth = ops.pixel_losses(pixel_embeddings, t_norm, log_temperature_text, y, w, precision)
+        loss, smooth = ops.pixel_losses(pixel_embeddings, t_norm, log_temperature_text, y, w, precision, t_bf16=t_bf16)
         aux["smoothness"] = smooth
         return loss, aux
     if shared2x2:
-        y, w = group_2x2(y.view(B, H, W)), group_2x2(w.view(B, H, W))
-        loss = ops.infonce(pixel_embeddings, t_norm, log_temperature_text, y, w, precision, rep=4)
+        K = int(contrast.shape[0])
+        if precision != "fp32" and D in (256, 512) and ops.bf16_path_supported(D, (H // 2) * (W // 2), K):
+            y, w = group_2x2(y.view(B, H, W)), group_2x2(w.view(B, H, W))
+            loss = ops.infonce(pixel_embeddings, t_norm, log_temperature_text, y, w, precision, rep=4, t_bf16=t_bf16)
+        else:
+            # outside what the four-target kernel covers (more than 256 contrast rows -- their number is data dependent,
+            # model.py:268 --, D not 256 / 512, fp32 parity mode): the loss of the upsampled tensor itself, as the decoder
+            # would emit it (decoder.py:113); autograd sums the four pixel gradients of a block below the interpolation
+            up = torch.nn.functional.interpolate(pixel_embeddings, scale_factor=2, mode="nearest")
+            loss = ops.infonce(up, t_norm, log_temperature_text, y, w, precision, t_bf16=t_bf16)
     else:
-        loss = ops.infonce(pixel_embeddings, t_norm, log_temperature_text, y, w, precision)
+        loss = ops.infonce(pixel_embeddings, t_norm, log_temperature_text, y, w, precision, t_bf16=t_bf16)
     return (loss, aux) if return_aux else loss
 
 
@@ -141,7 +151,7 @@ def image_contrastive_loss(area_embeddings, image_embeddings, log_temperature_im
             raise RuntimeError(f"image_contrastive_loss: the tensor-core path needs D in (256, 512), n % 8 == 0 and frozen "
                                f"image embeddings; got n={n}, D={D}")
         x = area_embeddings.float().t().contiguous().view(1, D, n, 1)
-        t_norm, _, _ = ops.text_prepare(image_embeddings, None, want_f32=True)
+        t_norm, _, _ = torch.ops.rangeclip.text_prepare(image_embeddings, None)
         y = torch.arange(n, device=x.device, dtype=torch.int32)
         w = torch.ones(n, device=x.device, dtype=torch.float32)
         return ops.infonce_kblocked(x, t_norm, log_temperature_image, y, w)
@@ -149,7 +159,7 @@ def image_contrastive_loss(area_embeddings, image_embeddings, log_temperature_im
     if image_embeddings.requires_grad:
         t_norm = torch.nn.functional.normalize(image_embeddings.float(), dim=1)
     else:
-        t_norm, _, _ = ops.text_prepare(image_embeddings, None, want_f32=True)
+        t_norm, _, _ = torch.ops.rangeclip.text_prepare(image_embeddings, None)
     y = torch.arange(n, device=x.device, dtype=torch.int32)
     w = torch.ones(n, device=x.device, dtype=torch.float32)
     return ops.infonce(x, t_norm, log_temperature_image, y, w, precision)
@@ -208,7 +218,9 @@ def _compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddi
 
     image_loss = torch.tensor(0.0, device=device)
     if area_embeddings is not None and image_embeddings is not None and area_embeddings.shape[0] > 1:
-        image_loss = image_contrastive_loss(area_embeddings, image_embeddings, log_tau_image)
+        # "fp32" is the parity mode of every term; an explicit "bf16" asks for the tensor cores where a term's shape allows them
+        image_loss = image_contrastive_loss(area_embeddings, image_embeddings, log_tau_image,
+                                            precision if precision == "fp32" else "auto")
     elif W_image > 0:
         dummy = torch.tensor(1.0, device=device, requires_grad=True)       # model.py:325-326 (Q14)
         image_loss = dummy * torch.exp(log_tau_image) * 0.0

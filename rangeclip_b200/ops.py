@@ -1,12 +1,19 @@
-"""Thin PyTorch-facing wrappers over the C ABI (``include/rangeclip_b200.h``).
+"""PyTorch-facing layer over the C ABI (``include/rangeclip_b200.h``).
 
-PyTorch is used for device memory, streams and autograd plumbing only; every computation is a
-kernel in ``librangeclip_b200.so``.  All functions require CUDA tensors on an sm_100 device and
-raise ``RuntimeError`` otherwise -- there is no CPU or eager-PyTorch fallback.
+Three tiers, top to bottom of this file:
+  * ``*_raw`` / plain helpers: allocate outputs with torch, pass pointers + the current stream to the C ABI (ctypes);
+  * ``torch.ops.rangeclip.*``: the same calls registered as PyTorch custom operators (``torch.library.custom_op`` with
+    fake-tensor rules and autograd formulas), so that the dispatcher, ``torch.compile`` and fake-tensor tracing see
+    them as single opaque nodes (north_star: "exposed as PyTorch custom ops");
+  * the public functions the drop-ins call (``infonce``, ``pixel_losses``, ``smoothness``, ``masked_pool``, ...), thin
+    shims over the registered operators.
+PyTorch is used for device memory, streams and autograd plumbing only; every computation is a kernel in
+``librangeclip_b200.so``.  All functions require CUDA tensors on an sm_100 device and raise ``RuntimeError``
+otherwise -- there is no CPU or eager-PyTorch fallback.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -68,7 +75,9 @@ def text_prepare(text: torch.Tensor, idx: Optional[torch.Tensor], want_f32=True,
     ttb = torch.empty(D, Kp, device=text.device, dtype=torch.bfloat16) if want_bf16 else None
     if idx is not None:
         idx = idx.to(torch.int64).contiguous()
-    check(_lib.lib().rc_text_prepare(_p(text), text.stride(0), _p(idx), K, D, _p(t32), _p(tb), _p(ttb),
+    # n_rows: an index outside [0, n_rows) yields a NaN row (the reference raises an index error at
+    # candidate_text_embeddings[index_tensor]; a kernel cannot raise, and a silent out-of-bounds read is worse)
+    check(_lib.lib().rc_text_prepare(_p(text), text.stride(0), text.shape[0], _p(idx), K, D, _p(t32), _p(tb), _p(ttb),
                                      _stream(text)), "rc_text_prepare")
     return t32, tb, ttb
 
@@ -107,11 +116,14 @@ def sample_weights(seg: torch.Tensor, rand_idx: Optional[torch.Tensor], label_ma
 
 def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch.Tensor, inv_tau: float,
                 need_dx: bool, need_dt: bool, precision: str = "auto",
-                grad_scale: Optional[torch.Tensor] = None, t_bf16=None, rep: int = 1):
+                grad_scale: Optional[torch.Tensor] = None, t_bf16=None, rep: int = 1, keep_bf16: bool = False,
+                flags: int = 0):
     """One fused pass: returns dict(loss_sum, w_sum (double[1] tensors), lse, dx, dt, dlogtau).
     loss = loss_sum / w_sum; dx/dt/dlogtau are gradients of that mean loss times grad_scale.
     rep = 4: every row of x is the embedding shared by a 2x2 block of pixels (decoder.py:113, Q8);
-    y / w are [rows, 4] and dx is the gradient w.r.t. the shared row (tensor-core path only)."""
+    y / w are [rows, 4] and dx is the gradient w.r.t. the shared row (tensor-core path only).
+    keep_bf16: leave the tensor-core path's dx in bf16 whatever x's dtype (the autograd wrappers widen and scale it
+    in one pass at backward time); flags: extra RC_INFONCE_* bits for rc_infonce_bf16 (e.g. RC_INFONCE_SS_KERNEL)."""
     _need_cuda(x, t_norm, y, w)
     x, B, D, HW = _emb3(x)
     K = t_norm.shape[0]
@@ -180,88 +192,14 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
         check(entry(_p(x), xdt, B, D, HW, _p(tb), _p(ttb), K, _p(y), _p(w), float(inv_tau), _p(lse),
                     acc[0:].data_ptr(), acc[1:].data_ptr(),
                     acc[3:].data_ptr() if need_grad else None, _p(gs), _p(dxb), _p(dt),
-                    acc[2:].data_ptr() if need_dx else None, _p(ws), ws_bytes, 0, st),
+                    acc[2:].data_ptr() if need_dx else None, _p(ws), ws_bytes, int(flags), st),
               "rc_infonce_bf16" if rep == 1 else "rc_infonce_bf16_rep4")
         dx = None
         if dxb is not None:
-            dx = dxb.view(x.shape) if x.dtype == torch.bfloat16 else dxb.view(x.shape).to(x.dtype)
+            dx = dxb.view(x.shape) if (x.dtype == torch.bfloat16 or keep_bf16) else scale_to(dxb.view(x.shape), x.dtype)
     else:
         raise RuntimeError(f"infonce: unknown precision {precision!r}")
     return dict(loss_sum=acc[0], w_sum=acc[1], dlogtau=acc[2], lse=lse, dx=dx, dt=dt, precision=precision)
-
-
-class _InfoNCE(torch.autograd.Function):
-    """loss = weighted InfoNCE(x, t_norm, y, w) / tau; gradients for x, t_norm and log_tau are
-    produced by the same fused kernel launch as the loss (single pass over X)."""
-
-    @staticmethod
-    def forward(ctx, x, t_norm, log_tau, y, w, precision, rep=1):
-        need_dx = x.requires_grad
-        need_dt = t_norm.requires_grad
-        need_tau = log_tau.requires_grad
-        inv_tau = float(torch.exp(-log_tau.detach().float()))          # one scalar sync, as .item() in the reference
-        r = infonce_raw(x.detach(), t_norm.detach(), y, w, inv_tau, need_dx or need_tau, need_dt, precision, rep=rep)
-        wsum = r["w_sum"]
-        loss = torch.where(wsum > 0, r["loss_sum"] / wsum.clamp_min(1e-300), torch.zeros_like(wsum)).float()
-        ctx.save_for_backward(r["dx"] if need_dx else None, r["dt"], r["dlogtau"].float())
-        ctx.flags = (need_dx, need_dt, need_tau)
-        ctx.x_dtype = x.dtype
-        return loss
-
-    @staticmethod
-    def backward(ctx, g):
-        dx, dt, dlt = ctx.saved_tensors
-        need_dx, need_dt, need_tau = ctx.flags
-        gx = gt = gl = None
-        if need_dx:
-            gx = dx
-            gdev = g.detach().reshape(1).float()
-            check(_lib.lib().rc_scale(_p(gx), _dt(gx), gx.numel(), _p(gdev), _stream(gx)), "rc_scale")
-        if need_dt:
-            gt = dt * g
-        if need_tau:
-            gl = (dlt * g).reshape(())
-        return gx, gt, gl, None, None, None, None
-
-
-class _PixelLosses(torch.autograd.Function):
-    """Text InfoNCE + smoothness of the SAME pixel embeddings as one autograd node, so that the backward is a
-    single pass: dX = g_text * dX_text (computed in the forward launch) + g_smooth * d(TV)/dX, written in
-    place by rc_tv_bwd(accumulate, dx_scale) -- X is read once, dX read and written once (model.py:272-291,
-    332-334 and their autograd)."""
-
-    @staticmethod
-    def forward(ctx, x, t_norm, log_tau, y, w, precision):
-        need_dx = x.requires_grad
-        need_dt = t_norm.requires_grad
-        need_tau = log_tau.requires_grad
-        inv_tau = float(torch.exp(-log_tau.detach().float()))
-        r = infonce_raw(x.detach(), t_norm.detach(), y, w, inv_tau, need_dx or need_tau, need_dt, precision)
-        wsum = r["w_sum"]
-        text = torch.where(wsum > 0, r["loss_sum"] / wsum.clamp_min(1e-300), torch.zeros_like(wsum)).float()
-        sums = tv_sums(x.detach())
-        dh, dv = tv_denominators(x.shape)
-        nan = torch.full((), float("nan"), device=x.device, dtype=torch.float64)
-        smooth = ((sums[0] / dh if dh > 0 else nan) + (sums[1] / dv if dv > 0 else nan)).float()
-        ctx.save_for_backward(x, r["dx"] if need_dx else None, r["dt"], r["dlogtau"].float())
-        ctx.flags = (need_dx, need_dt, need_tau)
-        return text, smooth
-
-    @staticmethod
-    def backward(ctx, g_text, g_smooth):
-        x, dx, dt, dlt = ctx.saved_tensors
-        need_dx, need_dt, need_tau = ctx.flags
-        gx = gt = gl = None
-        if need_dx:
-            dh, dv = tv_denominators(x.shape)
-            gs = g_smooth.float()
-            scale = torch.stack([gs / dh if dh > 0 else gs * 0, gs / dv if dv > 0 else gs * 0])
-            gx = tv_backward(x.detach(), scale, dx=dx, dx_scale=g_text.float())
-        if need_dt:
-            gt = dt * g_text
-        if need_tau:
-            gl = (dlt * g_text).reshape(())
-        return gx, gt, gl, None, None, None
 
 
 RC_INFONCE_KEEP_WEIGHT, RC_INFONCE_LSE_GIVEN = 2, 4
@@ -364,40 +302,6 @@ def infonce_kblocked_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor,
     return dict(loss=loss, lse=lse, dx=dx, dlogtau=dlogtau, w_sum=wsum)
 
 
-class _InfoNCEKBlocked(torch.autograd.Function):
-    """Autograd wrapper of ``infonce_kblocked_raw`` (gradients for x and log_tau; the candidate rows are constants)."""
-
-    @staticmethod
-    def forward(ctx, x, t_norm, log_tau, y, w):
-        need = x.requires_grad or log_tau.requires_grad
-        inv_tau = float(torch.exp(-log_tau.detach().float()))
-        r = infonce_kblocked_raw(x.detach(), t_norm.detach(), y, w, inv_tau, need)
-        ctx.save_for_backward(r["dx"], r["dlogtau"].float() if need else None)
-        ctx.flags = (x.requires_grad, log_tau.requires_grad)
-        return r["loss"].float()
-
-    @staticmethod
-    def backward(ctx, g):
-        dx, dlt = ctx.saved_tensors
-        need_dx, need_tau = ctx.flags
-        return (dx * g.to(dx.dtype)) if need_dx else None, None, (dlt * g).reshape(()) if need_tau else None, None, None
-
-
-def infonce_kblocked(x, t_norm, log_tau, y, w):
-    return _InfoNCEKBlocked.apply(x, t_norm, log_tau, y, w)
-
-
-def pixel_losses(x, t_norm, log_tau, y, w, precision="auto"):
-    """(text InfoNCE, smoothness) with a fused single-pass backward."""
-    return _PixelLosses.apply(x, t_norm, log_tau, y, w, precision)
-
-
-def infonce(x, t_norm, log_tau, y, w, precision="auto", rep=1):
-    """Autograd-aware fused InfoNCE; x [B,D,H,W], t_norm [K,D] normalised, y/w per pixel
-    (rep = 4: x holds the embeddings shared by 2x2 pixel blocks, y/w are [B*H*W, 4])."""
-    return _InfoNCE.apply(x, t_norm, log_tau, y, w, precision, rep)
-
-
 # ----------------------------------------------------------------------------------------------
 # smoothness (TV-L1)
 # ----------------------------------------------------------------------------------------------
@@ -419,44 +323,36 @@ def tv_denominators(shape) -> Tuple[float, float]:
 
 def tv_backward(x: torch.Tensor, scale: torch.Tensor, dx: Optional[torch.Tensor] = None,
                 dx_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dx (= or +=) scale[0] * d(sum_h)/dx + scale[1] * d(sum_v)/dx; if dx is given it is first
-    multiplied by dx_scale (device scalar) -- the fused late upstream scaling."""
+    """A FRESH tensor (x's dtype) = dx_scale * dx + scale[0] * d(sum_h)/dx + scale[1] * d(sum_v)/dx.  ``dx`` (optional)
+    is the gradient to accumulate onto and is left untouched (autograd may run a backward twice); it may be bf16
+    under an fp32 x -- the tensor-core InfoNCE gradient -- so the fused backward of an fp32 embedding tensor reads x
+    once, dx once and writes the result once (rc_tv_bwd_from)."""
+    _need_cuda(x, scale, dx)
     x = x.contiguous()
     B, D, H, W = x.shape
-    acc = 1
-    if dx is None:
-        dx = torch.empty_like(x)
-        acc = 0
+    out = torch.empty_like(x)
     scale = scale.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    if dx is None:
+        check(_lib.lib().rc_tv_bwd(_p(x), _dt(x), B * D, H, W, _p(scale), _p(out), 0, None, _stream(x)), "rc_tv_bwd")
+        return out
+    dx = dx.contiguous()
+    if dx.numel() != x.numel():
+        raise RuntimeError("tv_backward: dx must have x's shape")
     ds = None if dx_scale is None else dx_scale.detach().reshape(1).to(device=x.device, dtype=torch.float32)
-    check(_lib.lib().rc_tv_bwd(_p(x), _dt(x), B * D, H, W, _p(scale), _p(dx), acc, _p(ds), _stream(x)), "rc_tv_bwd")
-    return dx
+    check(_lib.lib().rc_tv_bwd_from(_p(x), _dt(x), B * D, H, W, _p(scale), _p(dx), _dt(dx), _p(ds), _p(out), _stream(x)),
+          "rc_tv_bwd_from")
+    return out
 
 
-class _Smoothness(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, denominators=None):
-        sums = tv_sums(x.detach())
-        dh, dv = tv_denominators(x.shape) if denominators is None else denominators
-        ctx.den = (dh, dv)
-        ctx.save_for_backward(x)
-        # l1_loss over an empty slice is NaN in the reference (W == 1 or H == 1); keep that
-        th = sums[0] / dh if dh > 0 else torch.full((), float("nan"), device=x.device, dtype=torch.float64)
-        tv = sums[1] / dv if dv > 0 else torch.full((), float("nan"), device=x.device, dtype=torch.float64)
-        return (th + tv).float()
-
-    @staticmethod
-    def backward(ctx, g):
-        (x,) = ctx.saved_tensors
-        dh, dv = ctx.den
-        scale = torch.stack([g.float() / dh if dh > 0 else g.float() * 0, g.float() / dv if dv > 0 else g.float() * 0])
-        return tv_backward(x.detach(), scale), None
-
-
-def smoothness(x: torch.Tensor, denominators=None) -> torch.Tensor:
-    """sum_h / dh + sum_v / dv; the denominators default to the element counts of x's own slices
-    (model.py:332-333) and can be overridden when x stands for a larger tensor (shared 2x2 blocks)."""
-    return _Smoothness.apply(x, denominators)
+def scale_to(x: torch.Tensor, out_dtype: torch.dtype, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A FRESH tensor of ``out_dtype`` = scale * x (scale: device scalar, None = 1): the late upstream scaling of a
+    saved gradient and the bf16 -> fp32 widening of the tensor-core gradient in ONE pass (rc_scale_to)."""
+    _need_cuda(x, scale)
+    x = x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    sc = None if scale is None else scale.detach().reshape(1).to(device=x.device, dtype=torch.float32)
+    check(_lib.lib().rc_scale_to(_p(x), _dt(x), _p(out), _dt(out), x.numel(), _p(sc), _stream(x)), "rc_scale_to")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -505,26 +401,6 @@ def pool_backward(g: torch.Tensor, cnt: torch.Tensor, seg, lut: torch.Tensor, lu
                                      g.shape[0], _p(dx), RC_F32 if dtype == torch.float32 else RC_BF16, 1 if i else 0,
                                      _stream(g)), "rc_pool_bwd")
     return dx
-
-
-class _MaskedPool(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, seg, lut, lut_per_image, n_slots):
-        out, cnt = pool_forward(x.detach(), seg, lut, lut_per_image, n_slots)
-        segs = list(seg) if isinstance(seg, (list, tuple)) else [seg]
-        ctx.save_for_backward(cnt, lut, *segs)
-        ctx.meta = (lut_per_image, tuple(x.shape), x.dtype)
-        return out.to(x.dtype) if x.dtype != torch.float32 else out
-
-    @staticmethod
-    def backward(ctx, g):
-        cnt, lut, *segs = ctx.saved_tensors
-        lut_per_image, shape, dtype = ctx.meta
-        return pool_backward(g, cnt, segs, lut, lut_per_image, shape, dtype), None, None, None, None
-
-
-def masked_pool(x, seg, lut, lut_per_image, n_slots):
-    return _MaskedPool.apply(x, seg, lut, lut_per_image, n_slots)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -629,6 +505,371 @@ def eval_fold(batch_hist: torch.Tensor, batch_index: int, acc: torch.Tensor, fir
           "rc_eval_fold")
 
 
+# ----------------------------------------------------------------------------------------------
+# torch.ops.rangeclip.* : the kernels as PyTorch custom operators (dispatcher / torch.compile / fake tensors)
+# ----------------------------------------------------------------------------------------------
+
+_DT_CODE = {torch.float32: 0, torch.bfloat16: 1}
+_CODE_DT = {0: torch.float32, 1: torch.bfloat16}
+_op = torch.library.custom_op
+
+
+def _empty(like: torch.Tensor) -> torch.Tensor:
+    return like.new_empty(0)
+
+
+def _infonce_plan(x: torch.Tensor, K: int, need_dt: bool, precision: str, rep: int) -> str:
+    """Which kernel family ``infonce_raw`` takes for this call: 'kblocked', 'bf16' or 'fp32' (shape logic only)."""
+    D = x.shape[1]
+    HW = x[0, 0].numel() if x.shape[0] and D else 0
+    if rep == 4:
+        return "bf16"
+    if precision == "auto" and K > 256 and not need_dt and kblocked_supported(D, HW):
+        return "kblocked"
+    if precision == "auto":
+        dt_on_tc = need_dt and D in (256, 512)
+        return "bf16" if (bf16_path_supported(D, HW, K) and (not need_dt or dt_on_tc)) else "fp32"
+    return precision
+
+
+def _mean_loss(r) -> torch.Tensor:
+    wsum = r["w_sum"]
+    return torch.where(wsum > 0, r["loss_sum"] / wsum.clamp_min(1e-300), torch.zeros_like(wsum)).float().reshape(())
+
+
+@_op("rangeclip::infonce", mutates_args=(), device_types="cuda")
+def _op_infonce(x: torch.Tensor, t_norm: torch.Tensor, log_tau: torch.Tensor, y: torch.Tensor, w: torch.Tensor,
+                need_grad: bool, need_dt: bool, precision: str, rep: int, t_bf16: Optional[torch.Tensor],
+                tt_bf16: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(loss, dx, dt, dlogtau): weighted InfoNCE(x, t_norm, y, w) / tau with the gradients of the MEAN loss produced by
+    the same fused launch (single pass over x).  dx stays in the kernel's dtype (bf16 on the tensor-core path)."""
+    inv_tau = float(torch.exp(-log_tau.detach().float()))          # one scalar sync, as .item() in the reference
+    tb = (t_bf16, tt_bf16) if (t_bf16 is not None and tt_bf16 is not None) else None
+    r = infonce_raw(x, t_norm, y, w, inv_tau, need_grad, need_dt, precision, t_bf16=tb, rep=rep, keep_bf16=True)
+    dx, dt = r["dx"], r["dt"]
+    return (_mean_loss(r), dx if dx is not None else _empty(x), dt if dt is not None else _empty(t_norm),
+            r["dlogtau"].float().reshape(()))
+
+
+@_op_infonce.register_fake
+def _(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, rep, t_bf16, tt_bf16):
+    plan = _infonce_plan(x, t_norm.shape[0], need_dt, precision, rep)
+    dx_dtype = torch.bfloat16 if plan == "bf16" else x.dtype
+    f32 = dict(device=x.device, dtype=torch.float32)
+    return (torch.empty((), **f32), torch.empty(x.shape, device=x.device, dtype=dx_dtype) if need_grad else _empty(x),
+            torch.empty(t_norm.shape, **f32) if need_dt else _empty(t_norm), torch.empty((), **f32))
+
+
+def _infonce_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1], output[2], output[3])
+    ctx.x_dtype = inputs[0].dtype
+
+
+def _infonce_backward(ctx, g, *_unused):
+    dx, dt, dlt = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    # the saved gradient is READ-ONLY: the scaled copy is a fresh tensor, so a second backward through the same graph
+    # (retain_graph, torch.autograd.grad + backward) sees the same dx again
+    gx = torch.ops.rangeclip.scale_to(dx, g, _DT_CODE[ctx.x_dtype]) if need[0] else None
+    gt = dt * g if need[1] else None
+    gl = (dlt * g).reshape(()) if need[2] else None
+    return (gx, gt, gl) + (None,) * 8
+
+
+_op_infonce.register_autograd(_infonce_backward, setup_context=_infonce_setup)
+
+
+@_op("rangeclip::pixel_losses", mutates_args=(), device_types="cuda")
+def _op_pixel_losses(x: torch.Tensor, t_norm: torch.Tensor, log_tau: torch.Tensor, y: torch.Tensor, w: torch.Tensor,
+                     need_grad: bool, need_dt: bool, precision: str, t_bf16: Optional[torch.Tensor],
+                     tt_bf16: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(text InfoNCE, smoothness, dx_text, dt, dlogtau) of the SAME pixel embeddings: one autograd node for both terms, so
+    that the backward is a single pass (model.py:272-291, 332-334 and their autograd)."""
+    loss, dx, dt, dlt = _op_infonce._init_fn(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, 1, t_bf16, tt_bf16)
+    sums = tv_sums(x)
+    dh, dv = tv_denominators(x.shape)
+    nan = torch.full((), float("nan"), device=x.device, dtype=torch.float64)
+    smooth = ((sums[0] / dh if dh > 0 else nan) + (sums[1] / dv if dv > 0 else nan)).float().reshape(())
+    return loss, smooth, dx, dt, dlt
+
+
+@_op_pixel_losses.register_fake
+def _(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, t_bf16, tt_bf16):
+    plan = _infonce_plan(x, t_norm.shape[0], need_dt, precision, 1)
+    dx_dtype = torch.bfloat16 if plan == "bf16" else x.dtype
+    f32 = dict(device=x.device, dtype=torch.float32)
+    return (torch.empty((), **f32), torch.empty((), **f32),
+            torch.empty(x.shape, device=x.device, dtype=dx_dtype) if need_grad else _empty(x),
+            torch.empty(t_norm.shape, **f32) if need_dt else _empty(t_norm), torch.empty((), **f32))
+
+
+def _pixel_losses_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], output[2], output[3], output[4])
+
+
+def _pixel_losses_backward(ctx, g_text, g_smooth, *_unused):
+    x, dx, dt, dlt = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    gx = None
+    if need[0]:
+        dh, dv = tv_denominators(x.shape)
+        gs = g_smooth.float()
+        scale = torch.stack([gs / dh if dh > 0 else gs * 0, gs / dv if dv > 0 else gs * 0])
+        # dX = g_text * dX_text (from the forward launch) + g_smooth * d(TV)/dX in ONE pass, into a fresh tensor
+        gx = torch.ops.rangeclip.tv_bwd(x, scale, dx, g_text.float())
+    gt = dt * g_text if need[1] else None
+    gl = (dlt * g_text).reshape(()) if need[2] else None
+    return (gx, gt, gl) + (None,) * 7
+
+
+_op_pixel_losses.register_autograd(_pixel_losses_backward, setup_context=_pixel_losses_setup)
+
+
+@_op("rangeclip::infonce_kblocked", mutates_args=(), device_types="cuda")
+def _op_infonce_kblocked(x: torch.Tensor, t_norm: torch.Tensor, log_tau: torch.Tensor, y: torch.Tensor, w: torch.Tensor,
+                         need_grad: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(loss, dx, dlogtau) against MORE than 256 candidates (``infonce_kblocked_raw``); the candidate rows are constants."""
+    inv_tau = float(torch.exp(-log_tau.detach().float()))
+    r = infonce_kblocked_raw(x, t_norm, y, w, inv_tau, need_grad)
+    z = torch.zeros((), device=x.device, dtype=torch.float32)
+    return (r["loss"].float().reshape(()), r["dx"] if r["dx"] is not None else _empty(x),
+            r["dlogtau"].float().reshape(()) if r["dlogtau"] is not None else z)
+
+
+@_op_infonce_kblocked.register_fake
+def _(x, t_norm, log_tau, y, w, need_grad):
+    f32 = dict(device=x.device, dtype=torch.float32)
+    return torch.empty((), **f32), torch.empty_like(x) if need_grad else _empty(x), torch.empty((), **f32)
+
+
+def _kblocked_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1], output[2])
+
+
+def _kblocked_backward(ctx, g, *_unused):
+    dx, dlt = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    return (dx * g.to(dx.dtype) if need[0] else None, None, (dlt * g).reshape(()) if need[2] else None, None, None, None)
+
+
+_op_infonce_kblocked.register_autograd(_kblocked_backward, setup_context=_kblocked_setup)
+
+
+@_op("rangeclip::scale_to", mutates_args=(), device_types="cuda")
+def _op_scale_to(x: torch.Tensor, scale: Optional[torch.Tensor], out_dtype: int) -> torch.Tensor:
+    return scale_to(x, _CODE_DT[out_dtype], scale)
+
+
+@_op_scale_to.register_fake
+def _(x, scale, out_dtype):
+    return torch.empty(x.shape, device=x.device, dtype=_CODE_DT[out_dtype])
+
+
+@_op("rangeclip::tv_sums", mutates_args=(), device_types="cuda")
+def _op_tv_sums(x: torch.Tensor) -> torch.Tensor:
+    return tv_sums(x)
+
+
+@_op_tv_sums.register_fake
+def _(x):
+    return torch.empty(2, device=x.device, dtype=torch.float64)
+
+
+@_op("rangeclip::tv_bwd", mutates_args=(), device_types="cuda")
+def _op_tv_bwd(x: torch.Tensor, scale: torch.Tensor, dx: Optional[torch.Tensor], dx_scale: Optional[torch.Tensor]) -> torch.Tensor:
+    return tv_backward(x, scale, dx if (dx is not None and dx.numel()) else None, dx_scale)
+
+
+@_op_tv_bwd.register_fake
+def _(x, scale, dx, dx_scale):
+    return torch.empty_like(x)
+
+
+@_op("rangeclip::smoothness", mutates_args=(), device_types="cuda")
+def _op_smoothness(x: torch.Tensor, den_h: float, den_v: float) -> torch.Tensor:
+    """sum_h / den_h + sum_v / den_v (model.py:332-333); NaN for an empty slice (W == 1 or H == 1), as l1_loss."""
+    sums = tv_sums(x)
+    nan = torch.full((), float("nan"), device=x.device, dtype=torch.float64)
+    return ((sums[0] / den_h if den_h > 0 else nan) + (sums[1] / den_v if den_v > 0 else nan)).float().reshape(())
+
+
+@_op_smoothness.register_fake
+def _(x, den_h, den_v):
+    return torch.empty((), device=x.device, dtype=torch.float32)
+
+
+def _smoothness_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+    ctx.den = (inputs[1], inputs[2])
+
+
+def _smoothness_backward(ctx, g):
+    (x,) = ctx.saved_tensors
+    dh, dv = ctx.den
+    gf = g.float()
+    scale = torch.stack([gf / dh if dh > 0 else gf * 0, gf / dv if dv > 0 else gf * 0])
+    return torch.ops.rangeclip.tv_bwd(x, scale, None, None), None, None
+
+
+_op_smoothness.register_autograd(_smoothness_backward, setup_context=_smoothness_setup)
+
+
+@_op("rangeclip::masked_pool", mutates_args=(), device_types="cuda")
+def _op_masked_pool(x: torch.Tensor, segs: Sequence[torch.Tensor], lut: torch.Tensor, lut_per_image: bool,
+                    n_slots: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(mean [n_slots, D] in x's dtype, count [n_slots] int32) of the segment-masked average pooling."""
+    out, cnt = pool_forward(x, list(segs), lut, lut_per_image, n_slots)
+    return (out.to(x.dtype) if x.dtype != torch.float32 else out), cnt
+
+
+@_op_masked_pool.register_fake
+def _(x, segs, lut, lut_per_image, n_slots):
+    return (torch.empty(n_slots, x.shape[1], device=x.device, dtype=x.dtype),
+            torch.empty(max(n_slots, 1), device=x.device, dtype=torch.int32))
+
+
+@_op("rangeclip::masked_pool_bwd", mutates_args=(), device_types="cuda")
+def _op_masked_pool_bwd(g: torch.Tensor, cnt: torch.Tensor, segs: Sequence[torch.Tensor], lut: torch.Tensor,
+                        lut_per_image: bool, shape: Sequence[int], dtype_code: int) -> torch.Tensor:
+    return pool_backward(g, cnt, list(segs), lut, lut_per_image, tuple(shape), _CODE_DT[dtype_code])
+
+
+@_op_masked_pool_bwd.register_fake
+def _(g, cnt, segs, lut, lut_per_image, shape, dtype_code):
+    return torch.empty(tuple(shape), device=g.device, dtype=_CODE_DT[dtype_code])
+
+
+def _masked_pool_setup(ctx, inputs, output):
+    x, segs, lut, lut_per_image, _n = inputs
+    ctx.save_for_backward(output[1], lut, *segs)
+    ctx.meta = (lut_per_image, tuple(x.shape), x.dtype)
+
+
+def _masked_pool_backward(ctx, g, _g_cnt):
+    cnt, lut, *segs = ctx.saved_tensors
+    lut_per_image, shape, dtype = ctx.meta
+    gx = torch.ops.rangeclip.masked_pool_bwd(g, cnt, segs, lut, lut_per_image, list(shape), _DT_CODE[dtype])
+    return gx, [None] * len(segs), None, None, None
+
+
+_op_masked_pool.register_autograd(_masked_pool_backward, setup_context=_masked_pool_setup)
+
+
+@_op("rangeclip::sample_weights", mutates_args=(), device_types="cuda")
+def _op_sample_weights(seg: torch.Tensor, rand_idx: Optional[torch.Tensor], label_map: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    return sample_weights(seg, rand_idx, label_map)
+
+
+@_op_sample_weights.register_fake
+def _(seg, rand_idx, label_map):
+    B = seg.shape[0]
+    HW = seg[0].numel() if B else 0
+    return (torch.empty(B, HW, device=seg.device, dtype=torch.float32), torch.empty(B, HW, device=seg.device, dtype=torch.int32))
+
+
+@_op("rangeclip::text_prepare", mutates_args=(), device_types="cuda")
+def _op_text_prepare(text: torch.Tensor, idx: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """F.normalize(text[idx], dim=1) as f32 [K,D], bf16 [Kp,D] and bf16 [D,Kp] (Kp = K rounded up to 64, zero pads)."""
+    return text_prepare(text, idx, want_f32=True, want_bf16=True)
+
+
+@_op_text_prepare.register_fake
+def _(text, idx):
+    K = idx.numel() if idx is not None else text.shape[0]
+    D = text.shape[1]
+    Kp = (K + 63) // 64 * 64
+    return (torch.empty(K, D, device=text.device, dtype=torch.float32), torch.empty(Kp, D, device=text.device, dtype=torch.bfloat16),
+            torch.empty(D, Kp, device=text.device, dtype=torch.bfloat16))
+
+
+@_op("rangeclip::eval_topk", mutates_args=(), device_types="cuda")
+def _op_eval_topk(x: torch.Tensor, t_norm: torch.Tensor, index_map: torch.Tensor, k: int, precision: str,
+                  t_bf16: Optional[torch.Tensor]) -> torch.Tensor:
+    return eval_topk(x, t_norm, index_map, k, precision, t_bf16)
+
+
+@_op_eval_topk.register_fake
+def _(x, t_norm, index_map, k, precision, t_bf16):
+    k = min(k, t_norm.shape[0])
+    return torch.empty((x.shape[0], k) + tuple(x.shape[2:]), device=x.device, dtype=torch.int64)
+
+
+@_op("rangeclip::eval_hist", mutates_args=("hist", "counters"), device_types="cuda")
+def _op_eval_hist(gt: torch.Tensor, topk: torch.Tensor, E_u8: torch.Tensor, cmap: torch.Tensor, hist: torch.Tensor,
+                  counters: torch.Tensor) -> None:
+    eval_hist(gt, topk, E_u8, cmap, hist, counters)
+
+
+@_op("rangeclip::eval_topk_hist", mutates_args=("hist", "counters"), device_types="cuda")
+def _op_eval_topk_hist(x: torch.Tensor, t_norm: torch.Tensor, index_map: torch.Tensor, k: int, gt: torch.Tensor, E_u8: torch.Tensor,
+                       cmap: torch.Tensor, hist: torch.Tensor, counters: torch.Tensor, t_bf16: Optional[torch.Tensor],
+                       want_ids: bool) -> torch.Tensor:
+    ids = eval_topk_hist(x, t_norm, index_map, k, gt, E_u8, cmap, hist, counters, t_bf16=t_bf16, want_ids=want_ids)
+    return ids if ids is not None else torch.empty(0, device=x.device, dtype=torch.int64)
+
+
+@_op_eval_topk_hist.register_fake
+def _(x, t_norm, index_map, k, gt, E_u8, cmap, hist, counters, t_bf16, want_ids):
+    k = min(k, t_norm.shape[0])
+    if not want_ids:
+        return torch.empty(0, device=x.device, dtype=torch.int64)
+    return torch.empty((x.shape[0], k) + tuple(x.shape[2:]), device=x.device, dtype=torch.int64)
+
+
+@_op("rangeclip::eval_fold", mutates_args=("acc", "first_seen"), device_types="cuda")
+def _op_eval_fold(batch_hist: torch.Tensor, batch_index: int, acc: torch.Tensor, first_seen: torch.Tensor) -> None:
+    eval_fold(batch_hist, batch_index, acc, first_seen)
+
+
+# ----------------------------------------------------------------------------------------------
+# public autograd-aware entry points (what losses.py / pooling.py call)
+# ----------------------------------------------------------------------------------------------
+
+def _tb(t_bf16):
+    return (None, None) if t_bf16 is None else (t_bf16[0], t_bf16[1])
+
+
+def infonce(x, t_norm, log_tau, y, w, precision="auto", rep=1, t_bf16=None):
+    """Autograd-aware fused InfoNCE (torch.ops.rangeclip.infonce); x [B,D,H,W], t_norm [K,D] normalised, y/w per pixel
+    (rep = 4: x holds the embeddings shared by 2x2 pixel blocks, y/w are [B*H*W, 4]).  ``t_bf16`` = (bf16 [Kp,D], bf16
+    [D,Kp]) copies of t_norm from ``text_prepare`` (optional: built on the fly otherwise)."""
+    _need_cuda(x, t_norm, y, w)
+    tb, ttb = _tb(t_bf16)
+    need_grad = bool(torch.is_grad_enabled() and (x.requires_grad or log_tau.requires_grad))
+    need_dt = bool(torch.is_grad_enabled() and t_norm.requires_grad)
+    return torch.ops.rangeclip.infonce(x, t_norm, log_tau, y, w, need_grad or need_dt, need_dt, precision, rep, tb, ttb)[0]
+
+
+def pixel_losses(x, t_norm, log_tau, y, w, precision="auto", t_bf16=None):
+    """(text InfoNCE, smoothness) with a fused single-pass backward (torch.ops.rangeclip.pixel_losses)."""
+    _need_cuda(x, t_norm, y, w)
+    tb, ttb = _tb(t_bf16)
+    need_grad = bool(torch.is_grad_enabled() and (x.requires_grad or log_tau.requires_grad))
+    need_dt = bool(torch.is_grad_enabled() and t_norm.requires_grad)
+    out = torch.ops.rangeclip.pixel_losses(x, t_norm, log_tau, y, w, need_grad or need_dt, need_dt, precision, tb, ttb)
+    return out[0], out[1]
+
+
+def infonce_kblocked(x, t_norm, log_tau, y, w):
+    _need_cuda(x, t_norm, y, w)
+    need = bool(torch.is_grad_enabled() and (x.requires_grad or log_tau.requires_grad))
+    return torch.ops.rangeclip.infonce_kblocked(x, t_norm, log_tau, y, w, need)[0]
+
+
+def smoothness(x: torch.Tensor, denominators=None) -> torch.Tensor:
+    """sum_h / dh + sum_v / dv; the denominators default to the element counts of x's own slices
+    (model.py:332-333) and can be overridden when x stands for a larger tensor (shared 2x2 blocks)."""
+    _need_cuda(x)
+    dh, dv = tv_denominators(x.shape) if denominators is None else denominators
+    return torch.ops.rangeclip.smoothness(x, float(dh), float(dv))
+
+
+def masked_pool(x, seg, lut, lut_per_image, n_slots):
+    _need_cuda(x, lut)
+    segs = list(seg) if isinstance(seg, (list, tuple)) else [seg]
+    return torch.ops.rangeclip.masked_pool(x, segs, lut, bool(lut_per_image), int(n_slots))[0]
+
+
 def debug_umma_gemm(a: torch.Tensor, b: torch.Tensor, variant: int) -> torch.Tensor:
     """Bring-up check of the TMA + tcgen05 + TMEM path: C[128,N] = A B^T in bf16 -> f32."""
     _need_cuda(a, b)
@@ -646,4 +887,14 @@ def debug_umma_gemm_2sm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     c = torch.empty(256, N, device=a.device, dtype=torch.float32)
     check(_lib.lib().rc_debug_umma_gemm_2sm(_p(a.contiguous()), _p(b.contiguous()), N, Kd, _p(c), _stream(a)),
           "rc_debug_umma_gemm_2sm")
+    return c
+
+
+def debug_umma_gemm_ts_2sm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Bring-up check of the TS-mode path (A in tensor memory): C[256,N] = A[256,Kd] B[N,Kd]^T, Kd <= 256."""
+    _need_cuda(a, b)
+    N, Kd = b.shape
+    c = torch.empty(256, N, device=a.device, dtype=torch.float32)
+    check(_lib.lib().rc_debug_umma_gemm_ts_2sm(_p(a.contiguous()), _p(b.contiguous()), N, Kd, _p(c), _stream(a)),
+          "rc_debug_umma_gemm_ts_2sm")
     return c

@@ -59,9 +59,12 @@ def block_seg(B, H, W, blk, labels, gen):
 
 
 def loss_case(name, sim_form, seed, B=2, D=64, H=16, W=16, C=40, k_distractors=12,
-              pcts=(0.0, 0.75, 0.25), n_obj=3, W_image=0.5, W_smooth=2e2, pct_sampling=0.7):
+              pcts=(0.0, 0.75, 0.25), n_obj=3, W_image=0.5, W_smooth=2e2, pct_sampling=0.7, bf16_exact=False):
     gen = torch.Generator().manual_seed(seed)
-    X = unit(torch.randn(B, D, H, W, generator=gen), 1).requires_grad_(True)
+    X = unit(torch.randn(B, D, H, W, generator=gen), 1)
+    if bf16_exact:      # values a bf16 tensor holds exactly: the tensor-core path then sees the reference's own inputs
+        X = X.to(torch.bfloat16).float()
+    X.requires_grad_(True)
     seg = block_seg(B, H, W, 4, list(range(0, 9)), gen)           # labels 0..8, 0 = background
     text = torch.randn(C, D, generator=gen)                        # un-normalised on purpose
     hard = {i: [int(v) for v in torch.randperm(C, generator=gen)[:6]] for i in range(C)}
@@ -258,6 +261,9 @@ if __name__ == "__main__":
     loss_case("list", "list", seed=202)                       # hard/medium silently unused
     loss_case("noimg", "dict", seed=303, n_obj=0)            # image branch: dummy * tau * 0 (Q14)
     loss_case("medium", "dict", seed=404, pcts=(0.25, 0.5, 0.25), k_distractors=20, n_obj=5)
+    # D = 256 / 512: the shapes the DEFAULT (tcgen05) path of compute_loss takes; K ~ 40 contrast rows, dict-form sets
+    loss_case("d256", "dict", seed=505, D=256, H=16, W=24, C=64, k_distractors=32, bf16_exact=True)
+    loss_case("d512", "dict", seed=606, D=512, H=16, W=24, C=64, k_distractors=32, bf16_exact=True)
     pool_case()
     predict_case()
     metrics_case()
