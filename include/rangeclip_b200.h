@@ -96,10 +96,10 @@ int rc_infonce_f32(const float* x, int B, int D, int64_t HW, int64_t ld_b,
  *                           round 2 = backward launches with both flags: dx and dlogtau of each block add up to the full gradient */
 #define RC_INFONCE_KEEP_WEIGHT 2
 #define RC_INFONCE_LSE_GIVEN 4
-/* Backward launches (dx given, no dt) of D = 256 / 512 run the kernel whose softmax tile is a tensor-memory operand of the dX
- * GEMM (TS-mode tcgen05.mma, csrc/infonce_ts.cu).  RC_INFONCE_SS_KERNEL selects the earlier kernel with both operands in
- * shared memory instead (csrc/infonce_umma2.cu; same results within bf16 rounding) -- kept for A/B timing. */
-#define RC_INFONCE_SS_KERNEL 8
+/* RC_INFONCE_TS_KERNEL: backward launches (dx given, no dt) of D = 256 / 512 run the kernel whose softmax tile is a
+ * tensor-memory operand of the dX GEMM (TS-mode tcgen05.mma, csrc/infonce_ts.cu) instead of the kernel with both operands
+ * in shared memory (csrc/infonce_umma2.cu).  Same results bit for bit; which one is faster is recorded in DESIGN.md. */
+#define RC_INFONCE_TS_KERNEL 8
 int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
                     const void* t_bf16, const void* tt_bf16, int K,
                     const int32_t* y, const float* w, float inv_tau,

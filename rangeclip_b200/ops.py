@@ -123,7 +123,7 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
     rep = 4: every row of x is the embedding shared by a 2x2 block of pixels (decoder.py:113, Q8);
     y / w are [rows, 4] and dx is the gradient w.r.t. the shared row (tensor-core path only).
     keep_bf16: leave the tensor-core path's dx in bf16 whatever x's dtype (the autograd wrappers widen and scale it
-    in one pass at backward time); flags: extra RC_INFONCE_* bits for rc_infonce_bf16 (e.g. RC_INFONCE_SS_KERNEL)."""
+    in one pass at backward time); flags: extra RC_INFONCE_* bits for rc_infonce_bf16 (e.g. RC_INFONCE_TS_KERNEL)."""
     _need_cuda(x, t_norm, y, w)
     x, B, D, HW = _emb3(x)
     K = t_norm.shape[0]

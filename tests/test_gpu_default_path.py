@@ -155,7 +155,7 @@ def test_fused_top5_histograms_one_map_k1024_vs_oracle():
     E = O.build_equivalence_tensor(eq, C); cmap = O.build_equivalence_class_map(E)
     text = torch.nn.functional.normalize(torch.randn(C, D, generator=g), dim=1)
     seg = torch.randint(0, C, (1, H // 16, W // 16), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2).contiguous()
-    x = torch.nn.functional.normalize(text[seg].permute(0, 3, 1, 2) + 0.09 * torch.randn(1, D, H, W, generator=g), dim=1).to(torch.bfloat16)
+    x = torch.nn.functional.normalize(text[seg].permute(0, 3, 1, 2) + 0.3 * torch.randn(1, D, H, W, generator=g), dim=1).to(torch.bfloat16)
     hist = torch.zeros(5, C, device=dev(), dtype=torch.int64); cnt = torch.zeros(3, device=dev(), dtype=torch.int64)
     idx = torch.arange(C, device=dev())
     ids = ops.eval_topk_hist(x.to(dev()), text.to(dev()), idx, k, seg.to(dev()), torch.tensor(E).to(dev()).to(torch.uint8),
@@ -171,7 +171,7 @@ def test_fused_top5_histograms_one_map_k1024_vs_oracle():
     assert [int(v) for v in cnt.tolist()] == [st.correct_top1, st.correct_topk, st.total]
     for name in ("mIoU_t1", "mIoU_tk", "pixel_accuracy_t1", "pixel_accuracy_tk"):
         assert fin[name] == fin_o[name], name
-    assert 0.2 < fin["pixel_accuracy_t1"] < 0.999          # the hit and the miss branches are both exercised
+    assert 0.1 < fin["pixel_accuracy_t1"] < 0.95          # the hit and the miss branches are both exercised
     # tie-aware id check on a strided sample of pixels (fp64 logits on bf16-rounded operands)
     sel = torch.arange(0, H * W, 97)
     xr = x[0].float().view(D, -1)[:, sel].t().double()

@@ -29,7 +29,7 @@ dx = torch.empty(B, D, HW, device=dev, dtype=torch.bfloat16)
 ws_bytes = int(L.rc_infonce_workspace_bytes(B, D, HW, K, _lib.RC_BF16))
 ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
 _lib.check(L.rc_weight_sum(w.data_ptr(), y.data_ptr(), M, acc[3:].data_ptr(), st), "wsum")
-flags = 8 if os.environ.get("SS") else 0
+flags = 0 if os.environ.get("SS") else 8
 for _ in range(int(os.environ.get("PROF_REPS", 4))):
     _lib.check(L.rc_infonce_bf16(x.data_ptr(), _lib.RC_BF16, B, D, HW, tb.data_ptr(), ttb.data_ptr(), K, y.data_ptr(), w.data_ptr(),
                                  1.0 / 0.07, lse.data_ptr(), acc[0:].data_ptr(), acc[1:].data_ptr(), acc[3:].data_ptr(), None,

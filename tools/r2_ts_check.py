@@ -70,8 +70,8 @@ def parity_stage():
     res = []
     for (B, D, HW, K, tau) in ((2, 512, 2048, 256, 0.07), (3, 256, 1000, 100, 0.07), (1, 512, 640, 64, 0.2), (2, 512, 4096, 200, 0.02)):
         x, text, tb, ttb, y, w = make_case(B, D, HW, K, 7 + B + K)
-        r_ts = run_infonce(x, tb, ttb, K, y, w, 1.0 / tau, 0)
-        r_ss = run_infonce(x, tb, ttb, K, y, w, 1.0 / tau, 8)
+        r_ts = run_infonce(x, tb, ttb, K, y, w, 1.0 / tau, 8)
+        r_ss = run_infonce(x, tb, ttb, K, y, w, 1.0 / tau, 0)
         rec = dict(B=B, D=D, HW=HW, K=K, tau=tau, loss_ts=r_ts["loss"], loss_ss=r_ss["loss"], dlt_ts=r_ts["dlogtau"], dlt_ss=r_ss["dlogtau"])
         d_ts, d_ss = r_ts["dx"].float(), r_ss["dx"].float()
         rec["dx_ts_vs_ss_maxrel"] = float((d_ts - d_ss).abs().max() / d_ss.abs().max())
@@ -111,7 +111,7 @@ def time_stage():
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
     _lib.check(L.rc_weight_sum(w.data_ptr(), y.data_ptr(), M, acc[3:].data_ptr(), st), "wsum")
     res = {}
-    for name, flags in (("ts", 0), ("ss", 8), ("ts2", 0), ("ss2", 8)):
+    for name, flags in (("ts", 8), ("ss", 0), ("ts2", 8), ("ss2", 0)):
         def launch():
             _lib.check(L.rc_infonce_bf16(x.data_ptr(), _lib.RC_BF16, B, D, HW, tb.data_ptr(), ttb.data_ptr(), K, y.data_ptr(), w.data_ptr(),
                                          1.0 / 0.07, lse.data_ptr(), acc[0:].data_ptr(), acc[1:].data_ptr(), acc[3:].data_ptr(), None,
