@@ -1,25 +1,24 @@
-// K1/K2, CTA-pair version with the softmax tile as a TENSOR-MEMORY operand (TS-mode tcgen05.mma).
+// K1/K2 with the softmax tile as a TENSOR-MEMORY operand (TS-mode tcgen05.mma) and TWO tile pairs in flight per CTA pair.
 //
-// Same problem as infonce_umma2.cu (fused pixel-text InfoNCE forward + backward, model.py:272-291 and its
-// autograd), different formulation of the backward GEMM.  infonce_umma2.cu computes dX^T = T^T P^T with both operands
-// in shared memory (SS mode); its tensor pipe runs at half its isolated rate because the operand reads (96-128 B/clk)
-// saturate the 128 B/clk shared-memory pipe that the TMA fills, the P stores, the row-norm reads and the dX staging
-// also need.  Here
-//   S  = X^T T^T    M = 256 px (128 per CTA; A = own X chunk [64 d][128 px], MN-major, shared memory),
-//                   N = Kp, B = text rows split Kp/2 per CTA; fp32 accumulators in TMEM columns [0, 256)
-//   dX = P T        M = 256 px (the SAME TMEM lanes), A = P as packed bf16 in TMEM columns [256, 384) written by the
-//                   softmax threads with tcgen05.st -- it never touches shared memory --, N = 128 channels per block,
-//                   B = own 64 rows of T^T [D][Kp] (K-major, shared memory): 32 B/clk of operand reads;
-//                   fp32 accumulator in TMEM columns [384, 512)
-// Pixels stay on the TMEM lanes for both GEMMs, so a CTA's softmax and dX epilogue work on its own tile only (no row
-// scale exchange between the CTAs).  The dX epilogue thread owns a pixel: 32 channels per step come out of TMEM, the x
-// values of the same [32 ch][32 px] box arrive by TMA in a small per-warp ring (the box doubles as the staging tile of
-// the TMA store), dx = acc - cs x is formed in place and the box goes back with one TMA store.
-//
-// MMA issue order per tile pair i (D = 512: four 128-channel blocks, eight 64-channel S chunks):
-//   [S(i+1) c0 c1] [dX(i) b0] [S(i+1) c2 c3] [dX(i) b1] [S(i+1) c4 c5] [dX(i) b2] [S(i+1) c6 c7] [dX(i) b3]
-// S(i+1) only needs the S columns (free as soon as the exp pass of tile i has read them); the single dX accumulator is
-// drained by the epilogue warps while the tensor pipe works on the next two S chunks.
+// Same problem as infonce_umma2.cu (fused pixel-text InfoNCE forward + backward, model.py:272-291 and its autograd).
+// That kernel computes dX^T = T^T P^T with both operands in shared memory (SS mode) and keeps ONE S accumulator: the tensor
+// pipe, the softmax warps and the dX epilogue wait for one another in a chain S(i) -> exp(i) -> P(i) -> dX(i), and the SS
+// operand reads (96-128 B/clk) saturate the 128 B/clk shared-memory pipe.  Here
+//   S  = X^T T^T    M = 256 px (128 per CTA; A = own X chunk [64 d][128 px], MN-major, shared memory), N = Kp,
+//                   B = text rows split Kp/2 per CTA; fp32 accumulators in the 256 tensor-memory columns of a SLOT
+//   P               the softmax threads overwrite the first 128 columns of the slot with the scaled softmax-minus-onehot
+//                   tile as packed bf16 (tcgen05.st): P never touches shared memory
+//   dX = P T        M = 256 px (the SAME TMEM lanes), A = P from tensor memory (TS mode), N = 64 channels per block,
+//                   B = own 32 rows of T^T [D][Kp] (K-major, shared memory: 32 B/clk of operand reads); two 64-column fp32
+//                   accumulators in the remaining 128 columns of the slot
+// Tensor memory holds TWO slots (2 x 256 columns); tile pairs alternate between them.  MMA issue order
+//   S(0) S(1) | dX(0) S(2) | dX(1) S(3) | dX(2) S(4) | ...
+// so the exp pass of pair j+1 runs while the tensor pipe works on dX(j) and S(j+2) of the OTHER slot: no role waits for a
+// hand-off it has just produced.  Pixels stay on the TMEM lanes for both GEMMs, so a CTA's softmax and dX epilogue work on
+// its own tile only (no row-scale exchange between the CTAs).  The dX epilogue thread owns a pixel: 32 channels per step
+// come out of TMEM, the x values of the same [32 ch][32 px] box arrive by TMA in a small per-warp ring (the box doubles as
+// the staging tile of the TMA store), dx = acc - cs x is formed in place and the box goes back with one TMA store.
+// The row norms 1/|x_p| (model.py:272 F.normalize) are computed by the relay warp from the X chunks in the operand ring.
 #include "common.cuh"
 #include "umma.cuh"
 #include <float.h>
@@ -31,15 +30,16 @@ using namespace umma;
 namespace ts {
 
 constexpr int kTilePx = 128;
-constexpr int kThreads = 640;          // warps: 0 text TMA, 1 MMA (leader CTA), 2 relay + TMEM alloc, 3 X TMA, 4-11 softmax, 12-19 dX epilogue
-constexpr int kXStages = 4;            // X ring: own X chunks [64 d][128 px]
-constexpr int kTStages = 4;            // text ring: text half-chunks [Kp/2][64 d] for S, own T^T rows [64 ch][<=128 k] for dX
+constexpr int kThreads = 640;          // warps: 0 text TMA, 1 MMA (leader CTA), 2 relay + row norms + TMEM alloc, 3 X TMA, 4-11 softmax, 12-19 dX epilogue
+constexpr int kXStages = 6;            // X ring: own X chunks [64 d][128 px]; deep, so that most of the next tile is resident early
+constexpr int kTStages = 3;            // text ring: text half-chunks [Kp/2][64 d] for S, own T^T rows [32 ch][Kp] of a dX block
 constexpr int kStageBytes = 16 * 1024;
-constexpr int kEpiBufs = 5;            // per epilogue warp: ring of [32 ch][32 px] bf16 boxes (x in, dX out)
-constexpr int kEpiAhead = 3;           // x boxes requested this many steps ahead
+constexpr int kEpiBufs = 4;            // per epilogue warp: ring of [32 ch][32 px] bf16 boxes (x in, dX out)
+constexpr int kEpiAhead = 2;           // x boxes requested this many steps ahead
 constexpr int kEpiBufBytes = 2048;
 constexpr int kTmemCols = 512;
-constexpr int kColP = 256, kColAcc = 384;
+constexpr int kSlotCols = 256;         // one slot: S [0,256) -> P [0,128) + two dX accumulators [128,192), [192,256)
+constexpr int kColAcc = 128, kAccCols = 64;
 constexpr int kRegsCtl = 48, kRegsSoftmax = 120;     // epilogue warps keep the entry allocation (96); 48 + 2*120 + 2*96 = 5*96
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -48,14 +48,14 @@ struct __align__(8) Bars {
   uint64_t xf[kXStages];        // own X chunk has landed (CTA-local; relayed to the leader's xfull)
   uint64_t xfull[kXStages], xempty[kXStages];
   uint64_t tfull[kTStages], tempty[kTStages];
-  uint64_t s_full, s_empty, p_full, p_empty;
-  uint64_t acc_full, acc_empty;
-  uint64_t sc_full[2];
-  uint64_t ebar[8][kEpiBufs];   // x box of an epilogue warp has landed
+  uint64_t s_full[2], p_full[2];                  // per slot
+  uint64_t acc_full[2][2], acc_empty[2][2];       // per slot, per accumulator
+  uint64_t sc_full[4];                            // projection coefficients of a tile (by pair index & 3)
+  uint64_t ebar[8][kEpiBufs];                     // x box of an epilogue warp has landed
   uint32_t tmem_base, pad;
 };
 
-constexpr int kScaleBufs = 3;          // the softmax warps run up to two tiles ahead of the dX epilogue warps
+constexpr int kScaleBufs = 4;          // the softmax warps run up to two tiles ahead of the dX epilogue warps
 constexpr int kOffT = kXStages * kStageBytes;
 constexpr int kOffEpi = kOffT + kTStages * kStageBytes;
 constexpr int kOffScale = kOffEpi + 8 * kEpiBufs * kEpiBufBytes;      // -cs per pixel: [kScaleBufs][128] float
@@ -70,7 +70,6 @@ struct Params {
   int64_t HW;
   int tiles_per_img, n_tiles, n_pairs;
   uint32_t tpi_magic;       // floor(2^32 / tiles_per_img)
-  int s_per_blk;            // S chunks of the next tile pair issued before each dX block of this one (2, 4 or 8 = all first)
   int keep_w;               // K-blocked launches, see infonce_umma2.cu
   const float* lse_in;
   int kb;
@@ -124,7 +123,7 @@ template <int R, bool kKB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW], box (64 px, 64 d, 1), 128B swizzle
                   const __grid_constant__ CUtensorMap map_t,     // T [Kp][D],    box (64 d, Kp/2 rows)
-                  const __grid_constant__ CUtensorMap map_tt,    // T^T [D][Kp],  box (64 k, 64 d)
+                  const __grid_constant__ CUtensorMap map_tt,    // T^T [D][Kp],  box (64 k, 32 d)
                   const __grid_constant__ CUtensorMap map_xe,    // X [B][D][HW], box (32 px, 32 d, 1), 64B swizzle
                   const __grid_constant__ CUtensorMap map_dx,    // dX [B][D][HW], box (32 px, 32 d, 1), 64B swizzle
                   const Params prm) {
@@ -135,22 +134,24 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
   const uint32_t rank = cluster_ctarank();
   const bool leader_cta = rank == 0;
   const int n_dchunks = prm.D / 64;      // 64-channel chunks of the S GEMM
-  const int n_blk = prm.D / 128;         // 128-channel blocks of the dX GEMM (two S chunks each)
+  const int n_blk = prm.D / 64;          // 64-channel blocks of the dX GEMM
   const int n_kchunks = prm.Kp / 64;
-  const int slots_per_blk = (n_kchunks + 1) / 2;
   const int Nh = prm.Kp / 2;             // text rows staged by each CTA
   const int n_clusters = gridDim.x / 2;
   const int cluster_id = blockIdx.x / 2;
+  const int my_pairs = cluster_id < prm.n_pairs ? (prm.n_pairs - cluster_id + n_clusters - 1) / n_clusters : 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x_s); tma_prefetch_desc(&map_t); tma_prefetch_desc(&map_tt);
     tma_prefetch_desc(&map_xe); tma_prefetch_desc(&map_dx);
+    // X ring: xfull = the relays of both CTAs, xempty = MMA commit + the eight softmax warps (row norms)
     for (int i = 0; i < kXStages; ++i) { mbar_init(&bars->xf[i], 1); mbar_init(&bars->xfull[i], 2); mbar_init(&bars->xempty[i], 9); }
     for (int i = 0; i < kTStages; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 1); }
-    mbar_init(&bars->s_full, 1); mbar_init(&bars->s_empty, 16);
-    mbar_init(&bars->p_full, 16); mbar_init(&bars->p_empty, 1);
-    mbar_init(&bars->acc_full, 1); mbar_init(&bars->acc_empty, 16);
-    mbar_init(&bars->sc_full[0], 4); mbar_init(&bars->sc_full[1], 4);
+    for (int sl = 0; sl < 2; ++sl) {
+      mbar_init(&bars->s_full[sl], 1); mbar_init(&bars->p_full[sl], 16);     // consumer releases: one arrival per warp
+      for (int ab = 0; ab < 2; ++ab) { mbar_init(&bars->acc_full[sl][ab], 1); mbar_init(&bars->acc_empty[sl][ab], 16); }
+    }
+    for (int i = 0; i < kScaleBufs; ++i) mbar_init(&bars->sc_full[i], 4);
     for (int i = 0; i < 8; ++i)
       for (int j = 0; j < kEpiBufs; ++j) mbar_init(&bars->ebar[i][j], 1);
     fence_barrier_init();
@@ -161,7 +162,7 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
   const uint32_t idesc_s = make_idesc_bf16(256, prm.Kp, /*A MN-major*/ 1, /*B K-major*/ 0);
-  const uint32_t idesc_d = make_idesc_bf16(256, 128, 0, 0);
+  const uint32_t idesc_d = make_idesc_bf16(256, kAccCols, 0, 0);
   auto arrive_leader = [&](uint64_t* bar) {
     if (leader_cta) mbar_arrive(bar);
     else mbar_arrive_remote(map_to_cta(bar, 0));
@@ -170,57 +171,53 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
     __syncwarp();
     if (elect_one()) arrive_leader(bar);
   };
+  // l-th tile pair of this cluster
+  auto pair_of = [&](int l) -> int { return cluster_id + l * n_clusters; };
   auto koff_of = [&](int pj) -> int { return (kKB && prm.kb > 0) ? div_tiles(prm, 2 * pj) * 256 : 0; };
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
     if (warp == 0 && lane == 0) {
       // =============================== text producer (both CTAs) ===============================
-      // ring order == MMA issue order: S(first), then per tile pair and 128-channel block: [2 chunks of S(next)] [dX block]
+      // ring order == MMA issue order: S(0) S(1) | dX(0) S(2) | dX(1) S(3) | ...
       uint32_t it = 0;
-      auto load_s = [&](int c_begin, int c_end, int koff) {
-        for (int c = c_begin; c < c_end; ++c, ++it) {   // own half (Nh rows) of text chunk c
+      auto load_s = [&](int l) {
+        const int koff = koff_of(pair_of(l));
+        for (int c = 0; c < n_dchunks; ++c, ++it) {   // own half (Nh rows) of text chunk c
           const int st = it % kTStages;
           mbar_wait(&bars->tempty[st], ((it / kTStages) & 1) ^ 1, 1);
           if (leader_cta) mbar_arrive_expect_tx(&bars->tfull[st], 2 * Nh * 128);
           tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_t, &bars->tfull[st], c * 64, koff + (int)rank * Nh);
         }
       };
-      auto load_dx = [&](int blk, int koff) {          // own 64 rows of T^T of this block, two 64-k tiles per slot
-        for (int j = 0; j < slots_per_blk; ++j, ++it) {
+      auto load_dx = [&](int l) {          // per 64-channel block: own 32 rows of T^T, all Kp columns (4 KB per 64 k)
+        const int koff = koff_of(pair_of(l));
+        for (int blk = 0; blk < n_blk; ++blk, ++it) {
           const int st = it % kTStages;
-          const int nt = min(2, n_kchunks - 2 * j);
           mbar_wait(&bars->tempty[st], ((it / kTStages) & 1) ^ 1, 2);
-          if (leader_cta) mbar_arrive_expect_tx(&bars->tfull[st], 2 * nt * 8192);
-          for (int t = 0; t < nt; ++t)
-            tma_load_2d_2sm(smem + kOffT + st * kStageBytes + t * 8192, &map_tt, &bars->tfull[st], koff + (2 * j + t) * 64,
-                            blk * 128 + (int)rank * 64);
+          if (leader_cta) mbar_arrive_expect_tx(&bars->tfull[st], 2 * n_kchunks * 4096);
+          for (int kc = 0; kc < n_kchunks; ++kc)
+            tma_load_2d_2sm(smem + kOffT + st * kStageBytes + kc * 4096, &map_tt, &bars->tfull[st], koff + kc * 64,
+                            blk * 64 + (int)rank * 32);
         }
       };
-      if (cluster_id < prm.n_pairs) load_s(0, n_dchunks, koff_of(cluster_id));
-      for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters) {
-        const bool has_next = pj + n_clusters < prm.n_pairs;
-        const int k_this = koff_of(pj), k_next = has_next ? koff_of(pj + n_clusters) : 0;
-        int c_done = 0;
-        for (int blk = 0; blk < n_blk; ++blk) {
-          const int c_to = has_next ? min(n_dchunks, c_done + prm.s_per_blk) : c_done;
-          load_s(c_done, c_to, k_next);
-          c_done = c_to;
-          load_dx(blk, k_this);
-        }
-        if (has_next) load_s(c_done, n_dchunks, k_next);
+      if (my_pairs > 0) load_s(0);
+      if (my_pairs > 1) load_s(1);
+      for (int l = 0; l < my_pairs; ++l) {
+        load_dx(l);
+        if (l + 2 < my_pairs) load_s(l + 2);
       }
     } else if (warp == 3 && lane == 0) {
       // =============================== X producer (both CTAs) ===============================
       uint32_t xit = 0;
-      for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters) {
+      for (int l = 0; l < my_pairs; ++l) {
         int b, px0;
-        tile_coords(prm, 2 * pj + (int)rank, b, px0);
+        tile_coords(prm, 2 * pair_of(l) + (int)rank, b, px0);
         for (int c = 0; c < n_dchunks; ++c, ++xit) {
           const int st = xit % kXStages;
           mbar_wait(&bars->xempty[st], ((xit / kXStages) & 1) ^ 1, 3);
           uint8_t* sb = smem + st * kStageBytes;
-          mbar_arrive_expect_tx(&bars->xf[st], 2 * 8192);          // CTA-local: the softmax warps read the chunk too
+          mbar_arrive_expect_tx(&bars->xf[st], 2 * 8192);          // CTA-local: the row-norm warp reads the chunk too
           const int bx = (kKB && prm.kb > 0) ? (b < prm.B ? 0 : 1) : b;      // kb mode: the one image of X (1 = out of bounds)
           tma_load_3d(sb, &map_x_s, &bars->xf[st], px0, c * 64, bx);
           tma_load_3d(sb + 8192, &map_x_s, &bars->xf[st], px0 + 64, c * 64, bx);
@@ -229,82 +226,77 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
     } else if (warp == 1 && leader_cta) {
       // =============================== MMA issuer (leader CTA) ================================
       // whole warp converged (addresses / descriptors in uniform registers), one elected lane issues
-      uint32_t it = 0, xit = 0, uc = 0;
+      uint32_t it = 0, xit = 0;
+      uint32_t acc_uses[2][2] = {{0, 0}, {0, 0}};      // per slot, per accumulator: launches so far
       const uint32_t smem_base = smem_u32(smem);
       const uint64_t dsc_x = desc_mnmajor_sw128(0, 8192);
       const uint64_t dsc_k = desc_kmajor_sw128(0);
-      auto issue_s = [&](uint32_t n, int c_begin, int c_end) {
-        if (c_begin == 0) {
-          mbar_wait_cluster(&bars->s_empty, (n & 1u) ^ 1u, 4);      // the softmax warps have read the previous S
-          tc_fence_after();
-        }
-        for (int c = c_begin; c < c_end; ++c, ++it, ++xit) {
+      // the slot's accumulators have been drained by the epilogue warps (all launches so far)
+      auto wait_acc_free = [&](int sl, int ab) {
+        mbar_wait(&bars->acc_empty[sl][ab], (acc_uses[sl][ab] & 1u) ^ 1u, 7);
+      };
+      auto issue_s = [&](int l) {
+        const int sl = l & 1;
+        const uint32_t s_tmem = tmem + sl * kSlotCols;
+        // S overwrites the slot: its P has been consumed (the dX MMAs were issued before, the pipe runs in order) and
+        // both dX accumulators must have been read out
+        wait_acc_free(sl, 0);
+        wait_acc_free(sl, 1);
+        tc_fence_after();
+        for (int c = 0; c < n_dchunks; ++c, ++it, ++xit) {
           const int sa = xit % kXStages, sb_ = it % kTStages;
-          mbar_wait_cluster(&bars->xfull[sa], (xit / kXStages) & 1, 5);
-          mbar_wait_cluster(&bars->tfull[sb_], (it / kTStages) & 1, 6);
+          mbar_wait(&bars->xfull[sa], (xit / kXStages) & 1, 5);
+          mbar_wait(&bars->tfull[sb_], (it / kTStages) & 1, 6);
           tc_fence_after();
           const uint64_t xa = dsc_x + ((smem_base + sa * kStageBytes) >> 4);
           const uint64_t tb = dsc_k + ((smem_base + kOffT + sb_ * kStageBytes) >> 4);
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              mma_bf16_ss_2sm(tmem, xa + ((ks * 2048) >> 4), tb + ((ks * 32) >> 4), idesc_s, (c | ks) != 0);
+              mma_bf16_ss_2sm(s_tmem, xa + ((ks * 2048) >> 4), tb + ((ks * 32) >> 4), idesc_s, (c | ks) != 0);
             mma_commit_2sm(&bars->xempty[sa]);
             mma_commit_2sm(&bars->tempty[sb_]);
-            if (c + 1 == n_dchunks) mma_commit_2sm(&bars->s_full);
+            if (c + 1 == n_dchunks) mma_commit_2sm(&bars->s_full[sl]);
           }
           __syncwarp();
         }
       };
-      auto issue_dx = [&](int blk) {
-        (void)blk;
-        mbar_wait_cluster(&bars->acc_empty, (uc & 1) ^ 1, 7);      // the epilogue warps have drained the accumulator
+      auto issue_dx = [&](int l) {
+        const int sl = l & 1;
+        const uint32_t base = tmem + sl * kSlotCols;
+        mbar_wait(&bars->p_full[sl], (l >> 1) & 1, 9);           // P(l) is in tensor memory
         tc_fence_after();
-        for (int j = 0; j < slots_per_blk; ++j, ++it) {
+        for (int blk = 0; blk < n_blk; ++blk, ++it) {
+          const int ab = blk & 1;
+          wait_acc_free(sl, ab);
           const int st = it % kTStages;
-          const int nt = min(2, n_kchunks - 2 * j);
-          mbar_wait_cluster(&bars->tfull[st], (it / kTStages) & 1, 8);
+          mbar_wait(&bars->tfull[st], (it / kTStages) & 1, 8);
           tc_fence_after();
           const uint64_t sb = dsc_k + ((smem_base + kOffT + st * kStageBytes) >> 4);
+          const uint32_t dcol = base + kColAcc + ab * kAccCols;
           if (elect_one()) {
-            for (int t = 0; t < nt; ++t) {
-              const int kc = 2 * j + t;
+            for (int kc = 0; kc < n_kchunks; ++kc) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)     // A: P [256 px][16 k] in TMEM (8 columns); B: own T^T rows [64 ch][16 k]
-                mma_bf16_ts_2sm(tmem + kColAcc, tmem + kColP + (kc * 4 + ks) * 8, sb + ((t * 8192 + ks * 32) >> 4), idesc_d,
-                                (kc | ks) != 0);
+              for (int ks = 0; ks < 4; ++ks)     // A: P [256 px][16 k] in TMEM (8 columns); B: own T^T rows [32 ch][16 k]
+                mma_bf16_ts_2sm(dcol, base + (kc * 4 + ks) * 8, sb + ((kc * 4096 + ks * 32) >> 4), idesc_d, (kc | ks) != 0);
             }
             mma_commit_2sm(&bars->tempty[st]);
+            mma_commit_2sm(&bars->acc_full[sl][ab]);
           }
           __syncwarp();
+          ++acc_uses[sl][ab];
         }
-        if (elect_one()) mma_commit_2sm(&bars->acc_full);
-        __syncwarp();
-        ++uc;
       };
-      if (cluster_id < prm.n_pairs) issue_s(0, 0, n_dchunks);
-      uint32_t lt = 0;
-      for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
-        const bool has_next = pj + n_clusters < prm.n_pairs;
-        int c_done = 0;
-        for (int blk = 0; blk < n_blk; ++blk) {
-          const int c_to = has_next ? min(n_dchunks, c_done + prm.s_per_blk) : c_done;
-          if (c_to > c_done) issue_s(lt + 1, c_done, c_to);
-          c_done = c_to;
-          if (blk == 0) {
-            mbar_wait_cluster(&bars->p_full, lt & 1, 9);           // P(lt) is in tensor memory
-            tc_fence_after();
-          }
-          issue_dx(blk);
-        }
-        if (elect_one()) mma_commit_2sm(&bars->p_empty);
-        __syncwarp();
-        if (has_next && c_done < n_dchunks) issue_s(lt + 1, c_done, n_dchunks);
+      if (my_pairs > 0) issue_s(0);
+      if (my_pairs > 1) issue_s(1);
+      for (int l = 0; l < my_pairs; ++l) {
+        issue_dx(l);
+        if (l + 2 < my_pairs) issue_s(l + 2);
       }
     } else if (warp == 2 && lane == 0) {
       // ========== relay (both CTAs): "own X chunk has landed" (CTA-local xf) -> the leader's full barrier ==========
       uint32_t xit = 0;
-      for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters)
+      for (int l = 0; l < my_pairs; ++l)
         for (int c = 0; c < n_dchunks; ++c, ++xit) {
           const int st = xit % kXStages;
           mbar_wait(&bars->xf[st], (xit / kXStages) & 1, 10);
@@ -318,8 +310,7 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
     const int row = (warp & 3) * 32 + lane;                 // pixel of the own tile == TMEM lane
     const int Kh = prm.Kp >> 1;
     const int cb = half * Kh;
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + cb;
-    const uint32_t prow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + kColP + (cb >> 1);
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* xch_base = reinterpret_cast<float*>(smem + kOffXch);
     float loss_acc = 0.f, w_acc = 0.f, dlt_acc = 0.f;
     float inv_wsum = 0.f, gscale = 1.f;
@@ -328,17 +319,18 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
       inv_wsum = ws > 0.0 ? (float)(1.0 / ws) : 0.f;
       if (prm.grad_scale) gscale = prm.grad_scale[0];
     }
-    float nx_inv_n = 0.f, nx_w = 0.f;
+    float nx_ok = 0.f, nx_w = 0.f;
     int nx_y = -1;
-    auto load_pixel_scalars = [&](int pj) {
-      nx_inv_n = 0.f; nx_w = 0.f; nx_y = -1;
-      const int t = 2 * pj + (int)rank;
-      if (pj < prm.n_pairs && t < prm.n_tiles) {
+    auto load_pixel_scalars = [&](int l) {
+      nx_ok = 0.f; nx_w = 0.f; nx_y = -1;
+      if (l >= my_pairs) return;
+      const int t = 2 * pair_of(l) + (int)rank;
+      if (t < prm.n_tiles) {
         const int tb = div_tiles(prm, t);
         const int tpx = (t - tb * prm.tiles_per_img) * kTilePx + row;
         if (tpx < prm.HW) {
           const int64_t tm = (int64_t)tb * prm.HW + tpx;
-          nx_inv_n = 1.f;
+          nx_ok = 1.f;
           if (R == 1) {
             nx_y = __ldg(prm.y + tm);
             nx_w = __ldg(prm.w + tm);
@@ -349,14 +341,15 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
         }
       }
     };
-    load_pixel_scalars(cluster_id);
-    // Row norms 1/|x_p| (model.py:272 F.normalize) of the NEXT tile from the X chunks in the operand ring
+    load_pixel_scalars(0);
+    // Row norms 1/|x_p| (model.py:272 F.normalize) of a tile from its X chunks where they sit in the operand ring
+    // ([64 d][2 x 64 px], 128-byte swizzle): thread = (8-pixel group, row phase); sums of squares meet in shared memory.
+    // The X ring holds most of a tile, so the chunks are normally resident when this runs (right before the tile's exp pass).
     float* part_s = reinterpret_cast<float*>(smem + kOffPart);   // [8 warps][128 px] partial sums of squares
     const int st_ = threadIdx.x - 128;                           // 0..255
     const int ng = st_ & 15, nr = st_ >> 4;
     uint32_t nit = 0;
-    float inv_n_next = 0.f;
-    auto norm_tile = [&]() {
+    auto norm_tile = [&]() -> float {
       float ss[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss[j] = 0.f;
@@ -371,7 +364,7 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
           const uint4 v = *reinterpret_cast<const uint4*>(base + rr * 2048 + ((ch ^ (rowd & 7)) << 4));
           const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 4; ++j) {       // FHFMA.BF16 on the word's halves: no unpack instructions
             ss[2 * j] = sqacc_bf16x2_lo(ss[2 * j], u[j]);
             ss[2 * j + 1] = sqacc_bf16x2_hi(ss[2 * j + 1], u[j]);
           }
@@ -379,6 +372,7 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
         __syncwarp();
         if (elect_one()) mbar_arrive(&bars->xempty[st]);
       }
+      // fixed-order reduction (bit-reproducible): lane pairs, then the eight warps' partials through shared memory
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], 16);
       if (lane < 16) {
@@ -390,29 +384,30 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
       float q = 0.f;
 #pragma unroll
       for (int wv = 0; wv < 8; ++wv) q += part_s[wv * 128 + row];
-      inv_n_next = 1.f / fmaxf(sqrtf(q), 1e-12f);
+      return 1.f / fmaxf(sqrtf(q), 1e-12f);
     };
-    if (cluster_id < prm.n_pairs) norm_tile();
     const bool use_bound = prm.inv_tau * (2.02f * kLog2e) < 100.f;
     const float ml_bound = prm.inv_tau * (1.01f * kLog2e);
-    uint32_t lt = 0;
-    for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
-      const int tile = 2 * pj + (int)rank;
+    for (int l = 0; l < my_pairs; ++l) {
+      const int sl = l & 1;
+      const int tile = 2 * pair_of(l) + (int)rank;
       const bool tile_ok = tile < prm.n_tiles;
       const int b = tile_ok ? div_tiles(prm, tile) : 0;
       const int px = tile_ok ? (tile - b * prm.tiles_per_img) * kTilePx + row : 0;
       const bool valid = tile_ok && px < prm.HW;
       const int64_t m = (int64_t)b * prm.HW + px;
       const int Kt = (kKB && prm.kb > 0) ? min(256, prm.K - 256 * b) : prm.K;
-      const bool px_ok = nx_inv_n != 0.f;
+      const bool px_ok = nx_ok != 0.f;
       const int yi = nx_y;
       const float wi = (R == 1 && (yi >= 0 || (kKB && prm.keep_w))) ? nx_w : 0.f;
-      load_pixel_scalars(pj + n_clusters);
-      float* xch = xch_base + (lt & 1) * (4 * 2 * 128);
-      const float inv_n = px_ok ? inv_n_next : 0.f;
+      load_pixel_scalars(l + 1);
+      float* xch = xch_base + (l & 1) * (4 * 2 * 128);
+      const uint32_t trow = lane_base + sl * kSlotCols + cb;
+      const float inv_n_tile = norm_tile();
+      const float inv_n = px_ok ? inv_n_tile : 0.f;
       const float zs = inv_n * prm.inv_tau;
       const float zl = zs * kLog2e;
-      mbar_wait(&bars->s_full, lt & 1u, 12);
+      mbar_wait(&bars->s_full[sl], (l >> 1) & 1, 12);
       tc_fence_after();
       float ml = ml_bound;
       if (!use_bound) {
@@ -474,8 +469,6 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
           }
         }
       }
-      tc_fence_before();
-      arrive_leader_warp(&bars->s_empty);      // S columns are free: the tensor pipe may start the next S in them
       float sum = (s0 + s1) + (s2 + s3);
       float sez = (q0 + q1) + (q2 + q3);
       int yj[R];
@@ -505,7 +498,11 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
       xch[(1 * 2 + half) * 128 + row] = sum;
       xch[(2 * 2 + half) * 128 + row] = sez;
       xch[(3 * 2 + half) * 128 + row] = tz;
+      // every softmax warp has read its S columns (tcgen05.wait::ld above): after this barrier the slot's columns may be
+      // overwritten with P
+      tc_fence_before();
       named_bar_sync(2, 256);
+      tc_fence_after();
       sum += xch[(1 * 2 + (half ^ 1)) * 128 + row];
       sez += xch[(2 * 2 + (half ^ 1)) * 128 + row];
       tz += xch[(3 * 2 + (half ^ 1)) * 128 + row];
@@ -523,15 +520,13 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
       const float rsv = inv_n * prm.inv_tau * coef * inv_sum;
       if (half == 0) {
         const float cj = coef * sez * zs * inv_sum - coefb * tz * zs;
-        sc_s[(lt % kScaleBufs) * 128 + row] = -(inv_n * inv_n * cj);      // dx = acc + (-cs) x
+        sc_s[(l & (kScaleBufs - 1)) * 128 + row] = -(inv_n * inv_n * cj);      // dx = acc + (-cs) x
         dlt_acc -= cj;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->sc_full[lt & 1]);
+        if (lane == 0) mbar_arrive(&bars->sc_full[l & (kScaleBufs - 1)]);
       }
-      // the dX MMAs of the previous pair have finished reading P out of tensor memory: store this pair's P
-      mbar_wait(&bars->p_empty, (lt & 1) ^ 1, 13);
-      tc_fence_after();
       {
+        const uint32_t prow = lane_base + sl * kSlotCols + (cb >> 1);
         const uint32_t rs2 = pack_bf16x2(rsv, rsv);
         // G[row][y_j] = rs (e_y - sum * (weight of target y_j) / (weight of the row)), formed in fp32 before rounding
         uint32_t g16[R];
@@ -576,10 +571,9 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
         }
         tmem_st_wait();
         tc_fence_before();
-        arrive_leader_warp(&bars->p_full);
+        arrive_leader_warp(&bars->p_full[sl]);
       }
       if (half == 0 && valid && prm.lse && !(kKB && prm.lse_in != nullptr)) prm.lse[m] = lse;
-      if (pj + n_clusters < prm.n_pairs) norm_tile();
     }
     if (half == 0) {
       loss_acc = warp_sum(loss_acc); w_acc = warp_sum(w_acc); dlt_acc = warp_sum(dlt_acc);
@@ -590,98 +584,112 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
       }
     }
   } else {
-    // ================ dX epilogue warps: own tile, thread = pixel, 32 channels per step ================
-    // warp (q, h): TMEM lane quarter q = pixels [32 q, +32) of the tile, accumulator columns [64 h, +64) of every block
+    // ================ dX epilogue warps: own tile, thread = pixel, one 64-channel block = one step of 32 channels ================
+    // warp (q, h): TMEM lane quarter q = pixels [32 q, +32) of the tile, accumulator columns [32 h, +32) of every block
     const int ew = warp - 12;
     const int q = warp & 3, h = ew >> 2;
-    const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + kColAcc + h * 64;
     uint8_t* ebuf = smem + kOffEpi + ew * (kEpiBufs * kEpiBufBytes);
     uint64_t* ebar = &bars->ebar[ew][0];
-    const int spp = n_blk * 2;                       // steps per tile pair
-    const int spp_shift = spp == 8 ? 3 : (spp == 4 ? 2 : 1);
-    const int my_pairs = cluster_id < prm.n_pairs ? (prm.n_pairs - cluster_id + n_clusters - 1) / n_clusters : 0;
-    const int total = my_pairs * spp;
+    const int total = my_pairs * n_blk;
     const uint64_t pol_first = l2_policy_evict_first();
-    // coordinates of step s: (pixel, channel, image of x, image of dX)
-    auto step_coords = [&](int s, int& cpx, int& cch, int& cbx, int& cbo) {
-      const int l = s >> spp_shift, u = s & (spp - 1);
+    // cursor over (pair, block): coordinates of a step's box = (pixel, channel, image of x, image of dX)
+    struct Cursor { int l, u, px, bo, bx; };
+    auto cursor_pair = [&](Cursor& cu) {
       int b, px0;
-      tile_coords(prm, 2 * (cluster_id + l * n_clusters) + (int)rank, b, px0);
-      cpx = px0 + q * 32;
-      cch = (u >> 1) * 128 + h * 64 + (u & 1) * 32;
-      cbo = b;
-      cbx = (kKB && prm.kb > 0) ? (b < prm.B ? 0 : 1) : b;
+      tile_coords(prm, 2 * pair_of(cu.l) + (int)rank, b, px0);
+      cu.px = px0 + q * 32;
+      cu.bo = b;
+      cu.bx = (kKB && prm.kb > 0) ? (b < prm.B ? 0 : 1) : b;
     };
-    auto request_x = [&](int s) {                    // lane 0
-      int cpx, cch, cbx, cbo;
-      step_coords(s, cpx, cch, cbx, cbo);
-      const int bi = s % kEpiBufs;
+    auto cursor_next = [&](Cursor& cu) {
+      if (++cu.u == n_blk) { cu.u = 0; ++cu.l; cursor_pair(cu); }
+    };
+    Cursor cs{0, 0, 0, 0, 0}, cr{0, 0, 0, 0, 0};      // step being stored / step being requested
+    cursor_pair(cs);
+    cursor_pair(cr);
+    int s_req = 0;
+    auto request_x = [&]() {                         // lane 0: the x box of step s_req
+      const int bi = s_req % kEpiBufs;
       mbar_arrive_expect_tx(&ebar[bi], kEpiBufBytes);
-      tma_load_3d(ebuf + bi * kEpiBufBytes, &map_xe, &ebar[bi], cpx, cch, cbx);
+      tma_load_3d(ebuf + bi * kEpiBufBytes, &map_xe, &ebar[bi], cr.px, cr.u * 64 + h * 32, cr.bx);
     };
-    if (lane == 0)
-      for (int s = 0; s < kEpiAhead && s < total; ++s) request_x(s);
-    // byte offset of this lane's pixel inside a box row, for the four swizzle phases of the 64-byte swizzle
-    uint32_t loff[4];
-#pragma unroll
-    for (int cj = 0; cj < 4; ++cj) loff[cj] = (uint32_t)((((lane >> 3) ^ cj) << 4) + (lane & 7) * 2);
+    for (; s_req < kEpiAhead && s_req < total; ++s_req) {
+      if (lane == 0) request_x();
+      cursor_next(cr);
+    }
+    // The step works on 8x8 b16 matrices: tcgen05.ld.16x256b hands out the accumulators in the mma fragment layout (thread t:
+    // pixel t/4 (+8), channel pair 2(t%4)), ldmatrix.trans reads x from the [32 ch][32 px] box (64-byte swizzle) in the SAME
+    // layout and stmatrix.trans writes dX back over it -- ~40 instructions per thread and step instead of ~150 two-byte ones.
+    // matrix (g, pb): channels [8g, +8) x pixels [8 pb, +8); one ldmatrix / stmatrix .x4 = the four pixel blocks of one g;
+    // thread t addresses row (channel) 8g + (t & 7) of pixel block t >> 3
+    const uint32_t moff = (uint32_t)((lane & 7) * 64 + ((((lane >> 3) ^ ((lane >> 1) & 3)) & 3) << 4));
     int s = 0;
-    uint32_t uc = 0, lt = 0;
-    for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
-      mbar_wait(&bars->sc_full[lt & 1], (lt >> 1) & 1, 14);
-      const float ncs = sc_s[(lt % kScaleBufs) * 128 + q * 32 + lane];
-      const uint32_t ncs2 = pack_bf16x2(ncs, ncs);
-      for (int blk = 0; blk < n_blk; ++blk, ++uc) {
-        mbar_wait(&bars->acc_full, uc & 1, 15);
-        tc_fence_after();
-        // all 64 accumulator columns of this warp at once, rounded to packed bf16 pairs (channels 2j, 2j+1), and the
-        // accumulator is handed back before any of it is processed: the next block's MMAs overlap the rest
-        uint32_t pa[32];
+    uint32_t acc_seen[2][2] = {{0, 0}, {0, 0}};
+    for (int l = 0; l < my_pairs; ++l) {
+      const int sl = l & 1;
+      mbar_wait(&bars->sc_full[l & (kScaleBufs - 1)], (l >> 2) & 1, 14);
+      uint32_t ncs2[4];                                // -cs of the thread's pixel in each of the four pixel blocks
 #pragma unroll
-        for (int hc = 0; hc < 2; ++hc) {
-          uint32_t r[32];
-          tmem_ld_32x32(tacc + hc * 32, r);
+      for (int pb = 0; pb < 4; ++pb) {
+        const float v = sc_s[(l & (kScaleBufs - 1)) * 128 + q * 32 + pb * 8 + (lane >> 2)];
+        ncs2[pb] = pack_bf16x2(v, v);
+      }
+      const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + sl * kSlotCols + kColAcc + h * 32;
+      for (int blk = 0; blk < n_blk; ++blk, ++s) {
+        const int ab = blk & 1;
+        mbar_wait(&bars->acc_full[sl][ab], acc_seen[sl][ab] & 1u, 15);
+        ++acc_seen[sl][ab];
+        tc_fence_after();
+        // accumulators of pixels [0,16) and [16,32) of the warp's lane quarter, 32 channel columns each, rounded to packed
+        // bf16 channel pairs; the accumulator is handed back before any of it is processed
+        uint32_t pa[4][4];                             // [g][pb]
+        {
+          uint32_t r[16];
+          tmem_ld_16x256b_x4(tacc + ab * kAccCols, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pa[hc * 16 + j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+          for (int g = 0; g < 4; ++g) {
+            pa[g][0] = pack_bf16x2(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]));
+            pa[g][1] = pack_bf16x2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+          }
+          tmem_ld_16x256b_x4(tacc + ab * kAccCols + (16u << 16), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            pa[g][2] = pack_bf16x2(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]));
+            pa[g][3] = pack_bf16x2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
+          }
         }
         tc_fence_before();
-        arrive_leader_warp(&bars->acc_empty);
+        arrive_leader_warp(&bars->acc_empty[sl][ab]);
+        const int bi = s % kEpiBufs;
+        mbar_wait(&ebar[bi], (s / kEpiBufs) & 1, 16);
+        // dx = acc - cs x in place on the box (same rounding as infonce_umma2.cu: the accumulator is rounded to bf16, then
+        // one fused multiply-add on packed pairs)
+        const uint32_t bx0 = smem_u32(ebuf + bi * kEpiBufBytes) + moff;
+        uint32_t xm[4][4];
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub, ++s) {
-          const int bi = s % kEpiBufs;
-          mbar_wait(&ebar[bi], (s / kEpiBufs) & 1, 16);
-          // dx = acc - cs x in place on the box, packed bf16x2 over channel pairs (same rounding as infonce_umma2.cu: the
-          // accumulator is rounded to bf16, then one fused multiply-add); all loads first, so that their latencies overlap
-          uint8_t* bp = ebuf + bi * kEpiBufBytes;
-          uint32_t xv[16];
+        for (int g = 0; g < 4; ++g) ldmatrix_x4_trans(bx0 + g * 512, xm[g]);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const uint32_t x0 = *reinterpret_cast<const uint16_t*>(bp + (2 * j) * 64 + loff[j & 3]);
-            const uint32_t x1 = *reinterpret_cast<const uint16_t*>(bp + (2 * j + 1) * 64 + loff[j & 3]);
-            xv[j] = __byte_perm(x0, x1, 0x5410);
-          }
+        for (int g = 0; g < 4; ++g) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const uint32_t o = bf2_fma(ncs2, xv[j], pa[sub * 16 + j]);
-            *reinterpret_cast<uint16_t*>(bp + (2 * j) * 64 + loff[j & 3]) = (uint16_t)o;
-            *reinterpret_cast<uint16_t*>(bp + (2 * j + 1) * 64 + loff[j & 3]) = (uint16_t)(o >> 16);
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            int cpx, cch, cbx, cbo;
-            step_coords(s, cpx, cch, cbx, cbo);
-            tma_store_3d_hint(&map_dx, ebuf + bi * kEpiBufBytes, cpx, cch, cbo, pol_first);
-            tma_store_commit();
-            if (s + kEpiAhead < total) {
-              // the box to refill was stored kEpiBufs - kEpiAhead steps ago: that store must have read it
-              asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kEpiBufs - kEpiAhead) : "memory");
-              request_x(s + kEpiAhead);
-            }
-          }
-          __syncwarp();
+          for (int pb = 0; pb < 4; ++pb) xm[g][pb] = bf2_fma(ncs2[pb], xm[g][pb], pa[g][pb]);
+          stmatrix_x4_trans(bx0 + g * 512, xm[g]);
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d_hint(&map_dx, ebuf + bi * kEpiBufBytes, cs.px, cs.u * 64 + h * 32, cs.bo, pol_first);
+          tma_store_commit();
+          if (s_req < total) {
+            // the box to refill was stored kEpiBufs - kEpiAhead steps ago: that store must have read it
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kEpiBufs - kEpiAhead) : "memory");
+            request_x();
+          }
+        }
+        cursor_next(cs);
+        if (s_req < total) { cursor_next(cr); ++s_req; }
+        __syncwarp();
       }
     }
     if (lane == 0) tma_store_wait_all0();       // shared memory must stay valid until the last bulk store has read it
@@ -719,7 +727,7 @@ int launch_infonce_ts(const void* xsrc, void* dx, const void* t_bf16, const void
     const uint32_t tbox[2] = {64, (uint32_t)(Kp / 2)};
     if ((rcode = make_tmap_bf16(&m_t, t_bf16, 2, tdims, tstr, tbox, "ts map_t"))) return rcode;
     const uint64_t ttdims[2] = {(uint64_t)Kall, (uint64_t)D}, ttstr[2] = {2, (uint64_t)Kall * 2};
-    const uint32_t ttbox[2] = {64, 64};
+    const uint32_t ttbox[2] = {64, 32};
     if ((rcode = make_tmap_bf16(&m_tt, tt_bf16, 2, ttdims, ttstr, ttbox, "ts map_tt"))) return rcode;
   }
   Params prm;
@@ -732,10 +740,6 @@ int launch_infonce_ts(const void* xsrc, void* dx, const void* t_bf16, const void
   prm.y = y; prm.w = w; prm.inv_tau = inv_tau; prm.grad_scale = grad_scale;
   prm.w_sum_in = w_sum_in; prm.lse = lse; prm.loss_sum = loss_sum; prm.w_sum = w_sum; prm.dlogtau = dlogtau;
   prm.keep_w = keep_w; prm.lse_in = lse_in; prm.kb = kb;
-  prm.s_per_blk = 2;
-#ifdef RC_BRINGUP
-  if (const char* e = getenv("RANGECLIP_B200_TS_SPB")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) prm.s_per_blk = v; }
-#endif
   if (kb > 0 && (prm.tiles_per_img & 1)) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16_kblocks: HW must be a multiple of 256");
   int n_clusters = num_sms() / 2;
   if (n_clusters > prm.n_pairs) n_clusters = prm.n_pairs;
@@ -800,7 +804,7 @@ debug_umma_gemm_ts_2sm_kernel(const __grid_constant__ CUtensorMap map_b, const _
     for (int ck = 0; ck < nck; ++ck) tma_load_2d_2sm(sbm + ck * nh * 128, &map_b, &bars->full, ck * 64, (int)rank * nh);
     if (rank == 0) {
       const uint32_t idesc = make_idesc_bf16(256, N, 0, 0);
-      mbar_wait_cluster(&bars->full, 0, 210);
+      mbar_wait(&bars->full, 0, 210);
       tc_fence_after();
       for (int ck = 0; ck < nck; ++ck)
         for (int ks = 0; ks < 4; ++ks)
@@ -808,7 +812,7 @@ debug_umma_gemm_ts_2sm_kernel(const __grid_constant__ CUtensorMap map_b, const _
                           (ck | ks) != 0);
       mma_commit_2sm(&bars->done);
     }
-    mbar_wait_cluster(&bars->done, 0, 211);
+    mbar_wait(&bars->done, 0, 211);
   }
   __syncthreads();
   tc_fence_after();

@@ -374,13 +374,13 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         const uint32_t sidx = kBwd ? 0u : (n & 1u);
         const uint32_t s_tmem = tmem + sidx * 256;
         if (c_begin == 0) {
-          RC_WAIT(mbar_wait_cluster, &bars->s_empty[sidx], (((kBwd ? n : (n >> 1)) & 1u) ^ 1u), 3);   // previous user has read it
+          RC_WAIT(mbar_wait, &bars->s_empty[sidx], (((kBwd ? n : (n >> 1)) & 1u) ^ 1u), 3);   // previous user has read it
           tc_fence_after();
         }
         for (int c = c_begin; c < c_end; ++c, ++it, ++xit) {
           const int sa = xit % kXStages, sb_ = it % kTStages;
-          RC_WAIT(mbar_wait_cluster, &bars->xfull[sa], (xit / kXStages) & 1, 4);
-          RC_WAIT(mbar_wait_cluster, &bars->tfull[sb_], (it / kTStages) & 1, 12);
+          RC_WAIT(mbar_wait, &bars->xfull[sa], (xit / kXStages) & 1, 4);
+          RC_WAIT(mbar_wait, &bars->tfull[sb_], (it / kTStages) & 1, 12);
           tc_fence_after();
           const uint64_t xa = dsc_x + ((smem_base + sa * kStageBytes) >> 4);
           const uint64_t tb = dsc_k + ((smem_base + kOffT + sb_ * kStageBytes) >> 4);
@@ -401,14 +401,14 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         for (int blk = b_begin; blk < b_end; ++blk) {
           for (int pxh = 0; pxh < 2; ++pxh, ++uc) {
             const int ab = uc & 1;
-            RC_WAIT(mbar_wait_cluster, &bars->acc_empty[ab], ((uc >> 1) & 1) ^ 1, 6);
+            RC_WAIT(mbar_wait, &bars->acc_empty[ab], ((uc >> 1) & 1) ^ 1, 6);
             tc_fence_after();
             RC_EV(lt, 3 + blk * 2 + pxh);     // dX unit issue starts (accumulator free)
             const uint32_t dcol = tmem + 256 + ab * 128;
             for (int kc = 0; kc < n_kchunks; ++kc) {
               const int st = (it + kc) % kTStages;
               if (pxh == 0) {          // the block's last text slot was requested only when the preceding S chunk retired:
-                RC_WAIT(mbar_wait_cluster, &bars->tfull[st], ((it + kc) / kTStages) & 1, 7);     // wait per slot, not up front
+                RC_WAIT(mbar_wait, &bars->tfull[st], ((it + kc) / kTStages) & 1, 7);     // wait per slot, not up front
                 tc_fence_after();
               }
               const uint64_t sb = dsc_k + ((smem_base + kOffT + st * kStageBytes) >> 4);
@@ -435,7 +435,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           RC_EV(lt + 1, 0);        // S(lt+1) issue started
         }
         if (kBwd) {
-          RC_WAIT(mbar_wait_cluster, &bars->p_full, lt & 1, 5);
+          RC_WAIT(mbar_wait, &bars->p_full, lt & 1, 5);
           tc_fence_after();
           RC_EV(lt, 2);            // dX(lt) issue starts (P(lt) is in shared memory)
           issue_dx(0, b_half);

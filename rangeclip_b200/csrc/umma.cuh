@@ -46,8 +46,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped kernel (CUDA error), never as a hung GPU.
+// Bring-up builds (-DRC_BRINGUP) bound every wait: a protocol bug must surface as a trapped kernel (CUDA error), never as a
+// hung GPU.  The shipped build spins on try_wait alone: the clock reads and the timeout branch are ~15 instructions per
+// wait in loops that are issue-bound.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+#ifdef RC_BRINGUP
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
@@ -57,6 +60,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
       __trap();
     }
   }
+#else
+  (void)tag;
+  while (!mbar_try_wait(bar, parity)) {}
+#endif
 }
 
 // ---- proxies / fences -------------------------------------------------------------------------
@@ -178,6 +185,30 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+// 16 lanes x 32 consecutive 32-bit columns in the accumulator-fragment layout of mma.m16n8: for column group g (8 columns),
+// r[4g+0], r[4g+1] = (lane taddr.lane + t/4, columns 8g + 2(t%4), +1) and r[4g+2], r[4g+3] = the same columns of lane + 8
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// four 8x8 b16 matrices, transposed on the way: thread t supplies the address of row (t & 7) of matrix (t >> 3) and
+// receives / provides, per matrix, the pair (column t/4 of rows 2(t%4), 2(t%4)+1)
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr)
+               : "memory");
+}
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t saddr, const uint32_t (&r)[4]) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
 }
 // 32 lanes x 16 columns register -> TMEM store (thread i writes lane taddr.lane + i) and its completion wait
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -312,6 +343,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag) {
+#ifdef RC_BRINGUP
   if (mbar_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
@@ -321,6 +353,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       __trap();
     }
   }
+#else
+  (void)tag;
+  while (!mbar_try_wait_cluster(bar, parity)) {}
+#endif
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in CTA 0 of the pair
 // 2-SM TMA loads: issued by either CTA of the pair into ITS OWN shared memory; the transaction bytes are
