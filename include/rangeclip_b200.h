@@ -76,7 +76,8 @@ int rc_infonce_f32(const float* x, int B, int D, int64_t HW, int64_t ld_b,
  *   x        [B][D][HW] f32 or bf16 (x_dtype); f32 input is rounded to bf16 by the pre-pass
  *   t_bf16   [Kp][D] bf16 normalised rows, Kp = K rounded up to 64, pad rows zero
  *   tt_bf16  [D][Kp] bf16 = transpose of t_bf16 (operand of the dX GEMM)
- *   dx       nullable; same dtype as x; = grad_scale * w_p/sum(w) * d(lse_p - z_py)/dx
+ *   dx       nullable; ALWAYS bf16 [B][D][HW] whatever x_dtype (the tensor cores' gradient; rc_scale_to / rc_tv_bwd_from widen
+ *            it in the pass that applies the upstream scale); = grad_scale * w_p/sum(w) * d(lse_p - z_py)/dx
  *   dt       nullable [K][D] f32, ADDED to; needs dx, D = 256 or 512 and a workspace of
  *            rc_infonce_workspace_bytes_dt: the fused kernel also writes G = rs (P - sum onehot)
  *            (bf16 [B][HW][Kp]) and a second tensor-core kernel adds G^T X (split-K over pixels)
@@ -100,6 +101,9 @@ int rc_infonce_f32(const float* x, int B, int D, int64_t HW, int64_t ld_b,
  * tensor-memory operand of the dX GEMM (TS-mode tcgen05.mma, csrc/infonce_ts.cu) instead of the kernel with both operands
  * in shared memory (csrc/infonce_umma2.cu).  Same results bit for bit; which one is faster is recorded in DESIGN.md. */
 #define RC_INFONCE_TS_KERNEL 8
+/* RC_INFONCE_ACCUMULATE_DX: dx += this launch's gradient instead of dx = (TMA reduce-add stores, bf16 accumulation).  The
+ * backward launches of the K-blocked scheme after the first one: the per-block gradients add up in ONE bf16 tensor. */
+#define RC_INFONCE_ACCUMULATE_DX 16
 int rc_infonce_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
                     const void* t_bf16, const void* tt_bf16, int K,
                     const int32_t* y, const float* w, float inv_tau,
@@ -155,6 +159,11 @@ int rc_text_prepare(const float* text, int64_t ld_text, int64_t n_rows, const in
 int rc_weight_sum(const float* w, const int32_t* y, int64_t n, double* w_sum, void* stream);
 int rc_sample_weights(const int64_t* seg, const int64_t* rand_idx, int B, int64_t HW, int64_t n_samples,
                       const int32_t* map, int C, float* w, int32_t* y, void* stream);
+/* counts[label] += number of sampled pixels (rand_idx [B][n_samples], nullable = every pixel once) carrying that label, labels
+ * outside [0, C) skipped; counts int32[C] is ADDED to.  The sampled foreground labels of model.py:222-233 (gather, drop 0,
+ * torch.unique) are the nonzero entries from 1 on -- no gather, no sort.  C <= 12000. */
+int rc_sample_label_counts(const int64_t* seg, const int64_t* rand_idx, int B, int64_t HW, int64_t n_samples, int C,
+                           int32_t* counts, void* stream);
 int rc_scale(void* x, rc_dtype dtype, int64_t n, const float* s, void* stream);
 /* out[i] = s[0] * x[i] (s nullable = 1) into a separate buffer, converting x_dtype -> out_dtype: the late upstream scaling of a
  * saved gradient (autograd may run a backward twice; the saved tensor must stay intact) and the bf16 -> f32 widening of the
@@ -228,7 +237,12 @@ int rc_eval_fold(const int64_t* batch_hist /*[5][C]*/, int C, int32_t batch_inde
  * building blocks (descriptor variants selected by `variant`), C[128][N] f32 row-major.
  *   variant 0: A K-major [128][Kd], B K-major [N][Kd]
  *   variant 1: A MN-major [Kd][128] (the NCHW pixel operand), B K-major [N][Kd]
+ *
+ * Bring-up entry points and environment switches (RANGECLIP_B200_ABLATE / _SPLIT / _INFONCE / _TV_*) exist ONLY in
+ * librangeclip_b200_bringup.so, built with -DRC_BRINGUP (`make -C rangeclip_b200/csrc bringup`); the shipped
+ * librangeclip_b200.so exports none of them and reads no environment variable.
  * ------------------------------------------------------------------------------------------- */
+#ifdef RC_BRINGUP
 /* Bring-up instrumentation: when set (device int64[32]), CTA 0 of rc_infonce_bf16 records per-barrier
  * wait cycles of its producer / MMA / softmax / epilogue roles; index 0 = role lifetime. NULL disables. */
 int rc_debug_set_timing_buffer(int64_t* dev_buf);
@@ -243,6 +257,7 @@ int rc_debug_max_active_clusters(int cluster_size, int threads, int smem_bytes);
 int rc_debug_umma_gemm_2sm(const void* a_bf16, const void* b_bf16, int N, int Kd, float* c, void* stream);
 /* Same GEMM with A as a tensor-memory operand (TS mode): the threads write A [256][Kd] (Kd <= 256) to TMEM with tcgen05.st. */
 int rc_debug_umma_gemm_ts_2sm(const void* a_bf16, const void* b_bf16, int N, int Kd, float* c, void* stream);
+#endif /* RC_BRINGUP */
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,7 @@ PROTOTYPES = {
     "rc_text_prepare": [_vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "rc_weight_sum": [_vp, _vp, _i64, _vp, _vp],
     "rc_sample_weights": [_vp, _vp, _i32, _i64, _i64, _vp, _i32, _vp, _vp, _vp],
+    "rc_sample_label_counts": [_vp, _vp, _i32, _i64, _i64, _i32, _vp, _vp],
     "rc_scale": [_vp, _i32, _i64, _vp, _vp],
     "rc_scale_to": [_vp, _i32, _vp, _i32, _i64, _vp, _vp],
     "rc_pool_fwd": [_vp, _i32, _i32, _i32, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp],
@@ -51,6 +52,9 @@ PROTOTYPES = {
                                _vp, _i64, _vp],
     "rc_eval_hist": [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "rc_eval_fold": [_vp, _i32, _i32, _vp, _vp, _vp],
+}
+# entry points that exist only in the bring-up build (librangeclip_b200_bringup.so, -DRC_BRINGUP)
+BRINGUP_PROTOTYPES = {
     "rc_debug_set_timing_buffer": [_vp],
     "rc_debug_max_active_clusters": [_i32, _i32, _i32],
     "rc_debug_umma_gemm_2sm": [_vp, _vp, _i32, _i32, _vp, _vp],
@@ -60,12 +64,14 @@ PROTOTYPES = {
 _RESTYPES = {"rc_last_error": C.c_char_p, "rc_launch_count": _i64, "rc_infonce_workspace_bytes": _i64,
              "rc_infonce_workspace_bytes_dt": _i64}
 
+BRINGUP_LIB_PATH = os.path.join(_HERE, "librangeclip_b200_bringup.so")
 _lib = None
+_bringup = None
 
 
 def build(verbose: bool = False) -> str:
     """Compile the CUDA sources for sm_100a (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    r = subprocess.run(["make", "-C", CSRC, "-j8", "all", "bringup"], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout[-4000:], r.stderr[-4000:])
     if r.returncode != 0:
@@ -90,6 +96,22 @@ def lib() -> C.CDLL:
             raise RuntimeError("librangeclip_b200.so: ABI version mismatch")
         _lib = l
     return _lib
+
+
+def bringup_lib() -> C.CDLL:
+    """The bring-up build of the same sources (adds the rc_debug_* entry points and the RANGECLIP_B200_* environment
+    switches); used by the tcgen05 building-block tests and the tools, never by the drop-ins."""
+    global _bringup
+    if _bringup is None:
+        if not os.path.exists(BRINGUP_LIB_PATH):
+            raise RuntimeError(f"{BRINGUP_LIB_PATH} is missing: run `make -C rangeclip_b200/csrc bringup`")
+        l = C.CDLL(BRINGUP_LIB_PATH)
+        for name, argtypes in {**PROTOTYPES, **BRINGUP_PROTOTYPES}.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        _bringup = l
+    return _bringup
 
 
 def check(status: int, what: str) -> None:

@@ -10,6 +10,7 @@ extern "C" int rc_abi_version(void) { return RC_ABI_VERSION; }
 extern "C" const char* rc_last_error(void) { return rc::g_err; }
 extern "C" int64_t rc_launch_count(void) { return (int64_t)rc::g_launches.load(); }
 
+#ifdef RC_BRINGUP
 // Bring-up query: how many clusters of `cluster_size` CTAs (threads, dynamic shared memory as given) the device can
 // keep resident at once -- 148 SMs need not tile into clusters larger than 2 (GPC sizes), which decides whether a
 // 4-CTA cluster with multicast operand loads is worth building.
@@ -36,3 +37,4 @@ extern "C" int rc_debug_max_active_clusters(int cluster_size, int threads, int s
   if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_debug_max_active_clusters: %s", cudaGetErrorString(e));
   return n;
 }
+#endif  // RC_BRINGUP

@@ -313,6 +313,26 @@ __global__ void sample_count_kernel(const int64_t* __restrict__ rand_idx, int B,
     if ((uint64_t)p < (uint64_t)HW) atomicAdd(&w[b * HW + p], 1.f);
   }
 }
+// counts[label] += 1 for every sampled pixel (label 0 and out-of-range labels included / skipped): the label histogram of
+// model.py:222-226's gather, from which the set of sampled foreground labels follows without gathering or sorting them
+__global__ void sample_label_count_kernel(const int64_t* __restrict__ seg, const int64_t* __restrict__ rand_idx, int B, int64_t HW,
+                                          int64_t n_samples, int C, int32_t* __restrict__ counts) {
+  extern __shared__ int32_t hist[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int64_t n = (int64_t)B * n_samples;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / n_samples;
+    const int64_t p = rand_idx ? rand_idx[i] : (i - b * n_samples);
+    if ((uint64_t)p < (uint64_t)HW) {
+      const int64_t lab = seg[b * HW + p];
+      if ((uint64_t)lab < (uint64_t)C) atomicAdd(&hist[lab], 1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x)
+    if (hist[i] != 0) atomicAdd(&counts[i], hist[i]);
+}
 __global__ void sample_map_kernel(const int64_t* __restrict__ seg, int64_t n, const int32_t* __restrict__ map, int C,
                                   float* __restrict__ w, int32_t* __restrict__ y, int have_counts) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -463,6 +483,19 @@ extern "C" int rc_sample_weights(const int64_t* seg, const int64_t* rand_idx, in
   const int64_t blocks = (n + 255) / 256;
   rc::sample_map_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, s>>>(seg, n, map, C, w, y, rand_idx != nullptr);
   return rc::check_launch("rc_sample_weights(map)");
+}
+
+extern "C" int rc_sample_label_counts(const int64_t* seg, const int64_t* rand_idx, int B, int64_t HW, int64_t n_samples, int C,
+                                      int32_t* counts, void* stream) {
+  RC_REQUIRE(seg && counts && B >= 0 && HW >= 0 && n_samples >= 0 && C >= 1, "rc_sample_label_counts: bad argument");
+  if (C > 12000) return rc::fail(RC_ERR_UNSUPPORTED, "rc_sample_label_counts: C=%d labels exceed the shared-memory histogram", C);
+  const int64_t ns = (int64_t)B * (rand_idx ? n_samples : HW);
+  if (ns == 0) return RC_OK;
+  const int64_t blocks = (ns + 1023) / 1024;
+  const int cap = rc::num_sms() * 4;
+  rc::sample_label_count_kernel<<<(int)(blocks < cap ? blocks : cap), 256, (size_t)C * 4, (cudaStream_t)stream>>>(
+      seg, rand_idx, B, HW, rand_idx ? n_samples : HW, C, counts);
+  return rc::check_launch("rc_sample_label_counts");
 }
 
 extern "C" int rc_scale(void* x, rc_dtype dtype, int64_t n, const float* sc, void* stream) {

@@ -71,6 +71,7 @@ struct Params {
   int tiles_per_img, n_tiles, n_pairs;
   uint32_t tpi_magic;       // floor(2^32 / tiles_per_img)
   int keep_w;               // K-blocked launches, see infonce_umma2.cu
+  int acc_dx;               // dX += this launch's gradient (TMA reduce-add store)
   const float* lse_in;
   int kb;
   const int32_t* y;
@@ -679,7 +680,8 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d_hint(&map_dx, ebuf + bi * kEpiBufBytes, cs.px, cs.u * 64 + h * 32, cs.bo, pol_first);
+          if (kKB && prm.acc_dx) tma_reduce_add_3d(&map_dx, ebuf + bi * kEpiBufBytes, cs.px, cs.u * 64 + h * 32, cs.bo);
+          else tma_store_3d_hint(&map_dx, ebuf + bi * kEpiBufBytes, cs.px, cs.u * 64 + h * 32, cs.bo, pol_first);
           tma_store_commit();
           if (s_req < total) {
             // the box to refill was stored kEpiBufs - kEpiAhead steps ago: that store must have read it
@@ -708,7 +710,7 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
 int launch_infonce_ts(const void* xsrc, void* dx, const void* t_bf16, const void* tt_bf16, int B, int D, int64_t HW, int K,
                       const int32_t* y, const float* w, float inv_tau, const float* grad_scale, const double* w_sum_in,
                       float* lse, double* loss_sum, double* w_sum, double* dlogtau, int rep, int keep_w, const float* lse_in,
-                      int kb, cudaStream_t s) {
+                      int kb, int acc_dx, cudaStream_t s) {
   using namespace ts;
   const int Kp = kb > 0 ? 256 : (K + 63) / 64 * 64;
   const int Kall = kb > 0 ? kb * 256 : Kp;          // rows of the text matrices
@@ -739,7 +741,7 @@ int launch_infonce_ts(const void* xsrc, void* dx, const void* t_bf16, const void
   prm.n_pairs = (prm.n_tiles + 1) / 2;
   prm.y = y; prm.w = w; prm.inv_tau = inv_tau; prm.grad_scale = grad_scale;
   prm.w_sum_in = w_sum_in; prm.lse = lse; prm.loss_sum = loss_sum; prm.w_sum = w_sum; prm.dlogtau = dlogtau;
-  prm.keep_w = keep_w; prm.lse_in = lse_in; prm.kb = kb;
+  prm.keep_w = keep_w; prm.lse_in = lse_in; prm.kb = kb; prm.acc_dx = acc_dx;
   if (kb > 0 && (prm.tiles_per_img & 1)) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16_kblocks: HW must be a multiple of 256");
   int n_clusters = num_sms() / 2;
   if (n_clusters > prm.n_pairs) n_clusters = prm.n_pairs;
@@ -751,7 +753,7 @@ int launch_infonce_ts(const void* xsrc, void* dx, const void* t_bf16, const void
     return check_launch("rc_infonce_bf16(ts)");
   };
   if (rep == 4) return launch(infonce_ts_kernel<4, false>);
-  if (keep_w || lse_in != nullptr || kb > 0) return launch(infonce_ts_kernel<1, true>);
+  if (keep_w || lse_in != nullptr || kb > 0 || acc_dx) return launch(infonce_ts_kernel<1, true>);
   return launch(infonce_ts_kernel<1, false>);
 }
 
@@ -829,6 +831,7 @@ debug_umma_gemm_ts_2sm_kernel(const __grid_constant__ CUtensorMap map_b, const _
 
 }  // namespace rc
 
+#ifdef RC_BRINGUP
 extern "C" int rc_debug_umma_gemm_ts_2sm(const void* a_bf16, const void* b_bf16, int N, int Kd, float* c, void* stream) {
   RC_REQUIRE(a_bf16 && b_bf16 && c, "rc_debug_umma_gemm_ts_2sm: null pointer");
   RC_REQUIRE(N >= 64 && N <= 256 && N % 64 == 0 && Kd >= 64 && Kd <= 256 && Kd % 64 == 0, "rc_debug_umma_gemm_ts_2sm: bad shape N=%d Kd=%d", N, Kd);
@@ -845,3 +848,4 @@ extern "C" int rc_debug_umma_gemm_ts_2sm(const void* a_bf16, const void* b_bf16,
   rc::debug_umma_gemm_ts_2sm_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(mb, (const __nv_bfloat16*)a_bf16, N, Kd, c);
   return rc::check_launch("rc_debug_umma_gemm_ts_2sm");
 }
+#endif  // RC_BRINGUP

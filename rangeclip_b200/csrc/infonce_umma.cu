@@ -690,6 +690,7 @@ static int check_sm100(const char* what) {
 
 }  // namespace rc
 
+#ifdef RC_BRINGUP
 extern "C" int rc_debug_umma_gemm(const void* a_bf16, const void* b_bf16, int N, int Kd, int variant, float* c, void* stream) {
   RC_REQUIRE(a_bf16 && b_bf16 && c, "rc_debug_umma_gemm: null pointer");
   RC_REQUIRE(N >= 32 && N <= 256 && N % 32 == 0 && Kd >= 64 && Kd % 64 == 0 && variant >= 0 && variant <= 2,
@@ -717,6 +718,7 @@ extern "C" int rc_debug_umma_gemm(const void* a_bf16, const void* b_bf16, int N,
   rc::debug_umma_gemm_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(ma, mb, N, Kd, variant, c);
   return rc::check_launch("rc_debug_umma_gemm");
 }
+#endif  // RC_BRINGUP
 
 extern "C" int64_t rc_infonce_workspace_bytes(int B, int D, int64_t HW, int K, rc_dtype x_dtype) {
   (void)K;
@@ -760,7 +762,9 @@ static int infonce_prepass_impl(const void* x, rc_dtype x_dtype, int B, int D, i
 }  // namespace rc
 
 namespace rc { static long long* g_dbg_buf = nullptr; long long* debug_timing_buffer() { return g_dbg_buf; } }
+#if defined(RC_BRINGUP) || defined(RC_TIMING)
 extern "C" int rc_debug_set_timing_buffer(int64_t* dev_buf) { rc::g_dbg_buf = (long long*)dev_buf; return RC_OK; }
+#endif
 
 extern "C" int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, void* workspace,
                                   int64_t workspace_bytes, void* stream) {
@@ -794,11 +798,17 @@ static int infonce_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, int6
   // single-CTA kernel (kept for D = 128 / 384 and as the A/B baseline).  The pair kernel computes 1/|x_p| itself
   // from the operand tiles in shared memory, so a bf16 input needs no pre-pass at all (an fp32 input still needs
   // its bf16 copy).
-  const char* impl = getenv("RANGECLIP_B200_INFONCE");
+#ifdef RC_BRINGUP
+  const char* impl = getenv("RANGECLIP_B200_INFONCE");     // bring-up A/B switch; never compiled into the shipped library
+#else
+  const char* impl = nullptr;
+#endif
   const bool use_pair = (rep != 1 || !(impl != nullptr && impl[0] == '1')) && infonce_pair_supported(D);
   const int keep_w = (flags & RC_INFONCE_KEEP_WEIGHT) ? 1 : 0;
+  const int acc_dx = (flags & RC_INFONCE_ACCUMULATE_DX) ? 1 : 0;
   const float* lse_in = (flags & RC_INFONCE_LSE_GIVEN) ? lse : nullptr;
-  if (keep_w || lse_in) {
+  if (acc_dx) RC_REQUIRE(bwd, "rc_infonce_bf16: RC_INFONCE_ACCUMULATE_DX needs dx");
+  if (keep_w || lse_in || acc_dx) {
     if (!use_pair || rep != 1 || dt != nullptr)
       return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16: the K-blocked flags need D = 256 or 512, one target per row and no dText");
     RC_REQUIRE(!(flags & RC_INFONCE_LSE_GIVEN) || lse != nullptr, "rc_infonce_bf16: RC_INFONCE_LSE_GIVEN needs lse");
@@ -822,16 +832,16 @@ static int infonce_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, int6
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
     void* g = ws + ((base + 255) / 256) * 256;
     if ((rcode = launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
-                                     loss_sum, w_sum, dlogtau, g, rep, 0, nullptr, 0, s))) return rcode;
+                                     loss_sum, w_sum, dlogtau, g, rep, 0, nullptr, 0, 0, s))) return rcode;
     return launch_infonce_dt(g, xsrc, B, D, HW, K, dt, s);
   }
   if (use_pair) {
     // RC_INFONCE_TS_KERNEL: backward launches with the softmax tile as a tensor-memory operand of the dX GEMM (infonce_ts.cu)
     if (bwd && (flags & RC_INFONCE_TS_KERNEL))
       return launch_infonce_ts(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, y, w, inv_tau, grad_scale, w_sum_in, lse, loss_sum, w_sum,
-                               dlogtau, rep, keep_w, lse_in, 0, s);
+                               dlogtau, rep, keep_w, lse_in, 0, acc_dx, s);
     return launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
-                               loss_sum, w_sum, dlogtau, nullptr, rep, keep_w, lse_in, 0, s);
+                               loss_sum, w_sum, dlogtau, nullptr, rep, keep_w, lse_in, 0, acc_dx, s);
   }
   const int Kp = (K + 63) / 64 * 64;
   CUtensorMap m_xs, m_t, m_tt, m_xe, m_dx;
@@ -912,9 +922,9 @@ extern "C" int rc_infonce_bf16_kblocks(const void* x, rc_dtype x_dtype, int D, i
   const float* lse_in = (flags & RC_INFONCE_LSE_GIVEN) ? lse : nullptr;
   if (bwd && (flags & RC_INFONCE_TS_KERNEL))
     return launch_infonce_ts(xsrc, dx_blocks, t_bf16_all, tt_bf16_all, n_blocks, D, HW, K, y_rel, w_rep, inv_tau, grad_scale, w_sum_in,
-                             lse, loss_sum, w_sum, dlogtau, 1, 1, lse_in, n_blocks, s);
+                             lse, loss_sum, w_sum, dlogtau, 1, 1, lse_in, n_blocks, 0, s);
   return launch_infonce_pair(xsrc, dx_blocks, t_bf16_all, tt_bf16_all, n_blocks, D, HW, K, inv_norm, y_rel, w_rep, inv_tau, grad_scale,
-                             w_sum_in, lse, loss_sum, w_sum, dlogtau, nullptr, 1, 1, lse_in, n_blocks, s);
+                             w_sum_in, lse, loss_sum, w_sum, dlogtau, nullptr, 1, 1, lse_in, n_blocks, 0, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -976,6 +986,7 @@ debug_umma_gemm_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
 
 }  // namespace rc
 
+#ifdef RC_BRINGUP
 extern "C" int rc_debug_umma_gemm_2sm(const void* a_bf16, const void* b_bf16, int N, int Kd, float* c, void* stream) {
   RC_REQUIRE(a_bf16 && b_bf16 && c, "rc_debug_umma_gemm_2sm: null pointer");
   RC_REQUIRE(N >= 64 && N <= 256 && N % 64 == 0 && Kd >= 64 && Kd % 64 == 0, "rc_debug_umma_gemm_2sm: bad shape N=%d Kd=%d", N, Kd);
@@ -996,3 +1007,4 @@ extern "C" int rc_debug_umma_gemm_2sm(const void* a_bf16, const void* b_bf16, in
   rc::debug_umma_gemm_2sm_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(ma, mb, N, Kd, c);
   return rc::check_launch("rc_debug_umma_gemm_2sm");
 }
+#endif  // RC_BRINGUP

@@ -134,6 +134,7 @@ struct Params {
   // dropped).  lse_in: the row's logsumexp over ALL candidates, from a first round of forward launches; the softmax of
   // this block is then exp(z - lse_in) instead of exp(z - m) / (block sum).
   int keep_w;
+  int acc_dx;               // K-blocked backward launches after the first: dX += this block's gradient (TMA reduce-add store)
   const float* lse_in;
   // kb > 0: ALL candidate blocks in one launch.  The "images" of the tile index are the kb blocks of 256 candidate rows:
   // X (one image) is read with image coordinate 0, everything else (y, w, lse, dX, text rows) is indexed by the block.
@@ -914,7 +915,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && !(prm.ablate & 2)) {
-              tma_store_3d_hint(&map_dx, stg, o_px + c * 32, o_d, o_b, pol_first);
+              if (kKB && prm.acc_dx) tma_reduce_add_3d(&map_dx, stg, o_px + c * 32, o_d, o_b);
+              else tma_store_3d_hint(&map_dx, stg, o_px + c * 32, o_d, o_b, pol_first);
               tma_store_commit();
             }
           }
@@ -953,7 +955,7 @@ bool infonce_pair_supported(int D) { return D == 256 || D == 512; }
 int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const void* tt_bf16, int B, int D, int64_t HW, int K,
                         const float* inv_norm, const int32_t* y, const float* w, float inv_tau, const float* grad_scale,
                         const double* w_sum_in, float* lse, double* loss_sum, double* w_sum, double* dlogtau, void* g_out,
-                        int rep, int keep_w, const float* lse_in, int kb, cudaStream_t s) {
+                        int rep, int keep_w, const float* lse_in, int kb, int acc_dx, cudaStream_t s) {
   using namespace pair;
   const bool bwd = dx != nullptr;
   // kb > 0: all kb blocks of 256 candidate rows in one launch -- B counts the blocks (virtual images), X has ONE image,
@@ -1000,13 +1002,16 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   prm.n_pairs = (prm.n_tiles + 1) / 2;
   prm.x = reinterpret_cast<const __nv_bfloat16*>(xsrc);
   prm.dx = reinterpret_cast<__nv_bfloat16*>(dx);
-  { const char* ab = getenv("RANGECLIP_B200_ABLATE"); prm.ablate = ab ? atoi(ab) : 0; }
+  prm.ablate = 0;
   prm.split_c = prm.split_b = -1;
+#ifdef RC_BRINGUP      // ablation / issue-order switches of the bring-up build; the shipped library has no environment knobs
+  { const char* ab = getenv("RANGECLIP_B200_ABLATE"); prm.ablate = ab ? atoi(ab) : 0; }
   if (const char* sp = getenv("RANGECLIP_B200_SPLIT")) sscanf(sp, "%d,%d", &prm.split_c, &prm.split_b);
+#endif
   prm.wide = (HW % 16 == 0) && (reinterpret_cast<uintptr_t>(xsrc) % 32 == 0) && (reinterpret_cast<uintptr_t>(dx) % 32 == 0);
   prm.inv_norm = inv_norm; prm.y = y; prm.w = w; prm.inv_tau = inv_tau; prm.grad_scale = grad_scale;
   prm.w_sum_in = w_sum_in; prm.lse = lse; prm.loss_sum = loss_sum; prm.w_sum = w_sum; prm.dlogtau = dlogtau;
-  prm.keep_w = keep_w; prm.lse_in = lse_in; prm.kb = kb;
+  prm.keep_w = keep_w; prm.lse_in = lse_in; prm.kb = kb; prm.acc_dx = acc_dx;
   if (kb > 0 && (prm.tiles_per_img & 1)) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16_kblocks: HW must be a multiple of 256");
   int n_clusters = num_sms() / 2;
   if (n_clusters > prm.n_pairs) n_clusters = prm.n_pairs;
@@ -1018,7 +1023,7 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
     return check_launch("rc_infonce_bf16(pair)");
   };
   if (rep == 4) return bwd ? launch(infonce_umma_pair_kernel<true, 4, false>) : launch(infonce_umma_pair_kernel<false, 4, false>);
-  if (keep_w || lse_in != nullptr || kb > 0) return bwd ? launch(infonce_umma_pair_kernel<true, 1, true>) : launch(infonce_umma_pair_kernel<false, 1, true>);
+  if (keep_w || lse_in != nullptr || kb > 0 || acc_dx) return bwd ? launch(infonce_umma_pair_kernel<true, 1, true>) : launch(infonce_umma_pair_kernel<false, 1, true>);
   return bwd ? launch(infonce_umma_pair_kernel<true, 1, false>) : launch(infonce_umma_pair_kernel<false, 1, false>);
 }
 

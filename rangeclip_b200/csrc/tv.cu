@@ -454,7 +454,9 @@ tv_bwd_direct_kernel(const T* __restrict__ x, int64_t planes, int H, int W, cons
 // split into two large tiles and a sliver).  RANGECLIP_B200_TV_ROWS / _TV_SMEM_KB override cap and budget (bring-up).
 static int tv_tile_budget_bytes(bool vec, int dflt) {
   int bytes = dflt;
+#ifdef RC_BRINGUP
   if (vec) if (const char* e = getenv("RANGECLIP_B200_TV_SMEM_KB")) { const int v = atoi(e); if (v >= 8 && v <= 224) bytes = v * 1024; }
+#endif
   return bytes;
 }
 static int tv_tile_rows(int H, int W, int halo, int elt_bytes, bool vec, bool fwd) {
@@ -462,7 +464,9 @@ static int tv_tile_rows(int H, int W, int halo, int elt_bytes, bool vec, bool fw
   const int budget = tv_tile_budget_bytes(vec, (big && fwd) ? 66 * 1024 + 512 : kTvSmemFloats * 4);
   int r = (budget / elt_bytes) / W - halo;
   int cap = big ? (fwd ? 128 : 94) : 32;
+#ifdef RC_BRINGUP
   if (const char* e = getenv("RANGECLIP_B200_TV_ROWS")) { const int v = atoi(e); if (v > 0) cap = v; }
+#endif
   if (r > cap) r = cap;
   if (r > H) r = H;
   if (r >= 1) {                        // balance: same number of tiles, equal heights

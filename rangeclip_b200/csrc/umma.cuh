@@ -135,6 +135,14 @@ __device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* m, const vo
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
                : "memory");
 }
+// bulk tensor store that ADDS the shared-memory box to global memory (element type from the tensor map: bf16 here); the
+// read-modify-write happens in the L2
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // L2 prefetch of one box (no shared-memory destination, no completion tracking)
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),

@@ -24,8 +24,11 @@ def build_contrast_indices(unique_labels: torch.Tensor, C: int, label_similarity
 
     Host logic, kept behaviour-identical to the reference including the ``label in container``
     membership test that silently disables hard/medium distractors for list-form sets (Q3) and
-    the order in which ``np.random`` and the CPU torch generator are consumed (Q6)."""
+    the order in which ``np.random`` and the CPU torch generator are consumed (Q6).  The index arithmetic
+    (model.py:259-268: arange / isin / randperm / cat / unique) runs on HOST tensors here -- same values, same
+    generators, but one device transfer of K indices at the end instead of a dozen tiny launches and syncs."""
     present = unique_labels.tolist()
+    present_set = set(present)
     n_medium = int(k_distractors * pct_medium)
     n_hard = int(k_distractors * pct_hard)
     n_rand = k_distractors - n_medium - n_hard
@@ -36,20 +39,21 @@ def build_contrast_indices(unique_labels: torch.Tensor, C: int, label_similarity
             for lab in present:
                 if lab in table:
                     candidates.update(table[lab])
-    candidates = [c for c in list(candidates) if c not in present]
+    candidates = [c for c in list(candidates) if c not in present_set]      # the set's own iteration order, as in the reference
     n_curriculum = n_medium + n_hard
     if len(candidates) >= n_curriculum:
         chosen = np.random.choice(candidates, size=n_curriculum, replace=False)
     else:
         chosen = candidates
-    chosen = torch.tensor(chosen, device=device, dtype=torch.long)
-    every = torch.arange(C, device=device)
-    free = every[~torch.isin(every, torch.cat([unique_labels, chosen], dim=0))]
+    chosen = torch.tensor(chosen, dtype=torch.long)
+    uniq_h = torch.tensor(present, dtype=torch.long)
+    every = torch.arange(C)
+    free = every[~torch.isin(every, torch.cat([uniq_h, chosen], dim=0))]
     if n_rand > 0 and len(free) > 0:
         rand_part = free[torch.randperm(len(free))[:n_rand]]
     else:
-        rand_part = torch.tensor([], device=device, dtype=torch.long)
-    return torch.unique(torch.cat([unique_labels, chosen, rand_part], dim=0))
+        rand_part = torch.tensor([], dtype=torch.long)
+    return torch.unique(torch.cat([uniq_h, chosen, rand_part], dim=0)).to(device)
 
 
 def text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embeddings, label_similarity_sets,
@@ -85,13 +89,18 @@ def text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embed
         n_samples = hw
     rand_indices = torch.randint(0, hw, (B, n_samples), device=device)
     target_flat = target_indices.reshape(B, -1)
-    label_samples = torch.gather(target_flat, 1, rand_indices)          # labels only: B*N int64
-    label_samples = label_samples[label_samples > 0]
     aux = dict(rand_indices=rand_indices, contrast_indices=None)
-    if label_samples.numel() == 0 or D == 0:
+    # the sampled foreground labels (model.py:222-233: gather, drop label 0, torch.unique) from a label histogram of the
+    # sampled pixels: one small kernel instead of a 3M-element gather + boolean index + sort
+    if C <= 12000:
+        counts = torch.ops.rangeclip.sample_label_counts(target_flat, rand_indices, C)
+        unique_labels = torch.nonzero(counts[1:]).reshape(-1) + 1
+    else:
+        label_samples = torch.gather(target_flat, 1, rand_indices)
+        unique_labels = torch.unique(label_samples[label_samples > 0])
+    if unique_labels.numel() == 0 or D == 0:
         print("Warning: No valid foreground pixels sampled for text contrastive loss.")
         return (zero(), aux) if return_aux else zero()
-    unique_labels = torch.unique(label_samples)
     contrast = build_contrast_indices(unique_labels, C, label_similarity_sets, k_distractors, pct_medium,
                                       pct_hard, pct_rand, device)
     aux["contrast_indices"] = contrast

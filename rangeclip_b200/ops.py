@@ -110,6 +110,21 @@ def sample_weights(seg: torch.Tensor, rand_idx: Optional[torch.Tensor], label_ma
     return w, y
 
 
+def sample_label_counts(seg: torch.Tensor, rand_idx: Optional[torch.Tensor], C: int) -> torch.Tensor:
+    """int32 [C]: how many sampled pixels carry each label (model.py:222-226's gathered labels as a histogram)."""
+    _need_cuda(seg, rand_idx)
+    B = seg.shape[0]
+    HW = seg[0].numel() if B else 0
+    seg = seg.to(torch.int64).contiguous()
+    counts = torch.zeros(C, device=seg.device, dtype=torch.int32)
+    n_s = 0
+    if rand_idx is not None:
+        rand_idx = rand_idx.to(torch.int64).contiguous()
+        n_s = rand_idx.shape[1]
+    check(_lib.lib().rc_sample_label_counts(_p(seg), _p(rand_idx), B, HW, n_s, C, _p(counts), _stream(seg)), "rc_sample_label_counts")
+    return counts
+
+
 # ----------------------------------------------------------------------------------------------
 # InfoNCE
 # ----------------------------------------------------------------------------------------------
@@ -202,7 +217,7 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
     return dict(loss_sum=acc[0], w_sum=acc[1], dlogtau=acc[2], lse=lse, dx=dx, dt=dt, precision=precision)
 
 
-RC_INFONCE_KEEP_WEIGHT, RC_INFONCE_LSE_GIVEN = 2, 4
+RC_INFONCE_KEEP_WEIGHT, RC_INFONCE_LSE_GIVEN, RC_INFONCE_TS_KERNEL, RC_INFONCE_ACCUMULATE_DX = 2, 4, 8, 16
 
 
 def kblocked_supported(D: int, HW: int) -> bool:
@@ -210,7 +225,7 @@ def kblocked_supported(D: int, HW: int) -> bool:
 
 
 def infonce_kblocked_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch.Tensor, inv_tau: float,
-                         need_dx: bool, block: int = 256):
+                         need_dx: bool, block: int = 256, keep_bf16: bool = False):
     """InfoNCE against MORE than 256 candidates on the tensor cores (model.py:304-321 at thousands of objects): the
     candidate rows are split into launches of <= 256.  Round 1: forward launches give the per-block logsumexp; their
     logsumexp is the row's lse over all candidates.  Round 2: fwd+bwd launches with that lse given produce per-block dx /
@@ -287,18 +302,26 @@ def infonce_kblocked_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor,
     dx = dlogtau = None
     if need_dx:
         dxb = torch.empty(B, D, HW, device=dev, dtype=torch.bfloat16)     # the tensor-core kernel always writes bf16
-        dx = None                                                          # fp32 sum of the per-block gradients
         acc2 = torch.zeros(nb, 4, device=dev, dtype=torch.float64)
         acc2[:, 3] = wsum
+        # up to four blocks: every launch after the first ADDS its gradient to the same bf16 tensor inside the kernel
+        # (RC_INFONCE_ACCUMULATE_DX, TMA reduce-add stores: one extra rounding per block, launch order = summation order);
+        # more blocks are summed in fp32 here, block by block
+        in_kernel = nb <= 4
+        dx = None
         for i, s0 in enumerate(starts):
             Kb = min(block, K - s0)
+            fl = 1 | RC_INFONCE_KEEP_WEIGHT | RC_INFONCE_LSE_GIVEN | (RC_INFONCE_ACCUMULATE_DX if (in_kernel and i > 0) else 0)
             check(L.rc_infonce_bf16(_p(x), xdt, B, D, HW, _p(texts[i][0]), _p(texts[i][1]), Kb, _p(ys[i]), _p(w), float(inv_tau),
                                     _p(lse), acc2[i, 0:].data_ptr(), acc2[i, 1:].data_ptr(), acc2[i, 3:].data_ptr(), None, _p(dxb),
-                                    None, acc2[i, 2:].data_ptr(), _p(ws), ws_bytes,
-                                    1 | RC_INFONCE_KEEP_WEIGHT | RC_INFONCE_LSE_GIVEN, st), "rc_infonce_bf16(K block, backward)")
-            dx = dxb.float() if dx is None else dx.add_(dxb)
+                                    None, acc2[i, 2:].data_ptr(), _p(ws), ws_bytes, fl, st), "rc_infonce_bf16(K block, backward)")
+            if not in_kernel:
+                dx = dxb.float() if dx is None else dx.add_(dxb)
         dlogtau = acc2[:, 2].sum()
-        dx = dx.view(x.shape).to(x.dtype)
+        if in_kernel:
+            dx = dxb.view(x.shape) if (x.dtype == torch.bfloat16 or keep_bf16) else scale_to(dxb.view(x.shape), x.dtype)
+        else:
+            dx = dx.view(x.shape).to(x.dtype)
     return dict(loss=loss, lse=lse, dx=dx, dlogtau=dlogtau, w_sum=wsum)
 
 
@@ -565,12 +588,31 @@ def _infonce_setup(ctx, inputs, output):
     ctx.x_dtype = inputs[0].dtype
 
 
+def _graph_is_retained() -> bool:
+    """True unless the running backward was started with retain_graph=False (then the graph's saved tensors are released
+    after this pass and may be consumed in place).  Unknown (tracing, no graph task) counts as retained."""
+    try:
+        if torch.compiler.is_compiling():
+            return True
+        return bool(torch._C._autograd._get_current_graph_task_keep_graph())
+    except Exception:  # noqa: BLE001
+        return True
+
+
 def _infonce_backward(ctx, g, *_unused):
     dx, dt, dlt = ctx.saved_tensors
     need = ctx.needs_input_grad
-    # the saved gradient is READ-ONLY: the scaled copy is a fresh tensor, so a second backward through the same graph
-    # (retain_graph, torch.autograd.grad + backward) sees the same dx again
-    gx = torch.ops.rangeclip.scale_to(dx, g, _DT_CODE[ctx.x_dtype]) if need[0] else None
+    gx = None
+    if need[0]:
+        if dx.dtype == ctx.x_dtype and not _graph_is_retained():
+            # the common training case (loss.backward()): nobody can run this node again, so the saved gradient is scaled
+            # in place -- and rc_scale returns after reading the scalar when the upstream gradient is exactly 1
+            torch.ops.rangeclip.scale_(dx, g)
+            gx = dx
+        else:
+            # retain_graph / autograd.grad: the saved gradient stays READ-ONLY, the scaled (and widened) copy is a fresh
+            # tensor, so a second backward through the same graph sees the same dx again
+            gx = torch.ops.rangeclip.scale_to(dx, g, _DT_CODE[ctx.x_dtype])
     gt = dt * g if need[1] else None
     gl = (dlt * g).reshape(()) if need[2] else None
     return (gx, gt, gl) + (None,) * 8
@@ -663,6 +705,13 @@ def _op_scale_to(x: torch.Tensor, scale: Optional[torch.Tensor], out_dtype: int)
 @_op_scale_to.register_fake
 def _(x, scale, out_dtype):
     return torch.empty(x.shape, device=x.device, dtype=_CODE_DT[out_dtype])
+
+
+@_op("rangeclip::scale_", mutates_args=("x",), device_types="cuda")
+def _op_scale_inplace(x: torch.Tensor, scale: torch.Tensor) -> None:
+    """x *= scale (device scalar), in place; no pass over memory when the scalar is exactly 1 (rc_scale)."""
+    sc = scale.detach().reshape(1).to(device=x.device, dtype=torch.float32)
+    check(_lib.lib().rc_scale(_p(x), _dt(x), x.numel(), _p(sc), _stream(x)), "rc_scale")
 
 
 @_op("rangeclip::tv_sums", mutates_args=(), device_types="cuda")
@@ -765,6 +814,16 @@ def _(seg, rand_idx, label_map):
     B = seg.shape[0]
     HW = seg[0].numel() if B else 0
     return (torch.empty(B, HW, device=seg.device, dtype=torch.float32), torch.empty(B, HW, device=seg.device, dtype=torch.int32))
+
+
+@_op("rangeclip::sample_label_counts", mutates_args=(), device_types="cuda")
+def _op_sample_label_counts(seg: torch.Tensor, rand_idx: Optional[torch.Tensor], C: int) -> torch.Tensor:
+    return sample_label_counts(seg, rand_idx, C)
+
+
+@_op_sample_label_counts.register_fake
+def _(seg, rand_idx, C):
+    return torch.empty(C, device=seg.device, dtype=torch.int32)
 
 
 @_op("rangeclip::text_prepare", mutates_args=(), device_types="cuda")
@@ -870,12 +929,17 @@ def masked_pool(x, seg, lut, lut_per_image, n_slots):
     return torch.ops.rangeclip.masked_pool(x, segs, lut, bool(lut_per_image), int(n_slots))[0]
 
 
+def _check_bringup(status: int, what: str) -> None:
+    if status != 0:
+        raise RuntimeError(f"{what} failed (status {status}): {_lib.bringup_lib().rc_last_error().decode('utf-8', 'replace')}")
+
+
 def debug_umma_gemm(a: torch.Tensor, b: torch.Tensor, variant: int) -> torch.Tensor:
     """Bring-up check of the TMA + tcgen05 + TMEM path: C[128,N] = A B^T in bf16 -> f32."""
     _need_cuda(a, b)
     N, Kd = b.shape
     c = torch.empty(128, N, device=a.device, dtype=torch.float32)
-    check(_lib.lib().rc_debug_umma_gemm(_p(a.contiguous()), _p(b.contiguous()), N, Kd, variant, _p(c), _stream(a)),
+    _check_bringup(_lib.bringup_lib().rc_debug_umma_gemm(_p(a.contiguous()), _p(b.contiguous()), N, Kd, variant, _p(c), _stream(a)),
           "rc_debug_umma_gemm")
     return c
 
@@ -885,7 +949,7 @@ def debug_umma_gemm_2sm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     _need_cuda(a, b)
     N, Kd = b.shape
     c = torch.empty(256, N, device=a.device, dtype=torch.float32)
-    check(_lib.lib().rc_debug_umma_gemm_2sm(_p(a.contiguous()), _p(b.contiguous()), N, Kd, _p(c), _stream(a)),
+    _check_bringup(_lib.bringup_lib().rc_debug_umma_gemm_2sm(_p(a.contiguous()), _p(b.contiguous()), N, Kd, _p(c), _stream(a)),
           "rc_debug_umma_gemm_2sm")
     return c
 
@@ -895,6 +959,6 @@ def debug_umma_gemm_ts_2sm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     _need_cuda(a, b)
     N, Kd = b.shape
     c = torch.empty(256, N, device=a.device, dtype=torch.float32)
-    check(_lib.lib().rc_debug_umma_gemm_ts_2sm(_p(a.contiguous()), _p(b.contiguous()), N, Kd, _p(c), _stream(a)),
+    _check_bringup(_lib.bringup_lib().rc_debug_umma_gemm_ts_2sm(_p(a.contiguous()), _p(b.contiguous()), N, Kd, _p(c), _stream(a)),
           "rc_debug_umma_gemm_ts_2sm")
     return c

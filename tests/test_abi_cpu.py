@@ -18,11 +18,22 @@ def test_library_exports_every_declared_symbol():
     if not os.path.exists(_lib.LIB_PATH):
         _lib.build()
     hdr = open(os.path.join(ROOT, "include", "rangeclip_b200.h")).read()
-    declared = set(re.findall(r"\b(rc_[a-z0-9_]+)\s*\(", hdr))
+    shipped, bringup = hdr.split("#ifdef RC_BRINGUP")[0], hdr.split("#ifdef RC_BRINGUP")[1].split("#endif /* RC_BRINGUP */")[0]
+    declared = set(re.findall(r"\b(rc_[a-z0-9_]+)\s*\(", shipped))
+    declared_bringup = set(re.findall(r"\b(rc_[a-z0-9_]+)\s*\(", bringup))
     assert declared == set(_lib.PROTOTYPES)
+    assert declared_bringup == set(_lib.BRINGUP_PROTOTYPES)
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
+    for name in declared_bringup:                   # the shipped library carries no bring-up entry point ...
+        assert not hasattr(lib, name), name
+    blib = ctypes.CDLL(_lib.BRINGUP_LIB_PATH)       # ... the bring-up build of the same sources carries both sets
+    for name in declared | declared_bringup:
+        assert hasattr(blib, name), name
+    import subprocess
+    strings = subprocess.run(["strings", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "RANGECLIP_B200_" not in strings        # no environment switch is compiled into the shipped library
     assert _lib.lib().rc_abi_version() == 1
     assert _lib.launch_count() >= 0
 
@@ -53,7 +64,7 @@ def test_shared_embedding_and_fused_eval_entry_points_validate_on_cpu():
                                   None, None, None, None, 0, 0, None) == -1
     assert L.rc_eval_topk_hist_bf16(None, _lib.RC_BF16, 1, 512, 64, None, 4, None, 1, None, None, None, None, 4, None, None,
                                     None, 0, None) == -1
-    assert L.rc_debug_max_active_clusters(0, 640, 1024) == -1            # bad cluster size
+    assert _lib.bringup_lib().rc_debug_max_active_clusters(0, 640, 1024) == -1            # bad cluster size
     with pytest.raises(RuntimeError):                                      # CPU tensors
         ops.infonce_raw(torch.zeros(1, 256, 2, 4), torch.zeros(3, 256), torch.zeros(8, 4, dtype=torch.int32), torch.zeros(8, 4),
                         10.0, True, False, "bf16", rep=4)

@@ -262,7 +262,7 @@ def _small_infonce_args(D=256, HW=64, K=40, requires_grad=True):
 
 def test_custom_ops_are_registered_and_pass_opcheck():
     import rangeclip_b200  # noqa: F401  (registers torch.ops.rangeclip.*)
-    for name in ("infonce", "pixel_losses", "infonce_kblocked", "smoothness", "tv_bwd", "scale_to", "masked_pool", "masked_pool_bwd",
+    for name in ("infonce", "pixel_losses", "infonce_kblocked", "smoothness", "tv_bwd", "scale_to", "scale_", "masked_pool", "masked_pool_bwd",
                  "sample_weights", "text_prepare", "eval_topk", "eval_hist", "eval_topk_hist", "eval_fold"):
         assert hasattr(torch.ops.rangeclip, name), name
     x, t, log_tau, y, w = _small_infonce_args()

@@ -24,7 +24,7 @@ def gemm_stage():
         a = torch.randn(256, Kd, device=dev, generator=g).to(torch.bfloat16)
         b = torch.randn(N, Kd, device=dev, generator=g).to(torch.bfloat16)
         c = torch.empty(256, N, device=dev, dtype=torch.float32)
-        _lib.check(L.rc_debug_umma_gemm_ts_2sm(a.data_ptr(), b.data_ptr(), N, Kd, c.data_ptr(), st), "ts gemm")
+        _lib.check(_lib.bringup_lib().rc_debug_umma_gemm_ts_2sm(a.data_ptr(), b.data_ptr(), N, Kd, c.data_ptr(), st), "ts gemm")
         torch.cuda.synchronize()
         ref = a.float() @ b.float().t()
         err = float((c - ref).abs().max())
