@@ -185,6 +185,18 @@ int rc_pool_bwd(const float* g, const int32_t* count, int B, int D, int64_t HW,
                 void* dx, rc_dtype x_dtype, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * L2-normalised pixel rows  (F.normalize(x, p=2, dim=1), the decoder tail utils/src/decoder.py:114, as one operator)
+ *   fwd: out[b][:,p] = x[b][:,p] / max(|x[b][:,p]|, 1e-12) as f32 whatever x's dtype (F.normalize is an fp32 op under
+ *        autocast), inv_norm[b][p] (nullable) = the factor
+ *   bwd: dx (x's dtype) = (g - xhat (xhat . g)) * inv_norm, xhat and g f32
+ * HW % 8 == 0, 32-byte aligned pointers.  Used where compute_loss_shared2x2 needs the normalised rows the decoder would
+ * have emitted (smoothness, area pooling) without eager PyTorch's ~10 full-tensor passes.
+ * ------------------------------------------------------------------------------------------- */
+int rc_normalize_rows_fwd(const void* x, rc_dtype dtype, int B, int D, int64_t HW, float* out, float* inv_norm, void* stream);
+int rc_normalize_rows_bwd(const float* xhat, const float* g, const float* inv_norm, rc_dtype dtype, int B, int D, int64_t HW,
+                          void* dx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Smoothness (TV-L1)  (replaces model.py:332-334 and its autograd)
  *   sums[0] += sum |x[..,w]-x[..,w+1]|, sums[1] += sum |x[..,h,:]-x[..,h+1,:]|  (double[2])
  *   bwd: dx (=|+=) scale_h * d(sum_h)/dx + scale_v * d(sum_v)/dx, sign(0) = 0;

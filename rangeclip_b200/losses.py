@@ -238,7 +238,10 @@ def _compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddi
     if W_smooth > 0 and shared2x2:
         B, D, h, w = pixel_embeddings.shape
         H, W = 2 * h, 2 * w
-        rows = torch.nn.functional.normalize(pixel_embeddings.float(), p=2, dim=1)       # decoder.py:114
+        if (h * w) % 8 == 0:
+            rows = ops.normalize_rows(pixel_embeddings)                                     # decoder.py:114, one kernel each way
+        else:
+            rows = torch.nn.functional.normalize(pixel_embeddings.float(), p=2, dim=1)
         smooth_loss = ops.smoothness(rows, denominators=(B * D * H * (W - 1) / 2.0, B * D * (H - 1) * W / 2.0))
     elif W_smooth > 0:
         smooth_loss = fused_smooth if fused_smooth is not None else ops.smoothness(pixel_embeddings)

@@ -379,6 +379,28 @@ def scale_to(x: torch.Tensor, out_dtype: torch.dtype, scale: Optional[torch.Tens
 
 
 # ----------------------------------------------------------------------------------------------
+# L2-normalised rows (decoder.py:114)
+# ----------------------------------------------------------------------------------------------
+
+def normalize_rows_raw(x: torch.Tensor):
+    """(F.normalize(x, p=2, dim=1), 1 / max(|x|, 1e-12) per pixel) for an NCHW tensor, one kernel (rc_normalize_rows_fwd)."""
+    _need_cuda(x)
+    x, B, D, HW = _emb3(x)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    inv = torch.empty(B, HW, device=x.device, dtype=torch.float32)
+    check(_lib.lib().rc_normalize_rows_fwd(_p(x), _dt(x), B, D, HW, _p(out), _p(inv), _stream(x)), "rc_normalize_rows_fwd")
+    return out, inv
+
+
+def normalize_rows_backward(xhat: torch.Tensor, g: torch.Tensor, inv: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    xhat, B, D, HW = _emb3(xhat)
+    g = g.float().contiguous()
+    dx = torch.empty(xhat.shape, device=xhat.device, dtype=dtype)
+    check(_lib.lib().rc_normalize_rows_bwd(_p(xhat), _p(g), _p(inv), _dt(dx), B, D, HW, _p(dx), _stream(xhat)), "rc_normalize_rows_bwd")
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------
 # masked pooling
 # ----------------------------------------------------------------------------------------------
 
@@ -763,6 +785,41 @@ def _smoothness_backward(ctx, g):
 _op_smoothness.register_autograd(_smoothness_backward, setup_context=_smoothness_setup)
 
 
+@_op("rangeclip::normalize_rows", mutates_args=(), device_types="cuda")
+def _op_normalize_rows(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(F.normalize(x, p=2, dim=1), per-pixel 1 / max(|x|, 1e-12)) of an NCHW tensor -- the decoder tail (decoder.py:114)."""
+    return normalize_rows_raw(x)
+
+
+@_op_normalize_rows.register_fake
+def _(x):
+    return (torch.empty(x.shape, device=x.device, dtype=torch.float32),
+            torch.empty(x.shape[0], x[0, 0].numel(), device=x.device, dtype=torch.float32))
+
+
+@_op("rangeclip::normalize_rows_bwd", mutates_args=(), device_types="cuda")
+def _op_normalize_rows_bwd(xhat: torch.Tensor, g: torch.Tensor, inv: torch.Tensor, dtype_code: int) -> torch.Tensor:
+    return normalize_rows_backward(xhat, g, inv, _CODE_DT[dtype_code])
+
+
+@_op_normalize_rows_bwd.register_fake
+def _(xhat, g, inv, dtype_code):
+    return torch.empty(xhat.shape, device=xhat.device, dtype=_CODE_DT[dtype_code])
+
+
+def _normalize_rows_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[0], output[1])
+    ctx.x_dtype = inputs[0].dtype
+
+
+def _normalize_rows_backward(ctx, g, _g_inv):
+    xhat, inv = ctx.saved_tensors
+    return torch.ops.rangeclip.normalize_rows_bwd(xhat, g, inv, _DT_CODE[ctx.x_dtype])
+
+
+_op_normalize_rows.register_autograd(_normalize_rows_backward, setup_context=_normalize_rows_setup)
+
+
 @_op("rangeclip::masked_pool", mutates_args=(), device_types="cuda")
 def _op_masked_pool(x: torch.Tensor, segs: Sequence[torch.Tensor], lut: torch.Tensor, lut_per_image: bool,
                     n_slots: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -921,6 +978,12 @@ def smoothness(x: torch.Tensor, denominators=None) -> torch.Tensor:
     _need_cuda(x)
     dh, dv = tv_denominators(x.shape) if denominators is None else denominators
     return torch.ops.rangeclip.smoothness(x, float(dh), float(dv))
+
+
+def normalize_rows(x: torch.Tensor) -> torch.Tensor:
+    """F.normalize(x, p=2, dim=1) of an NCHW tensor (f32 or bf16) as f32, with autograd, one kernel each way (HW % 8 == 0)."""
+    _need_cuda(x)
+    return torch.ops.rangeclip.normalize_rows(x)[0]
 
 
 def masked_pool(x, seg, lut, lut_per_image, n_slots):

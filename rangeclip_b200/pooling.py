@@ -41,8 +41,12 @@ def pool_objects_per_image(pixel_embeddings, segmentation, image_index, labels, 
     segmentation is full resolution: the mean over the nearest-upsampled, normalised tensor
     (decoder.py:113-114) is the count-weighted mean of the normalised half-resolution rows -- four
     accumulating passes over the small tensor, one per label sub-grid, instead of one over the large one."""
-    if shared2x2:
-        pixel_embeddings = torch.nn.functional.normalize(pixel_embeddings.float(), p=2, dim=1)     # decoder.py:114
+    if shared2x2:      # decoder.py:114
+        hw_lo = pixel_embeddings.shape[2] * pixel_embeddings.shape[3]
+        if hw_lo % 8 == 0 and pixel_embeddings.is_cuda:
+            pixel_embeddings = ops.normalize_rows(pixel_embeddings if differentiable else pixel_embeddings.detach())
+        else:
+            pixel_embeddings = torch.nn.functional.normalize(pixel_embeddings.float(), p=2, dim=1)
     B, D = pixel_embeddings.shape[0], pixel_embeddings.shape[1]
     device = pixel_embeddings.device
     image_index = torch.as_tensor(image_index, device=device, dtype=torch.long).reshape(-1)

@@ -353,3 +353,23 @@ def test_validate_model_two_ranks_equal_one_rank(golden_dir, tmp_path):
         for key in ("mIoU_t1", "mIoU_tk", "pixel_accuracy_t1", "pixel_accuracy_tk"):
             assert two[key] == one[key], (r, key, two[key], one[key])
     assert one["mIoU_tk"] > 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_normalize_rows_matches_f_normalize(dtype):
+    """rangeclip::normalize_rows (the decoder tail's F.normalize, decoder.py:114, one kernel each way) against PyTorch."""
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(2, 96, 8, 12, generator=g) * (0.2 + torch.rand(2, 1, 8, 12, generator=g))).to(dtype)
+    x[0, :, 0, 0] = 0                                   # a zero row: eps path (F.normalize clamps the norm at 1e-12)
+    up = torch.randn(2, 96, 8, 12, generator=g)
+    xr = x.float().clone().requires_grad_(True)
+    ref = torch.nn.functional.normalize(xr, p=2, dim=1)
+    (ref * up).sum().backward()
+    xd = x.detach().clone().to(dev()).requires_grad_(True)
+    out = ops.normalize_rows(xd)
+    assert out.dtype == torch.float32
+    (out * up.to(dev())).sum().backward()
+    assert xd.grad.dtype == dtype
+    assert maxrel(out.detach().cpu(), ref.detach()) < 1e-6
+    assert maxrel(xd.grad.float().cpu(), xr.grad) < (1e-5 if dtype == torch.float32 else 1e-2)
