@@ -9,9 +9,9 @@ wrapping (train_util.py:173-175), B images per GPU, 1 / 2 / 4 / 8 GPUs:
 variant  shared2x2  compute_loss_shared2x2 on the decoder's output_conv result (the 128x128 distinct embeddings)
          full       compute_loss on the decoder's full-resolution fp32 output (decoder.py:113-115 as written)
          eager      the reference's own compute_loss (model.py:178-355) on the same tensors -- the GPU incumbent
-One JSON line: step ms (max over ranks), Mpix/s over all ranks, and the step's decomposition -- backbone-only step (loss
-replaced by a mean), the step under DDP.no_sync (no gradient all-reduce) -- from which the loss path's share and the
-exposed NCCL share follow."""
+One JSON line: step ms (max over ranks) and Mpix/s over all ranks.  --phase backbone times the same step with the loss
+replaced by a mean (the loss path's share follows), --phase nosync the step under DDP.no_sync (no gradient all-reduce: the
+exposed NCCL share follows); tools/run_full_step.sh runs the three phases and merges the lines."""
 import json
 import os
 import sys
@@ -70,12 +70,14 @@ def run_full_step(args):
     torch.manual_seed(0)                       # identical initial weights on every rank, as DDP would broadcast
     core = DepthUNet('resnet', device, embedding_dim=D, use_batch_norm=True, activation_func='relu').to(device)   # train_util.py:133-144
     net = core if args.variant == "eager" else Backbone(core, args.variant == "shared2x2")
-    if world > 1:
-        # train_util.py:173 (the reference also calls _set_static_graph(), :174; not here: this benchmark switches the loss
-        # path between its timing phases, which a static graph forbids)
+    # train_util.py:173-174: DistributedDataParallel + _set_static_graph() (the static graph is what lets DDP live with the
+    # temperatures used outside forward and the backbone parameters that never receive a gradient).  A static graph must
+    # not change between iterations, so one process times ONE phase (--phase step | backbone | nosync).
+    if world > 1 and args.phase != "nosync":
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local])
-    else:
-        model = net
+        model._set_static_graph()
+    else:       # --phase nosync: the same step on every rank WITHOUT the wrapper = the step minus the gradient all-reduce
+        model = net      # (DDP.no_sync() is not available under a static graph)
     opt = torch.optim.Adam(core.parameters(), lr=1e-4)
     g = torch.Generator(device=device).manual_seed(1234 + rank)
     depth = torch.rand(B, 1, H, W, device=device, generator=g) + 0.5
@@ -94,8 +96,7 @@ def run_full_step(args):
 
     def forward_backward(mode, sync=True):
         """mode: 'loss' = the variant's loss path, 'backbone' = same backbone work with the loss replaced by a mean."""
-        ctx = model.no_sync() if (world > 1 and not sync) else torch.autocast("cuda", enabled=False)
-        with ctx:
+        if True:
             if args.variant == "eager":
                 # the reference as written: DepthUNet.forward (fp16 autocast inside, model.py:110), its own compute_loss, GradScaler
                 emb, _, _ = model(depth)
@@ -157,22 +158,25 @@ def run_full_step(args):
 
     np.random.seed(0)
     n0 = _lib.launch_count()
+    phase = args.phase
     with BN.ClockSampler(local) as clk:
-        t_full = timed(train_step, args.steps, max(args.warmup, 3))
+        if phase == "backbone":
+            t_full = timed(lambda: train_step("backbone"), args.steps, max(args.warmup, 3))
+        elif phase == "nosync":
+            t_full = timed(lambda: train_step("loss", sync=False), args.steps, max(args.warmup, 3))
+        else:
+            t_full = timed(train_step, args.steps, max(args.warmup, 3))
     launches = (_lib.launch_count() - n0)
-    t_backbone = timed(lambda: train_step("backbone"), max(3, args.steps // 2), 2)
-    t_nosync = timed(lambda: train_step("loss", sync=False), max(3, args.steps // 2), 2) if world > 1 else None
     n_params = sum(p.numel() for p in core.parameters())
     if rank == 0:
         line = {
             "metric": "full_training_step_throughput", "value": world * B * H * W / (t_full * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_full, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16 autocast (reference)" if args.variant == "eager" else "bf16", "data": "synthetic",
+            "phase": phase,
             "config": {"workload": f"configs[2]: reference ResNet-18-UNet+ASPP fwd+bwd + hybrid loss (text K=256 + area-image n=B + smoothness) + Adam, B={B}/GPU, 256x256, D=512",
                        "variant": args.variant, "parallelism": f"ddp{world}" if world > 1 else "single"},
             "clocks": clk.summary(), "gpu_launches": int(launches),
-            "backbone_only_ms": t_backbone, "loss_path_share": max(0.0, 1.0 - t_backbone / t_full),
-            "no_sync_ms": t_nosync, "exposed_allreduce_share": (max(0.0, 1.0 - t_nosync / t_full) if t_nosync else 0.0),
             "grad_bytes_allreduced_per_step": n_params * 4 if world > 1 else 0, "params_M": n_params / 1e6,
             "loss_info": {k: v for k, v in last.items() if isinstance(v, (int, float))},
         }
