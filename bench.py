@@ -527,10 +527,10 @@ def run_gpu(args):
     model = TemperatureHolder(c["tau"]).to(device)
     sets = similarity_sets(wl["contrast"].tolist(), c["G"], c["C"])
 
-    def api_loss(xd, sd, W_image=0.0, W_smooth=0.0, area=None, img=None, precision="auto"):
+    def api_loss(xd, sd, W_image=0.0, W_smooth=0.0, area=None, img=None, precision="auto", builder="reference"):
         return R.compute_loss(model, xd, sd, text, sets, area, img, W_text=1.0, W_image=W_image, W_smooth=W_smooth,
                               percent_image_sampling=c["pct_sampling"], k_distractors=K - c["G"], pct_medium=0.0, pct_hard=1.0,
-                              pct_rand=0.0, precision=precision)
+                              pct_rand=0.0, precision=precision, contrast_builder=builder)
 
     # ---- end to end through the public drop-in API with HOST buffers (pinned), loss read back
     e2e = None
@@ -578,6 +578,25 @@ def run_gpu(args):
                 "overhead_ms": t - ms / args.steps,
                 "api": "compute_loss(text term)+backward, bf16 X on the device, contrast-set builder + loss_info readback inside"}
     api_device = section(api_device_section)
+
+    # ---- the same call with the device-side contrast-set builder: no host synchronisation inside compute_loss
+    def api_sync_free_section():
+        xg = x.detach().requires_grad_(True)
+        params = [xg] + list(model.parameters())
+        info_box = []
+
+        def f():
+            total, info = api_loss(xg, seg, builder="device")
+            info_box[:] = [info]
+            return torch.autograd.grad(total, params, allow_unused=True)
+        np.random.seed(0); torch.manual_seed(0)
+        t = timed(f, max(3, args.steps // 2), 2)
+        li = info_box[0]
+        return {"ms_per_step": t, "value": world * M / (t * 1e-3) / 1e6, "unit": UNIT, "kernel_step_ms": ms / args.steps,
+                "overhead_ms": t - ms / args.steps, "over_kernel_step": t / (ms / args.steps), "loss": li["total_loss"],
+                "api": "compute_loss(text term, contrast_builder='device')+backward, bf16 X on the device: label histogram -> "
+                       "rc_contrast_build -> rc_infonce_bf16_dyn, loss_info fetched lazily (read once after the timed loop)"}
+    api_sync_free = section(api_sync_free_section)
 
     # ---- hybrid loss (text + area-image + smoothness) through compute_loss, device-resident X, bf16 and fp32 X
     def hybrid_section():
@@ -843,7 +862,7 @@ def run_gpu(args):
                        "l2": "inputs (4.3 GB bf16 per step) exceed the 126 MB L2; no flush needed",
                        "step": "rc_sample_weights + rc_weight_sum + fused tcgen05 kernel (row norms, S GEMM, softmax/CE, dX GEMM, projection)"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "ts_kernel": ts_kernel, "with_dtext": with_dtext, "api_device": api_device, "hybrid": hybrid, "kcliff": kcliff,
+            "ts_kernel": ts_kernel, "with_dtext": with_dtext, "api_device": api_device, "api_sync_free": api_sync_free, "hybrid": hybrid, "kcliff": kcliff,
             "area": area_cfg, "eval": ev, "gpu_eager": gpu_eager, "vs_gpu_eager": vs_gpu_eager, "gpu_eager_eval": eager_eval,
             "cpu_eval": cpu_eval, "cpu_full_step": cpu_full, "shared2x2": shared, "loss": loss,
         }

@@ -141,13 +141,27 @@ int rc_infonce_bf16_kblocks(const void* x, rc_dtype x_dtype, int D, int64_t HW,
                             const int32_t* y_rel, const float* w_rep, float inv_tau,
                             float* lse, double* loss_sum, double* w_sum, const double* w_sum_in, const float* grad_scale,
                             void* dx_blocks, double* dlogtau, void* workspace, int64_t workspace_bytes, int flags, void* stream);
+/* rc_infonce_bf16 / rc_infonce_bf16_rep4 (rep = 1 / 4) for callers that must not synchronise with the host:
+ * the number of valid candidate rows and the temperature are read from DEVICE memory when the kernel starts.
+ *   K        rows of t_bf16 / tt_bf16 the launch is shaped for (<= 256; rows past *k_dev are zero pad rows)
+ *   k_dev    device int32[1], valid rows in [1, K] (nullable = K); e.g. k_out[0] of rc_contrast_build
+ *   log_tau_dev device float[1] = log(tau) (model.py:99-103 `log_temperature_text`); replaces inv_tau = exp(-log tau)
+ * D = 256 or 512 (CTA-pair kernel), no dText, no K-blocked flags; everything else as rc_infonce_bf16. */
+int rc_infonce_bf16_dyn(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
+                        const void* t_bf16, const void* tt_bf16, int K, const int32_t* k_dev,
+                        const int32_t* y, const float* w, const float* log_tau_dev, int rep,
+                        float* lse, double* loss_sum, double* w_sum,
+                        const double* w_sum_in, const float* grad_scale,
+                        void* dx, double* dlogtau,
+                        void* workspace, int64_t workspace_bytes, int flags, void* stream);
 /* The pre-pass alone: 1/|x_p| of the bf16-rounded rows (+ bf16 copy of an f32 x) into workspace. */
 int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Helpers used by both paths.
  * rc_text_prepare: rows of `text[idx[k]]` (idx nullable = identity; `text` has n_rows rows, an index outside [0, n_rows)
- *   yields a row of NaN instead of an out-of-bounds read -- the reference raises an index error there) are L2-normalised
+ *   yields a row of NaN instead of an out-of-bounds read -- the reference raises an index error there; the pad value -1
+ *   of rc_contrast_build yields a zero row) are L2-normalised
  *   (F.normalize, eps 1e-12; model.py:272) and written as f32 [K][D] (nullable), bf16 [Kp][D]
  *   (nullable) and transposed bf16 [D][Kp] (nullable), Kp = round_up(K, 64), pads zeroed.
  * rc_weight_sum: w_sum[0] += sum_p w_p * (y_p >= 0)  (double).
@@ -162,6 +176,20 @@ int rc_sample_weights(const int64_t* seg, const int64_t* rand_idx, int B, int64_
 /* counts[label] += number of sampled pixels (rand_idx [B][n_samples], nullable = every pixel once) carrying that label, labels
  * outside [0, C) skipped; counts int32[C] is ADDED to.  The sampled foreground labels of model.py:222-233 (gather, drop 0,
  * torch.unique) are the nonzero entries from 1 on -- no gather, no sort.  C <= 12000. */
+/* Device-side contrast-set builder (model.py:234-268 without the .tolist() / np.random / randperm host round trips):
+ *   counts     int32[C] label histogram of the sampled pixels (rc_sample_label_counts); labels >= 1 with counts > 0 are "present"
+ *   sim_off / sim_items   CSR over labels (int32[C+1] / int32[nnz], nullable together): per label the union of the similarity
+ *              lists in use (label_similarity_sets['medium'] if n_medium > 0, ['hard'] if n_hard > 0)
+ *   n_curriculum = n_medium + n_hard candidates are drawn without replacement from the lists of the present labels (all of
+ *              them if there are fewer), n_rand from every label that is neither present nor chosen (label 0 included)
+ *   k_cap      rows the loss launch is shaped for: distractors are trimmed to fit (flag 2); present labels beyond it are
+ *              dropped from the map (flag 1)
+ *   seed       draws = the n smallest of key(c) = splitmix64(splitmix64(seed ^ phase << 56) + c), phase 1 / 2
+ * Outputs: label_map int32[C] (position in the sorted contrast set or -1), contrast int64[k_cap] (sorted ids, -1 pads:
+ * rc_text_prepare turns those into zero rows), k_out int32[4] = {K, flags, #present, #distractors}.  C <= 16384. */
+int rc_contrast_build(const int32_t* counts, int C, const int32_t* sim_off, const int32_t* sim_items,
+                      int n_curriculum, int n_rand, int k_cap, uint64_t seed,
+                      int32_t* label_map, int64_t* contrast, int32_t* k_out, void* stream);
 int rc_sample_label_counts(const int64_t* seg, const int64_t* rand_idx, int B, int64_t HW, int64_t n_samples, int C,
                            int32_t* counts, void* stream);
 int rc_scale(void* x, rc_dtype dtype, int64_t n, const float* s, void* stream);

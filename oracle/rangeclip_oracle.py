@@ -103,6 +103,78 @@ def build_contrast_set(unique_labels: torch.Tensor, C: int, label_similarity_set
 
 
 # ----------------------------------------------------------------------------
+# (f2) device-side contrast-set builder  --  the SET semantics of model.py:234-268 with the
+# counter-based draws of rangeclip_b200/csrc/contrast.cu (the reference's NumPy / randperm
+# streams cannot be reproduced on a GPU; SURVEY 8f-2: "parity then only statistical").
+# Checker for rc_contrast_build: bit-exact for a given seed.
+# ----------------------------------------------------------------------------
+
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def contrast_draw_key(seed: int, phase: int, c: int) -> int:
+    return _splitmix64((_splitmix64((seed ^ (phase << 56)) & _M64) + c) & _M64)
+
+
+def contrast_build_device(counts, sim_off, sim_items, n_curriculum: int, n_rand: int, k_cap: int, seed: int):
+    """(label_map [C], contrast [k_cap] padded with -1, (K, flags, n_present, n_distractors)).
+    present = labels >= 1 with a non-zero count (model.py:226,233); candidates = similarity lists of the present labels
+    minus present (model.py:240-252); n_curriculum of them (all if fewer, model.py:254-259) and n_rand of the labels that
+    are neither present nor chosen (model.py:261-266) are the ones with the smallest draw keys (ties of the top 44 key
+    bits by label order); the contrast set is the sorted union (model.py:268), capped at k_cap rows."""
+    counts = np.asarray(counts)
+    C = counts.shape[0]
+    present = [c for c in range(1, C) if counts[c] > 0]
+    pset = set(present)
+    cand = set()
+    if sim_off is not None and n_curriculum > 0:
+        for c in present:
+            for j in range(int(sim_off[c]), int(sim_off[c + 1])):
+                d = int(sim_items[j])
+                if 0 <= d < C and d not in pset:
+                    cand.add(d)
+    flags = 0
+    keep_present = len(present)
+    if keep_present > k_cap:
+        keep_present, flags = k_cap, flags | 1
+    take_cur = n_curriculum if len(cand) >= n_curriculum else len(cand)
+    room = k_cap - keep_present
+    if take_cur > room:
+        take_cur, flags = room, flags | 2
+    room -= take_cur
+    n_free = C - len(present) - take_cur
+    take_rand = max(0, min(n_rand, n_free))
+    if take_rand > room:
+        take_rand, flags = room, flags | 2
+
+    def smallest(elig, n, phase):
+        if n <= 0:
+            return []
+        if n >= len(elig):
+            return list(elig)
+        return sorted(elig, key=lambda c: (contrast_draw_key(seed, phase, c) >> 20, c))[:n]
+
+    chosen = smallest(sorted(cand), take_cur, 1)
+    cset = set(chosen)
+    rand = smallest([c for c in range(C) if c not in pset and c not in cset], take_rand, 2)
+    members = sorted(pset | cset | set(rand))
+    label_map = np.full(C, -1, dtype=np.int32)
+    contrast = np.full(k_cap, -1, dtype=np.int64)
+    for r, c in enumerate(members):
+        if r < k_cap:
+            label_map[c] = r
+            contrast[r] = c
+    return label_map, contrast, (min(len(members), k_cap), flags, len(present), take_cur + take_rand)
+
+
+# ----------------------------------------------------------------------------
 # (a3) logits + cross-entropy  --  model.py:272-291
 # ----------------------------------------------------------------------------
 

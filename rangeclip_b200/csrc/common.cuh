@@ -53,7 +53,8 @@ bool infonce_pair_supported(int D);
 int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const void* tt_bf16, int B, int D, int64_t HW, int K,
                         const float* inv_norm, const int32_t* y, const float* w, float inv_tau, const float* grad_scale,
                         const double* w_sum_in, float* lse, double* loss_sum, double* w_sum, double* dlogtau, void* g_out,
-                        int rep, int keep_w, const float* lse_in, int kb, int acc_dx, cudaStream_t s);
+                        int rep, int keep_w, const float* lse_in, int kb, int acc_dx, const int32_t* k_dev,
+                        const float* log_tau_dev, cudaStream_t s);
 // same problem with the softmax tile as a tensor-memory operand (infonce_ts.cu): backward launches without dText
 int launch_infonce_ts(const void* xsrc, void* dx, const void* t_bf16, const void* tt_bf16, int B, int D, int64_t HW, int K,
                       const int32_t* y, const float* w, float inv_tau, const float* grad_scale, const double* w_sum_in,

@@ -66,6 +66,26 @@ __device__ __forceinline__ void topk_insert(float (&bv)[kMaxK], int (&bi)[kMaxK]
     }
   }
 }
+// The same insertion with every comparison taken against the OLD list (depth 3 instead of k dependent compare-and-swap
+// stages): v goes to the first position p with v > bv[p], the entries behind it shift down by one, the last one drops.
+// A value that does not beat the k-th best changes nothing (all comparisons false), so callers need no guard.  Entries
+// that tie exactly keep their order (the serial network above re-orders equal values when it shifts past them).
+template <int KT>
+__device__ __forceinline__ void topk_insert_par(float (&bv)[kMaxK], int (&bi)[kMaxK], int k, float v, int id) {
+  constexpr int N = KT > 0 ? KT : kMaxK;
+  bool c[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) c[j] = (KT > 0 || j < k) && v > bv[j];
+#pragma unroll
+  for (int j = N - 1; j >= 1; --j) {       // descending: bv[j - 1] is still the old entry
+    const float sv = c[j - 1] ? bv[j - 1] : v;
+    const int si = c[j - 1] ? bi[j - 1] : id;
+    bv[j] = c[j] ? sv : bv[j];
+    bi[j] = c[j] ? si : bi[j];
+  }
+  bv[0] = c[0] ? v : bv[0];
+  bi[0] = c[0] ? id : bi[0];
+}
 // insertion with an explicit index tie-break (merging lists whose index ranges interleave)
 template <int KT>
 __device__ __forceinline__ void topk_insert_tie(float (&bv)[kMaxK], int (&bi)[kMaxK], int k, float v, int id) {
@@ -217,9 +237,14 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
             // The first 32 columns of a tile all beat the empty list: the candidate loop below would run 32 rounds of
             // dynamic register selection (a third of all its rounds in a K = 1024 scan).  Insert them with static
             // register indices instead: no bit scan, no select tree, no branch.
+            if (nvalid >= 32) {            // the common case without 32 guards
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < nvalid) topk_insert<KT>(bv, bi, prm.k, __uint_as_float(r[i]), k0 + i);
+              for (int i = 0; i < 32; ++i) topk_insert_par<KT>(bv, bi, prm.k, __uint_as_float(r[i]), k0 + i);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nvalid) topk_insert_par<KT>(bv, bi, prm.k, __uint_as_float(r[i]), k0 + i);
+            }
             if (KT > 0) {
               kth = bv[KT - 1];
             } else {
@@ -242,19 +267,28 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
           }
           uint32_t mask = (m0 | m1) | (m2 | m3);
           if (nvalid < 32) mask &= (1u << nvalid) - 1u;
-          while (mask) {
-            const int i = __ffs(mask) - 1;       // ascending column order: the earlier index wins ties
+          if (mask) {
+            // Software-pipelined candidate loop: the value of the NEXT candidate is selected (31-instruction tree) while the
+            // current one goes through the insertion -- two independent instruction streams per round instead of one
+            // serial chain (the scan warps are two per scheduler: their speed is the length of the dependent chain).
+            int i = __ffs(mask) - 1;             // ascending column order: the earlier index wins ties
             mask &= mask - 1;
-            const float v = select32(r, i);
-            if (v > kth) {
-              topk_insert<KT>(bv, bi, prm.k, v, k0 + i);
-              if (KT > 0) {
-                kth = bv[KT - 1];
-              } else {
-                kth = bv[0];
+            float v = select32(r, i);
+            for (;;) {
+              const uint32_t more = mask;
+              const int i2 = (__ffs(mask) - 1) & 31;
+              mask &= mask - 1;
+              const float v2 = select32(r, i2);
+              topk_insert_par<KT>(bv, bi, prm.k, v, k0 + i);       // a no-op when v no longer beats the k-th best
+              if (!more) break;
+              i = i2; v = v2;
+            }
+            if (KT > 0) {
+              kth = bv[KT - 1];
+            } else {
+              kth = bv[0];
 #pragma unroll
-                for (int j = 1; j < kMaxK; ++j) if (j < prm.k) kth = bv[j];
-              }
+              for (int j = 1; j < kMaxK; ++j) if (j < prm.k) kth = bv[j];
             }
           }
         }

@@ -265,6 +265,14 @@ __global__ void text_prepare_kernel(const float* __restrict__ text, int64_t ld_t
     return;
   }
   const int64_t src = idx ? idx[k] : (int64_t)k;
+  if (src == -1) {   // pad entry of a device-built index list (rc_contrast_build): a zero row, like the rows past K
+    for (int d = lane; d < D; d += 32) {
+      if (t_f32) t_f32[(int64_t)k * D + d] = 0.f;
+      if (t_bf16) t_bf16[(int64_t)k * D + d] = __float2bfloat16_rn(0.f);
+      if (tt_bf16) tt_bf16[(int64_t)d * Kp + k] = __float2bfloat16_rn(0.f);
+    }
+    return;
+  }
   if (src < 0 || src >= n_rows) {      // the reference raises an index error here (text[index_tensor]); a kernel cannot, and must not read out of bounds
     const float nan = __int_as_float(0x7fc00000);
     for (int d = lane; d < D; d += 32) {

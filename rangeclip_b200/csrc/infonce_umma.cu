@@ -779,7 +779,7 @@ static int infonce_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, int6
                              const void* tt_bf16, int K, const int32_t* y, const float* w, float inv_tau, float* lse,
                              double* loss_sum, double* w_sum, const double* w_sum_in, const float* grad_scale, void* dx,
                              float* dt, double* dlogtau, void* workspace, int64_t workspace_bytes, int flags, int rep,
-                             void* stream) {
+                             void* stream, const int32_t* k_dev = nullptr, const float* log_tau_dev = nullptr) {
   using namespace rc;
   RC_REQUIRE(x && t_bf16 && y && w && workspace, "rc_infonce_bf16: null pointer");
   RC_REQUIRE(B >= 0 && HW >= 0, "rc_infonce_bf16: bad shape");
@@ -792,6 +792,8 @@ static int infonce_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, int6
   if (B == 0 || HW == 0) return RC_OK;
   int rcode = check_sm100("rc_infonce_bf16");
   if (rcode) return rcode;
+  if ((k_dev != nullptr || log_tau_dev != nullptr) && !infonce_pair_supported(D))
+    return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16_dyn: device-side K / log tau need D = 256 or 512 (CTA-pair kernel)");
   cudaStream_t s = (cudaStream_t)stream;
   float* inv_norm; __nv_bfloat16* xb;
   // CTA-pair kernel (cta_group::2) when the channel count allows it; RANGECLIP_B200_INFONCE=1cta forces the
@@ -832,16 +834,16 @@ static int infonce_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, int6
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
     void* g = ws + ((base + 255) / 256) * 256;
     if ((rcode = launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
-                                     loss_sum, w_sum, dlogtau, g, rep, 0, nullptr, 0, 0, s))) return rcode;
+                                     loss_sum, w_sum, dlogtau, g, rep, 0, nullptr, 0, 0, k_dev, log_tau_dev, s))) return rcode;
     return launch_infonce_dt(g, xsrc, B, D, HW, K, dt, s);
   }
   if (use_pair) {
     // RC_INFONCE_TS_KERNEL: backward launches with the softmax tile as a tensor-memory operand of the dX GEMM (infonce_ts.cu)
-    if (bwd && (flags & RC_INFONCE_TS_KERNEL))
+    if (bwd && (flags & RC_INFONCE_TS_KERNEL) && k_dev == nullptr && log_tau_dev == nullptr)
       return launch_infonce_ts(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, y, w, inv_tau, grad_scale, w_sum_in, lse, loss_sum, w_sum,
                                dlogtau, rep, keep_w, lse_in, 0, acc_dx, s);
     return launch_infonce_pair(xsrc, dx, t_bf16, tt_bf16, B, D, HW, K, inv_norm, y, w, inv_tau, grad_scale, w_sum_in, lse,
-                               loss_sum, w_sum, dlogtau, nullptr, rep, keep_w, lse_in, 0, acc_dx, s);
+                               loss_sum, w_sum, dlogtau, nullptr, rep, keep_w, lse_in, 0, acc_dx, k_dev, log_tau_dev, s);
   }
   const int Kp = (K + 63) / 64 * 64;
   CUtensorMap m_xs, m_t, m_tt, m_xe, m_dx;
@@ -898,6 +900,19 @@ extern "C" int rc_infonce_bf16_rep4(const void* x, rc_dtype x_dtype, int B, int 
                            grad_scale, dx, dt, dlogtau, workspace, workspace_bytes, flags, 4, stream);
 }
 
+// rep = 1 or 4; the number of valid candidate rows (<= K, the rest are zero pad rows) and log(tau) come from device memory
+extern "C" int rc_infonce_bf16_dyn(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16,
+                                   const void* tt_bf16, int K, const int32_t* k_dev, const int32_t* y, const float* w,
+                                   const float* log_tau_dev, int rep, float* lse, double* loss_sum, double* w_sum,
+                                   const double* w_sum_in, const float* grad_scale, void* dx, double* dlogtau,
+                                   void* workspace, int64_t workspace_bytes, int flags, void* stream) {
+  RC_REQUIRE(log_tau_dev != nullptr, "rc_infonce_bf16_dyn: log_tau_dev is required");
+  RC_REQUIRE(rep == 1 || rep == 4, "rc_infonce_bf16_dyn: rep must be 1 or 4");
+  RC_REQUIRE(!(flags & (RC_INFONCE_KEEP_WEIGHT | RC_INFONCE_LSE_GIVEN | RC_INFONCE_ACCUMULATE_DX)), "rc_infonce_bf16_dyn: K-blocked flags are not supported");
+  return infonce_bf16_impl(x, x_dtype, B, D, HW, t_bf16, tt_bf16, K, y, w, 0.f, lse, loss_sum, w_sum, w_sum_in, grad_scale, dx,
+                           nullptr, dlogtau, workspace, workspace_bytes, flags, rep, stream, k_dev, log_tau_dev);
+}
+
 extern "C" int rc_infonce_bf16_kblocks(const void* x, rc_dtype x_dtype, int D, int64_t HW, const void* t_bf16_all,
                                        const void* tt_bf16_all, int K, int n_blocks, const int32_t* y_rel, const float* w_rep,
                                        float inv_tau, float* lse, double* loss_sum, double* w_sum, const double* w_sum_in,
@@ -924,7 +939,7 @@ extern "C" int rc_infonce_bf16_kblocks(const void* x, rc_dtype x_dtype, int D, i
     return launch_infonce_ts(xsrc, dx_blocks, t_bf16_all, tt_bf16_all, n_blocks, D, HW, K, y_rel, w_rep, inv_tau, grad_scale, w_sum_in,
                              lse, loss_sum, w_sum, dlogtau, 1, 1, lse_in, n_blocks, 0, s);
   return launch_infonce_pair(xsrc, dx_blocks, t_bf16_all, tt_bf16_all, n_blocks, D, HW, K, inv_norm, y_rel, w_rep, inv_tau, grad_scale,
-                             w_sum_in, lse, loss_sum, w_sum, dlogtau, nullptr, 1, 1, lse_in, n_blocks, 0, s);
+                             w_sum_in, lse, loss_sum, w_sum, dlogtau, nullptr, 1, 1, lse_in, n_blocks, 0, nullptr, nullptr, s);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -143,6 +143,10 @@ struct Params {
   const int32_t* y;
   const float* w;
   float inv_tau;
+  // sync-free callers (device-side contrast-set builder): the number of valid candidate rows and the log
+  // temperature are read from device memory at kernel start (nullable: K / inv_tau above are used)
+  const int32_t* k_dev;
+  const float* log_tau_dev;
   const float* grad_scale;
   const double* w_sum_in;
   float* lse;
@@ -549,8 +553,10 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       inv_n_next = 1.f / fmaxf(sqrtf(q), 1e-12f);
     };
     if (cluster_id < prm.n_pairs) norm_tile();
-    const bool use_bound = prm.inv_tau * (2.02f * kLog2e) < 100.f;
-    const float ml_bound = prm.inv_tau * (1.01f * kLog2e);
+    const float inv_tau = prm.log_tau_dev != nullptr ? expf(-__ldg(prm.log_tau_dev)) : prm.inv_tau;
+    const int K_valid = prm.k_dev != nullptr ? max(1, min(__ldg(prm.k_dev), prm.K)) : prm.K;      // rows past it are zero pads
+    const bool use_bound = inv_tau * (2.02f * kLog2e) < 100.f;
+    const float ml_bound = inv_tau * (1.01f * kLog2e);
     // peer copies of the row-scale arrays (same offsets in the other CTA's shared memory)
     const uint32_t sc_peer = map_to_cta(sc_s, rank ^ 1);
     const uint32_t sc_peer0 = map_to_cta(&bars->sc_full[0], rank ^ 1), sc_peer1 = map_to_cta(&bars->sc_full[1], rank ^ 1);
@@ -566,14 +572,14 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       if (kBwd && prm.store_g && threadIdx.x == 128) tma_store_wait_read0();
       const int64_t m = (int64_t)b * prm.HW + px;
       // candidates in this tile's block (kb mode: the last block may be short; its zero pad rows are masked like any pad)
-      const int Kt = (kKB && prm.kb > 0) ? min(256, prm.K - 256 * b) : prm.K;
+      const int Kt = (kKB && prm.kb > 0) ? min(256, prm.K - 256 * b) : K_valid;
       const bool px_ok = nx_inv_n != 0.f;
       const int yi = nx_y;
       const float wi = (R == 1 && (yi >= 0 || (kKB && prm.keep_w))) ? nx_w : 0.f;
       load_pixel_scalars(pj + n_clusters);
       float* xch = xch_base + (lt & 1) * (4 * 2 * 128);      // double-buffered: one named barrier per tile suffices
       const float inv_n = px_ok ? inv_n_next : 0.f;
-      const float zs = inv_n * prm.inv_tau;
+      const float zs = inv_n * inv_tau;
       const float zl = zs * kLog2e;
       // forward-only: the tensor pipe runs one pair ahead (two S buffers), so the next tile's row norms are taken
       // first -- its X chunks are already streaming and their ring slots are refilled only after these reads
@@ -726,7 +732,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         const float inv_sum = 1.f / sum;
         // P is stored pre-scaled: G[p][k] = rs_p (e_pk - sum_p [k = y_p]) = d loss / d(xhat_p . that_k) / |x_p|, so the
         // dX accumulators need no row scale and the same tile is the A operand of the dText GEMM (dT = G^T X).
-        const float rsv = inv_n * prm.inv_tau * coef * inv_sum;
+        const float rsv = inv_n * inv_tau * coef * inv_sum;
         if (half == 0) {
           const float cj = coef * sez * zs * inv_sum - coefb * tz * zs;
           const float csv = inv_n * inv_n * cj;
@@ -955,7 +961,8 @@ bool infonce_pair_supported(int D) { return D == 256 || D == 512; }
 int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const void* tt_bf16, int B, int D, int64_t HW, int K,
                         const float* inv_norm, const int32_t* y, const float* w, float inv_tau, const float* grad_scale,
                         const double* w_sum_in, float* lse, double* loss_sum, double* w_sum, double* dlogtau, void* g_out,
-                        int rep, int keep_w, const float* lse_in, int kb, int acc_dx, cudaStream_t s) {
+                        int rep, int keep_w, const float* lse_in, int kb, int acc_dx, const int32_t* k_dev,
+                        const float* log_tau_dev, cudaStream_t s) {
   using namespace pair;
   const bool bwd = dx != nullptr;
   // kb > 0: all kb blocks of 256 candidate rows in one launch -- B counts the blocks (virtual images), X has ONE image,
@@ -1012,6 +1019,7 @@ int launch_infonce_pair(const void* xsrc, void* dx, const void* t_bf16, const vo
   prm.inv_norm = inv_norm; prm.y = y; prm.w = w; prm.inv_tau = inv_tau; prm.grad_scale = grad_scale;
   prm.w_sum_in = w_sum_in; prm.lse = lse; prm.loss_sum = loss_sum; prm.w_sum = w_sum; prm.dlogtau = dlogtau;
   prm.keep_w = keep_w; prm.lse_in = lse_in; prm.kb = kb; prm.acc_dx = acc_dx;
+  prm.k_dev = k_dev; prm.log_tau_dev = log_tau_dev;
   if (kb > 0 && (prm.tiles_per_img & 1)) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_bf16_kblocks: HW must be a multiple of 256");
   int n_clusters = num_sms() / 2;
   if (n_clusters > prm.n_pairs) n_clusters = prm.n_pairs;

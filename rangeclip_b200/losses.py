@@ -56,10 +56,47 @@ def build_contrast_indices(unique_labels: torch.Tensor, C: int, label_similarity
     return torch.unique(torch.cat([uniq_h, chosen, rand_part], dim=0)).to(device)
 
 
+_CSR_CACHE = {}
+
+
+def similarity_csr(label_similarity_sets, C: int, use_medium: bool, use_hard: bool, device):
+    """The similarity tables as device CSR (int32 offsets [C+1], int32 items) for ``rc_contrast_build``: per label the union
+    of its 'medium' / 'hard' lists (those whose share of the distractors is non-zero, model.py:240-247).  Tables that are
+    not dicts never match a label in the reference (`label in table` on a list compares with its elements, quirk Q3); the
+    same here.  Built once per (tables object, C, selection, device) and cached."""
+    key = (id(label_similarity_sets), C, bool(use_medium), bool(use_hard), str(device))
+    hit = _CSR_CACHE.get(key)
+    if hit is not None and hit[0] is label_similarity_sets:
+        return hit[1], hit[2]
+    rows = [[] for _ in range(C)]
+    for use, name in ((use_medium, 'medium'), (use_hard, 'hard')):
+        table = label_similarity_sets.get(name) if (use and isinstance(label_similarity_sets, dict)) else None
+        if isinstance(table, dict):
+            for lab, items in table.items():
+                if isinstance(lab, int) and 0 <= lab < C:
+                    rows[lab].extend(int(v) for v in items)
+    off = np.zeros(C + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(r) for r in rows])
+    items = np.fromiter((v for r in rows for v in r), dtype=np.int32, count=int(off[-1]))
+    if items.size == 0:
+        items = np.zeros(1, dtype=np.int32)
+    off_d, items_d = torch.from_numpy(off).to(device), torch.from_numpy(items).to(device)
+    if len(_CSR_CACHE) > 16:
+        _CSR_CACHE.clear()
+    _CSR_CACHE[key] = (label_similarity_sets, off_d, items_d)
+    return off_d, items_d
+
+
+def device_builder_supported(D: int, hw_rows: int, C: int, text_requires_grad: bool, precision: str) -> bool:
+    """Shapes the sync-free path covers: CTA-pair kernel (D = 256 / 512, rows % 8 == 0), label histogram in shared memory
+    (C <= 12000), frozen text embeddings, not the fp32 parity mode."""
+    return D in (256, 512) and hw_rows > 0 and hw_rows % 8 == 0 and 2 <= C <= 12000 and not text_requires_grad and precision != "fp32"
+
+
 def text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embeddings, label_similarity_sets,
                           log_temperature_text, percent_image_sampling=0.7, k_distractors=50, pct_medium=0.0,
                           pct_hard=0.75, pct_rand=0.25, precision="auto", return_aux=False, with_smoothness=False,
-                          shared2x2=False):
+                          shared2x2=False, contrast_builder="reference", max_contrast=256):
     """Pixel-text InfoNCE of model.py:199-301 on the fused kernels.
 
     The reference gathers ``int(0.7*HW)`` pixel rows per image WITH replacement and drops label 0
@@ -80,7 +117,7 @@ def text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embed
             raise RuntimeError(f"text_contrastive_loss(shared2x2): targets must be {H}x{W}, got {tuple(target_indices.shape)}")
     C = candidate_text_embeddings.shape[0]
     device = pixel_embeddings.device
-    zero = lambda: torch.tensor(0.0, device=device)
+    zero = lambda: torch.zeros((), device=device)
     hw = H * W
     if hw == 0:
         raise RuntimeError("Input dimensions H or W are zero.")
@@ -90,6 +127,35 @@ def text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embed
     rand_indices = torch.randint(0, hw, (B, n_samples), device=device)
     target_flat = target_indices.reshape(B, -1)
     aux = dict(rand_indices=rand_indices, contrast_indices=None)
+    if contrast_builder not in ("reference", "device"):
+        raise RuntimeError(f"contrast_builder must be 'reference' or 'device', got {contrast_builder!r}")
+    rows_hw = (H // 2) * (W // 2) if shared2x2 else hw
+    if contrast_builder == "device" and device_builder_supported(D, rows_hw, C, candidate_text_embeddings.requires_grad, precision):
+        # ---- sync-free path: label histogram -> contrast set, label map, text operands and the loss launch
+        # without one device->host read; the set size and the temperature reach the kernel through device memory
+        n_medium = int(k_distractors * pct_medium)
+        n_hard = int(k_distractors * pct_hard)
+        n_rand = k_distractors - n_medium - n_hard
+        sim_off, sim_items = similarity_csr(label_similarity_sets, C, n_medium > 0, n_hard > 0, device)
+        k_cap = max(2, min(int(max_contrast), 256, C))
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())   # CPU generator (the stream the reference's randperm uses): no device sync
+        counts = torch.ops.rangeclip.sample_label_counts(target_flat, rand_indices, C)
+        label_map, contrast, kinfo = torch.ops.rangeclip.contrast_build(counts, sim_off, sim_items, n_medium + n_hard, n_rand,
+                                                                        k_cap, seed)
+        aux["contrast_indices"] = contrast
+        aux["contrast_info"] = kinfo
+        w, y = torch.ops.rangeclip.sample_weights(target_flat, rand_indices, label_map)
+        t_norm, tb, ttb = torch.ops.rangeclip.text_prepare(candidate_text_embeddings, contrast)
+        if with_smoothness:
+            loss, smooth = ops.pixel_losses(pixel_embeddings, t_norm, log_temperature_text, y, w, "bf16", t_bf16=(tb, ttb),
+                                            k_dev=kinfo)
+            aux["smoothness"] = smooth
+            return loss, aux
+        if shared2x2:
+            y, w = group_2x2(y.view(B, H, W)), group_2x2(w.view(B, H, W))
+        loss = ops.infonce(pixel_embeddings, t_norm, log_temperature_text, y, w, "bf16", rep=4 if shared2x2 else 1,
+                           t_bf16=(tb, ttb), k_dev=kinfo)
+        return (loss, aux) if return_aux else loss
     # the sampled foreground labels (model.py:222-233: gather, drop label 0, torch.unique) from a label histogram of the
     # sampled pixels: one small kernel instead of a 3M-element gather + boolean index + sort
     if C <= 12000:
@@ -177,17 +243,24 @@ def image_contrastive_loss(area_embeddings, image_embeddings, log_temperature_im
 def compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddings, label_similarity_sets,
                  area_embeddings, image_embeddings, W_text=1.0, W_image=0.5, W_smooth=2e2,
                  percent_image_sampling=0.7, k_distractors=50, pct_medium=0.0, pct_hard=0.75, pct_rand=0.25,
-                 precision="auto"):
-    """Hybrid contrastive loss: pixel-text + area-image + smoothness (model.py:178-355)."""
+                 precision="auto", contrast_builder="reference", max_contrast=256):
+    """Hybrid contrastive loss: pixel-text + area-image + smoothness (model.py:178-355).
+
+    ``contrast_builder="device"`` (opt-in): the contrast set is drawn on the GPU (``rc_contrast_build``, a
+    counter-based stream seeded from the CPU torch generator -- NOT the reference's NumPy / randperm streams, so the drawn
+    distractors differ from the reference's for the same seeds), its size and the temperatures stay in device memory, and
+    ``loss_info`` is a ``LazyLossInfo`` whose floats are fetched on first access: the call never synchronises with the
+    host.  At most ``max_contrast`` (<= 256) rows; distractors are trimmed to fit."""
     return _compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddings, label_similarity_sets,
                          area_embeddings, image_embeddings, W_text, W_image, W_smooth, percent_image_sampling,
-                         k_distractors, pct_medium, pct_hard, pct_rand, precision, shared2x2=False)
+                         k_distractors, pct_medium, pct_hard, pct_rand, precision, shared2x2=False,
+                         contrast_builder=contrast_builder, max_contrast=max_contrast)
 
 
 def compute_loss_shared2x2(self, decoder_output, target_indices, candidate_text_embeddings, label_similarity_sets,
                            area_embeddings, image_embeddings, W_text=1.0, W_image=0.5, W_smooth=2e2,
                            percent_image_sampling=0.7, k_distractors=50, pct_medium=0.0, pct_hard=0.75,
-                           pct_rand=0.25, precision="auto"):
+                           pct_rand=0.25, precision="auto", contrast_builder="reference", max_contrast=256):
     """``compute_loss`` of the tensor the decoder WOULD emit, taken before its tail.
 
     The reference decoder ends in ``output_conv -> F.interpolate(nearest, x2) -> F.normalize``
@@ -204,37 +277,39 @@ def compute_loss_shared2x2(self, decoder_output, target_indices, candidate_text_
     Same RNG streams as the reference (the pixel draw is over the full-resolution H*W)."""
     return _compute_loss(self, decoder_output, target_indices, candidate_text_embeddings, label_similarity_sets,
                          area_embeddings, image_embeddings, W_text, W_image, W_smooth, percent_image_sampling,
-                         k_distractors, pct_medium, pct_hard, pct_rand, precision, shared2x2=True)
+                         k_distractors, pct_medium, pct_hard, pct_rand, precision, shared2x2=True,
+                         contrast_builder=contrast_builder, max_contrast=max_contrast)
 
 
 def _compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddings, label_similarity_sets,
                   area_embeddings, image_embeddings, W_text, W_image, W_smooth, percent_image_sampling, k_distractors,
-                  pct_medium, pct_hard, pct_rand, precision, shared2x2):
+                  pct_medium, pct_hard, pct_rand, precision, shared2x2, contrast_builder="reference", max_contrast=256):
     device = pixel_embeddings.device
     log_tau_text = self.log_temperature_text
     log_tau_image = self.log_temperature_image
 
-    text_loss = torch.tensor(0.0, device=device)
+    text_loss = torch.zeros((), device=device)              # (a fill kernel: torch.tensor(0.0, device=...) is a blocking copy)
     fused_smooth = None
     if W_text > 0:
         fuse = W_smooth > 0 and pixel_embeddings.requires_grad and not shared2x2
         out = text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embeddings,
                                     label_similarity_sets, log_tau_text, percent_image_sampling,
                                     k_distractors, pct_medium, pct_hard, pct_rand, precision, return_aux=True,
-                                    with_smoothness=fuse, shared2x2=shared2x2)
+                                    with_smoothness=fuse, shared2x2=shared2x2, contrast_builder=contrast_builder,
+                                    max_contrast=max_contrast)
         text_loss = out[0]
         fused_smooth = out[1].get("smoothness")
 
-    image_loss = torch.tensor(0.0, device=device)
+    image_loss = torch.zeros((), device=device)
     if area_embeddings is not None and image_embeddings is not None and area_embeddings.shape[0] > 1:
         # "fp32" is the parity mode of every term; an explicit "bf16" asks for the tensor cores where a term's shape allows them
         image_loss = image_contrastive_loss(area_embeddings, image_embeddings, log_tau_image,
                                             precision if precision == "fp32" else "auto")
     elif W_image > 0:
-        dummy = torch.tensor(1.0, device=device, requires_grad=True)       # model.py:325-326 (Q14)
+        dummy = torch.ones((), device=device, requires_grad=True)          # model.py:325-326 (Q14)
         image_loss = dummy * torch.exp(log_tau_image) * 0.0
 
-    smooth_loss = torch.tensor(0.0, device=device)
+    smooth_loss = torch.zeros((), device=device)
     if W_smooth > 0 and shared2x2:
         B, D, h, w = pixel_embeddings.shape
         H, W = 2 * h, 2 * w
@@ -249,9 +324,13 @@ def _compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddi
     total = W_text * text_loss + W_image * image_loss + W_smooth * smooth_loss
 
     # one device->host transfer instead of the reference's six .item() syncs (model.py:343-349)
-    host = torch.stack([total.detach().float(), text_loss.detach().float(), image_loss.detach().float(),
-                        smooth_loss.detach().float(), torch.exp(log_tau_text.detach().float()),
-                        torch.exp(log_tau_image.detach().float())]).tolist()
+    stacked = torch.stack([total.detach().float(), text_loss.detach().float(), image_loss.detach().float(),
+                           smooth_loss.detach().float(), torch.exp(log_tau_text.detach().float()),
+                           torch.exp(log_tau_image.detach().float())])
+    if contrast_builder == "device":
+        # sync-free call: the six floats travel to pinned host memory asynchronously and are read on first access
+        return total, LazyLossInfo(stacked, W_text, W_image, W_smooth)
+    host = stacked.tolist()
     loss_info = {
         'total_loss': host[0],
         'text_contrastive_loss': host[1] if W_text > 0 else 0,
@@ -264,6 +343,70 @@ def _compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddi
         'W_smooth': W_smooth,
     }
     return total, loss_info
+
+
+class LazyLossInfo(dict):
+    """``loss_info`` of ``compute_loss(contrast_builder="device")``: same keys as the reference's dict (model.py:343-353); the
+    six device scalars are copied to pinned host memory asynchronously when the object is made and turned into Python floats
+    the first time anything is read -- a training loop that logs every n-th step synchronises every n-th step."""
+    _KEYS = ('total_loss', 'text_contrastive_loss', 'image_contrastive_loss', 'smoothness_loss', 'temperature_text',
+             'temperature_image')
+
+    _ring = []        # [pinned buffer, event of its last copy, weak reference to the owner]: cudaHostAlloc is slow and may block,
+                      # so a buffer is reused once its copy has completed and its owner has read it (or is gone)
+
+    @classmethod
+    def _slot(cls):
+        for slot in cls._ring:
+            owner = slot[2]() if slot[2] is not None else None
+            if (owner is None or owner._ready) and slot[1].query():
+                return slot
+        slot = [torch.empty(6, dtype=torch.float32, pin_memory=True), torch.cuda.Event(), None]
+        cls._ring.append(slot)
+        return slot
+
+    def __init__(self, stacked: torch.Tensor, W_text, W_image, W_smooth):
+        super().__init__()
+        import weakref
+        slot = self._slot()
+        slot[2] = weakref.ref(self)
+        self._host = slot[0]
+        self._host.copy_(stacked, non_blocking=True)
+        self._event = slot[1]
+        self._event.record()
+        self._weights = (W_text, W_image, W_smooth)
+        self._ready = False
+
+    def _fill(self):
+        if not self._ready:
+            self._ready = True
+            self._event.synchronize()
+            h = self._host.tolist()
+            W_text, W_image, W_smooth = self._weights
+            dict.update(self, {
+                'total_loss': h[0],
+                'text_contrastive_loss': h[1] if W_text > 0 else 0,
+                'image_contrastive_loss': h[2] if W_image > 0 else 0,
+                'smoothness_loss': h[3] if W_smooth > 0 else 0,
+                'temperature_text': h[4],
+                'temperature_image': h[5],
+                'W_text': W_text,
+                'W_image': W_image,
+                'W_smooth': W_smooth,
+            })
+
+    def __getitem__(self, k): self._fill(); return dict.__getitem__(self, k)
+    def __iter__(self): self._fill(); return dict.__iter__(self)
+    def __len__(self): self._fill(); return dict.__len__(self)
+    def __contains__(self, k): self._fill(); return dict.__contains__(self, k)
+    def __repr__(self): self._fill(); return dict.__repr__(self)
+    def __eq__(self, o): self._fill(); return dict.__eq__(self, o)
+    def get(self, k, d=None): self._fill(); return dict.get(self, k, d)
+    def keys(self): self._fill(); return dict.keys(self)
+    def values(self): self._fill(); return dict.values(self)
+    def items(self): self._fill(); return dict.items(self)
+    def copy(self): self._fill(); return dict(self)
+    __hash__ = None
 
 
 class DepthCLIPLossMixin:

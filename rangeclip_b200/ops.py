@@ -125,6 +125,23 @@ def sample_label_counts(seg: torch.Tensor, rand_idx: Optional[torch.Tensor], C: 
     return counts
 
 
+def contrast_build(counts: torch.Tensor, sim_off: Optional[torch.Tensor], sim_items: Optional[torch.Tensor], n_curriculum: int,
+                   n_rand: int, k_cap: int, seed: int):
+    """Device-side contrast set (rc_contrast_build; model.py:234-268 without host round trips): from the label histogram of
+    the sampled pixels to (label_map int32 [C], contrast int64 [k_cap] sorted ids padded with -1, kinfo int32 [4] =
+    K, flags, #present, #distractors) in one launch, nothing read back."""
+    _need_cuda(counts, sim_off, sim_items)
+    C = counts.numel()
+    counts = counts.to(torch.int32).contiguous()
+    label_map = torch.empty(C, device=counts.device, dtype=torch.int32)
+    contrast = torch.empty(int(k_cap), device=counts.device, dtype=torch.int64)
+    kinfo = torch.empty(4, device=counts.device, dtype=torch.int32)
+    check(_lib.lib().rc_contrast_build(_p(counts), C, _p(sim_off), _p(sim_items), int(n_curriculum), int(n_rand), int(k_cap),
+                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _p(label_map), _p(contrast), _p(kinfo), _stream(counts)),
+          "rc_contrast_build")
+    return label_map, contrast, kinfo
+
+
 # ----------------------------------------------------------------------------------------------
 # InfoNCE
 # ----------------------------------------------------------------------------------------------
@@ -132,13 +149,15 @@ def sample_label_counts(seg: torch.Tensor, rand_idx: Optional[torch.Tensor], C: 
 def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch.Tensor, inv_tau: float,
                 need_dx: bool, need_dt: bool, precision: str = "auto",
                 grad_scale: Optional[torch.Tensor] = None, t_bf16=None, rep: int = 1, keep_bf16: bool = False,
-                flags: int = 0):
+                flags: int = 0, k_dev: Optional[torch.Tensor] = None, log_tau_dev: Optional[torch.Tensor] = None):
     """One fused pass: returns dict(loss_sum, w_sum (double[1] tensors), lse, dx, dt, dlogtau).
     loss = loss_sum / w_sum; dx/dt/dlogtau are gradients of that mean loss times grad_scale.
     rep = 4: every row of x is the embedding shared by a 2x2 block of pixels (decoder.py:113, Q8);
     y / w are [rows, 4] and dx is the gradient w.r.t. the shared row (tensor-core path only).
     keep_bf16: leave the tensor-core path's dx in bf16 whatever x's dtype (the autograd wrappers widen and scale it
-    in one pass at backward time); flags: extra RC_INFONCE_* bits for rc_infonce_bf16 (e.g. RC_INFONCE_TS_KERNEL)."""
+    in one pass at backward time); flags: extra RC_INFONCE_* bits for rc_infonce_bf16 (e.g. RC_INFONCE_TS_KERNEL).
+    k_dev / log_tau_dev (device int32[>=1] / float[1]): the sync-free form (rc_infonce_bf16_dyn) -- the number of valid rows of
+    t_norm and log(tau) are read by the kernel from device memory; ``inv_tau`` is ignored; CTA-pair kernel shapes only."""
     _need_cuda(x, t_norm, y, w)
     x, B, D, HW = _emb3(x)
     K = t_norm.shape[0]
@@ -203,6 +222,19 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
         ws_bytes = int((L.rc_infonce_workspace_bytes_dt if need_dt else L.rc_infonce_workspace_bytes)(B, D, HW, K, xdt))
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         dxb = torch.empty(B, D, HW, device=dev, dtype=torch.bfloat16) if need_dx else None
+        if log_tau_dev is not None:
+            if need_dt or D not in (256, 512):
+                raise RuntimeError("infonce: the device-parameter form needs D in (256, 512) and no dText")
+            kd = k_dev.to(torch.int32) if k_dev is not None else None
+            lt = log_tau_dev.detach().reshape(1).to(device=dev, dtype=torch.float32)
+            check(L.rc_infonce_bf16_dyn(_p(x), xdt, B, D, HW, _p(tb), _p(ttb), K, _p(kd), _p(y), _p(w), _p(lt), rep, _p(lse),
+                                        acc[0:].data_ptr(), acc[1:].data_ptr(), acc[3:].data_ptr() if need_grad else None,
+                                        _p(gs), _p(dxb), acc[2:].data_ptr() if need_dx else None, _p(ws), ws_bytes, int(flags),
+                                        st), "rc_infonce_bf16_dyn")
+            dx = None
+            if dxb is not None:
+                dx = dxb.view(x.shape) if (x.dtype == torch.bfloat16 or keep_bf16) else scale_to(dxb.view(x.shape), x.dtype)
+            return dict(loss_sum=acc[0], w_sum=acc[1], dlogtau=acc[2], lse=lse, dx=dx, dt=None, precision=precision)
         entry = L.rc_infonce_bf16 if rep == 1 else L.rc_infonce_bf16_rep4
         check(entry(_p(x), xdt, B, D, HW, _p(tb), _p(ttb), K, _p(y), _p(w), float(inv_tau), _p(lse),
                     acc[0:].data_ptr(), acc[1:].data_ptr(),
@@ -585,20 +617,26 @@ def _mean_loss(r) -> torch.Tensor:
 @_op("rangeclip::infonce", mutates_args=(), device_types="cuda")
 def _op_infonce(x: torch.Tensor, t_norm: torch.Tensor, log_tau: torch.Tensor, y: torch.Tensor, w: torch.Tensor,
                 need_grad: bool, need_dt: bool, precision: str, rep: int, t_bf16: Optional[torch.Tensor],
-                tt_bf16: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+                tt_bf16: Optional[torch.Tensor], k_dev: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """(loss, dx, dt, dlogtau): weighted InfoNCE(x, t_norm, y, w) / tau with the gradients of the MEAN loss produced by
-    the same fused launch (single pass over x).  dx stays in the kernel's dtype (bf16 on the tensor-core path)."""
-    inv_tau = float(torch.exp(-log_tau.detach().float()))          # one scalar sync, as .item() in the reference
+    the same fused launch (single pass over x).  dx stays in the kernel's dtype (bf16 on the tensor-core path).
+    ``k_dev`` (int32 device tensor, first entry = valid rows of t_norm): the sync-free form -- the kernel reads the row
+    count and log(tau) from device memory, nothing is read back here."""
     tb = (t_bf16, tt_bf16) if (t_bf16 is not None and tt_bf16 is not None) else None
-    r = infonce_raw(x, t_norm, y, w, inv_tau, need_grad, need_dt, precision, t_bf16=tb, rep=rep, keep_bf16=True)
+    if k_dev is not None:
+        r = infonce_raw(x, t_norm, y, w, 0.0, need_grad, False, "bf16", t_bf16=tb, rep=rep, keep_bf16=True, k_dev=k_dev,
+                        log_tau_dev=log_tau)
+    else:
+        inv_tau = float(torch.exp(-log_tau.detach().float()))          # one scalar sync, as .item() in the reference
+        r = infonce_raw(x, t_norm, y, w, inv_tau, need_grad, need_dt, precision, t_bf16=tb, rep=rep, keep_bf16=True)
     dx, dt = r["dx"], r["dt"]
     return (_mean_loss(r), dx if dx is not None else _empty(x), dt if dt is not None else _empty(t_norm),
             r["dlogtau"].float().reshape(()))
 
 
 @_op_infonce.register_fake
-def _(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, rep, t_bf16, tt_bf16):
-    plan = _infonce_plan(x, t_norm.shape[0], need_dt, precision, rep)
+def _(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, rep, t_bf16, tt_bf16, k_dev=None):
+    plan = "bf16" if k_dev is not None else _infonce_plan(x, t_norm.shape[0], need_dt, precision, rep)
     dx_dtype = torch.bfloat16 if plan == "bf16" else x.dtype
     f32 = dict(device=x.device, dtype=torch.float32)
     return (torch.empty((), **f32), torch.empty(x.shape, device=x.device, dtype=dx_dtype) if need_grad else _empty(x),
@@ -608,6 +646,9 @@ def _(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, rep, t_bf16, tt_b
 def _infonce_setup(ctx, inputs, output):
     ctx.save_for_backward(output[1], output[2], output[3])
     ctx.x_dtype = inputs[0].dtype
+    # the auxiliary outputs (dx: the size of x) never carry an upstream gradient; without this autograd materialises a
+    # ZERO tensor of that size for each of them on every backward (a 4.3 GB fill at the headline size)
+    ctx.set_materialize_grads(False)
 
 
 def _graph_is_retained() -> bool:
@@ -625,6 +666,8 @@ def _infonce_backward(ctx, g, *_unused):
     dx, dt, dlt = ctx.saved_tensors
     need = ctx.needs_input_grad
     gx = None
+    if g is None:
+        return (None,) * 12
     if need[0]:
         if dx.dtype == ctx.x_dtype and not _graph_is_retained():
             # the common training case (loss.backward()): nobody can run this node again, so the saved gradient is scaled
@@ -637,7 +680,7 @@ def _infonce_backward(ctx, g, *_unused):
             gx = torch.ops.rangeclip.scale_to(dx, g, _DT_CODE[ctx.x_dtype])
     gt = dt * g if need[1] else None
     gl = (dlt * g).reshape(()) if need[2] else None
-    return (gx, gt, gl) + (None,) * 8
+    return (gx, gt, gl) + (None,) * 9
 
 
 _op_infonce.register_autograd(_infonce_backward, setup_context=_infonce_setup)
@@ -646,10 +689,10 @@ _op_infonce.register_autograd(_infonce_backward, setup_context=_infonce_setup)
 @_op("rangeclip::pixel_losses", mutates_args=(), device_types="cuda")
 def _op_pixel_losses(x: torch.Tensor, t_norm: torch.Tensor, log_tau: torch.Tensor, y: torch.Tensor, w: torch.Tensor,
                      need_grad: bool, need_dt: bool, precision: str, t_bf16: Optional[torch.Tensor],
-                     tt_bf16: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+                     tt_bf16: Optional[torch.Tensor], k_dev: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """(text InfoNCE, smoothness, dx_text, dt, dlogtau) of the SAME pixel embeddings: one autograd node for both terms, so
     that the backward is a single pass (model.py:272-291, 332-334 and their autograd)."""
-    loss, dx, dt, dlt = _op_infonce._init_fn(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, 1, t_bf16, tt_bf16)
+    loss, dx, dt, dlt = _op_infonce._init_fn(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, 1, t_bf16, tt_bf16, k_dev)
     sums = tv_sums(x)
     dh, dv = tv_denominators(x.shape)
     nan = torch.full((), float("nan"), device=x.device, dtype=torch.float64)
@@ -658,8 +701,8 @@ def _op_pixel_losses(x: torch.Tensor, t_norm: torch.Tensor, log_tau: torch.Tenso
 
 
 @_op_pixel_losses.register_fake
-def _(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, t_bf16, tt_bf16):
-    plan = _infonce_plan(x, t_norm.shape[0], need_dt, precision, 1)
+def _(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, t_bf16, tt_bf16, k_dev=None):
+    plan = "bf16" if k_dev is not None else _infonce_plan(x, t_norm.shape[0], need_dt, precision, 1)
     dx_dtype = torch.bfloat16 if plan == "bf16" else x.dtype
     f32 = dict(device=x.device, dtype=torch.float32)
     return (torch.empty((), **f32), torch.empty((), **f32),
@@ -669,12 +712,19 @@ def _(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, t_bf16, tt_bf16):
 
 def _pixel_losses_setup(ctx, inputs, output):
     ctx.save_for_backward(inputs[0], output[2], output[3], output[4])
+    ctx.set_materialize_grads(False)         # see _infonce_setup
 
 
 def _pixel_losses_backward(ctx, g_text, g_smooth, *_unused):
     x, dx, dt, dlt = ctx.saved_tensors
     need = ctx.needs_input_grad
     gx = None
+    if g_text is None and g_smooth is None:
+        return (None,) * 11
+    if g_text is None:
+        g_text = torch.zeros((), device=x.device, dtype=torch.float32)
+    if g_smooth is None:
+        g_smooth = torch.zeros((), device=x.device, dtype=torch.float32)
     if need[0]:
         dh, dv = tv_denominators(x.shape)
         gs = g_smooth.float()
@@ -683,7 +733,7 @@ def _pixel_losses_backward(ctx, g_text, g_smooth, *_unused):
         gx = torch.ops.rangeclip.tv_bwd(x, scale, dx, g_text.float())
     gt = dt * g_text if need[1] else None
     gl = (dlt * g_text).reshape(()) if need[2] else None
-    return (gx, gt, gl) + (None,) * 7
+    return (gx, gt, gl) + (None,) * 8
 
 
 _op_pixel_losses.register_autograd(_pixel_losses_backward, setup_context=_pixel_losses_setup)
@@ -708,11 +758,14 @@ def _(x, t_norm, log_tau, y, w, need_grad):
 
 def _kblocked_setup(ctx, inputs, output):
     ctx.save_for_backward(output[1], output[2])
+    ctx.set_materialize_grads(False)         # see _infonce_setup
 
 
 def _kblocked_backward(ctx, g, *_unused):
     dx, dlt = ctx.saved_tensors
     need = ctx.needs_input_grad
+    if g is None:
+        return (None,) * 6
     return (dx * g.to(dx.dtype) if need[0] else None, None, (dlt * g).reshape(()) if need[2] else None, None, None, None)
 
 
@@ -810,10 +863,13 @@ def _(xhat, g, inv, dtype_code):
 def _normalize_rows_setup(ctx, inputs, output):
     ctx.save_for_backward(output[0], output[1])
     ctx.x_dtype = inputs[0].dtype
+    ctx.set_materialize_grads(False)
 
 
 def _normalize_rows_backward(ctx, g, _g_inv):
     xhat, inv = ctx.saved_tensors
+    if g is None:
+        return None
     return torch.ops.rangeclip.normalize_rows_bwd(xhat, g, inv, _DT_CODE[ctx.x_dtype])
 
 
@@ -883,6 +939,18 @@ def _(seg, rand_idx, C):
     return torch.empty(C, device=seg.device, dtype=torch.int32)
 
 
+@_op("rangeclip::contrast_build", mutates_args=(), device_types="cuda")
+def _op_contrast_build(counts: torch.Tensor, sim_off: Optional[torch.Tensor], sim_items: Optional[torch.Tensor], n_curriculum: int,
+                       n_rand: int, k_cap: int, seed: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    return contrast_build(counts, sim_off, sim_items, n_curriculum, n_rand, k_cap, seed)
+
+
+@_op_contrast_build.register_fake
+def _(counts, sim_off, sim_items, n_curriculum, n_rand, k_cap, seed):
+    return (torch.empty(counts.numel(), device=counts.device, dtype=torch.int32),
+            torch.empty(k_cap, device=counts.device, dtype=torch.int64), torch.empty(4, device=counts.device, dtype=torch.int32))
+
+
 @_op("rangeclip::text_prepare", mutates_args=(), device_types="cuda")
 def _op_text_prepare(text: torch.Tensor, idx: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """F.normalize(text[idx], dim=1) as f32 [K,D], bf16 [Kp,D] and bf16 [D,Kp] (Kp = K rounded up to 64, zero pads)."""
@@ -945,7 +1013,7 @@ def _tb(t_bf16):
     return (None, None) if t_bf16 is None else (t_bf16[0], t_bf16[1])
 
 
-def infonce(x, t_norm, log_tau, y, w, precision="auto", rep=1, t_bf16=None):
+def infonce(x, t_norm, log_tau, y, w, precision="auto", rep=1, t_bf16=None, k_dev=None):
     """Autograd-aware fused InfoNCE (torch.ops.rangeclip.infonce); x [B,D,H,W], t_norm [K,D] normalised, y/w per pixel
     (rep = 4: x holds the embeddings shared by 2x2 pixel blocks, y/w are [B*H*W, 4]).  ``t_bf16`` = (bf16 [Kp,D], bf16
     [D,Kp]) copies of t_norm from ``text_prepare`` (optional: built on the fly otherwise)."""
@@ -953,16 +1021,16 @@ def infonce(x, t_norm, log_tau, y, w, precision="auto", rep=1, t_bf16=None):
     tb, ttb = _tb(t_bf16)
     need_grad = bool(torch.is_grad_enabled() and (x.requires_grad or log_tau.requires_grad))
     need_dt = bool(torch.is_grad_enabled() and t_norm.requires_grad)
-    return torch.ops.rangeclip.infonce(x, t_norm, log_tau, y, w, need_grad or need_dt, need_dt, precision, rep, tb, ttb)[0]
+    return torch.ops.rangeclip.infonce(x, t_norm, log_tau, y, w, need_grad or need_dt, need_dt, precision, rep, tb, ttb, k_dev)[0]
 
 
-def pixel_losses(x, t_norm, log_tau, y, w, precision="auto", t_bf16=None):
+def pixel_losses(x, t_norm, log_tau, y, w, precision="auto", t_bf16=None, k_dev=None):
     """(text InfoNCE, smoothness) with a fused single-pass backward (torch.ops.rangeclip.pixel_losses)."""
     _need_cuda(x, t_norm, y, w)
     tb, ttb = _tb(t_bf16)
     need_grad = bool(torch.is_grad_enabled() and (x.requires_grad or log_tau.requires_grad))
     need_dt = bool(torch.is_grad_enabled() and t_norm.requires_grad)
-    out = torch.ops.rangeclip.pixel_losses(x, t_norm, log_tau, y, w, need_grad or need_dt, need_dt, precision, tb, ttb)
+    out = torch.ops.rangeclip.pixel_losses(x, t_norm, log_tau, y, w, need_grad or need_dt, need_dt, precision, tb, ttb, k_dev)
     return out[0], out[1]
 
 

@@ -111,3 +111,40 @@ def test_candidate_set_builder_matches_reference(golden_dir):
     random.seed(int(g["seed"]))
     assert mine == O.build_candidate_set(seg, g["text"].shape[0], int(g["num_negatives"]))
     assert set(np.unique(g["topk"]).tolist()) <= set(mine)
+
+
+def test_device_contrast_builder_oracle_properties():
+    """oracle.contrast_build_device (the checker of rc_contrast_build): the SET semantics of model.py:234-268 -- present labels
+    always in, curriculum distractors only from the similarity lists of present labels, random ones from the rest, sorted
+    unique output, deterministic in the seed, capped at k_cap -- and the CSR form of the similarity tables (quirk Q3)."""
+    import numpy as np
+    from oracle import rangeclip_oracle as O
+    from rangeclip_b200 import losses
+    rng = np.random.default_rng(0)
+    C = 200
+    sets = {"hard": {c: [int(v) for v in rng.choice(C, 5, replace=False)] for c in range(0, C, 2)},
+            "medium": {c: [int(v) for v in rng.choice(C, 5, replace=False)] for c in range(C)}}
+    off, items = losses.similarity_csr(sets, C, False, True, "cpu")
+    off, items = off.numpy(), items.numpy()
+    for c in range(C):
+        assert list(items[off[c]:off[c + 1]]) == (sets["hard"][c] if c % 2 == 0 else [])
+    off_l, _ = losses.similarity_csr({"hard": [[1, 2], [3]], "medium": [[4]]}, C, True, True, "cpu")       # list form: never matches (Q3)
+    assert int(off_l[-1]) == 0
+    counts = np.zeros(C, dtype=np.int32)
+    present = rng.choice(np.arange(1, C), 25, replace=False)
+    counts[present] = 3
+    counts[0] = 100
+    lm, con, (K, flags, n_present, n_dis) = O.contrast_build_device(counts, off, items, 20, 10, 256, 99)
+    members = con[:K].tolist()
+    assert flags == 0 and n_present == 25 and n_dis == 30 and K == 55 and list(con[K:]) == [-1] * (256 - K)
+    assert members == sorted(set(members)) and set(present.tolist()) <= set(members)
+    pool = set(v for c in present.tolist() for v in sets["hard"].get(c, [])) - set(present.tolist())
+    assert len(set(members) & pool) >= 20
+    assert [lm[c] for c in members] == list(range(K)) and (lm >= 0).sum() == K
+    again = O.contrast_build_device(counts, off, items, 20, 10, 256, 99)
+    other = O.contrast_build_device(counts, off, items, 20, 10, 256, 100)
+    assert np.array_equal(again[1], con) and not np.array_equal(other[1], con)
+    _, con_c, (Kc, flags_c, _, n_dis_c) = O.contrast_build_device(counts, off, items, 20, 10, 40, 99)
+    assert Kc == 40 and flags_c == 2 and n_dis_c == 15 and set(present.tolist()) <= set(con_c[:Kc].tolist())
+    _, _, (Ko, flags_o, _, n_dis_o) = O.contrast_build_device(counts, off, items, 20, 10, 16, 99)
+    assert Ko == 16 and flags_o & 1 and n_dis_o == 0

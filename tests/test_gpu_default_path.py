@@ -240,9 +240,10 @@ def test_text_prepare_out_of_range_index_yields_nan_rows():
     reading out of bounds."""
     from rangeclip_b200 import ops
     text = torch.randn(10, 64, device=dev())
-    t32, tb, ttb = ops.text_prepare(text, torch.tensor([0, 3, 10, -1, 9], device=dev()), want_f32=True, want_bf16=True)
+    t32, tb, ttb = ops.text_prepare(text, torch.tensor([0, 3, 10, -2, 9, -1], device=dev()), want_f32=True, want_bf16=True)
     assert torch.isnan(t32[2]).all() and torch.isnan(t32[3]).all()
     assert torch.isfinite(t32[[0, 1, 4]]).all() and torch.isnan(tb[2].float()).all()
+    assert float(t32[5].abs().sum()) == 0.0 and float(tb[5].float().abs().sum()) == 0.0      # -1 = pad entry of rc_contrast_build: a zero row
     assert torch.allclose(t32[1], torch.nn.functional.normalize(text[3], dim=0), atol=1e-6)
 
 

@@ -1,0 +1,196 @@
+"""GPU tests of the sync-free loss path: rc_contrast_build against its oracle restatement (bit-exact), the
+device-parameter launch rc_infonce_bf16_dyn against the host-parameter launch, and compute_loss(contrast_builder="device")
+-- no host synchronisation anywhere in the call, loss / gradients equal to the oracle's for the contrast set it drew."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rangeclip_oracle as O
+
+pytestmark = pytest.mark.gpu
+BF16_MAXREL = 2e-2        # BASELINE.json north_star: bf16 path, max-relative on gradients
+BF16_LOSS_RTOL = 2e-3
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def maxrel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _csr(rng, C, per_label):
+    off = np.zeros(C + 1, dtype=np.int32)
+    items = []
+    for c in range(C):
+        if per_label and rng.random() < 0.7:
+            items += [int(v) for v in rng.integers(-1, C + 2, size=rng.integers(1, per_label + 1))]      # a few out-of-range ids too
+        off[c + 1] = len(items)
+    return off, np.asarray(items if items else [0], dtype=np.int32)
+
+
+@pytest.mark.parametrize("C,n_present,per_label,n_cur,n_rand,k_cap,seed", [
+    (33, 10, 4, 6, 4, 256, 1), (300, 40, 6, 30, 20, 256, 2), (1024, 63, 50, 193, 0, 256, 3), (1024, 63, 50, 100, 93, 256, 4),
+    (1024, 63, 0, 0, 193, 256, 5), (1024, 200, 50, 100, 100, 256, 6), (1024, 300, 10, 10, 10, 256, 7), (12000, 150, 20, 40, 60, 256, 8),
+    (64, 63, 3, 5, 50, 64, 9), (5, 0, 2, 2, 2, 5, 10), (2, 1, 0, 0, 3, 2, 11), (4096, 30, 3000, 200, 20, 200, 12)])
+def test_contrast_build_matches_oracle(C, n_present, per_label, n_cur, n_rand, k_cap, seed):
+    from rangeclip_b200 import ops
+    rng = np.random.default_rng(seed)
+    counts = np.zeros(C, dtype=np.int32)
+    if n_present:
+        counts[rng.choice(np.arange(1, C), size=min(n_present, C - 1), replace=False)] = rng.integers(1, 100, size=min(n_present, C - 1))
+    counts[0] = 7                                           # background is never "present" (model.py:226)
+    off, items = _csr(rng, C, per_label)
+    sd = int(rng.integers(0, 2 ** 62))
+    ref_map, ref_con, ref_info = O.contrast_build_device(counts, off if per_label else None, items if per_label else None, n_cur, n_rand, k_cap, sd)
+    d = dev()
+    lm, con, info = ops.contrast_build(torch.from_numpy(counts).to(d), torch.from_numpy(off).to(d) if per_label else None,
+                                       torch.from_numpy(items).to(d) if per_label else None, n_cur, n_rand, k_cap, sd)
+    assert tuple(info.tolist()) == tuple(ref_info)
+    assert np.array_equal(lm.cpu().numpy(), ref_map)
+    assert np.array_equal(con.cpu().numpy(), ref_con)
+    K = ref_info[0]
+    members = ref_con[:K]
+    assert np.all(np.diff(members) > 0)                     # sorted, unique (torch.unique, model.py:268)
+    if not (ref_info[1] & 1):
+        assert set(np.nonzero(counts[1:])[0] + 1) <= set(members.tolist())
+
+
+def test_contrast_build_draws_are_uniform():
+    """Statistical parity with model.py:261-264 (randperm[:n]): every free label is drawn with the same probability."""
+    from rangeclip_b200 import ops
+    C, n_rand, trials = 64, 8, 4000
+    counts = torch.zeros(C, dtype=torch.int32, device=dev())
+    counts[1:5] = 1
+    hits = torch.zeros(C, dtype=torch.int64, device=dev())
+    for s in range(trials):
+        lm, _, _ = ops.contrast_build(counts, None, None, 0, n_rand, 256, 1000003 * s + 17)
+        hits += (lm >= 0)
+    h = hits.cpu().numpy()
+    assert np.all(h[1:5] == trials)
+    free = np.concatenate([h[:1], h[5:]])
+    p = n_rand / 60.0
+    sigma = np.sqrt(trials * p * (1 - p))
+    assert np.all(np.abs(free - trials * p) < 5 * sigma), (free.min(), free.max(), trials * p)
+
+
+@pytest.mark.parametrize("rep", [1, 4])
+def test_infonce_dyn_equals_host_parameter_launch(rep):
+    """rc_infonce_bf16_dyn (K and log tau from device memory, pad rows past K) == rc_infonce_bf16 at K rows, bit for bit."""
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, D, H, W, K, Kcap = 2, 256, 16, 24, 100, 256
+    x = torch.randn(B, D, H, W, generator=g).to(torch.bfloat16).to(dev())
+    text = torch.randn(K, D, generator=g).to(dev())
+    y = torch.randint(-1, K, (B * H * W * rep,), generator=g, dtype=torch.int32).to(dev())
+    w = torch.randint(0, 3, (B * H * W * rep,), generator=g).float().to(dev())
+    log_tau = torch.log(torch.tensor(0.07)).to(dev())
+    idx = torch.arange(K, device=dev())
+    t32, tb, ttb = ops.text_prepare(text, idx, want_f32=True, want_bf16=True)
+    a = ops.infonce_raw(x, t32, y, w, float(torch.exp(-log_tau)), True, False, "bf16", t_bf16=(tb, ttb), rep=rep)
+    idx_p = torch.full((Kcap,), -1, device=dev(), dtype=torch.int64)
+    idx_p[:K] = idx
+    t32p, tbp, ttbp = ops.text_prepare(text, idx_p, want_f32=True, want_bf16=True)
+    assert float(t32p[K:].abs().sum()) == 0.0 and float(tbp[K:].float().abs().sum()) == 0.0
+    kd = torch.tensor([K, 0, 0, 0], device=dev(), dtype=torch.int32)
+    b = ops.infonce_raw(x, t32p, y, w, 0.0, True, False, "bf16", t_bf16=(tbp, ttbp), rep=rep, k_dev=kd, log_tau_dev=log_tau)
+    torch.cuda.synchronize()
+    # the temperature: expf on the device against torch.exp on the host -- the same value or one ulp apart
+    assert abs(float(a["loss_sum"]) - float(b["loss_sum"])) <= 1e-5 * abs(float(a["loss_sum"]))
+    assert maxrel(b["lse"].cpu(), a["lse"].cpu()) < 1e-5
+    assert maxrel(b["dx"].float().cpu(), a["dx"].float().cpu()) < 1e-2       # bf16 outputs: at most an ulp of the stored dtype
+    assert abs(float(a["dlogtau"]) - float(b["dlogtau"])) <= 1e-4 * abs(float(a["dlogtau"]))
+
+
+class _Model(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.log_temperature_text = torch.nn.Parameter(torch.log(torch.tensor(0.07)))
+        self.log_temperature_image = torch.nn.Parameter(torch.log(torch.tensor(0.1)))
+
+
+def _case(B=2, D=256, H=16, W=24, C=120, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, D, H, W, generator=g).to(torch.bfloat16).float()
+    seg = torch.randint(0, 40, (B, H, W), generator=g)                      # labels 0..39 present, 40..119 distractor material
+    text = torch.randn(C, D, generator=g)
+    rng = np.random.default_rng(seed)
+    sets = {"hard": {c: [int(v) for v in rng.choice(C, 8, replace=False)] for c in range(C)},
+            "medium": {c: [int(v) for v in rng.choice(C, 8, replace=False)] for c in range(C)}}
+    return x, seg, text, sets
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_compute_loss_device_builder_matches_oracle_and_never_syncs(shared):
+    import rangeclip_b200 as R
+    x, seg, text, sets = _case()
+    model = _Model().to(dev())
+    if shared:
+        seg = torch.nn.functional.interpolate(seg[:, None].float(), scale_factor=2, mode="nearest")[:, 0].long()   # [B, 2H, 2W] labels
+    xd = x.to(dev()).to(torch.bfloat16).requires_grad_(True)
+    segd, textd = seg.to(dev()), text.to(dev())
+    fn = R.compute_loss_shared2x2 if shared else R.compute_loss
+    kw = dict(W_text=1.0, W_image=0.0, W_smooth=0.0, percent_image_sampling=0.7, k_distractors=30, pct_medium=0.2, pct_hard=0.5,
+              pct_rand=0.3, contrast_builder="device")
+    torch.manual_seed(11)
+    total, info = fn(model, xd, segd, textd, sets, None, None, **kw)        # warm-up: allocator, CSR cache, module loading
+    total.backward()
+    torch.cuda.synchronize()
+    xd.grad = None; model.zero_grad()
+    torch.manual_seed(11)
+    from rangeclip_b200 import losses
+    torch.cuda.set_sync_debug_mode("error")                                 # any cudaStreamSynchronize / blocking copy raises
+    try:
+        total, info = fn(model, xd, segd, textd, sets, None, None, **kw)
+        total.backward()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+    assert isinstance(info, losses.LazyLossInfo)
+    # the set the device drew: the same seeds give the same CPU / CUDA generator draws
+    torch.manual_seed(11)
+    _, aux = losses.text_contrastive_loss(xd.detach(), segd, textd, sets, model.log_temperature_text.detach(), 0.7, 30, 0.2, 0.5, 0.3,
+                                          "auto", return_aux=True, shared2x2=shared, contrast_builder="device")
+    total2, info2 = total.detach(), info
+    K, flags, n_present, n_dis = aux["contrast_info"].tolist()
+    contrast = aux["contrast_indices"][:K].cpu()
+    assert flags == 0 and n_dis == 30 and K == n_present + 30
+    present = torch.unique(torch.gather(seg.reshape(seg.shape[0], -1), 1, aux["rand_indices"].cpu()))
+    present = present[present > 0]
+    assert set(present.tolist()) <= set(contrast.tolist()) and n_present == present.numel()
+    hard_or_medium = set(v for c in present.tolist() for v in sets["hard"][c] + sets["medium"][c]) - set(present.tolist())
+    assert len(set(contrast.tolist()) & hard_or_medium) >= 21               # n_medium + n_hard = 6 + 15 curriculum distractors
+    # oracle loss / gradients for exactly that set and draw (model.py:272-291 through the dense closed form)
+    xin = x if not shared else torch.nn.functional.interpolate(x, scale_factor=2, mode="nearest")
+    Bq, D = xin.shape[0], xin.shape[1]
+    w = O.sampling_weights(seg, aux["rand_indices"].cpu())
+    lm = torch.full((text.shape[0],), -1, dtype=torch.long)
+    lm[contrast] = torch.arange(K)
+    yy = lm[seg.reshape(Bq, -1)]
+    yy[seg.reshape(Bq, -1) == 0] = -1
+    rows = xin.permute(0, 2, 3, 1).reshape(-1, D)
+    ref = O.infonce_dense(rows, torch.nn.functional.normalize(text[contrast], dim=1), yy.reshape(-1), w.reshape(-1), 1 / 0.07)
+    assert abs(float(total2) - float(ref["loss"])) <= BF16_LOSS_RTOL * abs(float(ref["loss"]))
+    assert abs(info2["total_loss"] - float(ref["loss"])) <= BF16_LOSS_RTOL * abs(float(ref["loss"]))
+    assert set(info2.keys()) == {'total_loss', 'text_contrastive_loss', 'image_contrastive_loss', 'smoothness_loss',
+                                 'temperature_text', 'temperature_image', 'W_text', 'W_image', 'W_smooth'}
+    assert abs(info2["temperature_text"] - 0.07) < 1e-6
+    # gradients of the measured (sync-checked) call: same seeds, same draw
+    dx_ref = ref["dx"].reshape(Bq, xin.shape[2], xin.shape[3], D).permute(0, 3, 1, 2)
+    if shared:          # autograd below F.interpolate(nearest): the four pixel gradients of a block add up
+        dx_ref = dx_ref.reshape(Bq, D, x.shape[2], 2, x.shape[3], 2).sum(dim=(3, 5))
+    assert maxrel(xd.grad.float().cpu(), dx_ref) < BF16_MAXREL
+    assert abs(float(model.log_temperature_text.grad) - float(ref["dlogtau"])) <= BF16_MAXREL * abs(float(ref["dlogtau"]))
+
+
+def test_device_builder_falls_back_outside_its_shapes():
+    """D = 64 has no CTA-pair kernel: contrast_builder="device" silently takes the reference builder (a plain dict comes back)."""
+    import rangeclip_b200 as R
+    x, seg, text, sets = _case(D=64)
+    model = _Model().to(dev())
+    total, info = R.compute_loss(model, x.to(dev()).requires_grad_(True), seg.to(dev()), text.to(dev()), sets, None, None,
+                                 W_image=0.0, W_smooth=0.0, k_distractors=30, contrast_builder="device")
+    assert torch.isfinite(total) and info["total_loss"] == pytest.approx(float(total), rel=1e-6)
