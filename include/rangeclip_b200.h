@@ -282,6 +282,18 @@ int rc_eval_fold(const int64_t* batch_hist /*[5][C]*/, int C, int32_t batch_inde
  * librangeclip_b200_bringup.so, built with -DRC_BRINGUP (`make -C rangeclip_b200/csrc bringup`); the shipped
  * librangeclip_b200.so exports none of them and reads no environment variable.
  * ------------------------------------------------------------------------------------------- */
+/* ---------------------------------------------------------------------------------------------
+ * Object crops for the CLIP image encoder  (replaces dataloader.py:254,276: the per-object slice
+ * `image[:, ymin:ymax, xmin:xmax]` + `clip_processor(images=crops, return_tensors="pt", do_rescale=False)`,
+ * i.e. transformers 5.5.0 TorchvisionBackend._preprocess: bicubic antialiased resize of the shortest edge to
+ * `shortest_edge`, centre crop to crop_size x crop_size, (v - mean) / std) -- all crops of a batch in one launch.
+ *   images [B][C][H][W] f32 or bf16; boxes int32 [n][4] = xmin, ymin, xmax, ymax (pixels, exclusive max);
+ *   image_index int32 [n]; mean, stdv float[C]; out f32 [n][C][crop_size][crop_size].
+ * A box outside its image (the reference skips those on the host) yields a zero crop. */
+int rc_clip_crops(const void* images, rc_dtype dtype, int B, int C, int H, int W, const int32_t* boxes,
+                  const int32_t* image_index, int n, int shortest_edge, int crop_size, const float* mean,
+                  const float* stdv, float* out, void* stream);
+
 #ifdef RC_BRINGUP
 /* Bring-up instrumentation: when set (device int64[32]), CTA 0 of rc_infonce_bf16 records per-barrier
  * wait cycles of its producer / MMA / softmax / epilogue roles; index 0 = role lifetime. NULL disables. */

@@ -175,6 +175,76 @@ def contrast_build_device(counts, sim_off, sim_items, n_curriculum: int, n_rand:
 
 
 # ----------------------------------------------------------------------------
+# (f3) object crops for the CLIP image encoder  --  dataloader.py:254 (slice) + :276
+# `clip_processor(images=crops, return_tensors="pt", padding=True, do_rescale=False)`.
+# The processor is a THIRD-PARTY dependency (transformers 5.5.0, torchvision backend:
+# image_processing_backends.py TorchvisionBackend._preprocess; tvF.resize -> ATen
+# upsample_bicubic2d_aa).  Restated here from its published algorithm and pinned by
+# tests/golden/crops.npz, which holds outputs of the real CLIPImageProcessor
+# (tests/golden/make_golden_crops.py).
+# ----------------------------------------------------------------------------
+
+def _cubic_aa(x: np.float32) -> np.float32:
+    """ATen aa bicubic filter, a = -0.5 (UpSampleKernel.cpp: HelperInterpCubic::aa_filter)."""
+    f = np.float32
+    a, x = f(-0.5), np.abs(f(x))
+    if x < f(1.0):
+        return ((a + f(2.0)) * x - (a + f(3.0))) * x * x + f(1.0)
+    if x < f(2.0):
+        return (((x - f(5.0)) * x + f(8.0)) * x - f(4.0)) * a
+    return f(0.0)
+
+
+def _aa_axis(in_size: int, out_size: int):
+    """Per output index (lo, weights) of one axis: fp32 arithmetic in ATen's order (_compute_indices_weights_aa,
+    align_corners=False): scale = in/out, support = 2*max(scale,1), centre = scale*(i+0.5), weights / their sum."""
+    f = np.float32
+    scale = f(in_size) / f(out_size)
+    support = f(2.0) * scale if scale >= f(1.0) else f(2.0)
+    invscale = f(1.0) / scale if scale >= f(1.0) else f(1.0)
+    out = []
+    for i in range(out_size):
+        center = scale * (f(i) + f(0.5))
+        lo = max(int(center - support + f(0.5)), 0)
+        n = min(int(center + support + f(0.5)), in_size) - lo
+        ws = np.array([_cubic_aa((f(j + lo) - center + f(0.5)) * invscale) for j in range(n)], dtype=np.float32)
+        tot = f(0.0)
+        for w in ws:
+            tot = f(tot + w)
+        out.append((lo, ws / tot))
+    return out
+
+
+def clip_crops(images: np.ndarray, boxes, image_index, shortest_edge: int, crop_size: int, mean, std) -> np.ndarray:
+    """[n, C, crop, crop] f32 CLIP pixel values of the boxes (xmin, ymin, xmax, ymax) of images [B, C, H, W]:
+    slice (dataloader.py:254) -> resize shortest edge to `shortest_edge`, longest to int(S*long/short), bicubic antialiased
+    (horizontal pass, then vertical) -> centre crop at int((r - crop) / 2.0) -> (v - mean) / std."""
+    images = np.asarray(images, dtype=np.float32)
+    out = []
+    for (x0, y0, x1, y1), b in zip(boxes, image_index):
+        crop = images[b][:, y0:y1, x0:x1]
+        C, h, w = crop.shape
+        if w <= h:
+            rw, rh = shortest_edge, int(shortest_edge * h / w)
+        else:
+            rh, rw = shortest_edge, int(shortest_edge * w / h)
+        ax, ay = _aa_axis(w, rw), _aa_axis(h, rh)
+        top, left = int((rh - crop_size) / 2.0), int((rw - crop_size) / 2.0)
+        res = np.zeros((C, crop_size, crop_size), dtype=np.float32)
+        for oy in range(crop_size):
+            ylo, wy = ay[top + oy]
+            rows = crop[:, ylo:ylo + len(wy), :]                                   # [C, ny, w]
+            for ox in range(crop_size):
+                xlo, wx = ax[left + ox]
+                hsum = (rows[:, :, xlo:xlo + len(wx)] * wx[None, None, :]).sum(axis=2, dtype=np.float32)
+                res[:, oy, ox] = (hsum * wy[None, :]).sum(axis=1, dtype=np.float32)
+        m = np.asarray(mean, dtype=np.float32)[:, None, None]
+        sd = np.asarray(std, dtype=np.float32)[:, None, None]
+        out.append((res - m) / sd)
+    return np.stack(out).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------
 # (a3) logits + cross-entropy  --  model.py:272-291
 # ----------------------------------------------------------------------------
 

@@ -43,6 +43,7 @@ PROTOTYPES = {
     "rc_sample_label_counts": [_vp, _vp, _i32, _i64, _i64, _i32, _vp, _vp],
     "rc_scale": [_vp, _i32, _i64, _vp, _vp],
     "rc_scale_to": [_vp, _i32, _vp, _i32, _i64, _vp, _vp],
+    "rc_clip_crops": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "rc_pool_fwd": [_vp, _i32, _i32, _i32, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp],
     "rc_pool_finish": [_vp, _vp, _i32, _i32, _vp],
     "rc_pool_bwd": [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp],

@@ -125,6 +125,33 @@ def sample_label_counts(seg: torch.Tensor, rand_idx: Optional[torch.Tensor], C: 
     return counts
 
 
+def clip_crops(images: torch.Tensor, boxes: torch.Tensor, image_index: torch.Tensor, shortest_edge: int, crop_size: int,
+               mean, std) -> torch.Tensor:
+    """All object crops of a batch as CLIP pixel values in one launch (rc_clip_crops; dataloader.py:254,276 with the
+    torchvision-backend CLIP processor): images [B,C,H,W] (f32 / bf16), boxes int [n,4] = xmin, ymin, xmax, ymax,
+    image_index int [n] -> f32 [n, C, crop_size, crop_size]."""
+    _need_cuda(images, boxes, image_index)
+    if images.dim() != 4:
+        raise RuntimeError("clip_crops: images must be [B, C, H, W]")
+    if images.dtype not in (torch.float32, torch.bfloat16):
+        images = images.float()
+    images = images.contiguous()
+    B, C, H, W = images.shape
+    n = int(image_index.numel())
+    boxes = boxes.to(torch.int32).contiguous()
+    image_index = image_index.to(torch.int32).contiguous()
+    if boxes.numel() != 4 * n:
+        raise RuntimeError("clip_crops: boxes must be [n, 4]")
+    m = torch.as_tensor(list(mean), dtype=torch.float32).to(images.device, non_blocking=True)
+    sd = torch.as_tensor(list(std), dtype=torch.float32).to(images.device, non_blocking=True)
+    if m.numel() != C or sd.numel() != C:
+        raise RuntimeError(f"clip_crops: mean / std must have {C} entries")
+    out = torch.empty(n, C, int(crop_size), int(crop_size), device=images.device, dtype=torch.float32)
+    check(_lib.lib().rc_clip_crops(_p(images), _dt(images), B, C, H, W, _p(boxes), _p(image_index), n, int(shortest_edge),
+                                   int(crop_size), _p(m), _p(sd), _p(out), _stream(images)), "rc_clip_crops")
+    return out
+
+
 def contrast_build(counts: torch.Tensor, sim_off: Optional[torch.Tensor], sim_items: Optional[torch.Tensor], n_curriculum: int,
                    n_rand: int, k_cap: int, seed: int):
     """Device-side contrast set (rc_contrast_build; model.py:234-268 without host round trips): from the label histogram of

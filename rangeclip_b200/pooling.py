@@ -74,9 +74,33 @@ def pool_objects_per_image(pixel_embeddings, segmentation, image_index, labels, 
     return pooled
 
 
+def fused_crop_config(clip_processor):
+    """(shortest_edge, crop_size, mean, std) when ``clip_processor`` is a torchvision-backend CLIP-style image processor
+    whose pipeline rc_clip_crops reproduces (bicubic antialiased shortest-edge resize -> square centre crop -> normalise),
+    else None.  The PIL backend rounds the resized image to uint8 (image_transforms.resize), so it is never replaced."""
+    p = getattr(clip_processor, "image_processor", clip_processor)       # CLIPProcessor (train_util.py:126) wraps the image processor
+    try:
+        if getattr(p, "backend", None) != "torchvision":
+            return None
+        size, crop = p.size, p.crop_size
+        short = size["shortest_edge"] if isinstance(size, dict) else getattr(size, "shortest_edge", None)
+        longest = size.get("longest_edge") if isinstance(size, dict) else getattr(size, "longest_edge", None)
+        ch = crop["height"] if isinstance(crop, dict) else getattr(crop, "height", None)
+        cw = crop["width"] if isinstance(crop, dict) else getattr(crop, "width", None)
+        resample = int(getattr(p.resample, "value", p.resample))
+        ok = (p.do_resize and p.do_center_crop and p.do_normalize and short and not longest and ch and ch == cw and resample == 3
+              and not getattr(p, "do_pad", False))
+        if not ok:
+            return None
+        return int(short), int(ch), [float(v) for v in p.image_mean], [float(v) for v in p.image_std]
+    except Exception:  # noqa: BLE001
+        return None
+
+
 @torch.no_grad()
 def prepare_image_contrast_data(image_processed_batch, object_bbox_batch, object_label_batch, segmentation_batch,
-                                pixel_embeddings_batch, clip_image_encoder, clip_processor, device, shared2x2=False):
+                                pixel_embeddings_batch, clip_image_encoder, clip_processor, device, shared2x2=False,
+                                fused_crops="auto"):
     """Area embeddings + CLIP crop embeddings for the image contrastive loss (dataloader.py:205-305).
     Validation, cropping and the CLIP call are the reference's host logic; the per-object masked
     means (dataloader.py:286-304) run as one pooling kernel.  ``@torch.no_grad`` as in the
@@ -96,10 +120,23 @@ def prepare_image_contrast_data(image_processed_batch, object_bbox_batch, object
         return None, None
     boxes = object_bbox_batch.tolist()          # one transfer instead of 4*B .item() calls
     labels = object_label_batch.tolist()
-    crops, keep, keep_labels = [], [], []
+    cfg = fused_crop_config(clip_processor) if fused_crops in ("auto", True) else None
+    if fused_crops is True and cfg is None:
+        raise RuntimeError("prepare_image_contrast_data(fused_crops=True): the processor is not a torchvision-backend CLIP-style "
+                           "pipeline (bicubic shortest-edge resize, square centre crop, normalise)")
+    fused = cfg is not None and image_processed_batch.is_cuda and image_processed_batch.shape[1] == len(cfg[2])
+    crops, keep, keep_labels, keep_boxes = [], [], [], []
     for b in range(B):
         xmin, ymin, xmax, ymax = boxes[b]
         if xmax > xmin and ymax > ymin and xmin >= 0 and ymin >= 0 and xmax <= W_proc and ymax <= H_proc:
+            if fused:             # the crop is never sliced out: rc_clip_crops reads the box straight from the image
+                if int(ymax) > int(ymin) and int(xmax) > int(xmin):
+                    keep.append(b)
+                    keep_labels.append(int(labels[b]))
+                    keep_boxes.append([int(xmin), int(ymin), int(xmax), int(ymax)])
+                else:
+                    print(f"Warning: Skipping item {b}, cropped processed tensor is empty for bbox [{xmin},{ymin},{xmax},{ymax}].")
+                continue
             crop = image_processed_batch[b][:, int(ymin):int(ymax), int(xmin):int(xmax)]
             if crop.numel() > 0:
                 crops.append(crop)
@@ -109,13 +146,20 @@ def prepare_image_contrast_data(image_processed_batch, object_bbox_batch, object
                 print(f"Warning: Skipping item {b}, cropped processed tensor is empty for bbox [{xmin},{ymin},{xmax},{ymax}].")
         else:
             print(f"Debug: Skipping item {b}, invalid bbox [{xmin},{ymin},{xmax},{ymax}] relative to processed dims ({H_proc}, {W_proc}) for label {labels[b]}.")
-    if not crops:
+    if not keep:
         return None, None
-    try:
-        image_inputs = clip_processor(images=crops, return_tensors="pt", padding=True, do_rescale=False).to(device)
-    except Exception as e:  # same contract as dataloader.py:276-278
-        print(f"Error during clip_processor processing cropped tensors: {e}")
-        return None, None
+    if fused:
+        # dataloader.py:254,276 for every object in ONE launch: box -> bicubic antialiased resize -> centre crop -> normalise
+        short, csize, mean, std = cfg
+        bx = torch.tensor(keep_boxes, dtype=torch.int32).to(image_processed_batch.device, non_blocking=True)
+        ix = torch.tensor(keep, dtype=torch.int32).to(image_processed_batch.device, non_blocking=True)
+        image_inputs = {'pixel_values': ops.clip_crops(image_processed_batch, bx, ix, short, csize, mean, std).to(device)}
+    else:
+        try:
+            image_inputs = clip_processor(images=crops, return_tensors="pt", padding=True, do_rescale=False).to(device)
+        except Exception as e:  # same contract as dataloader.py:276-278
+            print(f"Error during clip_processor processing cropped tensors: {e}")
+            return None, None
     try:
         image_embeddings = clip_image_encoder.get_image_features(pixel_values=image_inputs['pixel_values'])
     except Exception as e:

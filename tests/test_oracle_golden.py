@@ -224,3 +224,16 @@ def test_shared_embedding_form_equals_reference(golden_dir, case):
         (Ws * sm).backward()
         dE = dE + El.grad
     assert np.allclose(dE.numpy(), g["dE"], rtol=2e-4, atol=2e-7)
+
+
+def test_clip_crops_oracle_matches_the_real_clip_processor(golden_dir):
+    """oracle.clip_crops (slice -> antialiased bicubic shortest-edge resize -> centre crop -> normalise, ATen's fp32 order)
+    against pixel values produced by the real CLIPImageProcessor of transformers 5.5.0 (tests/golden/make_golden_crops.py;
+    dataloader.py:254,276).  fp32 path: 1e-5 relative to the value range."""
+    g = np.load(os.path.join(golden_dir, "crops.npz"))
+    for tag in ("small", "default"):
+        S, Sc = (int(v) for v in g[tag + "_cfg"])
+        ref = g["pixel_values_" + tag]
+        out = O.clip_crops(g["images"], g["boxes_" + tag].tolist(), g["index_" + tag].tolist(), S, Sc, g["mean"], g["std"])
+        assert out.shape == ref.shape
+        assert float(np.abs(out - ref).max()) <= 1e-5 * float(np.abs(ref).max())
