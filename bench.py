@@ -883,6 +883,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="full_step: images per GPU")
     ap.add_argument("--variant", default="shared2x2", choices=["shared2x2", "full", "eager"], help="full_step: loss path")
     ap.add_argument("--phase", default="step", choices=["step", "backbone", "nosync"], help="full_step: what is timed")
+    ap.add_argument("--builder", default="device", choices=["device", "reference"],
+                    help="full_step: contrast-set builder of compute_loss (device = sync-free, SURVEY 8f-2; reference = host RNG parity)")
     args = ap.parse_args()
     if args.workload == "full_step":
         from tools.full_step import run_full_step

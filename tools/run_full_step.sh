@@ -1,14 +1,14 @@
 #!/bin/bash
 # configs[2] at N GPUs: the three timing phases of tools/full_step.py (each its own launch: static-graph DDP), merged into
-# gpurun_out/full_step_n${N}_${VARIANT}.json.   usage: tools/run_full_step.sh N [variant] [batch] [steps]
-N=${1:-1}; V=${2:-shared2x2}; B=${3:-64}; S=${4:-8}
+# gpurun_out/full_step_n${N}_${VARIANT}.json.   usage: tools/run_full_step.sh N [variant] [batch] [steps] [builder]
+N=${1:-1}; V=${2:-shared2x2}; B=${3:-64}; S=${4:-8}; BLD=${5:-device}
 mkdir -p gpurun_out
 for PH in step backbone nosync; do
   if [ "$PH" = nosync ] && [ "$N" = 1 ]; then continue; fi
   if [ "$N" = 1 ]; then
-    python bench.py --workload full_step --variant $V --batch $B --phase $PH --gpus 1 --steps $S --warmup 3 > gpurun_out/fs_${N}_${V}_${PH}.json 2> gpurun_out/fs_${N}_${V}_${PH}.err
+    python bench.py --workload full_step --variant $V --batch $B --phase $PH --builder $BLD --gpus 1 --steps $S --warmup 3 > gpurun_out/fs_${N}_${V}_${PH}.json 2> gpurun_out/fs_${N}_${V}_${PH}.err
   else
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --workload full_step --variant $V --batch $B --phase $PH --gpus $N --steps $S --warmup 3 > gpurun_out/fs_${N}_${V}_${PH}.json 2> gpurun_out/fs_${N}_${V}_${PH}.err
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --workload full_step --variant $V --batch $B --phase $PH --builder $BLD --gpus $N --steps $S --warmup 3 > gpurun_out/fs_${N}_${V}_${PH}.json 2> gpurun_out/fs_${N}_${V}_${PH}.err
   fi
   echo "phase $PH rc=$?"
 done
