@@ -635,3 +635,30 @@ def test_infonce_auto_takes_tensor_cores_beyond_256_candidates():
     (2.0 * l).backward()
     assert maxrel(xg.grad.float().cpu(), 2.0 * ref["dx4"]) < BF16_MAXREL
     assert abs(float(lt.grad) - 2.0 * float(ref["dlogtau"])) <= BF16_MAXREL * abs(2.0 * float(ref["dlogtau"]))
+
+
+@pytest.mark.parametrize("B,D,H,W,K,rep", [(2, 512, 32, 64, 256, 1), (3, 256, 25, 40, 100, 1), (1, 512, 16, 40, 33, 1), (2, 256, 16, 24, 200, 4)])
+def test_infonce_ts_kernel_matches_oracle_and_ss_kernel(B, D, H, W, K, rep):
+    """The TS-mode kernel (csrc/infonce_ts.cu, flag RC_INFONCE_TS_KERNEL: softmax tile as a tensor-memory operand of the dX
+    GEMM, two tile pairs in flight) against the fp64 oracle at the bf16 tolerances, and against the shipped SS pair kernel."""
+    from rangeclip_b200 import ops
+    x, t, y, w, inv_tau = _infonce_case(B, D, H, W, K, seed=B * 31 + D + K + rep, bf16_exact=True)
+    if rep == 4:
+        g = torch.Generator().manual_seed(K)
+        y = torch.randint(-1, K, (B * H * W, 4), generator=g, dtype=torch.int32)
+        w = torch.randint(0, 3, (B * H * W, 4), generator=g).float()
+        rows = x.permute(0, 2, 3, 1).reshape(-1, D)
+        ref = O.infonce_dense_rep(rows, t, y, w, inv_tau)
+        ref["dx4"] = ref["dx"].reshape(B, H, W, D).permute(0, 3, 1, 2)
+    else:
+        ref = _oracle_infonce(x, t, y, w, inv_tau)
+    xd = x.to(dev()).to(torch.bfloat16)
+    ts = ops.infonce_raw(xd, t.to(dev()), y.to(dev()), w.to(dev()), inv_tau, True, False, "bf16", rep=rep, flags=ops.RC_INFONCE_TS_KERNEL)
+    ss = ops.infonce_raw(xd, t.to(dev()), y.to(dev()), w.to(dev()), inv_tau, True, False, "bf16", rep=rep)
+    torch.cuda.synchronize()
+    loss = float(ts["loss_sum"] / ts["w_sum"])
+    assert abs(loss - float(ref["loss"])) <= 2e-3 * abs(float(ref["loss"]))
+    assert maxrel(ts["dx"].float().cpu(), ref["dx4"]) < BF16_MAXREL
+    assert abs(float(ts["dlogtau"]) - float(ref["dlogtau"])) <= BF16_MAXREL * abs(float(ref["dlogtau"]))
+    assert maxrel(ts["dx"].float().cpu(), ss["dx"].float().cpu()) < 1e-2
+    assert abs(loss - float(ss["loss_sum"] / ss["w_sum"])) <= 1e-5 * abs(loss)
