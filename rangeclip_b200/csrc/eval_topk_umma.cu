@@ -112,6 +112,42 @@ __device__ __forceinline__ float select32(const uint32_t (&r)[32], int i) {
   return (i & 16) ? a[1] : a[0];
 }
 
+// The same select with its first level on the FMA pipe.  Selects, compares and logic operations share the ALU pipe, which
+// takes one warp instruction every two cycles per scheduler, and the candidate loop is ~90 % such instructions; the FMA pipe
+// next to it is idle.  p in {0.0, 1.0}: r1 * p + r0 * (1 - p) is exact for finite values (one product is the value itself,
+// the other a zero), at two FMA-pipe instructions per pair instead of one ALU select.
+__device__ __forceinline__ float select32_fma(const uint32_t (&r)[32], int i) {
+  float p, q;
+  {
+    uint32_t pb;
+    asm("mad.lo.u32 %0, %1, 0x3f800000, 0;" : "=r"(pb) : "r"((uint32_t)i & 1u));      // IMAD: FMA pipe
+    p = __uint_as_float(pb);
+    q = 1.0f - p;
+  }
+  float a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float t;
+    asm("mul.f32 %0, %1, %2;" : "=f"(t) : "f"(__uint_as_float(r[2 * j])), "f"(q));
+    asm("fma.rn.f32 %0, %1, %2, %3;" : "=f"(a[j]) : "f"(__uint_as_float(r[2 * j + 1])), "f"(p), "f"(t));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = (i & 2) ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] = (i & 4) ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) a[j] = (i & 8) ? a[2 * j + 1] : a[2 * j];
+  return (i & 16) ? a[1] : a[0];
+}
+
+// bit 0 of the result = (v > kth), the previous bits move up: one FMA-pipe subtraction (the sign of kth - v) and one funnel
+// shift per column instead of a compare, a select and an add on the ALU pipe
+__device__ __forceinline__ uint32_t push_gt(uint32_t m, float v, float kth) {
+  const uint32_t d = __float_as_uint(kth - v);
+  asm("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(m) : "r"(d));
+  return m;
+}
+
 template <int KT>
 __global__ void __launch_bounds__(kThreads, 1)
 eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][HW], box (64 px, 64 d, 1)
@@ -213,13 +249,12 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
         const int sbuf = nbc & 1;
         mbar_wait(&bars->s_full[sbuf], (nbc >> 1) & 1, 6);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < kNB / 64; ++c) {
-          const int k0 = nb * kNB + half * 128 + c * 32;
-          if (k0 >= prm.K) break;
-          uint32_t r[32];
-          tmem_ld_32x32(trow + sbuf * kNB + c * 32, r);
-          tmem_ld_wait();
+        // The TMEM load of the NEXT 32 columns is in flight while this chunk is scanned (two register buffers): with two
+        // scan warps per scheduler the exposed tcgen05.ld latency of every chunk was a fifth of the scan time.
+        const int kbase = nb * kNB + half * 128;
+        const int n_chunks = min(kNB / 64, max(0, (prm.K - kbase + 31) >> 5));
+        auto scan_chunk = [&](const uint32_t (&r)[32], int c) {
+          const int k0 = kbase + c * 32;
           const int nvalid = prm.K - k0;
           if (KT == 1) {
             // arg-max: a branch-free running maximum with static register indices (3 instructions per column) is
@@ -231,7 +266,7 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
               bv[0] = better ? v : bv[0];
               bi[0] = better ? k0 + i : bi[0];
             }
-            continue;
+            return;
           }
           if (nb == 0 && c == 0) {
             // The first 32 columns of a tile all beat the empty list: the candidate loop below would run 32 rounds of
@@ -252,20 +287,20 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
 #pragma unroll
               for (int j = 1; j < kMaxK; ++j) if (j < prm.k) kth = bv[j];
             }
-            continue;
+            return;
           }
           // Per thread only ~k ln(K/k) values ever enter the top-k, but with 32 pixels per warp some lane qualifies at
           // almost every column.  So: a branch-free candidate bitmask first (four independent chains), then a short
           // per-thread loop over the set bits -- the warp iterates max-over-lanes(#candidates), not once per column.
           uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            m0 |= (__uint_as_float(r[i]) > kth) ? (1u << i) : 0u;
-            m1 |= (__uint_as_float(r[8 + i]) > kth) ? (1u << (8 + i)) : 0u;
-            m2 |= (__uint_as_float(r[16 + i]) > kth) ? (1u << (16 + i)) : 0u;
-            m3 |= (__uint_as_float(r[24 + i]) > kth) ? (1u << (24 + i)) : 0u;
+          for (int i = 7; i >= 0; --i) {            // last pushed = lowest bit: column 8 q + i ends at bit i of chain q
+            m0 = push_gt(m0, __uint_as_float(r[i]), kth);
+            m1 = push_gt(m1, __uint_as_float(r[8 + i]), kth);
+            m2 = push_gt(m2, __uint_as_float(r[16 + i]), kth);
+            m3 = push_gt(m3, __uint_as_float(r[24 + i]), kth);
           }
-          uint32_t mask = (m0 | m1) | (m2 | m3);
+          uint32_t mask = __byte_perm(__byte_perm(m0, m1, 0x0040), __byte_perm(m2, m3, 0x0040), 0x5410);
           if (nvalid < 32) mask &= (1u << nvalid) - 1u;
           if (mask) {
             // Software-pipelined candidate loop: the value of the NEXT candidate is selected (31-instruction tree) while the
@@ -273,12 +308,12 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
             // serial chain (the scan warps are two per scheduler: their speed is the length of the dependent chain).
             int i = __ffs(mask) - 1;             // ascending column order: the earlier index wins ties
             mask &= mask - 1;
-            float v = select32(r, i);
+            float v = select32_fma(r, i);
             for (;;) {
               const uint32_t more = mask;
               const int i2 = (__ffs(mask) - 1) & 31;
               mask &= mask - 1;
-              const float v2 = select32(r, i2);
+              const float v2 = select32_fma(r, i2);
               topk_insert_par<KT>(bv, bi, prm.k, v, k0 + i);       // a no-op when v no longer beats the k-th best
               if (!more) break;
               i = i2; v = v2;
@@ -289,6 +324,21 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
               kth = bv[0];
 #pragma unroll
               for (int j = 1; j < kMaxK; ++j) if (j < prm.k) kth = bv[j];
+            }
+          }
+        };
+        {
+          uint32_t ra[32], rb[32];
+          if (n_chunks > 0) tmem_ld_32x32(trow + sbuf * kNB, ra);
+#pragma unroll 1
+          for (int c = 0; c < n_chunks; c += 2) {
+            tmem_ld_wait32(ra);
+            if (c + 1 < n_chunks) tmem_ld_32x32(trow + sbuf * kNB + (c + 1) * 32, rb);
+            scan_chunk(ra, c);
+            if (c + 1 < n_chunks) {
+              tmem_ld_wait32(rb);
+              if (c + 2 < n_chunks) tmem_ld_32x32(trow + sbuf * kNB + (c + 2) * 32, ra);
+              scan_chunk(rb, c + 1);
             }
           }
         }
