@@ -23,19 +23,26 @@ constexpr int kTilePx = 128;
 constexpr int kXBytes = 128 * 1024;      // X tile [D <= 512][128 px] bf16: D/64 chunks of 16 KB
 constexpr int kStages = 3;
 constexpr int kStageBytes = 32 * 1024;   // text block chunk [256 k][64 d]
+// CTA-pair form (cta_group::2, two tiles per pair): each CTA stages HALF of a text chunk ([128 k][64 d], 16 KB) and the tensor
+// cores read the other half from the peer -- half the shared-memory fill and B-operand traffic per SM, which is what paced
+// the single-CTA MMA (48 KB of operand reads + 32 KB of fill per chunk against 128 B/clk); the ring gets twice the stages
+constexpr int kPairStages = 6;
+constexpr int kPairStageBytes = 16 * 1024;
+constexpr int kMaxStages = 6;
 constexpr int kNB = 256;                 // text rows per block (MMA N)
 constexpr int kTmemCols = 512;
 constexpr int kMaxK = 8;
 constexpr int kMaxChunks = 8;            // D <= 512
 
 struct __align__(8) Bars {
-  uint64_t full[kStages], empty[kStages];
+  uint64_t full[kMaxStages], empty[kMaxStages];
   uint64_t x_full[kMaxChunks], x_empty[kMaxChunks];   // per 64-channel chunk of the resident X tile
   uint64_t s_full[2], s_empty[2];
   uint32_t tmem_base, pad;
 };
 constexpr int kOffRing = kXBytes;
 constexpr int kOffBars = kOffRing + kStages * kStageBytes;
+static_assert(kPairStages * kPairStageBytes == kStages * kStageBytes, "both forms use the same ring bytes");
 constexpr int kSmemBytes = kOffBars + (int)sizeof(Bars);
 static_assert(kSmemBytes <= 232448, "shared-memory budget of one SM (227 KB)");
 
@@ -148,81 +155,122 @@ __device__ __forceinline__ uint32_t push_gt(uint32_t m, float v, float kth) {
   return m;
 }
 
-template <int KT>
+// kPair: launched as clusters of two CTAs (cudaLaunchAttributeClusterDimension); unit of work = a PAIR of tiles, CTA rank r owns
+// tile 2 * pair + r; only the leader (rank 0) issues MMAs, which span both SMs (M = 256); completion is multicast to the
+// barriers of both CTAs, the scan warps of both CTAs release the S buffer at the leader.
+template <int KT, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][HW], box (64 px, 64 d, 1)
-                      const __grid_constant__ CUtensorMap map_t,    // T [Kp][D], box (64 d, 256 rows), OOB rows = 0
+                      const __grid_constant__ CUtensorMap map_t,    // T [Kp][D], box (64 d, 256 rows; pair: 128 rows), OOB rows = 0
                       const Params prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem + kOffBars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_dchunks = prm.D / 64;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader_cta = rank == 0;
+  constexpr int kRingStages = kPair ? kPairStages : kStages;
+  constexpr int kRingBytes = kPair ? kPairStageBytes : kStageBytes;
+  // units of work: tiles (single CTA) or tile pairs (CTA pair); a pair's second tile may lie past the end (TMA zero fill)
+  const int unit0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_units = kPair ? (prm.n_tiles + 1) / 2 : prm.n_tiles;
+  auto tile_of = [&](int u) -> int { return kPair ? 2 * u + (int)rank : u; };
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_t);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < kMaxChunks; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 256); }
+    // S buffers: released by ONE arrival per scan warp (of both CTAs in the pair form)
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], kPair ? 16 : 8); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(&bars->tmem_base);
+  if (warp == 2) {
+    if (kPair) tmem_alloc_2sm<kTmemCols>(&bars->tmem_base);
+    else tmem_alloc<kTmemCols>(&bars->tmem_base);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync();      // both CTAs' barriers are initialised before any remote arrive / 2-SM TMA credit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  const uint32_t idesc = make_idesc_bf16(128, kNB, /*A MN-major*/ 1, /*B K-major*/ 0);
+  const uint32_t idesc = make_idesc_bf16(kPair ? 256 : 128, kNB, /*A MN-major*/ 1, /*B K-major*/ 0);
 
   if (warp == 0 && lane == 0) {
     // =============================== TMA producer ===============================
     // X chunk c of the next tile is refilled as soon as the last text block of this tile has consumed it, so the
     // tile transition overlaps with the tail of the tensor work.
     uint32_t it = 0, lt = 0;
-    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
-      const int b = tile / prm.tiles_per_img;
-      const int px0 = (tile - b * prm.tiles_per_img) * kTilePx;
+    for (int u = unit0; u < n_units; u += unit_step, ++lt) {
+      const int tile = tile_of(u);
+      const bool tile_ok = tile < prm.n_tiles;
+      const int b = tile_ok ? tile / prm.tiles_per_img : prm.B;           // image index B: out of bounds, TMA fills zeros
+      const int px0 = tile_ok ? (tile - b * prm.tiles_per_img) * kTilePx : 0;
       for (int nb = 0; nb < prm.n_blocks; ++nb)
         for (int c = 0; c < n_dchunks; ++c, ++it) {
           if (nb == 0) {
             mbar_wait(&bars->x_empty[c], (lt & 1) ^ 1, 1);
-            mbar_arrive_expect_tx(&bars->x_full[c], 16384);
-            tma_load_3d(smem + c * 16384, &map_x, &bars->x_full[c], px0, c * 64, b);
-            tma_load_3d(smem + c * 16384 + 8192, &map_x, &bars->x_full[c], px0 + 64, c * 64, b);
+            if (kPair) {          // both CTAs' bytes are credited to the leader's barrier
+              if (leader_cta) mbar_arrive_expect_tx(&bars->x_full[c], 2 * 16384);
+              tma_load_3d_2sm(smem + c * 16384, &map_x, &bars->x_full[c], px0, c * 64, b);
+              tma_load_3d_2sm(smem + c * 16384 + 8192, &map_x, &bars->x_full[c], px0 + 64, c * 64, b);
+            } else {
+              mbar_arrive_expect_tx(&bars->x_full[c], 16384);
+              tma_load_3d(smem + c * 16384, &map_x, &bars->x_full[c], px0, c * 64, b);
+              tma_load_3d(smem + c * 16384 + 8192, &map_x, &bars->x_full[c], px0 + 64, c * 64, b);
+            }
           }
-          const int st = it % kStages;
-          mbar_wait(&bars->empty[st], ((it / kStages) & 1) ^ 1, 2);
-          mbar_arrive_expect_tx(&bars->full[st], kStageBytes);
-          tma_load_2d(smem + kOffRing + st * kStageBytes, &map_t, &bars->full[st], c * 64, nb * kNB);
+          const int st = it % kRingStages;
+          mbar_wait(&bars->empty[st], ((it / kRingStages) & 1) ^ 1, 2);
+          if (kPair) {            // own half (128 rows) of the block's chunk
+            if (leader_cta) mbar_arrive_expect_tx(&bars->full[st], 2 * kRingBytes);
+            tma_load_2d_2sm(smem + kOffRing + st * kRingBytes, &map_t, &bars->full[st], c * 64, nb * kNB + (int)rank * (kNB / 2));
+          } else {
+            mbar_arrive_expect_tx(&bars->full[st], kRingBytes);
+            tma_load_2d(smem + kOffRing + st * kRingBytes, &map_t, &bars->full[st], c * 64, nb * kNB);
+          }
         }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ================================
+  } else if (warp == 1 && leader_cta) {
+    // =============================== MMA issuer (leader CTA in the pair form) ================================
     // whole warp converged (addresses / descriptors in uniform registers), one elected lane issues
     uint32_t it = 0, lt = 0, nbc = 0;
     const uint32_t smem_base = smem_u32(smem);
     const uint64_t dsc_x = desc_mnmajor_sw128(0, 8192) + (smem_base >> 4);
     const uint64_t dsc_t = desc_kmajor_sw128(0) + ((smem_base + kOffRing) >> 4);
-    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++lt) {
+    for (int u = unit0; u < n_units; u += unit_step, ++lt) {
       for (int nb = 0; nb < prm.n_blocks; ++nb, ++nbc) {
         const int sbuf = nbc & 1;
         mbar_wait(&bars->s_empty[sbuf], ((nbc >> 1) & 1) ^ 1, 4);
         tc_fence_after();
         const bool last = nb + 1 == prm.n_blocks;
         for (int c = 0; c < n_dchunks; ++c, ++it) {
-          const int st = it % kStages;
+          const int st = it % kRingStages;
           if (nb == 0) mbar_wait(&bars->x_full[c], lt & 1, 3);
-          mbar_wait(&bars->full[st], (it / kStages) & 1, 5);
+          mbar_wait(&bars->full[st], (it / kRingStages) & 1, 5);
           tc_fence_after();
           const uint64_t xa = dsc_x + ((c * 16384) >> 4);
-          const uint64_t tb = dsc_t + ((st * kStageBytes) >> 4);
+          const uint64_t tb = dsc_t + ((st * kRingBytes) >> 4);
           if (elect_one()) {
+            if (kPair) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              mma_bf16_ss(tmem + sbuf * kNB, xa + ((ks * 2048) >> 4), tb + ((ks * 32) >> 4), idesc, (c | ks) != 0);
-            mma_commit(&bars->empty[st]);
-            if (last) mma_commit(&bars->x_empty[c]);       // this X chunk has been read for the last time
+              for (int ks = 0; ks < 4; ++ks)
+                mma_bf16_ss_2sm(tmem + sbuf * kNB, xa + ((ks * 2048) >> 4), tb + ((ks * 32) >> 4), idesc, (c | ks) != 0);
+              mma_commit_2sm(&bars->empty[st]);
+              if (last) mma_commit_2sm(&bars->x_empty[c]);
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                mma_bf16_ss(tmem + sbuf * kNB, xa + ((ks * 2048) >> 4), tb + ((ks * 32) >> 4), idesc, (c | ks) != 0);
+              mma_commit(&bars->empty[st]);
+              if (last) mma_commit(&bars->x_empty[c]);       // this X chunk has been read for the last time
+            }
           }
           __syncwarp();
         }
-        if (elect_one()) mma_commit(&bars->s_full[sbuf]);
+        if (elect_one()) {
+          if (kPair) mma_commit_2sm(&bars->s_full[sbuf]);
+          else mma_commit(&bars->s_full[sbuf]);
+        }
         __syncwarp();
       }
     }
@@ -237,9 +285,11 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
     const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + half * 128;
     uint32_t nbc = 0;
     unsigned int m_c1 = 0, m_ck = 0, m_tot = 0;      // fused metrics: per-thread counters
-    for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
-      const int b = tile / prm.tiles_per_img;
-      const int px = (tile - b * prm.tiles_per_img) * kTilePx + row;
+    for (int u = unit0; u < n_units; u += unit_step) {
+      const int tile = tile_of(u);
+      const bool tile_ok = tile < prm.n_tiles;         // (a pair's second tile past the end: scanned, never written)
+      const int b = tile_ok ? tile / prm.tiles_per_img : 0;
+      const int px = tile_ok ? (tile - b * prm.tiles_per_img) * kTilePx + row : (int)min((int64_t)0x7fffffff, prm.HW);
       float bv[kMaxK];
       int bi[kMaxK];
 #pragma unroll
@@ -365,7 +415,11 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
           }
         }
         tc_fence_before();
-        mbar_arrive(&bars->s_empty[sbuf]);
+        __syncwarp();                                   // one release per warp (at the leader in the pair form)
+        if (lane == 0) {
+          if (leader_cta) mbar_arrive(&bars->s_empty[sbuf]);
+          else mbar_arrive_remote(map_to_cta(&bars->s_empty[sbuf], 0));
+        }
       }
       if (half == 0) {               // warps 4-7: lane = pixel, 32 consecutive pixels of one image per warp
         const bool inb = px < prm.HW;
@@ -413,8 +467,13 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem); }
+  if (kPair) cluster_sync();      // no CTA leaves while its peer may still touch its barriers / shared memory
+  else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    if (kPair) tmem_dealloc_2sm<kTmemCols>(tmem);
+    else tmem_dealloc<kTmemCols>(tmem);
+  }
 }
 
 }  // namespace topk
@@ -469,17 +528,48 @@ static int eval_topk_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, in
   prm.index_map = index_map; prm.out = out;
   prm.gt = gt; prm.E = E; prm.cmap = cmap; prm.C = C;
   prm.hist = reinterpret_cast<unsigned long long*>(hist); prm.counters = reinterpret_cast<unsigned long long*>(counters);
-  const int grid = prm.n_tiles < num_sms() ? prm.n_tiles : num_sms();
-  auto launch = [&](auto kernel) -> int {
+  // CTA pairs (two tiles per cluster, text chunks shared between the two SMs) whenever there is more than one tile
+  const bool pair = prm.n_tiles >= 2;
+  CUtensorMap m_tp = m_t;
+  if (pair) {
+    const uint64_t tdims[2] = {(uint64_t)D, (uint64_t)Kp}, tstr[2] = {2, (uint64_t)D * 2};
+    const uint32_t tbox[2] = {64, (uint32_t)(topk::kNB / 2)};
+    if ((rcode = make_tmap_bf16(&m_tp, t_bf16, 2, tdims, tstr, tbox, "topk map_t (pair)"))) return rcode;
+  }
+  auto launch = [&](auto kernel, bool is_pair) -> int {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, topk::kSmemBytes);
     if (e != cudaSuccess) return fail(RC_ERR_CUDA, "%s: smem opt-in: %s", who, cudaGetErrorString(e));
-    kernel<<<grid, topk::kThreads, topk::kSmemBytes, s>>>(m_x, m_t, prm);
+    if (!is_pair) {
+      const int grid = prm.n_tiles < num_sms() ? prm.n_tiles : num_sms();
+      kernel<<<grid, topk::kThreads, topk::kSmemBytes, s>>>(m_x, m_t, prm);
+      return check_launch(who);
+    }
+    const int n_pairs = (prm.n_tiles + 1) / 2;
+    int n_clusters = num_sms() / 2;
+    if (n_clusters > n_pairs) n_clusters = n_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_clusters);
+    cfg.blockDim = dim3(topk::kThreads);
+    cfg.dynamicSmemBytes = topk::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kernel, m_x, m_tp, prm);
+    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "%s: cluster launch: %s", who, cudaGetErrorString(e));
     return check_launch(who);
   };
   // the two k the reference evaluates with (validate.py: top-1 and top-5) get fixed-size insertion networks
-  if (k == 1) return launch(topk::eval_topk_umma_kernel<1>);
-  if (k == 5) return launch(topk::eval_topk_umma_kernel<5>);
-  return launch(topk::eval_topk_umma_kernel<0>);
+  if (pair) {
+    if (k == 1) return launch(topk::eval_topk_umma_kernel<1, true>, true);
+    if (k == 5) return launch(topk::eval_topk_umma_kernel<5, true>, true);
+    return launch(topk::eval_topk_umma_kernel<0, true>, true);
+  }
+  if (k == 1) return launch(topk::eval_topk_umma_kernel<1, false>, false);
+  if (k == 5) return launch(topk::eval_topk_umma_kernel<5, false>, false);
+  return launch(topk::eval_topk_umma_kernel<0, false>, false);
 }
 
 extern "C" int rc_eval_topk_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16, int K,
