@@ -41,7 +41,8 @@ struct __align__(8) Bars {
   uint32_t tmem_base, pad;
 };
 constexpr int kOffRing = kXBytes;
-constexpr int kOffBars = kOffRing + kStages * kStageBytes;
+constexpr int kOffThr = kOffRing + kStages * kStageBytes;      // k-th best of every scan thread, read by its partner [256] f32
+constexpr int kOffBars = kOffThr + 256 * 4;
 static_assert(kPairStages * kPairStageBytes == kStages * kStageBytes, "both forms use the same ring bytes");
 constexpr int kSmemBytes = kOffBars + (int)sizeof(Bars);
 static_assert(kSmemBytes <= 232448, "shared-memory budget of one SM (227 KB)");
@@ -158,8 +159,10 @@ __device__ __forceinline__ uint32_t push_gt(uint32_t m, float v, float kth) {
 // kPair: launched as clusters of two CTAs (cudaLaunchAttributeClusterDimension); unit of work = a PAIR of tiles, CTA rank r owns
 // tile 2 * pair + r; only the leader (rank 0) issues MMAs, which span both SMs (M = 256); completion is multicast to the
 // barriers of both CTAs, the scan warps of both CTAs release the S buffer at the leader.
-template <int KT, bool kPair>
-__global__ void __launch_bounds__(kThreads, 1)
+// P = scan threads per pixel (2 or 4): each keeps its own running top-k over 256 / P columns of every block; more lists mean
+// more insertions in total but twice the warps to hide the dependent chains behind.
+template <int KT, bool kPair, int P>
+__global__ void __launch_bounds__(128 + 128 * P, 1)
 eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][HW], box (64 px, 64 d, 1)
                       const __grid_constant__ CUtensorMap map_t,    // T [Kp][D], box (64 d, 256 rows; pair: 128 rows), OOB rows = 0
                       const Params prm) {
@@ -181,7 +184,7 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < kMaxChunks; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], 1); }
     // S buffers: released by ONE arrival per scan warp (of both CTAs in the pair form)
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], kPair ? 16 : 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], (kPair ? 2 : 1) * 4 * P); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -195,6 +198,9 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
   const uint32_t tmem = bars->tmem_base;
   const uint32_t idesc = make_idesc_bf16(kPair ? 256 : 128, kNB, /*A MN-major*/ 1, /*B K-major*/ 0);
 
+  if (warp < 4) {
+  // 640 threads x 96 registers at launch (P = 4): the four control warps give registers to the sixteen scan warps
+  if (P == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0 && lane == 0) {
     // =============================== TMA producer ===============================
     // X chunk c of the next tile is refilled as soon as the last text block of this tile has consumed it, so the
@@ -274,17 +280,27 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
         __syncwarp();
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    if (P == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // =============================== top-k scan ================================
     // Two warps per TMEM lane quarter: half 0 (warps 4-7) scans text columns [0,128) of every 256-row block, half 1
     // (warps 8-11) columns [128,256); each thread keeps a running top-k, the two lists of a pixel are merged at the
     // end of the tile (half 1 parks its list in its own, already scanned TMEM columns).
-    const int half = warp >= 8 ? 1 : 0;
+    const int half = (warp - 4) >> 2;          // which 256 / P columns of a block this thread scans ("half": P = 2)
+    constexpr int kCols = kNB / P;             // columns per thread per block
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + half * 128;
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + half * kCols;
     uint32_t nbc = 0;
     unsigned int m_c1 = 0, m_ck = 0, m_tot = 0;      // fused metrics: per-thread counters
+    // The two scan threads of a pixel publish their running k-th best; the partner's value (possibly stale -- every earlier
+    // value is still a valid bound) tightens the candidate filter: a value below the k-th best of EITHER column half cannot
+    // be among the pixel's top k.  Values EQUAL to the partner's bound stay candidates (the index tie-break is the merge's).
+    volatile float* thr_mine = reinterpret_cast<volatile float*>(smem + kOffThr) + (threadIdx.x - 128);
+    volatile float* thr_peer = reinterpret_cast<volatile float*>(smem + kOffThr) + ((threadIdx.x - 128) ^ 128);
+    *thr_mine = -FLT_MAX;
+    named_bar_sync(4 + quarter, 64);
     for (int u = unit0; u < n_units; u += unit_step) {
       const int tile = tile_of(u);
       const bool tile_ok = tile < prm.n_tiles;         // (a pair's second tile past the end: scanned, never written)
@@ -301,8 +317,8 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
         tc_fence_after();
         // The TMEM load of the NEXT 32 columns is in flight while this chunk is scanned (two register buffers): with two
         // scan warps per scheduler the exposed tcgen05.ld latency of every chunk was a fifth of the scan time.
-        const int kbase = nb * kNB + half * 128;
-        const int n_chunks = min(kNB / 64, max(0, (prm.K - kbase + 31) >> 5));
+        const int kbase = nb * kNB + half * kCols;
+        const int n_chunks = min(kCols / 32, max(0, (prm.K - kbase + 31) >> 5));
         auto scan_chunk = [&](const uint32_t (&r)[32], int c) {
           const int k0 = kbase + c * 32;
           const int nvalid = prm.K - k0;
@@ -337,18 +353,27 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
 #pragma unroll
               for (int j = 1; j < kMaxK; ++j) if (j < prm.k) kth = bv[j];
             }
+            if (P == 2) *thr_mine = kth;
             return;
           }
           // Per thread only ~k ln(K/k) values ever enter the top-k, but with 32 pixels per warp some lane qualifies at
           // almost every column.  So: a branch-free candidate bitmask first (four independent chains), then a short
           // per-thread loop over the set bits -- the warp iterates max-over-lanes(#candidates), not once per column.
+          float kf = kth;
+          if (P == 2) {
+            const float pk = *thr_peer;
+            if (pk > kth) {              // v >= pk  <=>  v > the float just below pk
+              const uint32_t ub = __float_as_uint(pk);
+              kf = __uint_as_float(pk > 0.f ? ub - 1u : (pk < 0.f ? ub + 1u : 0x80000001u));
+            }
+          }
           uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
 #pragma unroll
           for (int i = 7; i >= 0; --i) {            // last pushed = lowest bit: column 8 q + i ends at bit i of chain q
-            m0 = push_gt(m0, __uint_as_float(r[i]), kth);
-            m1 = push_gt(m1, __uint_as_float(r[8 + i]), kth);
-            m2 = push_gt(m2, __uint_as_float(r[16 + i]), kth);
-            m3 = push_gt(m3, __uint_as_float(r[24 + i]), kth);
+            m0 = push_gt(m0, __uint_as_float(r[i]), kf);
+            m1 = push_gt(m1, __uint_as_float(r[8 + i]), kf);
+            m2 = push_gt(m2, __uint_as_float(r[16 + i]), kf);
+            m3 = push_gt(m3, __uint_as_float(r[24 + i]), kf);
           }
           uint32_t mask = __byte_perm(__byte_perm(m0, m1, 0x0040), __byte_perm(m2, m3, 0x0040), 0x5410);
           if (nvalid < 32) mask &= (1u << nvalid) - 1u;
@@ -375,9 +400,10 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
 #pragma unroll
               for (int j = 1; j < kMaxK; ++j) if (j < prm.k) kth = bv[j];
             }
+            if (P == 2) *thr_mine = kth;
           }
         };
-        {
+        if (P == 2) {
           uint32_t ra[32], rb[32];
           if (n_chunks > 0) tmem_ld_32x32(trow + sbuf * kNB, ra);
 #pragma unroll 1
@@ -391,27 +417,40 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
               scan_chunk(rb, c + 1);
             }
           }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < n_chunks; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(trow + sbuf * kNB + c * 32, r);
+            tmem_ld_wait();
+            scan_chunk(r, c);
+          }
         }
         if (nb + 1 == prm.n_blocks) {
-          // merge the two halves' lists through TMEM columns [128,144) of this buffer (half 1's own, scanned range)
-          const uint32_t tpark = tmem + ((uint32_t)(quarter * 32) << 16) + sbuf * kNB + 128;
-          if (half == 1) {
+          // merge the P lists of a pixel: parts 1.. park theirs in 16 TMEM columns of their own, already scanned range of
+          // this buffer; part 0 folds them into its list (explicit index tie-break: the ranges interleave across blocks)
+          const uint32_t tq = tmem + ((uint32_t)(quarter * 32) << 16) + sbuf * kNB;
+          *thr_mine = -FLT_MAX;            // the bound belongs to this tile's pixel: reset before the barrier both partners pass
+          if (half != 0) {
             uint32_t pkd[16];
 #pragma unroll
             for (int j = 0; j < kMaxK; ++j) { pkd[j] = __float_as_uint(bv[j]); pkd[8 + j] = (uint32_t)bi[j]; }
-            tmem_st_32x16(tpark, pkd);
+            tmem_st_32x16(tq + half * kCols, pkd);
             tmem_st_wait();
             tc_fence_before();
-            named_bar_sync(4 + quarter, 64);
+            named_bar_sync(4 + quarter, 32 * P);
           } else {
-            named_bar_sync(4 + quarter, 64);
+            named_bar_sync(4 + quarter, 32 * P);
             tc_fence_after();
-            uint32_t pkd[16];
-            tmem_ld_32x16(tpark, pkd);
-            tmem_ld_wait();
+#pragma unroll 1
+            for (int part = 1; part < P; ++part) {
+              uint32_t pkd[16];
+              tmem_ld_32x16(tq + part * kCols, pkd);
+              tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < kMaxK; ++j)
-              if (j < prm.k && (int)pkd[8 + j] >= 0) topk_insert_tie<KT>(bv, bi, prm.k, __uint_as_float(pkd[j]), (int)pkd[8 + j]);
+              for (int j = 0; j < kMaxK; ++j)
+                if (j < prm.k && (int)pkd[8 + j] >= 0) topk_insert_tie<KT>(bv, bi, prm.k, __uint_as_float(pkd[j]), (int)pkd[8 + j]);
+            }
           }
         }
         tc_fence_before();
@@ -529,19 +568,19 @@ static int eval_topk_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, in
   prm.gt = gt; prm.E = E; prm.cmap = cmap; prm.C = C;
   prm.hist = reinterpret_cast<unsigned long long*>(hist); prm.counters = reinterpret_cast<unsigned long long*>(counters);
   // CTA pairs (two tiles per cluster, text chunks shared between the two SMs) whenever there is more than one tile
-  const bool pair = prm.n_tiles >= 2;
+  const bool pair = prm.n_tiles >= 2 && (prm.n_blocks >= 2 || k == 1);       // one text block per tile: nothing to share, the coupling costs 5 %
   CUtensorMap m_tp = m_t;
   if (pair) {
     const uint64_t tdims[2] = {(uint64_t)D, (uint64_t)Kp}, tstr[2] = {2, (uint64_t)D * 2};
     const uint32_t tbox[2] = {64, (uint32_t)(topk::kNB / 2)};
     if ((rcode = make_tmap_bf16(&m_tp, t_bf16, 2, tdims, tstr, tbox, "topk map_t (pair)"))) return rcode;
   }
-  auto launch = [&](auto kernel, bool is_pair) -> int {
+  auto launch = [&](auto kernel, bool is_pair, int threads) -> int {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, topk::kSmemBytes);
     if (e != cudaSuccess) return fail(RC_ERR_CUDA, "%s: smem opt-in: %s", who, cudaGetErrorString(e));
     if (!is_pair) {
       const int grid = prm.n_tiles < num_sms() ? prm.n_tiles : num_sms();
-      kernel<<<grid, topk::kThreads, topk::kSmemBytes, s>>>(m_x, m_t, prm);
+      kernel<<<grid, threads, topk::kSmemBytes, s>>>(m_x, m_t, prm);
       return check_launch(who);
     }
     const int n_pairs = (prm.n_tiles + 1) / 2;
@@ -549,7 +588,7 @@ static int eval_topk_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, in
     if (n_clusters > n_pairs) n_clusters = n_pairs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * n_clusters);
-    cfg.blockDim = dim3(topk::kThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = topk::kSmemBytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -562,14 +601,17 @@ static int eval_topk_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, in
     return check_launch(who);
   };
   // the two k the reference evaluates with (validate.py: top-1 and top-5) get fixed-size insertion networks
+  // Two scan threads per pixel.  Measured, not adopted (P = 4, 640 threads, setmaxnreg 40 / 104): four lists per pixel mean 23 %
+  // more insertions and the scan is close to its instruction-throughput bound (ALU + FMA pipe at one warp instruction per two
+  // cycles each): K = 1024 top-5 1041 against 1147 Mpix/s, K = 256 2258 against 2764.
   if (pair) {
-    if (k == 1) return launch(topk::eval_topk_umma_kernel<1, true>, true);
-    if (k == 5) return launch(topk::eval_topk_umma_kernel<5, true>, true);
-    return launch(topk::eval_topk_umma_kernel<0, true>, true);
+    if (k == 1) return launch(topk::eval_topk_umma_kernel<1, true, 2>, true, 384);
+    if (k == 5) return launch(topk::eval_topk_umma_kernel<5, true, 2>, true, 384);
+    return launch(topk::eval_topk_umma_kernel<0, true, 2>, true, 384);
   }
-  if (k == 1) return launch(topk::eval_topk_umma_kernel<1, false>, false);
-  if (k == 5) return launch(topk::eval_topk_umma_kernel<5, false>, false);
-  return launch(topk::eval_topk_umma_kernel<0, false>, false);
+  if (k == 1) return launch(topk::eval_topk_umma_kernel<1, false, 2>, false, 384);
+  if (k == 5) return launch(topk::eval_topk_umma_kernel<5, false, 2>, false, 384);
+  return launch(topk::eval_topk_umma_kernel<0, false, 2>, false, 384);
 }
 
 extern "C" int rc_eval_topk_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16, int K,

@@ -479,6 +479,28 @@ def test_eval_topk_ties_go_to_smaller_index():
     assert torch.equal(out[:, :, dup_is_top[0]], want[:, :, dup_is_top[0]])
 
 
+def test_eval_topk_ties_across_the_shared_threshold():
+    """The two scan threads of a pixel tighten their candidate filter with the partner's k-th best.  Five copies of the winning
+    row in the columns of one thread (its k-th best becomes the tied value at once) and two more, with SMALLER indices, in
+    columns the other thread scans later: values equal to the partner's bound must stay candidates, and the merge must hand
+    the top-k to the smallest indices."""
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    B, D, H, W, K, k = 1, 256, 16, 16, 700, 5
+    text = unit(torch.randn(K, D, generator=g), 1).to(torch.bfloat16).float()
+    base = text[128].clone()
+    dups = (100, 120, 128, 129, 130, 131, 132, 300, 650)
+    for idx in dups:
+        text[idx] = base
+    emb = (base.view(1, D, 1, 1) + 0.05 * torch.randn(B, D, H, W, generator=g)).to(torch.bfloat16).float()
+    out = ops.eval_topk(emb.to(dev()).to(torch.bfloat16), text.to(dev()), torch.arange(K).to(dev()), k, "bf16").cpu()
+    logits = torch.einsum('bdn,cd->bcn', emb.view(B, D, H * W).double(), text.double())
+    dup_is_top = (logits[:, 128] >= logits.max(dim=1).values - 1e-12).view(B, H, W)
+    assert dup_is_top.float().mean() > 0.9
+    want = torch.tensor(sorted(dups)[:k]).view(1, k, 1, 1).expand(B, k, H, W)
+    assert torch.equal(out[:, :, dup_is_top[0]], want[:, :, dup_is_top[0]])
+
+
 def test_validate_model_golden(golden_dir):
     """Drop-in validate_model against the reference's recorded run (fake model, three batches)."""
     import rangeclip_b200 as R
