@@ -743,6 +743,18 @@ def run_gpu(args):
                       "fused tcgen05 top-5 + equivalence-aware histograms (one kernel per batch) + fold, one int64 all-reduce at the end"}
         assert fin["total_pixels"] == tot_pix
 
+        # the top-k kernel alone (rc_eval_topk_bf16, ids written) on one resident batch: what the scan / MMA halves sustain
+        def eval_kernel_section():
+            xe, _ = pool_b[0]
+            out = {}
+            for kk in (5, 1):
+                t = timed(lambda: ops.eval_topk(xe, text_e, idx_map, kk, "bf16", t_bf16=tbe), 5, 2)
+                tf = 2.0 * Ce * D * B * HW / (t * 1e-3) / 1e12
+                out[f"top{kk}"] = {"ms": t, "value": B * HW / (t * 1e-3) / 1e6, "unit": "Mpix/s", "tflops": tf, "frac_of_burst_peak": tf / pk["tf_burst"]}
+            out["note"] = "eval_topk_umma_kernel (CTA-pair form) on one batch of 64 maps, K=1024, ids [B,k,HW] int64 written"
+            return out
+        ev["kernel"] = section(eval_kernel_section)
+
         # the reference's eager CUDA evaluation of ONE batch (predict tail + python metric loops with .item() syncs)
         def eager_eval_section():
             xe, se = pool_b[0]
