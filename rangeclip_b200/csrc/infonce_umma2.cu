@@ -36,7 +36,14 @@ namespace pair {
 
 constexpr int kTilePx = 128;
 constexpr int kThreads = 640;          // warps: 0 TMA, 1 MMA (leader CTA only), 2 TMEM alloc, 3 idle, 4-11 softmax, 12-19 dX epilogue
-constexpr int kXStages = 4;            // X ring: own X chunks [64 d][128 px] (first touch: HBM latency; also read by the row norms)
+// RC_PAIR_STG2: two dX staging buffers per epilogue warp (a chunk's TMA store reads its buffer while the next chunk is staged)
+// paid for with one X-ring stage (shared memory is full).  Measured, not adopted: 2.83 ms against 2.41 ms -- the X ring is the
+// first-touch HBM path and three stages starve the S GEMM (with the dX stores ablated: 2.51 against 2.13 ms).
+#ifndef RC_PAIR_STG2
+#define RC_PAIR_STG2 0
+#endif
+constexpr int kXStages = RC_PAIR_STG2 ? 3 : 4;   // X ring: own X chunks [64 d][128 px] (first touch: HBM latency; also read by the row norms)
+constexpr int kStgBufs = RC_PAIR_STG2 ? 2 : 1;
 constexpr int kTStages = 4;            // text ring: text half-chunks [Kp/2][64 d] for S, own T^T rows [128 d][64 k] for dX (L2 hits)
 constexpr int kStageBytes = 16 * 1024;
 static_assert(kTStages >= 4, "a dX block keeps Kp/64 <= 4 slots of the text ring at once");
@@ -73,7 +80,7 @@ constexpr int kOffScale = kOffP + kPBytes;                  // {rs, -cs} bf16x2 
 constexpr int kOffXch = kOffScale + 2 * kScaleBufs * 2 * 128 * 4;
 constexpr int kOffStg = kOffXch + 2 * 4 * 2 * 128 * 4;      // exchange: [2 tile parities][max, sum, sez, sy][2 halves][128]
 constexpr int kStgBytes = 32 * 32 * 2;                      // dX staging of one epilogue warp: [32 d][32 px] bf16, 64-byte swizzle
-constexpr int kOffPart = kOffStg + 8 * kStgBytes;           // one staging buffer per epilogue warp
+constexpr int kOffPart = kOffStg + 8 * kStgBufs * kStgBytes;           // kStgBufs staging buffers per epilogue warp
 constexpr int kOffBars = kOffPart + 8 * 128 * 4;            // row-norm partial sums of squares [8 softmax warps][128 px]
 constexpr int kSmemBytes = kOffBars + (int)sizeof(Bars);
 static_assert(kSmemBytes <= 232448, "shared-memory budget of one SM (227 KB)");
@@ -122,7 +129,7 @@ struct Params {
   int64_t HW;
   int tiles_per_img, n_tiles, n_pairs;
   uint32_t tpi_magic;       // floor(2^32 / tiles_per_img): tile / tiles_per_img as a multiply-high + one correction
-  int ablate;               // bring-up only (RANGECLIP_B200_ABLATE): 1 no epilogue x loads, 2 no dX stores, 64 no row-norm reads, 128 no dX staging
+  int ablate;               // bring-up only (RANGECLIP_B200_ABLATE): 1 no epilogue x loads, 2 no dX stores, 64 no row-norm reads, 128 no dX staging, 256 no text reloads
   int store_g;              // 1: also write G = rs (P - sum onehot) (bf16 [B][HW][Kp]) for the dText GEMM
   int wide;                 // 1: rows of X / dX are 32-byte aligned (256-bit global accesses allowed)
   int split_c, split_b;     // bring-up (RANGECLIP_B200_SPLIT="c,b"): S chunks / dX blocks issued in the first half of an iteration; -1 = default
@@ -324,6 +331,10 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         for (int c = c_begin; c < c_end; ++c, ++it) {   // own half (Nh rows) of text chunk c
           const int st = it % kTStages;
           RC_WAIT(mbar_wait, &bars->tempty[st], ((it / kTStages) & 1) ^ 1, 1);
+          if ((prm.ablate & 256) && it >= (uint32_t)kTStages) {      // bring-up: no text traffic after the first ring pass (stale operands)
+            if (leader_cta) mbar_arrive(&bars->tfull[st]);
+            continue;
+          }
           if (leader_cta) mbar_arrive_expect_tx(&bars->tfull[st], 2 * Nh * 128);
           tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_t, &bars->tfull[st], c * 64, koff + (int)rank * Nh);
         }
@@ -333,6 +344,10 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           for (int kc = 0; kc < n_kchunks; ++kc, ++it) {   // own 128 rows of T^T for this 256-channel block, 64 k at a time
             const int st = it % kTStages;
             RC_WAIT(mbar_wait, &bars->tempty[st], ((it / kTStages) & 1) ^ 1, 2);
+            if ((prm.ablate & 256) && it >= (uint32_t)kTStages) {
+              if (leader_cta) mbar_arrive(&bars->tfull[st]);
+              continue;
+            }
             if (leader_cta) mbar_arrive_expect_tx(&bars->tfull[st], 2 * 16384);
             tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_tt, &bars->tfull[st], koff + kc * 64, blk * 256 + (int)rank * 128);
           }
@@ -866,7 +881,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       for (int j = 0; j < 2; ++j)
         ldg_px16(prm.x + f_off + (int64_t)(j - lb) * prm.HW + c * 32 + lb * 16, wide, n8, &xq[c][j * 8], pol_x);
     };
-    uint8_t* stg = smem + kOffStg + (warp - 12) * kStgBytes;
+    uint8_t* stg0 = smem + kOffStg + (warp - 12) * kStgBufs * kStgBytes;
+    uint32_t sc_ = 0;                                    // chunks staged so far (buffer = parity)
     const uint64_t pol_first = l2_policy_evict_first();  // dX is write-once: keep it from displacing X in L2
     cursor_set();
     fetch(0); fetch(1);
@@ -910,7 +926,12 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           {
             // own row of the warp's [32 d][32 px] staging tile (64-byte swizzle), then one TMA store per warp
             RC_T0(t5);
-            if (lane == 0) tma_store_wait_read0();            // the previous store of this warp has read the buffer
+            uint8_t* stg = stg0 + (kStgBufs == 2 ? (sc_ & 1u) * kStgBytes : 0u);
+            ++sc_;
+            if (lane == 0) {                                  // the store that last used THIS buffer has read it
+              if (kStgBufs == 2) tma_store_wait_read0_keep1();
+              else tma_store_wait_read0();
+            }
             __syncwarp();
             RC_TACC(5, t5);
             uint8_t* srow = stg + lane * 64;
