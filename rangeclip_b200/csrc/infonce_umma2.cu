@@ -42,6 +42,35 @@ constexpr int kThreads = 640;          // warps: 0 TMA, 1 MMA (leader CTA only),
 #ifndef RC_PAIR_STG2
 #define RC_PAIR_STG2 0
 #endif
+// RC_PAIR_NORM_WARP: the row norms 1/|x_p| are taken by the relay warp (warp 2, otherwise one busy lane) as soon as a chunk
+// lands, instead of by the eight softmax warps between their hand-offs: an X-ring slot is then released by the MMA commit and
+// ONE early reader (was: eight readers that get to it only after their exp pass), and the softmax warps lose the pass.
+// Measured, not adopted: 2.54 ms against 2.41 ms -- one warp's 64 dependent-latency LDS rounds per chunk release the slot
+// later than eight warps' four, and warp 2 issues last on its scheduler.
+// A/B knobs (tools/ablate_pair.py ab ...): L2 eviction hint of the text operand loads (0 none, 1 evict_last) and of the epilogue's
+// x loads (1 evict_first, 0 none)
+#ifndef RC_PAIR_TEXT_HINT
+#define RC_PAIR_TEXT_HINT 0
+#endif
+#ifndef RC_EPI_X_HINT
+#define RC_EPI_X_HINT 1
+#endif
+#ifndef RC_EPI_FETCH_EARLY
+#define RC_EPI_FETCH_EARLY 0      // measured (same box): early 2.50 ms, late 2.45 ms
+#endif
+#ifndef RC_PAIR_NORM_WARP
+#define RC_PAIR_NORM_WARP 0
+#endif
+// RC_PAIR_CTL_HIGH: the four control warps (text TMA, MMA issuer, relay, X TMA) are the HIGHEST warp ids of the CTA.  The
+// schedulers pick the highest eligible warp id first; as warps 0-3 the producers and the MMA issuer issue after the four busy
+// softmax / epilogue warps that share their scheduler.
+// Measured: 2.64 ms against 2.41 ms -- the control warps' barrier polling then takes issue slots from the workers.
+// RC_PAIR_CTL_HIGH == 2: control warps stay lowest, but the SOFTMAX warps (the exp pass is on the S -> P -> dX dependency cycle)
+// get the highest warp ids and the epilogue warps the middle ones: 2.56 ms.  The shipped order (control < softmax < epilogue)
+// is the best of the three: the epilogue is the role with the least slack.
+#ifndef RC_PAIR_CTL_HIGH
+#define RC_PAIR_CTL_HIGH 0
+#endif
 constexpr int kXStages = RC_PAIR_STG2 ? 3 : 4;   // X ring: own X chunks [64 d][128 px] (first touch: HBM latency; also read by the row norms)
 constexpr int kStgBufs = RC_PAIR_STG2 ? 2 : 1;
 constexpr int kTStages = 4;            // text ring: text half-chunks [Kp/2][64 d] for S, own T^T rows [128 d][64 k] for dX (L2 hits)
@@ -70,6 +99,7 @@ struct __align__(8) Bars {
   uint64_t s_full[2], s_empty[2], p_full, p_empty;   // S: one TMEM buffer with a backward, two (columns 0 / 256) forward-only
   uint64_t acc_full[2], acc_empty[2];
   uint64_t sc_full[2];
+  uint64_t n_full[2], n_empty[2];   // row norms of a tile are in shared memory / have been read (RC_PAIR_NORM_WARP; by tile parity)
   uint32_t tmem_base, pad;
 };
 
@@ -259,7 +289,13 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
   extern __shared__ __align__(1024) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem + kOffBars);
   uint32_t* sc_s = reinterpret_cast<uint32_t*>(smem + kOffScale);   // -cs as bf16x2 of a pixel PAIR: [kScaleBufs tiles][2 owner CTAs][64 pairs]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // `warp` is the ROLE index (0-3 control, 4-11 softmax, 12-19 epilogue); with RC_PAIR_CTL_HIGH the control roles run on the
+  // hardware warps 16-19 (the TMEM lane quarter of a softmax / epilogue warp, warp & 3, is the same either way)
+  const int lane = threadIdx.x & 31;
+  const int pwarp = (int)(threadIdx.x >> 5);
+  const int warp = RC_PAIR_CTL_HIGH == 1 ? (pwarp + 4) % (kThreads / 32)
+                 : RC_PAIR_CTL_HIGH == 2 ? (pwarp < 4 ? pwarp : (pwarp < 12 ? pwarp + 8 : pwarp - 8)) : pwarp;
+  const int rtid = warp * 32 + lane;          // thread index in role order
   const uint32_t rank = cluster_ctarank();
   const bool leader_cta = rank == 0;
   const int n_dchunks = prm.D / 64;      // 64-channel chunks of the S GEMM
@@ -278,7 +314,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     if (kBwd) { tma_prefetch_desc(&map_tt); tma_prefetch_desc(&map_dx); }
     // X ring: xfull = the relays of both CTAs, xempty = MMA commit + the eight softmax warps (row norms);
     // text ring: tfull = the leader's expect_tx (bytes of both CTAs), tempty = MMA commit
-    for (int i = 0; i < kXStages; ++i) { mbar_init(&bars->xf[i], 1); mbar_init(&bars->xfull[i], 2); mbar_init(&bars->xempty[i], 9); }
+    for (int i = 0; i < kXStages; ++i) { mbar_init(&bars->xf[i], 1); mbar_init(&bars->xfull[i], 2); mbar_init(&bars->xempty[i], RC_PAIR_NORM_WARP ? 2 : 9); }
+    mbar_init(&bars->n_full[0], 1); mbar_init(&bars->n_full[1], 1); mbar_init(&bars->n_empty[0], 8); mbar_init(&bars->n_empty[1], 8);
     for (int i = 0; i < kTStages; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 1); }
     // consumer releases are ONE arrival per warp (after __syncwarp), not one per thread: an mbarrier arrive is a
     // shared-memory atomic, and 512 of them per hand-off (half of them remote) cost the leader's shared-memory pipe
@@ -325,6 +362,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       // text ring, in MMA issue order: S(first), then per tile pair
       //   [S(next) first half] [dX(this) first blocks] [S(next) second half] [dX(this) remaining blocks]
       uint32_t it = 0;
+      const uint64_t pol_text = RC_PAIR_TEXT_HINT ? l2_policy_evict_last() : 0;
       // first candidate row of the pair's block (kb mode: both tiles of a pair lie in one block, tiles_per_img is even)
       auto koff_of = [&](int pj) -> int { return (kKB && prm.kb > 0) ? div_tiles(prm, 2 * pj) * 256 : 0; };
       auto load_s = [&](int c_begin, int c_end, int koff) {
@@ -336,7 +374,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
             continue;
           }
           if (leader_cta) mbar_arrive_expect_tx(&bars->tfull[st], 2 * Nh * 128);
-          tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_t, &bars->tfull[st], c * 64, koff + (int)rank * Nh);
+          if (RC_PAIR_TEXT_HINT) tma_load_2d_2sm_hint(smem + kOffT + st * kStageBytes, &map_t, &bars->tfull[st], c * 64, koff + (int)rank * Nh, pol_text);
+          else tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_t, &bars->tfull[st], c * 64, koff + (int)rank * Nh);
         }
       };
       auto load_dx = [&](int b_begin, int b_end, int koff) {
@@ -349,7 +388,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
               continue;
             }
             if (leader_cta) mbar_arrive_expect_tx(&bars->tfull[st], 2 * 16384);
-            tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_tt, &bars->tfull[st], koff + kc * 64, blk * 256 + (int)rank * 128);
+            if (RC_PAIR_TEXT_HINT) tma_load_2d_2sm_hint(smem + kOffT + st * kStageBytes, &map_tt, &bars->tfull[st], koff + kc * 64, blk * 256 + (int)rank * 128, pol_text);
+            else tma_load_2d_2sm(smem + kOffT + st * kStageBytes, &map_tt, &bars->tfull[st], koff + kc * 64, blk * 256 + (int)rank * 128);
           }
       };
       if (cluster_id < prm.n_pairs) load_s(0, n_dchunks, koff_of(cluster_id));
@@ -472,15 +512,46 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         }
       }
     }
-    else if (warp == 2 && lane == 0) {
+    else if (warp == 2 && (RC_PAIR_NORM_WARP || lane == 0)) {
       // ========== relay (both CTAs): "own X chunk has landed" (CTA-local xf) -> the leader's full barrier ==========
-      uint32_t xit = 0;
-      for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters)
+      // + (RC_PAIR_NORM_WARP) the row norms 1/|x_p| (model.py:272 F.normalize) of the tile, read from the chunk where it sits in
+      // the operand ring ([64 d][2 x 64 px], 128-byte swizzle): lane = 4 consecutive pixels (8 bytes of every channel row),
+      // channel rows and chunks summed in a fixed order (bit-reproducible); the slot is released right after the read
+      uint32_t xit = 0, lt = 0;
+      float* nrm = reinterpret_cast<float*>(smem + kOffPart);          // [2 tile parities][128 px]
+      const uint8_t* lane_base = smem + (lane >> 4) * 8192 + (lane & 1) * 8;
+      const int gran = (lane & 15) >> 1;                               // 16-byte granule of the row (before the swizzle)
+      for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters, ++lt) {
+        float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
         for (int c = 0; c < n_dchunks; ++c, ++xit) {
           const int st = xit % kXStages;
           RC_WAIT(mbar_wait, &bars->xf[st], (xit / kXStages) & 1, 14);
-          arrive_leader(&bars->xfull[st]);
+          if (lane == 0) arrive_leader(&bars->xfull[st]);
+          if (RC_PAIR_NORM_WARP) {
+            const uint8_t* base = lane_base + st * kStageBytes;
+            if (!(prm.ablate & 64)) {
+#pragma unroll 8
+              for (int rowd = 0; rowd < 64; ++rowd) {
+                const uint2 v = *reinterpret_cast<const uint2*>(base + rowd * 128 + ((gran ^ (rowd & 7)) << 4));
+                ss0 = sqacc_bf16x2_lo(ss0, v.x); ss1 = sqacc_bf16x2_hi(ss1, v.x);
+                ss2 = sqacc_bf16x2_lo(ss2, v.y); ss3 = sqacc_bf16x2_hi(ss3, v.y);
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->xempty[st]);
+          }
         }
+        if (RC_PAIR_NORM_WARP) {
+          // nrm[lt & 1] was last read by the softmax warps of tile lt - 2
+          if (lt >= 2) RC_WAIT(mbar_wait, &bars->n_empty[lt & 1], ((lt >> 1) & 1) ^ 1, 13);
+          float4 o;
+          o.x = 1.f / fmaxf(sqrtf(ss0), 1e-12f); o.y = 1.f / fmaxf(sqrtf(ss1), 1e-12f);
+          o.z = 1.f / fmaxf(sqrtf(ss2), 1e-12f); o.w = 1.f / fmaxf(sqrtf(ss3), 1e-12f);
+          reinterpret_cast<float4*>(nrm + (lt & 1) * 128)[lane] = o;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->n_full[lt & 1]);
+        }
+      }
     }
   } else if (warp < 12) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
@@ -526,7 +597,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     // otherwise wait for its S GEMM: the X chunks are read where they sit in the operand ring ([64 d][2 x 64 px],
     // 128-byte swizzle).  thread = (8-pixel group g, row phase r); sums of squares meet in shared memory.
     float* part_s = reinterpret_cast<float*>(smem + kOffPart);   // [8 warps][128 px] partial sums of squares
-    const int st_ = threadIdx.x - 128;                           // 0..255
+    const int st_ = rtid - 128;                                  // 0..255
     const int ng = st_ & 15, nr = st_ >> 4;
     uint32_t nit = 0;
     float inv_n_next = 0.f;
@@ -567,7 +638,8 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       for (int wv = 0; wv < 8; ++wv) q += part_s[wv * 128 + row];
       inv_n_next = 1.f / fmaxf(sqrtf(q), 1e-12f);
     };
-    if (cluster_id < prm.n_pairs) norm_tile();
+    if (!RC_PAIR_NORM_WARP && cluster_id < prm.n_pairs) norm_tile();
+    const float* nrm = reinterpret_cast<const float*>(smem + kOffPart);
     const float inv_tau = prm.log_tau_dev != nullptr ? expf(-__ldg(prm.log_tau_dev)) : prm.inv_tau;
     const int K_valid = prm.k_dev != nullptr ? max(1, min(__ldg(prm.k_dev), prm.K)) : prm.K;      // rows past it are zero pads
     const bool use_bound = inv_tau * (2.02f * kLog2e) < 100.f;
@@ -584,7 +656,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       const bool valid = tile_ok && px < prm.HW;
       // dText mode: the bulk store of the previous tile's G must have read the P buffer before anyone rewrites it
       // (every thread passes the named barrier below before its next P store)
-      if (kBwd && prm.store_g && threadIdx.x == 128) tma_store_wait_read0();
+      if (kBwd && prm.store_g && rtid == 128) tma_store_wait_read0();
       const int64_t m = (int64_t)b * prm.HW + px;
       // candidates in this tile's block (kb mode: the last block may be short; its zero pad rows are masked like any pad)
       const int Kt = (kKB && prm.kb > 0) ? min(256, prm.K - 256 * b) : K_valid;
@@ -593,12 +665,18 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       const float wi = (R == 1 && (yi >= 0 || (kKB && prm.keep_w))) ? nx_w : 0.f;
       load_pixel_scalars(pj + n_clusters);
       float* xch = xch_base + (lt & 1) * (4 * 2 * 128);      // double-buffered: one named barrier per tile suffices
+      if (RC_PAIR_NORM_WARP) {
+        RC_WAIT(mbar_wait, &bars->n_full[lt & 1], (lt >> 1) & 1, 15);
+        inv_n_next = nrm[(lt & 1) * 128 + row];
+        __syncwarp();
+        if (elect_one()) mbar_arrive(&bars->n_empty[lt & 1]);
+      }
       const float inv_n = px_ok ? inv_n_next : 0.f;
       const float zs = inv_n * inv_tau;
       const float zl = zs * kLog2e;
       // forward-only: the tensor pipe runs one pair ahead (two S buffers), so the next tile's row norms are taken
       // first -- its X chunks are already streaming and their ring slots are refilled only after these reads
-      if (!kBwd && pj + n_clusters < prm.n_pairs) norm_tile();
+      if (!RC_PAIR_NORM_WARP && !kBwd && pj + n_clusters < prm.n_pairs) norm_tile();
       const uint32_t sidx = kBwd ? 0u : (lt & 1u);
       const uint32_t trow = trow0 + sidx * 256;
       ROLE_WAIT_SMX(warp == 4, &bars->s_full[sidx], (kBwd ? lt : (lt >> 1)) & 1u, 8, 8);
@@ -808,18 +886,18 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         RC_TACC(2, tst);
         if (prm.store_g) {                        // dText: the finished G tile goes to global memory as it sits in smem
           named_bar_sync(6, 256);
-          if (threadIdx.x == 128 && tile_ok) {
+          if (rtid == 128 && tile_ok) {
             const int gpx0 = px - row;
             for (int j = 0; j < n_kchunks; ++j) tma_store_3d(&map_g, smem + kOffP + j * 16384, j * 64, gpx0, b);
             tma_store_commit();
           }
         }
         if (half == 0 && valid && prm.lse && !(kKB && prm.lse_in != nullptr)) prm.lse[m] = lse;      // after the hand-off: nothing waits behind this store
-        if (pj + n_clusters < prm.n_pairs) norm_tile();
+        if (!RC_PAIR_NORM_WARP && pj + n_clusters < prm.n_pairs) norm_tile();
         if (warp == 4) RC_EV(lt, 14);  // row norms of the next tile done
       }
     }
-    if (kBwd && prm.store_g && threadIdx.x == 128) tma_store_wait_all0();
+    if (kBwd && prm.store_g && rtid == 128) tma_store_wait_all0();
     if (half == 0) {
       loss_acc = warp_sum(loss_acc); w_acc = warp_sum(w_acc); dlt_acc = warp_sum(dlt_acc);
       if (lane == 0) {
@@ -864,7 +942,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
     // covers 16 rows x 64 contiguous bytes instead of 32 rows x 32 bytes (half the L1 tag work).  A 2x2 exchange
     // inside the pair (pair_swap) turns "row 2p+j, piece b" into "own row, piece j" and back.
     const int lb = lane & 1;
-    const uint64_t pol_x = l2_policy_evict_first();     // last use of these X lines in this kernel
+    const uint64_t pol_x = RC_EPI_X_HINT ? l2_policy_evict_first() : 0;     // last use of these X lines in this kernel
     uint32_t xq[2][16];       // chunk c of the current unit; before pair_swap: [j][8] = (row 2p+j, piece b)
     auto pair_swap = [&](uint32_t* e) {
 #pragma unroll
@@ -923,6 +1001,14 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
               o[i] = bf2_fma(cs4[j], xq[c][i], a);
             }
           }
+          // x of the NEXT unit's chunk c: requested as soon as this chunk's x registers are free (before the staging wait
+          // and the store, not after them) -- the first use of the prefetched x is the hottest stall of the launch
+          if (RC_EPI_FETCH_EARLY) {
+            RC_T0(t6);
+            if (c == 0) cursor_next();        // both chunks of the next unit are fetched relative to the advanced cursor
+            fetch(c);
+            RC_TACC(6, t6);
+          }
           {
             // own row of the warp's [32 d][32 px] staging tile (64-byte swizzle), then one TMA store per warp
             RC_T0(t5);
@@ -947,10 +1033,12 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
               tma_store_commit();
             }
           }
-          RC_T0(t6);
-          if (c == 0) cursor_next();        // both chunks of the next unit are fetched relative to the advanced cursor
-          fetch(c);
-          RC_TACC(6, t6);
+          if (!RC_EPI_FETCH_EARLY) {
+            RC_T0(t6);
+            if (c == 0) cursor_next();
+            fetch(c);
+            RC_TACC(6, t6);
+          }
         }
         RC_TACC(2, tep);
         if (warp == 12) RC_EV(lt, 21 + unit * 2);      // unit drained and stored

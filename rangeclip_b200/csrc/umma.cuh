@@ -34,7 +34,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // try_wait suspends the thread in hardware until the phase completes or the time hint expires; with the default
 // (short) limit a waiting warp comes back every ~100 cycles and its polling loop steals issue slots from the
 // warps that share its scheduler.
-constexpr uint32_t kSuspendHintNs = 200000u;
+#ifndef RC_SUSPEND_NS
+#define RC_SUSPEND_NS 200000u
+#endif
+constexpr uint32_t kSuspendHintNs = RC_SUSPEND_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

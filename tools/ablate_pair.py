@@ -5,7 +5,7 @@ import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     sys.path.insert(0, ROOT)
-    os.environ["RANGECLIP_B200_LIB"] = os.path.join(ROOT, "rangeclip_b200", "librangeclip_b200_bringup.so")
+    os.environ["RANGECLIP_B200_LIB"] = os.environ.get("RC_AB_LIB") or os.path.join(ROOT, "rangeclip_b200", "librangeclip_b200_bringup.so")
     import torch
     from rangeclip_b200 import _lib, ops
     dev = torch.device("cuda")
@@ -34,7 +34,15 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     for _ in range(7):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); run(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-    print(json.dumps({"ablate": int(os.environ.get("RANGECLIP_B200_ABLATE", 0)), "ms_min": min(ts), "ms_med": sorted(ts)[3]}))
+    print(json.dumps({"lib": os.path.basename(os.environ["RANGECLIP_B200_LIB"]), "ablate": int(os.environ.get("RANGECLIP_B200_ABLATE", 0)), "ms_min": min(ts), "ms_med": sorted(ts)[3]}))
+elif len(sys.argv) > 1 and sys.argv[1] == "ab":
+    # same-box A/B of library variants (make -C rangeclip_b200/csrc variant NAME=.. DEFS=..): python tools/ablate_pair.py ab base norm ...
+    names = sys.argv[2:]
+    for rep in range(2):
+        for n in names:
+            lib = os.path.join(ROOT, "rangeclip_b200", "librangeclip_b200_bringup.so" if n == "base" else f"librangeclip_b200_var_{n}.so")
+            r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, RC_AB_LIB=lib, RANGECLIP_B200_ABLATE="0"), capture_output=True, text=True, timeout=300)
+            print(r.stdout.strip() or r.stderr[-400:], flush=True)
 else:
     for bits in ([int(v) for v in sys.argv[1:]] or [0, 256, 1, 2, 64, 257, 259, 323, 0]):
         r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, RANGECLIP_B200_ABLATE=str(bits)), capture_output=True, text=True, timeout=300)
