@@ -29,6 +29,10 @@ using namespace umma;
 
 namespace ts {
 
+#ifndef RC_TS_X_HINT
+#define RC_TS_X_HINT 0      // A/B: evict_last on the X loads of the S GEMM
+#endif
+
 constexpr int kTilePx = 128;
 constexpr int kThreads = 640;          // warps: 0 text TMA, 1 MMA (leader CTA), 2 relay + row norms + TMEM alloc, 3 X TMA, 4-11 softmax, 12-19 dX epilogue
 constexpr int kXStages = 6;            // X ring: own X chunks [64 d][128 px]; deep, so that most of the next tile is resident early
@@ -211,6 +215,7 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
     } else if (warp == 3 && lane == 0) {
       // =============================== X producer (both CTAs) ===============================
       uint32_t xit = 0;
+      const uint64_t pol_keep = RC_TS_X_HINT ? l2_policy_evict_last() : 0;
       for (int l = 0; l < my_pairs; ++l) {
         int b, px0;
         tile_coords(prm, 2 * pair_of(l) + (int)rank, b, px0);
@@ -220,8 +225,13 @@ infonce_ts_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B][D][HW]
           uint8_t* sb = smem + st * kStageBytes;
           mbar_arrive_expect_tx(&bars->xf[st], 2 * 8192);          // CTA-local: the row-norm warp reads the chunk too
           const int bx = (kKB && prm.kb > 0) ? (b < prm.B ? 0 : 1) : b;      // kb mode: the one image of X (1 = out of bounds)
-          tma_load_3d(sb, &map_x_s, &bars->xf[st], px0, c * 64, bx);
-          tma_load_3d(sb + 8192, &map_x_s, &bars->xf[st], px0 + 64, c * 64, bx);
+          if (RC_TS_X_HINT) {       // the tile is read again by the dX epilogue two iterations later: keep it in the L2
+            tma_load_3d_hint(sb, &map_x_s, &bars->xf[st], px0, c * 64, bx, pol_keep);
+            tma_load_3d_hint(sb + 8192, &map_x_s, &bars->xf[st], px0 + 64, c * 64, bx, pol_keep);
+          } else {
+            tma_load_3d(sb, &map_x_s, &bars->xf[st], px0, c * 64, bx);
+            tma_load_3d(sb + 8192, &map_x_s, &bars->xf[st], px0 + 64, c * 64, bx);
+          }
         }
       }
     } else if (warp == 1 && leader_cta) {

@@ -27,7 +27,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     def run():
         _lib.check(L.rc_infonce_bf16(x.data_ptr(), _lib.RC_BF16, B, D, HW, tb.data_ptr(), ttb.data_ptr(), K, y.data_ptr(), w.data_ptr(), 1 / 0.07,
                                      lse.data_ptr(), acc[0:].data_ptr(), acc[1:].data_ptr(), acc[3:].data_ptr(), None, dx.data_ptr(), None,
-                                     acc[2:].data_ptr(), ws.data_ptr(), wsb, 0, st), "infonce")
+                                     acc[2:].data_ptr(), ws.data_ptr(), wsb, int(os.environ.get('RC_AB_FLAGS', 0)), st), "infonce")
     for _ in range(3): run()
     torch.cuda.synchronize()
     ts = []
