@@ -52,6 +52,9 @@ constexpr int kThreads = 640;          // warps: 0 TMA, 1 MMA (leader CTA only),
 #ifndef RC_PAIR_TEXT_HINT
 #define RC_PAIR_TEXT_HINT 0
 #endif
+#ifndef RC_PAIR_X_HINT
+#define RC_PAIR_X_HINT 0      // evict_last on the X tile loads of the S GEMM (kBwd launches)
+#endif
 #ifndef RC_EPI_X_HINT
 #define RC_EPI_X_HINT 1
 #endif
@@ -406,6 +409,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       // own X chunks of every tile, as far ahead as the X ring allows (the next tile's first chunks are in flight
       // while the dX GEMM of the previous pair runs)
       uint32_t xit = 0;
+      const uint64_t pol_keep = RC_PAIR_X_HINT ? l2_policy_evict_last() : 0;
       for (int pj = cluster_id; pj < prm.n_pairs; pj += n_clusters) {
         int b, px0;
         tile_coords(prm, 2 * pj + (int)rank, b, px0);
@@ -415,8 +419,13 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           uint8_t* sb = smem + st * kStageBytes;
           mbar_arrive_expect_tx(&bars->xf[st], 2 * 8192);          // CTA-local: the softmax warps read the chunk too
           const int bx = (kKB && prm.kb > 0) ? (b < prm.B ? 0 : 1) : b;      // kb mode: the one image of X (1 = out of bounds)
-          tma_load_3d(sb, &map_x_s, &bars->xf[st], px0, c * 64, bx);
-          tma_load_3d(sb + 8192, &map_x_s, &bars->xf[st], px0 + 64, c * 64, bx);
+          if (RC_PAIR_X_HINT) {       // the dX epilogue reads the tile again about one and a half iterations later
+            tma_load_3d_hint(sb, &map_x_s, &bars->xf[st], px0, c * 64, bx, pol_keep);
+            tma_load_3d_hint(sb + 8192, &map_x_s, &bars->xf[st], px0 + 64, c * 64, bx, pol_keep);
+          } else {
+            tma_load_3d(sb, &map_x_s, &bars->xf[st], px0, c * 64, bx);
+            tma_load_3d(sb + 8192, &map_x_s, &bars->xf[st], px0 + 64, c * 64, bx);
+          }
         }
       }
     } else if (warp == 1 && leader_cta) {
@@ -984,10 +993,13 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           tmem_ld_32x32(trow_acc + ab * 128 + c * 32, acc);
           tmem_ld_wait();
           RC_TACC(3, t3);
+          RC_T0(t13);
           if (c == 1) { tc_fence_before(); arrive_leader_warp(&bars->acc_empty[ab]); }
+          RC_TACC(13, t13);
           RC_T0(t4);
           pair_swap(&xq[c][0]);             // -> own row, pixels [c*32, +32) in order
           RC_TACC(4, t4);                   // first use of the prefetched x: exposed global-load latency shows here
+          RC_T0(t7);
           const uint4* scp = reinterpret_cast<const uint4*>(sc + pxh * 32 + c * 16);    // -cs2 of 16 pixel pairs
           uint32_t o[16];
 #pragma unroll
@@ -1001,6 +1013,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
               o[i] = bf2_fma(cs4[j], xq[c][i], a);
             }
           }
+          RC_TACC(7, t7);
           // x of the NEXT unit's chunk c: requested as soon as this chunk's x registers are free (before the staging wait
           // and the store, not after them) -- the first use of the prefetched x is the hottest stall of the launch
           if (RC_EPI_FETCH_EARLY) {
@@ -1020,18 +1033,24 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
             }
             __syncwarp();
             RC_TACC(5, t5);
+            RC_T0(t8);
             uint8_t* srow = stg + lane * 64;
             const int sw64 = (lane >> 1) & 3;
 #pragma unroll
             for (int g = 0; g < ((prm.ablate & 128) ? 0 : 4); ++g)
               *reinterpret_cast<uint4*>(srow + ((g ^ sw64) << 4)) = make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
+            RC_TACC(8, t8);
+            RC_T0(t9);
             fence_proxy_async_smem();
             __syncwarp();
+            RC_TACC(9, t9);
+            RC_T0(t12);
             if (lane == 0 && !(prm.ablate & 2)) {
               if (kKB && prm.acc_dx) tma_reduce_add_3d(&map_dx, stg, o_px + c * 32, o_d, o_b);
               else tma_store_3d_hint(&map_dx, stg, o_px + c * 32, o_d, o_b, pol_first);
               tma_store_commit();
             }
+            RC_TACC(12, t12);
           }
           if (!RC_EPI_FETCH_EARLY) {
             RC_T0(t6);

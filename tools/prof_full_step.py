@@ -32,7 +32,8 @@ contrast = torch.unique(torch.cat([torch.arange(1, c["G"] + 1, device=dev), rest
 sets = BN.similarity_sets(contrast.tolist(), c["G"], C)
 img = torch.nn.functional.normalize(torch.randn(B, D, device=dev, generator=g), dim=1)
 labs = seg[:, H // 2, W // 2].tolist()
-kw = dict(W_text=1.0, W_image=0.5, W_smooth=2e2, percent_image_sampling=0.7, k_distractors=K - c["G"], pct_medium=0.0, pct_hard=1.0, pct_rand=0.0)
+kw = dict(W_text=1.0, W_image=0.5, W_smooth=2e2, percent_image_sampling=0.7, k_distractors=K - c["G"], pct_medium=0.0, pct_hard=1.0, pct_rand=0.0,
+          contrast_builder=os.environ.get("BUILDER", "device"))
 
 
 def step():

@@ -3,6 +3,8 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["RANGECLIP_B200_LIB"] = os.path.abspath("rangeclip_b200/librangeclip_b200_timing.so")
 from rangeclip_b200 import _lib, ops
+import ctypes
+_lib.lib().rc_debug_set_timing_buffer.argtypes = [ctypes.c_void_p]      # (a bring-up entry point: not in _lib.PROTOTYPES)
 B = 32
 dev = torch.device("cuda:0")
 D, H, W, K = 512, 256, 256, 256
