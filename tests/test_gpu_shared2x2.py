@@ -175,3 +175,34 @@ def test_area_pooling_shared2x2():
     # the no-grad drop-in form returns the same values
     out2 = R.pool_objects_per_image(E.to(dev()), seg.to(dev()), items, labels, shared2x2=True)
     assert torch.equal(out2, out.detach())
+
+
+def test_normalize_rows_handover_between_pooling_and_loss():
+    """The no_grad normalisation of the area pooling is handed to the next call on the same data (one kernel instead of two per
+    step) -- and only then: an in-place change of the tensor (version counter) or another tensor gets a fresh result."""
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 256, 8, 16, generator=g).to(torch.bfloat16).to(dev())
+    n0 = _launches()
+    with torch.no_grad():
+        a = ops.normalize_rows(x.detach())
+    xg = x.requires_grad_(True)
+    b = ops.normalize_rows(xg)                              # same storage, same version: handed over
+    assert _launches() - n0 == 1 and torch.equal(a, b) and b.requires_grad
+    b.sum().backward()
+    assert xg.grad is not None
+    with torch.no_grad():
+        a2 = ops.normalize_rows(x.detach())
+        x.detach().mul_(2.0)                                # in-place change: the version counter moves
+    c = ops.normalize_rows(x.detach())
+    assert torch.allclose(c, a2, atol=1e-6) and c.data_ptr() != a2.data_ptr()
+    with torch.no_grad():
+        ops.normalize_rows(x.detach())
+    y = torch.randn(2, 256, 8, 16, generator=g).to(torch.bfloat16).to(dev())
+    d = ops.normalize_rows(y)
+    assert torch.allclose(d, torch.nn.functional.normalize(y.float(), dim=1), atol=1e-6)
+
+
+def _launches():
+    from rangeclip_b200 import _lib
+    return _lib.launch_count()
