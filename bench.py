@@ -598,6 +598,29 @@ def run_gpu(args):
                        "rc_contrast_build -> rc_infonce_bf16_dyn, loss_info fetched lazily (read once after the timed loop)"}
     api_sync_free = section(api_sync_free_section)
 
+    # ---- the sync-free call + backward captured in ONE CUDA graph (possible because nothing in it talks to the host): replay cost
+    def api_graph_section():
+        xg = x.detach().requires_grad_(True)
+        params = [xg] + list(model.parameters())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                total, _info = api_loss(xg, seg, builder="device")
+                torch.autograd.grad(total, params, allow_unused=True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            total, info = api_loss(xg, seg, builder="device")
+            grads = torch.autograd.grad(total, params, allow_unused=True)
+        t = timed(graph.replay, max(3, args.steps // 2), 2)
+        out = {"ms_per_step": t, "value": world * M / (t * 1e-3) / 1e6, "unit": UNIT, "over_kernel_step": t / (ms / args.steps),
+               "loss": info["total_loss"], "api": "torch.cuda.graph over compute_loss(contrast_builder='device') + autograd.grad; replay only"}
+        del graph, grads, total
+        return out
+    api_graph = section(api_graph_section)
+
     # ---- hybrid loss (text + area-image + smoothness) through compute_loss, device-resident X, bf16 and fp32 X
     def hybrid_section():
         from rangeclip_b200 import pool_objects_per_image
@@ -874,7 +897,7 @@ def run_gpu(args):
                        "l2": "inputs (4.3 GB bf16 per step) exceed the 126 MB L2; no flush needed",
                        "step": "rc_sample_weights + rc_weight_sum + fused tcgen05 kernel (row norms, S GEMM, softmax/CE, dX GEMM, projection)"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "ts_kernel": ts_kernel, "with_dtext": with_dtext, "api_device": api_device, "api_sync_free": api_sync_free, "hybrid": hybrid, "kcliff": kcliff,
+            "ts_kernel": ts_kernel, "with_dtext": with_dtext, "api_device": api_device, "api_sync_free": api_sync_free, "api_graph": api_graph, "hybrid": hybrid, "kcliff": kcliff,
             "area": area_cfg, "eval": ev, "gpu_eager": gpu_eager, "vs_gpu_eager": vs_gpu_eager, "gpu_eager_eval": eager_eval,
             "cpu_eval": cpu_eval, "cpu_full_step": cpu_full, "shared2x2": shared, "loss": loss,
         }

@@ -185,10 +185,12 @@ int rc_sample_weights(const int64_t* seg, const int64_t* rand_idx, int B, int64_
  *   k_cap      rows the loss launch is shaped for: distractors are trimmed to fit (flag 2); present labels beyond it are
  *              dropped from the map (flag 1)
  *   seed       draws = the n smallest of key(c) = splitmix64(splitmix64(seed ^ phase << 56) + c), phase 1 / 2
+ *   seed_dev   nullable device int64[1]: XORed into `seed` by the kernel -- a seed produced on the device (e.g. by a graph-safe
+ *              generator) gives every replay of a captured CUDA graph its own draw
  * Outputs: label_map int32[C] (position in the sorted contrast set or -1), contrast int64[k_cap] (sorted ids, -1 pads:
  * rc_text_prepare turns those into zero rows), k_out int32[4] = {K, flags, #present, #distractors}.  C <= 16384. */
 int rc_contrast_build(const int32_t* counts, int C, const int32_t* sim_off, const int32_t* sim_items,
-                      int n_curriculum, int n_rand, int k_cap, uint64_t seed,
+                      int n_curriculum, int n_rand, int k_cap, uint64_t seed, const int64_t* seed_dev,
                       int32_t* label_map, int64_t* contrast, int32_t* k_out, void* stream);
 int rc_sample_label_counts(const int64_t* seg, const int64_t* rand_idx, int B, int64_t HW, int64_t n_samples, int C,
                            int32_t* counts, void* stream);

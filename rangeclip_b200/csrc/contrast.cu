@@ -138,9 +138,11 @@ __device__ void select_smallest(uint8_t* state, int C, uint8_t any_of, uint8_t n
 __global__ void __launch_bounds__(kThreads, 1)
 contrast_build_kernel(const int32_t* __restrict__ counts, int C, const int32_t* __restrict__ sim_off,
                       const int32_t* __restrict__ sim_items, int n_curriculum, int n_rand, int k_cap, uint64_t seed,
-                      int32_t* __restrict__ label_map, int64_t* __restrict__ contrast_out, int32_t* __restrict__ k_out) {
+                      const int64_t* __restrict__ seed_dev, int32_t* __restrict__ label_map, int64_t* __restrict__ contrast_out,
+                      int32_t* __restrict__ k_out) {
   extern __shared__ uint8_t state[];        // [C] flags
   __shared__ Shared sh;
+  if (seed_dev != nullptr) seed ^= (uint64_t)seed_dev[0];      // a seed that lives on the device (CUDA-graph replays: a new draw each time)
   for (int c = threadIdx.x; c < C; c += kThreads) state[c] = (c >= 1 && counts[c] > 0) ? kPresent : 0;
   __syncthreads();
   if (sim_off != nullptr && n_curriculum > 0) {
@@ -196,14 +198,14 @@ contrast_build_kernel(const int32_t* __restrict__ counts, int C, const int32_t* 
 }  // namespace rc
 
 extern "C" int rc_contrast_build(const int32_t* counts, int C, const int32_t* sim_off, const int32_t* sim_items,
-                                 int n_curriculum, int n_rand, int k_cap, uint64_t seed, int32_t* label_map,
-                                 int64_t* contrast, int32_t* k_out, void* stream) {
+                                 int n_curriculum, int n_rand, int k_cap, uint64_t seed, const int64_t* seed_dev,
+                                 int32_t* label_map, int64_t* contrast, int32_t* k_out, void* stream) {
   using namespace rc::contrast;
   RC_REQUIRE(counts && label_map && contrast && k_out, "rc_contrast_build: null pointer");
   RC_REQUIRE(C >= 1 && k_cap >= 1 && n_curriculum >= 0 && n_rand >= 0, "rc_contrast_build: bad argument");
   RC_REQUIRE((sim_off == nullptr) == (sim_items == nullptr), "rc_contrast_build: sim_off and sim_items go together");
   if (C > kMaxC) return rc::fail(RC_ERR_UNSUPPORTED, "rc_contrast_build: C=%d labels exceed %d", C, kMaxC);
   contrast_build_kernel<<<1, kThreads, (size_t)C, (cudaStream_t)stream>>>(counts, C, sim_off, sim_items, n_curriculum, n_rand,
-                                                                         k_cap, seed, label_map, contrast, k_out);
+                                                                         k_cap, seed, seed_dev, label_map, contrast, k_out);
   return rc::check_launch("rc_contrast_build");
 }

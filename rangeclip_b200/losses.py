@@ -138,10 +138,17 @@ def text_contrastive_loss(pixel_embeddings, target_indices, candidate_text_embed
         n_rand = k_distractors - n_medium - n_hard
         sim_off, sim_items = similarity_csr(label_similarity_sets, C, n_medium > 0, n_hard > 0, device)
         k_cap = max(2, min(int(max_contrast), 256, C))
-        seed = int(torch.empty((), dtype=torch.int64).random_().item())   # CPU generator (the stream the reference's randperm uses): no device sync
+        seed_dev = None
+        if torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture: a host-side seed would be frozen into the graph.  The CUDA generator is graph-safe (its
+            # Philox offset advances per replay), so the seed is drawn on the device and read by the kernel from memory.
+            seed = 0
+            seed_dev = torch.randint(0, 2 ** 62, (1,), device=device, dtype=torch.int64)
+        else:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())   # CPU generator (the stream the reference's randperm uses): no device sync
         counts = torch.ops.rangeclip.sample_label_counts(target_flat, rand_indices, C)
         label_map, contrast, kinfo = torch.ops.rangeclip.contrast_build(counts, sim_off, sim_items, n_medium + n_hard, n_rand,
-                                                                        k_cap, seed)
+                                                                        k_cap, seed, seed_dev)
         aux["contrast_indices"] = contrast
         aux["contrast_info"] = kinfo
         w, y = torch.ops.rangeclip.sample_weights(target_flat, rand_indices, label_map)
@@ -368,19 +375,30 @@ class LazyLossInfo(dict):
     def __init__(self, stacked: torch.Tensor, W_text, W_image, W_smooth):
         super().__init__()
         import weakref
-        slot = self._slot()
-        slot[2] = weakref.ref(self)
-        self._host = slot[0]
-        self._host.copy_(stacked, non_blocking=True)
-        self._event = slot[1]
-        self._event.record()
+        if torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture: the copy becomes a node of the graph (every replay refreshes the pinned buffer); an
+            # event recorded during capture cannot be waited on from the host, so reading the values is the caller's business
+            # AFTER it has synchronised with a replay -- until then this object reports itself as not ready
+            self._host = torch.empty(6, dtype=torch.float32, pin_memory=True)
+            self._host.copy_(stacked, non_blocking=True)
+            self._event = None
+        else:
+            slot = self._slot()
+            slot[2] = weakref.ref(self)
+            self._host = slot[0]
+            self._host.copy_(stacked, non_blocking=True)
+            self._event = slot[1]
+            self._event.record()
         self._weights = (W_text, W_image, W_smooth)
         self._ready = False
 
     def _fill(self):
-        if not self._ready:
+        if not self._ready or self._event is None:       # (captured: re-read the pinned buffer every time -- replays refresh it)
             self._ready = True
-            self._event.synchronize()
+            if self._event is not None:
+                self._event.synchronize()
+            else:
+                torch.cuda.current_stream().synchronize()
             h = self._host.tolist()
             W_text, W_image, W_smooth = self._weights
             dict.update(self, {

@@ -153,7 +153,7 @@ def clip_crops(images: torch.Tensor, boxes: torch.Tensor, image_index: torch.Ten
 
 
 def contrast_build(counts: torch.Tensor, sim_off: Optional[torch.Tensor], sim_items: Optional[torch.Tensor], n_curriculum: int,
-                   n_rand: int, k_cap: int, seed: int):
+                   n_rand: int, k_cap: int, seed: int, seed_dev: Optional[torch.Tensor] = None):
     """Device-side contrast set (rc_contrast_build; model.py:234-268 without host round trips): from the label histogram of
     the sampled pixels to (label_map int32 [C], contrast int64 [k_cap] sorted ids padded with -1, kinfo int32 [4] =
     K, flags, #present, #distractors) in one launch, nothing read back."""
@@ -163,8 +163,11 @@ def contrast_build(counts: torch.Tensor, sim_off: Optional[torch.Tensor], sim_it
     label_map = torch.empty(C, device=counts.device, dtype=torch.int32)
     contrast = torch.empty(int(k_cap), device=counts.device, dtype=torch.int64)
     kinfo = torch.empty(4, device=counts.device, dtype=torch.int32)
+    if seed_dev is not None:
+        seed_dev = seed_dev.to(torch.int64).contiguous()
     check(_lib.lib().rc_contrast_build(_p(counts), C, _p(sim_off), _p(sim_items), int(n_curriculum), int(n_rand), int(k_cap),
-                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _p(label_map), _p(contrast), _p(kinfo), _stream(counts)),
+                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _p(seed_dev), _p(label_map), _p(contrast), _p(kinfo),
+                                       _stream(counts)),
           "rc_contrast_build")
     return label_map, contrast, kinfo
 
@@ -984,12 +987,12 @@ def _(seg, rand_idx, C):
 
 @_op("rangeclip::contrast_build", mutates_args=(), device_types="cuda")
 def _op_contrast_build(counts: torch.Tensor, sim_off: Optional[torch.Tensor], sim_items: Optional[torch.Tensor], n_curriculum: int,
-                       n_rand: int, k_cap: int, seed: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    return contrast_build(counts, sim_off, sim_items, n_curriculum, n_rand, k_cap, seed)
+                       n_rand: int, k_cap: int, seed: int, seed_dev: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    return contrast_build(counts, sim_off, sim_items, n_curriculum, n_rand, k_cap, seed, seed_dev)
 
 
 @_op_contrast_build.register_fake
-def _(counts, sim_off, sim_items, n_curriculum, n_rand, k_cap, seed):
+def _(counts, sim_off, sim_items, n_curriculum, n_rand, k_cap, seed, seed_dev=None):
     return (torch.empty(counts.numel(), device=counts.device, dtype=torch.int32),
             torch.empty(k_cap, device=counts.device, dtype=torch.int64), torch.empty(4, device=counts.device, dtype=torch.int32))
 

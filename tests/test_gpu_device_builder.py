@@ -194,3 +194,41 @@ def test_device_builder_falls_back_outside_its_shapes():
     total, info = R.compute_loss(model, x.to(dev()).requires_grad_(True), seg.to(dev()), text.to(dev()), sets, None, None,
                                  W_image=0.0, W_smooth=0.0, k_distractors=30, contrast_builder="device")
     assert torch.isfinite(total) and info["total_loss"] == pytest.approx(float(total), rel=1e-6)
+
+
+def test_sync_free_compute_loss_is_cuda_graph_capturable():
+    """compute_loss(contrast_builder="device") + backward captured in ONE CUDA graph (no host synchronisation inside, seeds
+    drawn by the graph-safe CUDA generator): every replay draws new pixels / distractors, stays close to the eager loss on
+    the same inputs, refreshes loss_info, and its gradient equals the oracle's for the loss it reports being near."""
+    import rangeclip_b200 as R
+    x, seg, text, sets = _case(B=2, D=256, H=32, W=32, C=120, seed=5)
+    model = _Model().to(dev())
+    xd = x.to(dev()).to(torch.bfloat16).requires_grad_(True)
+    segd, textd = seg.to(dev()), text.to(dev())
+    kw = dict(W_text=1.0, W_image=0.0, W_smooth=0.0, percent_image_sampling=0.7, k_distractors=30, pct_medium=0.2, pct_hard=0.5,
+              pct_rand=0.3, contrast_builder="device")
+    params = [xd, model.log_temperature_text]
+    eager = []
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                      # warm-up off the default stream, as CUDA-graph capture wants it
+        for _ in range(3):
+            total, info = R.compute_loss(model, xd, segd, textd, sets, None, None, **kw)
+            grads = torch.autograd.grad(total, params)
+            eager.append(float(total))
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        total, info = R.compute_loss(model, xd, segd, textd, sets, None, None, **kw)
+        gx, gtau = torch.autograd.grad(total, params)
+    losses = []
+    for _ in range(4):
+        graph.replay()
+        torch.cuda.synchronize()
+        losses.append(float(total))
+        assert info["total_loss"] == pytest.approx(float(total), rel=1e-6)
+        assert torch.isfinite(gx).all() and float(gx.float().abs().sum()) > 0 and torch.isfinite(gtau)
+    assert len(set(losses)) > 1                        # the draws advance from replay to replay
+    mean_eager = sum(eager) / len(eager)
+    assert all(abs(l - mean_eager) < 0.1 * abs(mean_eager) for l in losses), (losses, eager)
