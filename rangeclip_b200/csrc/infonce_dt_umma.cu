@@ -13,6 +13,7 @@
 // HBM bound: G is read D/256 times (2 x 2.1 GB at the headline size), X once.
 #include "common.cuh"
 #include "umma.cuh"
+#include <stdlib.h>
 
 namespace rc {
 using namespace umma;
@@ -132,6 +133,119 @@ infonce_dt_umma_kernel(const __grid_constant__ CUtensorMap map_g,    // G [B][HW
   if (warp == 1) { tc_fence_after(); tmem_dealloc<kTmemCols>(tmem); }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair form (Kp > 128): the single-CTA kernel above reads G once per 256-channel half, i.e. twice.  Here a cluster of two
+// CTAs owns every (gridDim / 2)-th 64-pixel slab and ALL 512 channels: `tcgen05.mma.cta_group::2` with M = 256 text rows (CTA r
+// stages and accumulates rows [128 r, 128 r + 128)) and N = 256 channels per MMA, two MMAs per 16 pixels (channels [0,256) and
+// [256,512) -> TMEM columns [0,256) / [256,512) of each CTA); the B operand is split over the pair (CTA r stages channel rows
+// [256 n + 128 r, +128) of block n).  G and X are each read ONCE: 2.1 + 4.3 GB at the headline size instead of 4.3 + 4.3.
+// ------------------------------------------------------------------------------------------------------------------
+namespace pairk {
+constexpr int kStages = 4;
+constexpr int kGBytes = 2 * 8192;        // own 128 text rows: two [64 px][64 k] sub-tiles
+constexpr int kXBytes = 2 * 16384;       // own 128 channel rows of each of the two 256-channel blocks: 2 x [128 d][64 px]
+constexpr int kStageBytes = kGBytes + kXBytes;
+constexpr int kOffBars = kStages * kStageBytes;
+constexpr int kSmemBytes = kOffBars + (int)sizeof(Bars) + 64;
+static_assert(kStages <= 4 && kSmemBytes <= 232448, "shared-memory budget of one SM (227 KB)");
+}  // namespace pairk
+
+struct BarsP {
+  uint64_t full[pairk::kStages], empty[pairk::kStages];
+  uint64_t done;
+  uint32_t tmem_base, pad;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+infonce_dt_umma_pair_kernel(const __grid_constant__ CUtensorMap map_g,    // G [B][HW][Kp], box (64 k, 64 px, 1)
+                            const __grid_constant__ CUtensorMap map_x,    // X [B][D][HW],  box (64 px, 128 d, 1)
+                            const Params prm) {
+  using namespace pairk;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  BarsP* bars = reinterpret_cast<BarsP*>(smem + pairk::kOffBars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int range = blockIdx.x >> 1, n_ranges = gridDim.x >> 1;
+  const int n_nb = prm.D / 256;                   // 256-channel blocks (N of the MMA): 1 or 2
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_g); tma_prefetch_desc(&map_x);
+    for (int i = 0; i < pairk::kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    mbar_init(&bars->done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<kTmemCols>(&bars->tmem_base);
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    // =============================== TMA producer (both CTAs) ===============================
+    uint32_t it = 0;
+    for (int sl = range; sl < prm.n_slabs; sl += n_ranges, ++it) {
+      const int b = sl / prm.slabs_per_img;
+      const int px0 = (sl - b * prm.slabs_per_img) * kSlabPx;
+      const int st = it % pairk::kStages;
+      mbar_wait(&bars->empty[st], ((it / pairk::kStages) & 1) ^ 1, 1);
+      uint8_t* sb = smem + st * pairk::kStageBytes;
+      if (leader) mbar_arrive_expect_tx(&bars->full[st], 2 * (pairk::kGBytes + n_nb * 16384));      // both CTAs' bytes; out-of-range boxes arrive as zeros
+      for (int j = 0; j < 2; ++j) tma_load_3d_2sm(sb + j * 8192, &map_g, &bars->full[st], (int)rank * 128 + j * 64, px0, b);
+      for (int n = 0; n < n_nb; ++n)
+        tma_load_3d_2sm(sb + pairk::kGBytes + n * 16384, &map_x, &bars->full[st], px0, n * 256 + (int)rank * 128, b);
+    }
+  } else if (warp == 1 && leader) {
+    // =============================== MMA issuer (leader CTA; converged warp, one elected lane) ===============================
+    const uint32_t idesc = make_idesc_bf16(256, 256, /*A MN-major*/ 1, /*B K-major*/ 0);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t dsc_g = desc_mnmajor_sw128(0, 8192);      // two 64-row groups of text rows, 8 KB apart
+    const uint64_t dsc_x = desc_kmajor_sw128(0);
+    uint32_t it = 0;
+    for (int sl = range; sl < prm.n_slabs; sl += n_ranges, ++it) {
+      const int st = it % pairk::kStages;
+      mbar_wait(&bars->full[st], (it / pairk::kStages) & 1, 2);
+      tc_fence_after();
+      const uint32_t sb = smem_base + st * pairk::kStageBytes;
+      if (elect_one()) {
+        for (int n = 0; n < n_nb; ++n) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)       // 16 pixels per MMA
+            mma_bf16_ss_2sm(tmem + n * 256, dsc_g + ((sb + ks * 2048) >> 4), dsc_x + ((sb + pairk::kGBytes + n * 16384 + ks * 32) >> 4),
+                            idesc, (it | ks) != 0);
+        }
+        mma_commit_2sm(&bars->empty[st]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) mma_commit_2sm(&bars->done);
+    __syncwarp();
+  } else if (warp >= 2) {
+    // ======================= final reduction: own 128 text rows x all channels -> dt (fp32, vector reductions) =======================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    mbar_wait(&bars->done, 0, 3);
+    tc_fence_after();
+    const bool any = range < prm.n_slabs;       // a pair without work has undefined accumulators
+    const int k = (int)rank * 128 + row;
+    for (int c = 0; c < n_nb * 8 && any; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      if (k < prm.K) {
+        float* dst = prm.dt + (int64_t)k * prm.D + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(r[i])),
+                       "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i + 2])), "f"(__uint_as_float(r[i + 3]))
+                       : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_2sm<kTmemCols>(tmem); }
+}
+
 }  // namespace dtk
 
 int launch_infonce_dt(const void* g, const void* xsrc, int B, int D, int64_t HW, int K, float* dt, cudaStream_t s) {
@@ -158,6 +272,35 @@ int launch_infonce_dt(const void* g, const void* xsrc, int B, int D, int64_t HW,
   prm.n_slabs = B * prm.slabs_per_img;
   prm.n_dh = D / 256;
   prm.dt = dt;
+  bool use_pair = Kp > 128 && prm.n_slabs >= 2;
+#ifdef RC_BRINGUP
+  { const char* v = getenv("RANGECLIP_B200_DT"); if (v != nullptr && v[0] == '1') use_pair = false; }      // A/B: "1cta"
+#endif
+  if (use_pair) {
+    // CTA pairs: every pair takes all channels, each CTA half of the text rows -- G and X are read once
+    CUtensorMap m_xp;
+    const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)D, (uint64_t)B};
+    const uint64_t str[3] = {2, (uint64_t)HW * 2, (uint64_t)D * HW * 2};
+    const uint32_t box[3] = {(uint32_t)kSlabPx, 128, 1};
+    if ((rcode = make_tmap_bf16(&m_xp, xsrc, 3, dims, str, box, "dt map_x (pair)"))) return rcode;
+    int n_clusters = num_sms() / 2;
+    if (n_clusters > prm.n_slabs) n_clusters = prm.n_slabs;
+    cudaError_t e = cudaFuncSetAttribute(infonce_dt_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pairk::kSmemBytes);
+    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_infonce_bf16(dText): smem opt-in: %s", cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pairk::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, infonce_dt_umma_pair_kernel, m_g, m_xp, prm);
+    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "rc_infonce_bf16(dText): cluster launch: %s", cudaGetErrorString(e));
+    return check_launch("rc_infonce_bf16(dText)");
+  }
   int grid = num_sms() / prm.n_dh * prm.n_dh;
   if (grid > prm.n_slabs * prm.n_dh) grid = prm.n_slabs * prm.n_dh;
   cudaError_t e = cudaFuncSetAttribute(infonce_dt_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
