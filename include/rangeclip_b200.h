@@ -185,13 +185,15 @@ int rc_sample_weights(const int64_t* seg, const int64_t* rand_idx, int B, int64_
  *   k_cap      rows the loss launch is shaped for: distractors are trimmed to fit (flag 2); present labels beyond it are
  *              dropped from the map (flag 1)
  *   seed       draws = the n smallest of key(c) = splitmix64(splitmix64(seed ^ phase << 56) + c), phase 1 / 2
+ *   include_label0  0: label 0 is background and never "present" (compute_loss, model.py:226); 1: it is a label like any other
+ *              (the reduced candidate set of predict, model.py:147-156: GT labels of the batch + num_negatives random others)
  *   seed_dev   nullable device int64[1]: XORed into `seed` by the kernel -- a seed produced on the device (e.g. by a graph-safe
  *              generator) gives every replay of a captured CUDA graph its own draw
  * Outputs: label_map int32[C] (position in the sorted contrast set or -1), contrast int64[k_cap] (sorted ids, -1 pads:
  * rc_text_prepare turns those into zero rows), k_out int32[4] = {K, flags, #present, #distractors}.  C <= 16384. */
 int rc_contrast_build(const int32_t* counts, int C, const int32_t* sim_off, const int32_t* sim_items,
                       int n_curriculum, int n_rand, int k_cap, uint64_t seed, const int64_t* seed_dev,
-                      int32_t* label_map, int64_t* contrast, int32_t* k_out, void* stream);
+                      int include_label0, int32_t* label_map, int64_t* contrast, int32_t* k_out, void* stream);
 int rc_sample_label_counts(const int64_t* seg, const int64_t* rand_idx, int B, int64_t HW, int64_t n_samples, int C,
                            int32_t* counts, void* stream);
 int rc_scale(void* x, rc_dtype dtype, int64_t n, const float* s, void* stream);
@@ -267,6 +269,15 @@ int rc_eval_topk_hist_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_
                            const int64_t* gt /*[B*HW]*/, const uint8_t* E, const int64_t* cmap, int C,
                            int64_t* hist /*[5][C]*/, int64_t* counters /*[3]*/,
                            void* workspace, int64_t workspace_bytes, void* stream);
+/* rc_eval_topk_bf16 / rc_eval_topk_hist_bf16 with the number of valid text rows read from DEVICE memory when the kernel starts
+ * (a candidate set built by rc_contrast_build: model.py:147-161 without the unique().tolist() / random.sample round trip):
+ * K = rows the launch is shaped for (t_bf16 has round_up(K, 64) rows, rows past *k_dev are pads), k_dev device int32[1] in
+ * [1, K].  `out` and `hist` are both optional; at least one must be given. */
+int rc_eval_topk_dyn_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
+                          const void* t_bf16, int K, const int32_t* k_dev, const int64_t* index_map, int k,
+                          int64_t* out /*nullable*/, const int64_t* gt, const uint8_t* E, const int64_t* cmap, int C,
+                          int64_t* hist /*nullable [5][C]*/, int64_t* counters /*[3]*/,
+                          void* workspace, int64_t workspace_bytes, void* stream);
 int rc_eval_hist(const int64_t* gt, const int64_t* topk, int B, int64_t HW, int k,
                  const uint8_t* E, const int64_t* cmap, int C,
                  int64_t* hist /*[5][C]*/, int64_t* counters /*[3]*/, void* stream);

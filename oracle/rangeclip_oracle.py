@@ -123,7 +123,8 @@ def contrast_draw_key(seed: int, phase: int, c: int) -> int:
     return _splitmix64((_splitmix64((seed ^ (phase << 56)) & _M64) + c) & _M64)
 
 
-def contrast_build_device(counts, sim_off, sim_items, n_curriculum: int, n_rand: int, k_cap: int, seed: int):
+def contrast_build_device(counts, sim_off, sim_items, n_curriculum: int, n_rand: int, k_cap: int, seed: int,
+                          include_label0: bool = False):
     """(label_map [C], contrast [k_cap] padded with -1, (K, flags, n_present, n_distractors)).
     present = labels >= 1 with a non-zero count (model.py:226,233); candidates = similarity lists of the present labels
     minus present (model.py:240-252); n_curriculum of them (all if fewer, model.py:254-259) and n_rand of the labels that
@@ -131,7 +132,7 @@ def contrast_build_device(counts, sim_off, sim_items, n_curriculum: int, n_rand:
     bits by label order); the contrast set is the sorted union (model.py:268), capped at k_cap rows."""
     counts = np.asarray(counts)
     C = counts.shape[0]
-    present = [c for c in range(1, C) if counts[c] > 0]
+    present = [c for c in range(0 if include_label0 else 1, C) if counts[c] > 0]      # predict (model.py:147) keeps label 0
     pset = set(present)
     cand = set()
     if sim_off is not None and n_curriculum > 0:

@@ -33,7 +33,7 @@ PROTOTYPES = {
                              _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "rc_infonce_bf16_dyn": [_vp, _i32, _i32, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp, _i64, _i32, _vp],
-    "rc_contrast_build": [_vp, _i32, _vp, _vp, _i32, _i32, _i32, C.c_uint64, _vp, _vp, _vp, _vp, _vp],
+    "rc_contrast_build": [_vp, _i32, _vp, _vp, _i32, _i32, _i32, C.c_uint64, _vp, _i32, _vp, _vp, _vp, _vp],
     "rc_infonce_bf16_kblocks": [_vp, _i32, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _i64, _i32, _vp],
     "rc_infonce_prepass": [_vp, _i32, _i32, _i32, _i64, _vp, _i64, _vp],
@@ -56,6 +56,8 @@ PROTOTYPES = {
     "rc_eval_topk_bf16": [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _i64, _vp],
     "rc_eval_topk_hist_bf16": [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp,
                                _vp, _i64, _vp],
+    "rc_eval_topk_dyn_bf16": [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp,
+                              _vp, _i64, _vp],
     "rc_eval_hist": [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "rc_eval_fold": [_vp, _i32, _i32, _vp, _vp, _vp],
 }

@@ -4,7 +4,8 @@
 // .tolist() -> Python set logic over the similarity tables -> np.random.choice / torch.randperm -> torch.unique of the
 // concatenation.  Every step of that is a device->host synchronisation in front of the fused loss kernel.  This kernel does
 // the same construction from the label histogram of the sampled pixels (rc_sample_label_counts) in ONE launch of one block:
-//   present   = labels >= 1 with a non-zero count                                  (model.py:226,233)
+//   present   = labels >= 1 with a non-zero count                                  (model.py:226,233; include_label0: >= 0,
+//               the candidate set of predict, model.py:147-156, keeps the background label)
 //   candidate = union of the similarity lists of the present labels, minus present  (model.py:240-252)
 //   chosen    = n_curriculum candidates drawn without replacement (all of them if there are fewer)   (model.py:254-259)
 //   random    = n_rand labels drawn without replacement from everything not present / chosen         (model.py:261-266)
@@ -138,12 +139,12 @@ __device__ void select_smallest(uint8_t* state, int C, uint8_t any_of, uint8_t n
 __global__ void __launch_bounds__(kThreads, 1)
 contrast_build_kernel(const int32_t* __restrict__ counts, int C, const int32_t* __restrict__ sim_off,
                       const int32_t* __restrict__ sim_items, int n_curriculum, int n_rand, int k_cap, uint64_t seed,
-                      const int64_t* __restrict__ seed_dev, int32_t* __restrict__ label_map, int64_t* __restrict__ contrast_out,
-                      int32_t* __restrict__ k_out) {
+                      const int64_t* __restrict__ seed_dev, int first_label, int32_t* __restrict__ label_map,
+                      int64_t* __restrict__ contrast_out, int32_t* __restrict__ k_out) {
   extern __shared__ uint8_t state[];        // [C] flags
   __shared__ Shared sh;
   if (seed_dev != nullptr) seed ^= (uint64_t)seed_dev[0];      // a seed that lives on the device (CUDA-graph replays: a new draw each time)
-  for (int c = threadIdx.x; c < C; c += kThreads) state[c] = (c >= 1 && counts[c] > 0) ? kPresent : 0;
+  for (int c = threadIdx.x; c < C; c += kThreads) state[c] = (c >= first_label && counts[c] > 0) ? kPresent : 0;
   __syncthreads();
   if (sim_off != nullptr && n_curriculum > 0) {
     for (int c = threadIdx.x; c < C; c += kThreads) {
@@ -199,13 +200,13 @@ contrast_build_kernel(const int32_t* __restrict__ counts, int C, const int32_t* 
 
 extern "C" int rc_contrast_build(const int32_t* counts, int C, const int32_t* sim_off, const int32_t* sim_items,
                                  int n_curriculum, int n_rand, int k_cap, uint64_t seed, const int64_t* seed_dev,
-                                 int32_t* label_map, int64_t* contrast, int32_t* k_out, void* stream) {
+                                 int include_label0, int32_t* label_map, int64_t* contrast, int32_t* k_out, void* stream) {
   using namespace rc::contrast;
   RC_REQUIRE(counts && label_map && contrast && k_out, "rc_contrast_build: null pointer");
   RC_REQUIRE(C >= 1 && k_cap >= 1 && n_curriculum >= 0 && n_rand >= 0, "rc_contrast_build: bad argument");
   RC_REQUIRE((sim_off == nullptr) == (sim_items == nullptr), "rc_contrast_build: sim_off and sim_items go together");
   if (C > kMaxC) return rc::fail(RC_ERR_UNSUPPORTED, "rc_contrast_build: C=%d labels exceed %d", C, kMaxC);
   contrast_build_kernel<<<1, kThreads, (size_t)C, (cudaStream_t)stream>>>(counts, C, sim_off, sim_items, n_curriculum, n_rand,
-                                                                         k_cap, seed, seed_dev, label_map, contrast, k_out);
+                                                                         k_cap, seed, seed_dev, include_label0 ? 0 : 1, label_map, contrast, k_out);
   return rc::check_launch("rc_contrast_build");
 }

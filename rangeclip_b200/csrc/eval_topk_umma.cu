@@ -51,6 +51,7 @@ struct Params {
   int B, D, K, k;
   int64_t HW;
   int tiles_per_img, n_tiles, n_blocks;
+  const int32_t* k_dev;                  // nullable: number of valid text rows (<= K) read from device memory at kernel start
   const int64_t* index_map;
   int64_t* out;                          // nullable when only the metrics are wanted
   // fused metrics (validate.py:88-139), all nullable together: the histograms of this batch are added to `hist`
@@ -179,6 +180,9 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
   const int unit_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int n_units = kPair ? (prm.n_tiles + 1) / 2 : prm.n_tiles;
   auto tile_of = [&](int u) -> int { return kPair ? 2 * u + (int)rank : u; };
+  // the candidate set may have been built on the device (rc_contrast_build): its size is read here, by every role alike
+  const int Kv = prm.k_dev != nullptr ? max(1, min(__ldg(prm.k_dev), prm.K)) : prm.K;
+  const int n_blocks = prm.k_dev != nullptr ? (Kv + kNB - 1) / kNB : prm.n_blocks;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_t);
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
@@ -211,7 +215,7 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
       const bool tile_ok = tile < prm.n_tiles;
       const int b = tile_ok ? tile / prm.tiles_per_img : prm.B;           // image index B: out of bounds, TMA fills zeros
       const int px0 = tile_ok ? (tile - b * prm.tiles_per_img) * kTilePx : 0;
-      for (int nb = 0; nb < prm.n_blocks; ++nb)
+      for (int nb = 0; nb < n_blocks; ++nb)
         for (int c = 0; c < n_dchunks; ++c, ++it) {
           if (nb == 0) {
             mbar_wait(&bars->x_empty[c], (lt & 1) ^ 1, 1);
@@ -244,11 +248,11 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
     const uint64_t dsc_x = desc_mnmajor_sw128(0, 8192) + (smem_base >> 4);
     const uint64_t dsc_t = desc_kmajor_sw128(0) + ((smem_base + kOffRing) >> 4);
     for (int u = unit0; u < n_units; u += unit_step, ++lt) {
-      for (int nb = 0; nb < prm.n_blocks; ++nb, ++nbc) {
+      for (int nb = 0; nb < n_blocks; ++nb, ++nbc) {
         const int sbuf = nbc & 1;
         mbar_wait(&bars->s_empty[sbuf], ((nbc >> 1) & 1) ^ 1, 4);
         tc_fence_after();
-        const bool last = nb + 1 == prm.n_blocks;
+        const bool last = nb + 1 == n_blocks;
         for (int c = 0; c < n_dchunks; ++c, ++it) {
           const int st = it % kRingStages;
           if (nb == 0) mbar_wait(&bars->x_full[c], lt & 1, 3);
@@ -311,17 +315,17 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
 #pragma unroll
       for (int j = 0; j < kMaxK; ++j) { bv[j] = -FLT_MAX; bi[j] = -1; }
       float kth = -FLT_MAX;              // current k-th best: cheap reject before the insertion network
-      for (int nb = 0; nb < prm.n_blocks; ++nb, ++nbc) {
+      for (int nb = 0; nb < n_blocks; ++nb, ++nbc) {
         const int sbuf = nbc & 1;
         mbar_wait(&bars->s_full[sbuf], (nbc >> 1) & 1, 6);
         tc_fence_after();
         // The TMEM load of the NEXT 32 columns is in flight while this chunk is scanned (two register buffers): with two
         // scan warps per scheduler the exposed tcgen05.ld latency of every chunk was a fifth of the scan time.
         const int kbase = nb * kNB + half * kCols;
-        const int n_chunks = min(kCols / 32, max(0, (prm.K - kbase + 31) >> 5));
+        const int n_chunks = min(kCols / 32, max(0, (Kv - kbase + 31) >> 5));
         auto scan_chunk = [&](const uint32_t (&r)[32], int c) {
           const int k0 = kbase + c * 32;
-          const int nvalid = prm.K - k0;
+          const int nvalid = Kv - k0;
           if (KT == 1) {
             // arg-max: a branch-free running maximum with static register indices (3 instructions per column) is
             // cheaper than the bitmask + candidate loop at every position of the scan
@@ -426,7 +430,7 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
             scan_chunk(r, c);
           }
         }
-        if (nb + 1 == prm.n_blocks) {
+        if (nb + 1 == n_blocks) {
           // merge the P lists of a pixel: parts 1.. park theirs in 16 TMEM columns of their own, already scanned range of
           // this buffer; part 0 folds them into its list (explicit index tie-break: the ranges interleave across blocks)
           const uint32_t tq = tmem + ((uint32_t)(quarter * 32) << 16) + sbuf * kNB;
@@ -521,7 +525,7 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
 static int eval_topk_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16, int K,
                                const int64_t* index_map, int k, int64_t* out, const int64_t* gt, const uint8_t* E,
                                const int64_t* cmap, int C, int64_t* hist, int64_t* counters, void* workspace,
-                               int64_t workspace_bytes, void* stream, const char* who) {
+                               int64_t workspace_bytes, void* stream, const char* who, const int32_t* k_dev = nullptr) {
   using namespace rc;
   RC_REQUIRE(x && t_bf16 && index_map && (out || hist), "%s: null pointer", who);
   RC_REQUIRE(B >= 0 && HW >= 0 && K >= 1 && k >= 1 && k <= topk::kMaxK && k <= K, "%s: bad shape (k=%d K=%d)", who, k, K);
@@ -564,7 +568,7 @@ static int eval_topk_bf16_impl(const void* x, rc_dtype x_dtype, int B, int D, in
   if ((int64_t)B * prm.tiles_per_img > 0x7fffffff) return fail(RC_ERR_UNSUPPORTED, "%s: too many tiles", who);
   prm.n_tiles = B * prm.tiles_per_img;
   prm.n_blocks = (K + topk::kNB - 1) / topk::kNB;
-  prm.index_map = index_map; prm.out = out;
+  prm.index_map = index_map; prm.out = out; prm.k_dev = k_dev;
   prm.gt = gt; prm.E = E; prm.cmap = cmap; prm.C = C;
   prm.hist = reinterpret_cast<unsigned long long*>(hist); prm.counters = reinterpret_cast<unsigned long long*>(counters);
   // CTA pairs (two tiles per cluster, text chunks shared between the two SMs) whenever there is more than one tile
@@ -629,4 +633,15 @@ extern "C" int rc_eval_topk_hist_bf16(const void* x, rc_dtype x_dtype, int B, in
   RC_REQUIRE(hist, "rc_eval_topk_hist_bf16: null pointer");
   return eval_topk_bf16_impl(x, x_dtype, B, D, HW, t_bf16, K, index_map, k, out, gt, E, cmap, C, hist, counters, workspace,
                              workspace_bytes, stream, "rc_eval_topk_hist_bf16");
+}
+
+/* Same with the number of valid text rows read from device memory (a candidate set built by rc_contrast_build: K is the row
+ * count the launch is shaped for, rows past *k_dev are pads); out and hist are both optional, at least one must be given. */
+extern "C" int rc_eval_topk_dyn_bf16(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW, const void* t_bf16, int K,
+                                     const int32_t* k_dev, const int64_t* index_map, int k, int64_t* out, const int64_t* gt,
+                                     const uint8_t* E, const int64_t* cmap, int C, int64_t* hist, int64_t* counters,
+                                     void* workspace, int64_t workspace_bytes, void* stream) {
+  RC_REQUIRE(k_dev != nullptr, "rc_eval_topk_dyn_bf16: k_dev is required");
+  return eval_topk_bf16_impl(x, x_dtype, B, D, HW, t_bf16, K, index_map, k, out, gt, E, cmap, C, hist, counters, workspace,
+                             workspace_bytes, stream, "rc_eval_topk_dyn_bf16", k_dev);
 }

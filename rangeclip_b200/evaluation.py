@@ -28,11 +28,43 @@ def build_reduced_candidates(segmentation: torch.Tensor, total_candidates: int, 
     return sorted(list(gt.union(negatives)))
 
 
-def predict_from_embeddings(pixel_embeddings, candidate_text_embeddings, segmentation, num_negatives=300, top_k=5,
-                            precision="auto"):
-    """model.py:144-173 given the decoder output: returns (topk ids [B,k,H,W] int64 in the ORIGINAL
-    index space, L2-normalised embeddings).  The [B,Kr,HW] logits are never materialised."""
+def device_candidates_supported(pixel_embeddings, total_candidates: int) -> bool:
+    D = pixel_embeddings.shape[1]
+    hw = pixel_embeddings[0, 0].numel() if pixel_embeddings.shape[0] else 0
+    return pixel_embeddings.is_cuda and ops.topk_bf16_supported(D, hw) and 2 <= total_candidates <= 12000
+
+
+def build_reduced_candidates_device(segmentation: torch.Tensor, candidate_text_embeddings: torch.Tensor, num_negatives: int):
+    """model.py:147-161 without the host round trip: the label histogram of the batch -> GT labels (label 0
+    included, as ``torch.unique(segmentation)`` includes it) + ``num_negatives`` labels drawn without replacement from the
+    rest (``rc_contrast_build``'s counter-based stream seeded from Python's ``random`` -- the generator the reference's
+    ``random.sample`` uses; not its draws), sorted.  Returns (index list [K_cap] int64 padded with -1, bf16 rows [K_cap', D],
+    kinfo int32 [4] with the set size first) -- all on the device, nothing read back."""
     total = candidate_text_embeddings.shape[0]
+    seg = segmentation.reshape(segmentation.shape[0], -1)
+    counts = torch.ops.rangeclip.sample_label_counts(seg, None, total)
+    seed_dev = None
+    if torch.cuda.is_current_stream_capturing():
+        seed, seed_dev = 0, torch.randint(0, 2 ** 62, (1,), device=seg.device, dtype=torch.int64)
+    else:
+        seed = random.getrandbits(62)
+    _, reduced, kinfo = torch.ops.rangeclip.contrast_build(counts, None, None, 0, int(num_negatives), total, seed, seed_dev, True)
+    _, tb, _ = torch.ops.rangeclip.text_prepare(candidate_text_embeddings, reduced)
+    return reduced, tb, kinfo
+
+
+def predict_from_embeddings(pixel_embeddings, candidate_text_embeddings, segmentation, num_negatives=300, top_k=5,
+                            precision="auto", candidate_builder="reference"):
+    """model.py:144-173 given the decoder output: returns (topk ids [B,k,H,W] int64 in the ORIGINAL
+    index space, L2-normalised embeddings).  The [B,Kr,HW] logits are never materialised.
+    ``candidate_builder="device"``: the reduced candidate set is built on the GPU and its size stays there
+    (``build_reduced_candidates_device``): no host synchronisation; a pixel gets -1 where fewer than ``top_k`` candidates exist."""
+    total = candidate_text_embeddings.shape[0]
+    if candidate_builder == "device" and segmentation is not None and device_candidates_supported(pixel_embeddings, total) \
+            and precision != "fp32":
+        reduced, tb, kinfo = build_reduced_candidates_device(segmentation, candidate_text_embeddings, num_negatives)
+        topk = ops.eval_topk_dyn(pixel_embeddings, tb, kinfo, reduced, min(top_k, total))
+        return topk, F.normalize(pixel_embeddings, dim=1)
     reduced = build_reduced_candidates(segmentation, total, num_negatives)
     index_tensor = torch.tensor(reduced, device=pixel_embeddings.device)
     t_norm, _, _ = ops.text_prepare(candidate_text_embeddings, index_tensor, want_f32=True)
@@ -41,11 +73,17 @@ def predict_from_embeddings(pixel_embeddings, candidate_text_embeddings, segment
 
 
 def predict_and_accumulate(pixel_embeddings, candidate_text_embeddings, segmentation, accumulator, num_negatives=300, top_k=5,
-                           batch_index=None, want_ids=True):
+                           batch_index=None, want_ids=True, candidate_builder="reference"):
     """``predict_from_embeddings`` + ``MetricAccumulator.update`` as one fused kernel per batch: same reduced candidate
     set (same ``random.sample`` draw, Q6), same ids, same histograms -- the ids never make the round trip through HBM
-    between the two steps.  Returns (topk ids or None, L2-normalised embeddings)."""
+    between the two steps.  Returns (topk ids or None, L2-normalised embeddings).  ``candidate_builder="device"``: see
+    ``predict_from_embeddings`` -- the whole validation batch then runs without a host synchronisation."""
     total = candidate_text_embeddings.shape[0]
+    if candidate_builder == "device" and device_candidates_supported(pixel_embeddings, total):
+        reduced, tb, kinfo = build_reduced_candidates_device(segmentation, candidate_text_embeddings, num_negatives)
+        ids = accumulator.update_from_device_candidates(pixel_embeddings, tb, kinfo, reduced, segmentation, min(top_k, total),
+                                                        batch_index=batch_index, want_ids=want_ids)
+        return ids, F.normalize(pixel_embeddings, dim=1)
     reduced = build_reduced_candidates(segmentation, total, num_negatives)
     index_tensor = torch.tensor(reduced, device=pixel_embeddings.device)
     t_norm, _, _ = ops.text_prepare(candidate_text_embeddings, index_tensor, want_f32=True)
@@ -54,8 +92,9 @@ def predict_and_accumulate(pixel_embeddings, candidate_text_embeddings, segmenta
     return ids, F.normalize(pixel_embeddings, dim=1)
 
 
-def predict(self, depth_maps, candidate_text_embeddings, segmentation, num_negatives=300, top_k=5):
-    """Drop-in for ``DepthUNet.predict`` (model.py:119-175): backbone in PyTorch, tail on the kernels."""
+def predict(self, depth_maps, candidate_text_embeddings, segmentation, num_negatives=300, top_k=5, candidate_builder="reference"):
+    """Drop-in for ``DepthUNet.predict`` (model.py:119-175): backbone in PyTorch, tail on the kernels.
+    ``candidate_builder="device"`` (an addition): see ``predict_from_embeddings``."""
     self.eval()
     B, _, H, W = depth_maps.shape
     with torch.no_grad():
@@ -63,7 +102,7 @@ def predict(self, depth_maps, candidate_text_embeddings, segmentation, num_negat
             _, encoder_features, final_feature_map = self.depth_encoder(depth_maps)
             pixel_embeddings = self.depth_decoder(final_feature_map, encoder_features, (H, W))
         topk, pixel_embeddings = predict_from_embeddings(pixel_embeddings.float(), candidate_text_embeddings,
-                                                         segmentation, num_negatives, top_k)
+                                                         segmentation, num_negatives, top_k, candidate_builder=candidate_builder)
         return topk, pixel_embeddings, self.temperature_text
 
 
@@ -96,6 +135,16 @@ class MetricAccumulator:
         self._hist.zero_()
         ids = ops.eval_topk_hist(pixel_embeddings, t_norm, index_tensor, top_k, segmentation, self.E, self.cmap, self._hist,
                                  self.counters, t_bf16=t_bf16, want_ids=want_ids)
+        ops.eval_fold(self._hist, self.n_batches if batch_index is None else batch_index, self.acc, self.first_seen)
+        self.n_batches += 1
+        return ids
+
+    def update_from_device_candidates(self, pixel_embeddings, t_bf16, kinfo, index_tensor, segmentation, top_k: int = 5,
+                                      batch_index: Optional[int] = None, want_ids: bool = True):
+        """``update_from_embeddings`` for a candidate set whose size lives on the device (``build_reduced_candidates_device``)."""
+        self._hist.zero_()
+        ids = ops.eval_topk_dyn(pixel_embeddings, t_bf16, kinfo, index_tensor, top_k, segmentation, self.E, self.cmap, self._hist,
+                                self.counters, want_ids=want_ids)
         ops.eval_fold(self._hist, self.n_batches if batch_index is None else batch_index, self.acc, self.first_seen)
         self.n_batches += 1
         return ids

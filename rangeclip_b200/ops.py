@@ -153,7 +153,7 @@ def clip_crops(images: torch.Tensor, boxes: torch.Tensor, image_index: torch.Ten
 
 
 def contrast_build(counts: torch.Tensor, sim_off: Optional[torch.Tensor], sim_items: Optional[torch.Tensor], n_curriculum: int,
-                   n_rand: int, k_cap: int, seed: int, seed_dev: Optional[torch.Tensor] = None):
+                   n_rand: int, k_cap: int, seed: int, seed_dev: Optional[torch.Tensor] = None, include_label0: bool = False):
     """Device-side contrast set (rc_contrast_build; model.py:234-268 without host round trips): from the label histogram of
     the sampled pixels to (label_map int32 [C], contrast int64 [k_cap] sorted ids padded with -1, kinfo int32 [4] =
     K, flags, #present, #distractors) in one launch, nothing read back."""
@@ -166,8 +166,8 @@ def contrast_build(counts: torch.Tensor, sim_off: Optional[torch.Tensor], sim_it
     if seed_dev is not None:
         seed_dev = seed_dev.to(torch.int64).contiguous()
     check(_lib.lib().rc_contrast_build(_p(counts), C, _p(sim_off), _p(sim_items), int(n_curriculum), int(n_rand), int(k_cap),
-                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _p(seed_dev), _p(label_map), _p(contrast), _p(kinfo),
-                                       _stream(counts)),
+                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _p(seed_dev), 1 if include_label0 else 0, _p(label_map), _p(contrast),
+                                       _p(kinfo), _stream(counts)),
           "rc_contrast_build")
     return label_map, contrast, kinfo
 
@@ -602,6 +602,39 @@ def eval_topk_hist(x: torch.Tensor, t_norm: torch.Tensor, index_map: torch.Tenso
     return out
 
 
+def eval_topk_dyn(x: torch.Tensor, t_bf16: torch.Tensor, k_dev: torch.Tensor, index_map: torch.Tensor, k: int, gt=None, E_u8=None,
+                  cmap=None, hist=None, counters=None, want_ids: bool = True):
+    """``eval_topk`` / ``eval_topk_hist`` for a candidate set built on the device (rc_contrast_build): ``t_bf16`` [Kp, D] holds the
+    normalised rows of the padded index list ``index_map`` [K], ``k_dev`` (int32, first entry) how many of them are valid -- read by
+    the kernel from device memory, nothing is read back here (rc_eval_topk_dyn_bf16).  With ``hist`` / ``counters`` the metrics
+    are fused as in ``eval_topk_hist``."""
+    _need_cuda(x, t_bf16, k_dev, index_map)
+    x, B, D, HW = _emb3(x)
+    if not topk_bf16_supported(D, HW):
+        raise RuntimeError(f"eval_topk_dyn: the tensor-core kernel does not cover D={D}, HW={HW}")
+    K = int(index_map.numel())
+    k = min(int(k), K)
+    out = torch.empty((B, k) + tuple(x.shape[2:]), device=x.device, dtype=torch.int64) if (want_ids or hist is None) else None
+    index_map = index_map.to(torch.int64).contiguous()
+    C = 0
+    if hist is not None:
+        C = cmap.numel()
+        gt = gt.reshape(-1).to(torch.int64).contiguous()
+        if gt.numel() != B * HW or hist.dtype != torch.int64 or tuple(hist.shape) != (5, C) or counters.numel() != 3:
+            raise RuntimeError("eval_topk_dyn: gt must have one entry per pixel, hist must be int64 [5, C], counters int64 [3]")
+        E_u8, cmap = E_u8.contiguous(), cmap.to(torch.int64).contiguous()
+    L = _lib.lib()
+    xdt = _dt(x)
+    ws, ws_bytes = None, 0
+    if xdt == RC_F32:
+        ws_bytes = int(L.rc_infonce_workspace_bytes(B, D, HW, K, xdt))
+        ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+    check(L.rc_eval_topk_dyn_bf16(_p(x), xdt, B, D, HW, _p(t_bf16), K, _p(k_dev.to(torch.int32)), _p(index_map), k, _p(out), _p(gt),
+                                  _p(E_u8), _p(cmap), C, _p(hist), _p(counters), _p(ws), ws_bytes, _stream(x)),
+          "rc_eval_topk_dyn_bf16")
+    return out
+
+
 def eval_hist(gt: torch.Tensor, topk: torch.Tensor, E_u8: torch.Tensor, cmap: torch.Tensor,
               hist: Optional[torch.Tensor] = None, counters: Optional[torch.Tensor] = None):
     """One batch of validate.py:88-139 as five class histograms + three counters (int64, added to)."""
@@ -987,12 +1020,13 @@ def _(seg, rand_idx, C):
 
 @_op("rangeclip::contrast_build", mutates_args=(), device_types="cuda")
 def _op_contrast_build(counts: torch.Tensor, sim_off: Optional[torch.Tensor], sim_items: Optional[torch.Tensor], n_curriculum: int,
-                       n_rand: int, k_cap: int, seed: int, seed_dev: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    return contrast_build(counts, sim_off, sim_items, n_curriculum, n_rand, k_cap, seed, seed_dev)
+                       n_rand: int, k_cap: int, seed: int, seed_dev: Optional[torch.Tensor] = None,
+                       include_label0: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    return contrast_build(counts, sim_off, sim_items, n_curriculum, n_rand, k_cap, seed, seed_dev, include_label0)
 
 
 @_op_contrast_build.register_fake
-def _(counts, sim_off, sim_items, n_curriculum, n_rand, k_cap, seed, seed_dev=None):
+def _(counts, sim_off, sim_items, n_curriculum, n_rand, k_cap, seed, seed_dev=None, include_label0=False):
     return (torch.empty(counts.numel(), device=counts.device, dtype=torch.int32),
             torch.empty(k_cap, device=counts.device, dtype=torch.int64), torch.empty(4, device=counts.device, dtype=torch.int32))
 

@@ -232,3 +232,70 @@ def test_sync_free_compute_loss_is_cuda_graph_capturable():
     assert len(set(losses)) > 1                        # the draws advance from replay to replay
     mean_eager = sum(eager) / len(eager)
     assert all(abs(l - mean_eager) < 0.1 * abs(mean_eager) for l in losses), (losses, eager)
+
+
+def test_contrast_build_with_label0_matches_oracle():
+    """include_label0 (the reduced candidate set of predict, model.py:147-156: torch.unique(segmentation) keeps label 0)."""
+    from rangeclip_b200 import ops
+    rng = np.random.default_rng(21)
+    C = 700
+    counts = np.zeros(C, dtype=np.int32)
+    counts[rng.choice(C, 40, replace=False)] = 9
+    counts[0] = 123
+    ref_map, ref_con, ref_info = O.contrast_build_device(counts, None, None, 0, 300, C, 77, include_label0=True)
+    lm, con, info = ops.contrast_build(torch.from_numpy(counts).to(dev()), None, None, 0, 300, C, 77, None, True)
+    assert tuple(info.tolist()) == tuple(ref_info) and ref_con[0] == 0 and ref_info[0] == ref_info[2] + 300
+    assert np.array_equal(lm.cpu().numpy(), ref_map) and np.array_equal(con.cpu().numpy(), ref_con)
+
+
+@pytest.mark.parametrize("B,D,H,W,C,neg", [(2, 512, 16, 16, 1024, 300), (1, 256, 16, 24, 150, 50), (1, 256, 8, 16, 40, 300)])
+def test_predict_with_device_side_candidate_set(B, D, H, W, C, neg):
+    """predict's tail with candidate_builder="device" (model.py:147-173 without the unique().tolist() / random.sample round
+    trip): the set holds the batch's GT labels (0 included) + min(neg, rest) others, sorted; the top-k ids equal the oracle's
+    for THAT set (tie-aware); the fused metric path gives the histograms of the ids it returns, bit for bit; no host sync."""
+    import random as pyrandom
+    from rangeclip_b200 import MetricAccumulator, evaluation
+    g = torch.Generator().manual_seed(B * 7 + C)
+    text = torch.randn(C, D, generator=g)
+    tn = torch.nn.functional.normalize(text, dim=1).to(torch.bfloat16).float()
+    seg = torch.randint(0, min(C, 30), (B, H, W), generator=g)
+    emb = (tn[seg].permute(0, 3, 1, 2) + 0.3 * torch.randn(B, D, H, W, generator=g)).to(torch.bfloat16).float()
+    embd, textd, segd = emb.to(dev()).to(torch.bfloat16), tn.to(dev()), seg.to(dev())
+    pyrandom.seed(5)
+    reduced, tb, kinfo = evaluation.build_reduced_candidates_device(segd, textd, neg)
+    K = int(kinfo[0])
+    members = reduced[:K].cpu().tolist()
+    gt = sorted(set(seg.reshape(-1).tolist()))
+    assert members == sorted(set(members)) and set(gt) <= set(members) and K == len(gt) + min(neg, C - len(gt))
+    assert reduced[K:].eq(-1).all()
+    pyrandom.seed(5)                                        # the same draw again, through the drop-in, with the sync check on
+    evaluation.predict_from_embeddings(embd, textd, segd, neg, 5, candidate_builder="device")          # warm-up
+    torch.cuda.synchronize()
+    pyrandom.seed(5)
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        topk, xn = evaluation.predict_from_embeddings(embd, textd, segd, neg, 5, candidate_builder="device")
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    # model.py:159-173 in fp64 on the operands the tensor cores see (text rows normalised, THEN rounded to bf16 by rc_text_prepare):
+    # a sharp tie criterion
+    rows = tb[:K].float().cpu().double()
+    xh = torch.nn.functional.normalize(emb.double(), dim=1)
+    logits = torch.einsum('bdn,cd->bcn', xh.view(B, D, H * W), rows)
+    k = min(5, K)
+    ref_topk = torch.tensor(members)[logits.topk(k, dim=1).indices.view(B, k, H, W)]
+    out = topk.cpu().numpy()[:, :k]
+    glob = {c: i for i, c in enumerate(members)}
+    ref = ref_topk.numpy()
+    bad = np.argwhere(out != ref)
+    for b, j, h, w_ in bad:                                 # every disagreement is a near-tie of the oracle's logits
+        la = float(logits[b, glob[int(out[b, j, h, w_])], h * W + w_]); lb = float(logits[b, glob[int(ref[b, j, h, w_])], h * W + w_])
+        assert abs(la - lb) < 1e-5
+    assert len(bad) <= 0.003 * out.size + 4                 # (a swapped near-tie shows up at two positions)
+    # fused metrics on the device-built set == histograms of the returned ids
+    E = torch.eye(C, dtype=torch.uint8); cmap = torch.arange(C)
+    acc_a = MetricAccumulator(E, cmap, device=dev()); acc_b = MetricAccumulator(E, cmap, device=dev())
+    pyrandom.seed(5)
+    ids, _ = evaluation.predict_and_accumulate(embd, textd, segd, acc_a, neg, 5, candidate_builder="device")
+    acc_b.update(segd, ids)
+    assert torch.equal(acc_a.acc, acc_b.acc) and torch.equal(acc_a.counters, acc_b.counters) and torch.equal(ids, topk)
