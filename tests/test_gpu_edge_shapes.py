@@ -77,7 +77,9 @@ def test_infonce_tensor_core_edge_shapes(B, D, H, W, K, rep):
 
 
 @pytest.mark.parametrize("B,D,H,W,K,k", [(1, 64, 1, 8, 1, 1), (1, 512, 1, 8, 5, 5), (2, 128, 2, 8, 2000, 5), (1, 256, 1, 136, 257, 8),
-                                         (70, 64, 1, 8, 300, 3)])
+                                         (70, 64, 1, 8, 300, 3),
+                                         # an ODD number of 128-pixel tiles: the CTA-pair form scans a tile past the end and must not write it
+                                         (1, 256, 1, 264, 600, 5), (5, 128, 1, 8, 1024, 1), (3, 512, 3, 128, 300, 5)])
 def test_eval_topk_edge_shapes(B, D, H, W, K, k):
     from rangeclip_b200 import ops
     g = torch.Generator().manual_seed(B + D + W + K + k)
@@ -99,3 +101,19 @@ def test_sample_weights_without_draws():
     assert float(w.sum()) == float((seg > 0).sum())
     w0, _ = ops.sample_weights(seg, torch.zeros(2, 0, dtype=torch.int64, device=dev()), lm)
     assert w0.shape == w.shape
+
+
+def test_fused_topk_histograms_with_an_odd_tile_count():
+    """rc_eval_topk_hist_bf16 in the CTA-pair form on 3 tiles (the pair's fourth tile lies past the end): the histograms and
+    counters equal those of the returned ids (nothing from the phantom tile is counted)."""
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    B, D, H, W, K, k, C = 1, 256, 3, 128, 600, 5, 600
+    t = torch.nn.functional.normalize(torch.randn(K, D, generator=g), dim=1).to(dev())
+    gt = torch.randint(0, C, (B, H, W), generator=g).to(dev())
+    x = (t[gt].permute(0, 3, 1, 2) + 0.3 * torch.randn(B, D, H, W, generator=g).to(dev())).to(torch.bfloat16)
+    E = torch.eye(C, dtype=torch.uint8, device=dev()); cmap = torch.arange(C, device=dev())
+    hist = torch.zeros(5, C, dtype=torch.int64, device=dev()); cnt = torch.zeros(3, dtype=torch.int64, device=dev())
+    ids = ops.eval_topk_hist(x, t, torch.arange(K, device=dev()), k, gt, E, cmap, hist, cnt)
+    hist2, cnt2 = ops.eval_hist(gt, ids, E, cmap)
+    assert torch.equal(hist, hist2) and torch.equal(cnt, cnt2) and int(cnt[2]) == B * H * W
