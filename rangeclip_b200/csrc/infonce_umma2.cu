@@ -58,6 +58,15 @@ constexpr int kThreads = 640;          // warps: 0 TMA, 1 MMA (leader CTA only),
 #ifndef RC_EPI_X_HINT
 #define RC_EPI_X_HINT 1
 #endif
+// RC_PAIR_SMX_UNIT: the dX epilogue is the role that paces the launch (four accumulator units per tile pair, one after the other
+// on eight warps), while the softmax warps idle between their P hand-off and the next S.  With this switch the softmax warps
+// drain ONE of the four units (unit 1: channel block 0, pixels [64,128) of both tiles) in that window -- TMEM load, projection,
+// direct 256-bit global stores (they have no staging tile) -- and the epilogue warps skip it.  Measured, not adopted (same box,
+// base 2.43 ms): after the row norms (1) 3.18 ms, before them (2) 2.90 ms.  The softmax warps' wait for the next S is not slack:
+// they sit on the S -> exp -> P -> dX dependency cycle, and whatever they do in between delays the exp pass of the next tile.
+#ifndef RC_PAIR_SMX_UNIT
+#define RC_PAIR_SMX_UNIT 0
+#endif
 #ifndef RC_EPI_FETCH_EARLY
 #define RC_EPI_FETCH_EARLY 0      // measured (same box): early 2.50 ms, late 2.45 ms
 #endif
@@ -902,8 +911,84 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
           }
         }
         if (half == 0 && valid && prm.lse && !(kKB && prm.lse_in != nullptr)) prm.lse[m] = lse;      // after the hand-off: nothing waits behind this store
-        if (!RC_PAIR_NORM_WARP && pj + n_clusters < prm.n_pairs) norm_tile();
+        uint32_t sxq[2][16];
+        int s_n8 = 0;
+        int64_t s_off = 0;
+        const bool smx_unit = RC_PAIR_SMX_UNIT && !(kKB && prm.acc_dx);
+        if (smx_unit) {
+          // x of unit 1 (own channel row, pixels [64,128) of the tile this warp half covers): requested now, used after the norms
+          const int t1 = 2 * pj + half;
+          if (t1 < prm.n_tiles) {
+            const int b1 = div_tiles(prm, t1);
+            const int px1 = (t1 - b1 * prm.tiles_per_img) * kTilePx + 64;
+            const int d1 = (int)rank * 128 + row;
+            s_off = ((int64_t)((kKB && prm.kb > 0) ? 0 : b1) * prm.D + d1) * prm.HW + px1;
+            const int64_t left = prm.HW - px1;
+            s_n8 = left >= 64 ? 8 : (left > 0 ? (int)(left >> 3) : 0);
+          }
+          const int slb = lane & 1;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int n8 = min(2, max(0, s_n8 - (c * 2 + slb) * 2));
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              ldg_px16(prm.x + s_off + (int64_t)(j - slb) * prm.HW + c * 32 + slb * 16, prm.wide != 0, n8, &sxq[c][j * 8], 0);
+          }
+        }
+        if (RC_PAIR_SMX_UNIT != 2 && !RC_PAIR_NORM_WARP && pj + n_clusters < prm.n_pairs) norm_tile();
         if (warp == 4) RC_EV(lt, 14);  // row norms of the next tile done
+        if (smx_unit) {
+          const int slb = lane & 1;
+          const uint32_t upp = 2u * (uint32_t)n_blk;
+          const uint32_t uc1 = lt * upp + 1u;                                   // the epilogue's unit counter at (this pair, unit 1)
+          RC_WAIT(mbar_wait, &bars->sc_full[lt & 1], (lt >> 1) & 1, 10);       // -cs of both tiles (the peer's arrive by st.async)
+          const uint32_t* sc = sc_s + (lt % kScaleBufs) * 128 + half * 64;
+          RC_WAIT(mbar_wait, &bars->acc_full[1], (uc1 >> 1) & 1, 11);
+          tc_fence_after();
+          const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256 + half * 64 + 128;     // accumulator buffer 1
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t acc[32];
+            tmem_ld_32x32(tacc + c * 32, acc);
+            tmem_ld_wait();
+            if (c == 1) { tc_fence_before(); arrive_leader_warp(&bars->acc_empty[1]); }
+            {       // (row 2p+j, piece b) -> own row, pixels [c*32, +32)
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                const uint32_t send = slb ? sxq[c][r] : sxq[c][8 + r];
+                const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                if (slb) sxq[c][r] = recv; else sxq[c][8 + r] = recv;
+              }
+            }
+            const uint4* scp = reinterpret_cast<const uint4*>(sc + 32 + c * 16);          // pxh = 1
+            uint32_t o[16];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 sv = scp[g];
+              const uint32_t cs4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int i = 4 * g + j;
+                const uint32_t a = pack_bf16x2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+                o[i] = bf2_fma(cs4[j], sxq[c][i], a);
+              }
+            }
+            {       // own row -> (row 2p+j, piece b): 64 contiguous bytes per lane pair and row, straight to global memory
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                const uint32_t send = slb ? o[r] : o[8 + r];
+                const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                if (slb) o[r] = recv; else o[8 + r] = recv;
+              }
+            }
+            const int n8 = min(2, max(0, s_n8 - (c * 2 + slb) * 2));
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              stg_px16(prm.dx + ((kKB && prm.kb > 0) ? (int64_t)div_tiles(prm, 2 * pj + half) * prm.D * prm.HW : 0) + s_off +
+                           (int64_t)(j - slb) * prm.HW + c * 32 + slb * 16, prm.wide != 0, n8, &o[j * 8]);
+          }
+        }
+        if (RC_PAIR_SMX_UNIT == 2 && !RC_PAIR_NORM_WARP && pj + n_clusters < prm.n_pairs) norm_tile();
       }
     }
     if (kBwd && prm.store_g && rtid == 128) tma_store_wait_all0();
@@ -942,8 +1027,11 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
         f_n8 = left >= 64 ? 8 : (left > 0 ? (int)(left >> 3) : 0);
       }
     };
+    const bool smx_unit = RC_PAIR_SMX_UNIT && !(kKB && prm.acc_dx);      // unit 1 of every pair is drained by the softmax warps
     auto cursor_next = [&]() {
-      if (++f_unit == units_per_pair) { f_unit = 0; f_pj += n_clusters; }
+      ++f_unit;
+      if (smx_unit && f_unit == 1) ++f_unit;
+      if (f_unit >= units_per_pair) { f_unit = 0; f_pj += n_clusters; }
       cursor_set();
     };
     // Global accesses are made by lane PAIRS: lanes 2p, 2p+1 own channel rows 2p, 2p+1; access j of a 32-pixel chunk
@@ -978,6 +1066,7 @@ infonce_umma_pair_kernel(const __grid_constant__ CUtensorMap map_x_s,   // X [B]
       ROLE_WAIT_EPI(warp == 12, &bars->sc_full[lt & 1], (lt >> 1) & 1, 10, 7);
       const uint32_t* sc = sc_s + (lt % kScaleBufs) * 128 + half * 64;
       for (int unit = 0; unit < units_per_pair; ++unit, ++uc) {
+        if (smx_unit && unit == 1) continue;
         const int ab = uc & 1;
         const int pxh = unit & 1;
         // where this unit's output goes (same cursor arithmetic as the prefetch, one unit behind)
