@@ -228,6 +228,13 @@ int rc_normalize_rows_fwd(const void* x, rc_dtype dtype, int B, int D, int64_t H
 int rc_normalize_rows_bwd(const float* xhat, const float* g, const float* inv_norm, rc_dtype dtype, int B, int D, int64_t HW,
                           void* dx, void* stream);
 
+/* Backward of the smoothness term through the normalisation in ONE kernel (model.py:332-334 on decoder.py:114's output):
+ *   dx = d/dx [ scale[0] * sum |xh[..,w]-xh[..,w+1]| + scale[1] * sum |xh[..,h,:]-xh[..,h+1,:]| ],  xh = x / max(|x|, 1e-12)
+ * from the saved xhat / inv_norm of rc_normalize_rows_fwd; scale = device float[2]; sign(0) = 0; dx in `dtype`; W % 8 == 0.
+ * (Instead of rc_tv_bwd -> a gradient tensor the size of xhat -> rc_normalize_rows_bwd.) */
+int rc_tv_normalize_bwd(const float* xhat, const float* inv_norm, const float* scale, rc_dtype dtype, int B, int D, int H, int W,
+                        void* dx, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Smoothness (TV-L1)  (replaces model.py:332-334 and its autograd)
  *   sums[0] += sum |x[..,w]-x[..,w+1]|, sums[1] += sum |x[..,h,:]-x[..,h+1,:]|  (double[2])

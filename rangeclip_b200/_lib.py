@@ -49,6 +49,7 @@ PROTOTYPES = {
     "rc_pool_bwd": [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp],
     "rc_normalize_rows_fwd": [_vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp],
     "rc_normalize_rows_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _vp],
+    "rc_tv_normalize_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     "rc_tv_fwd": [_vp, _i32, _i64, _i32, _i32, _vp, _vp],
     "rc_tv_bwd": [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp],
     "rc_tv_bwd_from": [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp],

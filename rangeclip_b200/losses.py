@@ -320,11 +320,17 @@ def _compute_loss(self, pixel_embeddings, target_indices, candidate_text_embeddi
     if W_smooth > 0 and shared2x2:
         B, D, h, w = pixel_embeddings.shape
         H, W = 2 * h, 2 * w
-        if (h * w) % 8 == 0:
-            rows = ops.normalize_rows(pixel_embeddings)                                     # decoder.py:114, one kernel each way
+        dens = (B * D * H * (W - 1) / 2.0, B * D * (H - 1) * W / 2.0)
+        if w % 8 == 0 and pixel_embeddings.dtype in (torch.float32, torch.bfloat16):
+            # decoder.py:114 + model.py:332-333 as one operator: normalise (handed over from the area pooling when it ran on the
+            # same tensor), TV sums, and ONE backward kernel through both
+            smooth_loss = ops.smoothness_normalized(pixel_embeddings, denominators=dens)
         else:
-            rows = torch.nn.functional.normalize(pixel_embeddings.float(), p=2, dim=1)
-        smooth_loss = ops.smoothness(rows, denominators=(B * D * H * (W - 1) / 2.0, B * D * (H - 1) * W / 2.0))
+            if (h * w) % 8 == 0:
+                rows = ops.normalize_rows(pixel_embeddings)
+            else:
+                rows = torch.nn.functional.normalize(pixel_embeddings.float(), p=2, dim=1)
+            smooth_loss = ops.smoothness(rows, denominators=dens)
     elif W_smooth > 0:
         smooth_loss = fused_smooth if fused_smooth is not None else ops.smoothness(pixel_embeddings)
 

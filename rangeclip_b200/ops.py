@@ -917,6 +917,64 @@ def _smoothness_backward(ctx, g):
 _op_smoothness.register_autograd(_smoothness_backward, setup_context=_smoothness_setup)
 
 
+def tv_normalize_backward(xhat: torch.Tensor, inv: torch.Tensor, scale: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """d/dx of scale[0] * sum_h + scale[1] * sum_v of normalize(x) from the saved xhat / inv (rc_tv_normalize_bwd): one kernel
+    instead of rc_tv_bwd -> gradient tensor -> rc_normalize_rows_bwd."""
+    _need_cuda(xhat, inv, scale)
+    B, D, H, W = xhat.shape
+    dx = torch.empty(xhat.shape, device=xhat.device, dtype=dtype)
+    scale = scale.detach().to(device=xhat.device, dtype=torch.float32).contiguous()
+    check(_lib.lib().rc_tv_normalize_bwd(_p(xhat), _p(inv), _p(scale), _dt(dx), B, D, H, W, _p(dx), _stream(xhat)), "rc_tv_normalize_bwd")
+    return dx
+
+
+@_op("rangeclip::smoothness_normalized", mutates_args=(), device_types="cuda")
+def _op_smoothness_normalized(x: torch.Tensor, den_h: float, den_v: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(smoothness of F.normalize(x, dim=1), xhat, 1/|x|): model.py:332-333 on the decoder tail's output (decoder.py:114) with the
+    normalisation inside the operator, so that its backward is ONE kernel (rc_tv_normalize_bwd)."""
+    xhat, inv = normalize_rows_raw(x)
+    sums = tv_sums(xhat)
+    nan = torch.full((), float("nan"), device=x.device, dtype=torch.float64)
+    loss = ((sums[0] / den_h if den_h > 0 else nan) + (sums[1] / den_v if den_v > 0 else nan)).float().reshape(())
+    return loss, xhat, inv
+
+
+@_op_smoothness_normalized.register_fake
+def _(x, den_h, den_v):
+    return (torch.empty((), device=x.device, dtype=torch.float32), torch.empty(x.shape, device=x.device, dtype=torch.float32),
+            torch.empty(x.shape[0], x[0, 0].numel(), device=x.device, dtype=torch.float32))
+
+
+@_op("rangeclip::tv_normalize_bwd", mutates_args=(), device_types="cuda")
+def _op_tv_normalize_bwd(xhat: torch.Tensor, inv: torch.Tensor, scale: torch.Tensor, dtype_code: int) -> torch.Tensor:
+    return tv_normalize_backward(xhat, inv, scale, _CODE_DT[dtype_code])
+
+
+@_op_tv_normalize_bwd.register_fake
+def _(xhat, inv, scale, dtype_code):
+    return torch.empty(xhat.shape, device=xhat.device, dtype=_CODE_DT[dtype_code])
+
+
+def _smoothness_normalized_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1], output[2])
+    ctx.den = (inputs[1], inputs[2])
+    ctx.x_dtype = inputs[0].dtype
+    ctx.set_materialize_grads(False)
+
+
+def _smoothness_normalized_backward(ctx, g, _g_xhat, _g_inv):
+    if g is None:
+        return None, None, None
+    xhat, inv = ctx.saved_tensors
+    dh, dv = ctx.den
+    gf = g.float()
+    scale = torch.stack([gf / dh if dh > 0 else gf * 0, gf / dv if dv > 0 else gf * 0])
+    return torch.ops.rangeclip.tv_normalize_bwd(xhat, inv, scale, _DT_CODE[ctx.x_dtype]), None, None
+
+
+_op_smoothness_normalized.register_autograd(_smoothness_normalized_backward, setup_context=_smoothness_normalized_setup)
+
+
 @_op("rangeclip::normalize_rows", mutates_args=(), device_types="cuda")
 def _op_normalize_rows(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """(F.normalize(x, p=2, dim=1), per-pixel 1 / max(|x|, 1e-12)) of an NCHW tensor -- the decoder tail (decoder.py:114)."""
@@ -1126,6 +1184,13 @@ def smoothness(x: torch.Tensor, denominators=None) -> torch.Tensor:
     _need_cuda(x)
     dh, dv = tv_denominators(x.shape) if denominators is None else denominators
     return torch.ops.rangeclip.smoothness(x, float(dh), float(dv))
+
+
+def smoothness_normalized(x: torch.Tensor, denominators=None) -> torch.Tensor:
+    """``smoothness(F.normalize(x, dim=1), denominators)`` with a fused single-kernel backward (x NCHW f32 / bf16, W % 8 == 0)."""
+    _need_cuda(x)
+    dh, dv = tv_denominators(x.shape) if denominators is None else denominators
+    return torch.ops.rangeclip.smoothness_normalized(x, float(dh), float(dv))[0]
 
 
 def normalize_rows(x: torch.Tensor) -> torch.Tensor:

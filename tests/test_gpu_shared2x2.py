@@ -206,3 +206,34 @@ def test_normalize_rows_handover_between_pooling_and_loss():
 def _launches():
     from rangeclip_b200 import _lib
     return _lib.launch_count()
+
+
+@pytest.mark.parametrize("dtype,shape", [(torch.float32, (2, 96, 8, 16)), (torch.bfloat16, (1, 256, 12, 24)), (torch.bfloat16, (2, 64, 1, 8)),
+                                         (torch.float32, (1, 32, 5, 8))])
+def test_smoothness_normalized_matches_the_two_step_path(dtype, shape):
+    """smoothness(normalize(x)) with the fused backward (rc_tv_normalize_bwd) against PyTorch autograd of the same expression
+    (F.normalize + l1 means, model.py:332-334 / decoder.py:114), including repeated values (sign(0) = 0) and zero rows."""
+    from rangeclip_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g)
+    x[..., 1::2] = x[..., 0::2]                     # horizontally repeated pixels, as after a nearest x2 upsample (quirk Q8)
+    x[0, :, 0, 0] = 0
+    x = x.to(dtype)
+    B, D, H, W = shape
+    xr = x.float().clone().requires_grad_(True)
+    xh = torch.nn.functional.normalize(xr, p=2, dim=1)
+    dh, dv = float(B * D * H * (W - 1)), float(B * D * (H - 1) * W)
+    ref = (xh[..., :-1] - xh[..., 1:]).abs().sum() / dh
+    if H > 1:
+        ref = ref + (xh[:, :, :-1] - xh[:, :, 1:]).abs().sum() / dv
+    (3.0 * ref).backward()
+    xd = x.to(dev()).requires_grad_(True)
+    if H > 1:
+        out = ops.smoothness_normalized(xd)
+    else:
+        out = ops.smoothness_normalized(xd, denominators=(dh, 1.0))       # (H = 1: the vertical term is empty)
+    (3.0 * out).backward()
+    assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref)) + 1e-9
+    # the kernel's sign(0) = 0 is autograd's abs'(0) = 0; tolerance: fp32 path 1e-5, bf16 output 1e-2
+    err = float((xd.grad.float().cpu() - xr.grad).abs().max() / xr.grad.abs().max())
+    assert err < (1e-5 if dtype == torch.float32 else 1e-2), err
