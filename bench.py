@@ -762,6 +762,7 @@ def run_gpu(args):
               "pixel_accuracy_tk": fin["pixel_accuracy_tk"], "mIoU_t1": fin["mIoU_t1"], "mIoU_tk": fin["mIoU_tk"],
               "tensor_tflops": 2.0 * Ce * D * tot_pix / (float(tm) * 1e-3) / 1e12,
               "frac_of_burst_peak": 2.0 * Ce * D * tot_pix / (float(tm) * 1e-3) / 1e12 / pk["tf_burst"],
+              "frac_of_sustained_peak": 2.0 * Ce * D * tot_pix / (float(tm) * 1e-3) / 1e12 / pk["tf_sust"],
               "note": "78x64+8 synthetic maps, X = normalize(text[gt] + 0.3 randn) (two resident batches re-used), synonym chain on 10% of the ids; "
                       "fused tcgen05 top-5 + equivalence-aware histograms (one kernel per batch) + fold, one int64 all-reduce at the end"}
         assert fin["total_pixels"] == tot_pix
@@ -771,10 +772,12 @@ def run_gpu(args):
             xe, _ = pool_b[0]
             out = {}
             for kk in (5, 1):
+                # a kernel timed ALONE is compared with the burst peak: let the 0.3 s evaluation loop above drain out of the power window
+                torch.cuda.synchronize(); time.sleep(1.5)
                 t = timed(lambda: ops.eval_topk(xe, text_e, idx_map, kk, "bf16", t_bf16=tbe), 5, 2)
                 tf = 2.0 * Ce * D * B * HW / (t * 1e-3) / 1e12
                 out[f"top{kk}"] = {"ms": t, "value": B * HW / (t * 1e-3) / 1e6, "unit": "Mpix/s", "tflops": tf, "frac_of_burst_peak": tf / pk["tf_burst"]}
-            out["note"] = "eval_topk_umma_kernel (CTA-pair form) on one batch of 64 maps, K=1024, ids [B,k,HW] int64 written"
+            out["note"] = "eval_topk_umma_kernel (CTA-pair form) on one batch of 64 maps, K=1024, ids [B,k,HW] int64 written; 1.5 s idle before each timing (burst regime; the 5000-map loop above is the sustained one)"
             return out
         ev["kernel"] = section(eval_kernel_section)
 

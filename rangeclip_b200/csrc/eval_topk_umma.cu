@@ -181,8 +181,13 @@ eval_topk_umma_kernel(const __grid_constant__ CUtensorMap map_x,    // X [B][D][
   const int n_units = kPair ? (prm.n_tiles + 1) / 2 : prm.n_tiles;
   auto tile_of = [&](int u) -> int { return kPair ? 2 * u + (int)rank : u; };
   // the candidate set may have been built on the device (rc_contrast_build): its size is read here, by every role alike
+#if RC_TOPK_STATIC_K       // A/B only (tools/ab_topk.py): the set size as a launch parameter, as before rc_eval_topk_dyn_bf16 existed
+  const int Kv = prm.K;
+  const int n_blocks = prm.n_blocks;
+#else
   const int Kv = prm.k_dev != nullptr ? max(1, min(__ldg(prm.k_dev), prm.K)) : prm.K;
   const int n_blocks = prm.k_dev != nullptr ? (Kv + kNB - 1) / kNB : prm.n_blocks;
+#endif
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_t);
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
