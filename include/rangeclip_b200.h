@@ -157,6 +157,18 @@ int rc_infonce_bf16_dyn(const void* x, rc_dtype x_dtype, int B, int D, int64_t H
 /* The pre-pass alone: 1/|x_p| of the bf16-rounded rows (+ bf16 copy of an f32 x) into workspace. */
 int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW,
                        void* workspace, int64_t workspace_bytes, void* stream);
+/* f32 x [B][D][H][W] with W % 8 == 0: the same pre-pass AND the smoothness sums of rc_tv_fwd (model.py:332-334; ADDED to
+ * tv_sums[0] = sum |x[h][w+1] - x[h][w]|, tv_sums[1] = sum |x[h+1][w] - x[h][w]|) from ONE read of x; follow with
+ * rc_infonce_bf16(..., flags | RC_INFONCE_PREPASS_DONE) on the same workspace. */
+int rc_infonce_prepass_tv(const float* x, int B, int D, int H, int W, void* workspace,
+                          int64_t workspace_bytes, double* tv_sums, uint32_t* tv_codes, void* stream);
+/* tv_codes (nullable, [B][D][H][W/8] words) keeps the SIGNS of those differences, 4 bits per element: pixel j of an 8-pixel
+ * group at bits 16 (j & 1) + 4 (j >> 1) .. +3 = {sgn(x[h][w] - x[h][w+1]), sgn(x[h][w] - x[h+1][w])}, each a 2-bit
+ * two's-complement -1/0/+1 (an opaque format between these two entry points).
+ * rc_tv_bwd_codes is rc_tv_bwd_from computed from them instead of from x (the autograd of model.py:332-334 needs nothing
+ * else): dx_out (f32) = dx_scale[0] * dx_in (f32 | bf16, nullable) + scale[0] d(sum_w)/dx + scale[1] d(sum_h)/dx. */
+int rc_tv_bwd_codes(const uint32_t* codes, int64_t planes, int H, int W, const float* scale,
+                    const void* dx_in, rc_dtype dx_in_dtype, const float* dx_scale, float* dx_out, void* stream);
 
 /* Helpers used by both paths.
  * rc_text_prepare: rows of `text[idx[k]]` (idx nullable = identity; `text` has n_rows rows, an index outside [0, n_rows)

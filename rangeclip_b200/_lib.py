@@ -37,6 +37,8 @@ PROTOTYPES = {
     "rc_infonce_bf16_kblocks": [_vp, _i32, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _i64, _i32, _vp],
     "rc_infonce_prepass": [_vp, _i32, _i32, _i32, _i64, _vp, _i64, _vp],
+    "rc_infonce_prepass_tv": [_vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp],
+    "rc_tv_bwd_codes": [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp],
     "rc_text_prepare": [_vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "rc_weight_sum": [_vp, _vp, _i64, _vp, _vp],
     "rc_sample_weights": [_vp, _vp, _i32, _i64, _i64, _vp, _i32, _vp, _vp, _vp],

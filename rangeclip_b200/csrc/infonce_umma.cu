@@ -107,6 +107,130 @@ rownorm_kernel(const T* __restrict__ x, int B, int D, int64_t HW, __nv_bfloat16*
   }
 }
 
+// fp32 X: the same pre-pass AND the smoothness sums (tv.cu: sums[0] = sum |x[h][w+1] - x[h][w]|, sums[1] = sum |x[h+1][w] - x[h][w]|)
+// from ONE read of X.  A thread owns a strip of R rows x 8 pixels and walks the channels; per channel it loads its R rows plus the
+// row below (the only re-read: (R+1)/R of X, mostly L2 hits), takes the right-hand neighbour from the next lane (consecutive
+// lanes = consecutive 8-pixel groups of the same rows), rounds to bf16 for the copy and the norms, and keeps the TV terms on
+// the unrounded fp32 values as rc_tv_fwd does.  kCodes: the signs of those differences are kept as well -- 4 bits per element,
+// one 32-bit word per 8-pixel group: pixel j at bits 4j..4j+3, low pair sgn(x[h][w] - x[h][w+1]), high pair
+// sgn(x[h][w] - x[h+1][w]), each a 2-bit two's-complement -1 / 0 / +1 (0 past the last column / row) -- which is all the
+// smoothness BACKWARD needs (rc_tv_bwd_codes: 0.5 bytes per element read instead of x again).
+#ifndef RC_PREPASS_TV_UNROLL
+#define RC_PREPASS_TV_UNROLL 1
+#endif
+#ifndef RC_PREPASS_TV_BLOCKS
+#define RC_PREPASS_TV_BLOCKS 2
+#endif
+constexpr int kPrepassTvUnroll = RC_PREPASS_TV_UNROLL;
+// 2-bit two's-complement sgn(d0) at bit 0 and sgn(d1) at bit 16: the pair is compared as packed bf16 (two results per
+// instruction); scaling by 2^64 first keeps a denormal difference from rounding to zero (an overflow to +-inf keeps its sign)
+__device__ __forceinline__ uint32_t sgn_codes2(float d0, float d1) {
+  const float k = 18446744073709551616.f;
+  uint32_t pk, g, l;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(d1 * k), "f"(d0 * k));
+  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(g) : "r"(pk), "r"(0u));
+  asm("set.lt.u32.bf16x2 %0, %1, %2;" : "=r"(l) : "r"(pk), "r"(0u));
+  return ((g | l) & 0x00010001u) | (l & 0x00020002u);
+}
+
+template <int R, bool kCodes>
+__global__ void __launch_bounds__(256, RC_PREPASS_TV_BLOCKS)
+rownorm_tv_kernel(const float* __restrict__ x, int B, int D, int H, int W, __nv_bfloat16* __restrict__ xb,
+                  float* __restrict__ inv_norm, double* __restrict__ tv_sums, uint32_t* __restrict__ codes) {
+  const int gpr = W >> 3;                                   // 8-pixel groups per row
+  const int strips = (H + R - 1) / R;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t n = (int64_t)B * strips * gpr;
+  const int lane = threadIdx.x & 31;
+  double acc_h = 0.0, acc_v = 0.0;
+  for (int64_t u0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); u0 < n; u0 += (int64_t)gridDim.x * blockDim.x) {
+    const bool live = u0 + lane < n;                        // warp-uniform trip count: dead lanes shadow the last unit, store nothing
+    const int64_t u = live ? u0 + lane : n - 1;
+    const int gi = (int)(u % gpr);
+    const int64_t bs = u / gpr;
+    const int strip = (int)(bs % strips);
+    const int64_t b = bs / strips;
+    const int h0 = strip * R;
+    const int rows = min(R, H - h0);
+    const bool has_below = h0 + rows < H;
+    const bool has_right = gi + 1 < gpr;
+    const bool right_shfl = has_right && lane < 31;         // lane + 1 then holds group gi + 1 of the same rows
+    const int64_t off = b * (int64_t)D * HW + (int64_t)h0 * W + gi * 8;
+    const float* src = x + off;
+    __nv_bfloat16* dst = xb + off;
+    uint32_t* cdst = kCodes ? codes + (b * (int64_t)D * H + h0) * gpr + gi : nullptr;
+    float ss[R][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss[r][j] = 0.f;
+#pragma unroll kPrepassTvUnroll
+    for (int d = 0; d < D; ++d) {
+      const float* p = src + (int64_t)d * HW;
+      float v[R + 1][8];
+#pragma unroll
+      for (int r = 0; r <= R; ++r)
+        if (r < rows || (r == rows && has_below)) load8(p + (int64_t)r * W, v[r]);
+      float sh = 0.f, sv = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float right = __shfl_down_sync(0xffffffffu, v[r][0], 1);
+        if (r < rows) {
+          // a missing neighbour is replaced by the value itself: difference 0, sign code 0
+          if (!right_shfl) right = has_right ? __ldg(p + (int64_t)r * W + 8) : v[r][7];
+          const bool below = r + 1 < rows || has_below;
+          uint32_t pk[4];
+          float dh[8], dv[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            pk[i] = pack_bf16x2(v[r][2 * i], v[r][2 * i + 1]);                 // the tensor cores see the rounded value
+            ss[r][2 * i] = sqacc_bf16x2_lo(ss[r][2 * i], pk[i]);
+            ss[r][2 * i + 1] = sqacc_bf16x2_hi(ss[r][2 * i + 1], pk[i]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            dh[j] = v[r][j] - (j < 7 ? v[r][j + 1] : right);
+            dv[j] = below ? v[r][j] - v[r + 1][j] : 0.f;
+            sh += fabsf(dh[j]);
+            sv += fabsf(dv[j]);
+          }
+          if (live) *reinterpret_cast<uint4*>(dst + (int64_t)d * HW + (int64_t)r * W) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if (kCodes) {
+            // word layout: pixel 2i at bits 4i.., pixel 2i+1 at bits 16+4i..; +0 horizontal, +2 vertical
+            uint32_t word = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              word |= (sgn_codes2(dh[2 * i], dh[2 * i + 1]) << (4 * i)) | (sgn_codes2(dv[2 * i], dv[2 * i + 1]) << (4 * i + 2));
+            if (live) cdst[((int64_t)d * H + r) * gpr] = word;
+          }
+        }
+      }
+      if (live) { acc_h += (double)sh; acc_v += (double)sv; }
+    }
+    if (live) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (r < rows) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = 1.f / fmaxf(sqrtf(ss[r][j]), 1e-12f);
+          store8(inv_norm + b * HW + (int64_t)(h0 + r) * W + gi * 8, o);
+        }
+    }
+  }
+  acc_h = warp_sum(acc_h);
+  acc_v = warp_sum(acc_v);
+  __shared__ double red[2][8];
+  if (lane == 0) { red[0][threadIdx.x >> 5] = acc_h; red[1][threadIdx.x >> 5] = acc_v; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c = 0;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; c += red[1][i]; }
+    atomicAdd(&tv_sums[0], a);
+    atomicAdd(&tv_sums[1], c);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------
@@ -772,6 +896,33 @@ extern "C" int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D,
   int rcode = rc::check_sm100("rc_infonce_prepass");
   if (rcode) return rcode;
   return rc::infonce_prepass_impl(x, x_dtype, B, D, HW, workspace, workspace_bytes, (cudaStream_t)stream, &inv_norm, &xb);
+}
+
+#ifndef RC_PREPASS_TV_ROWS
+#define RC_PREPASS_TV_ROWS 4
+#endif
+// fp32 x [B][D][H][W], W % 8 == 0: the pre-pass of rc_infonce_bf16 (bf16 copy + 1/|x_p| into workspace, to be followed by
+// RC_INFONCE_PREPASS_DONE) and the smoothness sums of rc_tv_fwd (ADDED to tv_sums[0..1]) from a single read of x; tv_codes
+// (nullable, [B][D][H][W/8] words): the difference signs for rc_tv_bwd_codes.
+extern "C" int rc_infonce_prepass_tv(const float* x, int B, int D, int H, int W, void* workspace, int64_t workspace_bytes,
+                                     double* tv_sums, uint32_t* tv_codes, void* stream) {
+  using namespace rc;
+  RC_REQUIRE(x && workspace && tv_sums, "rc_infonce_prepass_tv: null pointer");
+  RC_REQUIRE(B >= 0 && D >= 1 && H >= 0 && W >= 0, "rc_infonce_prepass_tv: bad shape");
+  if (W % 8 != 0) return fail(RC_ERR_UNSUPPORTED, "rc_infonce_prepass_tv: W=%d must be a multiple of 8", W);
+  int rcode = check_sm100("rc_infonce_prepass_tv");
+  if (rcode) return rcode;
+  const int64_t HW = (int64_t)H * W;
+  float* inv_norm; __nv_bfloat16* xb;
+  if ((rcode = infonce_prepass_impl(x, RC_F32, B, D, HW, workspace, workspace_bytes, (cudaStream_t)-1, &inv_norm, &xb))) return rcode;
+  if (B == 0 || HW == 0) return RC_OK;
+  constexpr int R = RC_PREPASS_TV_ROWS;
+  const int64_t units = (int64_t)B * ((H + R - 1) / R) * (W / 8);
+  const int64_t blocks = (units + 255) / 256;
+  const int grid = (int)(blocks < (int64_t)num_sms() * 8 ? blocks : (int64_t)num_sms() * 8);
+  if (tv_codes != nullptr) rownorm_tv_kernel<R, true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, D, H, W, xb, inv_norm, tv_sums, tv_codes);
+  else rownorm_tv_kernel<R, false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, D, H, W, xb, inv_norm, tv_sums, nullptr);
+  return check_launch("rc_infonce_prepass_tv");
 }
 
 // rep = 1: rc_infonce_bf16; rep = 4: rc_infonce_bf16_rep4 (y, w are [B*HW][4])

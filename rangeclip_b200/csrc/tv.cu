@@ -483,6 +483,46 @@ static int tv_allow_smem(K kernel, size_t bytes, const char* what) {
   return RC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Smoothness backward from the difference signs the fused fp32 pre-pass kept (rc_infonce_prepass_tv: one word per 8-pixel
+// group, pixel j at bits 16 (j & 1) + 4 (j >> 1) .. +3 = {sgn(x[h][w] - x[h][w+1]), sgn(x[h][w] - x[h+1][w])} as 2-bit two's
+// complement):
+// dx = dx_scale * dx_in + sh * (c_h[w] - c_h[w-1]) + sv * (c_v[h] - c_v[h-1]) -- 0.5 bytes per element read instead of the
+// fp32 x (the same arithmetic as tv_bwd_vec_kernel up to the order of the +-sh / +-sv additions).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sext2(uint32_t w, int pos) { return ((int)(w << (30 - pos))) >> 30; }
+
+template <typename TI>
+__global__ void __launch_bounds__(256)
+tv_bwd_codes_kernel(const uint32_t* __restrict__ codes, int64_t planes, int H, int W, const float* __restrict__ scale,
+                    float* __restrict__ dx, const TI* __restrict__ dx_in, const float* __restrict__ dx_scale) {
+  const int gpr = W >> 3;
+  const int64_t n = planes * (int64_t)H * gpr;
+  const float sh = scale[0], sv = scale[1];
+  const float ds = (dx_scale != nullptr) ? dx_scale[0] : 1.f;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x) {
+    const int gi = (int)(g % gpr);
+    const int h = (int)((g / gpr) % H);
+    const uint32_t cw = __ldg(codes + g);
+    const uint32_t lw = gi > 0 ? __ldg(codes + g - 1) : 0u;
+    const uint32_t aw = h > 0 ? __ldg(codes + g - gpr) : 0u;
+    float e[8], o[8];
+    if (dx_in != nullptr) load8(dx_in + g * 8, e);
+    int prev = sext2(lw, 28);               // pixel 7 of the group to the left
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int pos = 16 * (j & 1) + 4 * (j >> 1);
+      const int ch = sext2(cw, pos);
+      const int a = ch - prev;
+      prev = ch;
+      const int b = sext2(cw, pos + 2) - sext2(aw, pos + 2);
+      const float t = fmaf(sv, (float)b, sh * (float)a);
+      o[j] = dx_in != nullptr ? fmaf(ds, e[j], t) : t;
+    }
+    store8(dx + g * 8, o);
+  }
+}
+
 }  // namespace rc
 
 extern "C" int rc_tv_fwd(const void* x, rc_dtype x_dtype, int64_t planes, int H, int W, double* sums, void* stream) {
@@ -579,4 +619,24 @@ extern "C" int rc_tv_bwd_from(const void* x, rc_dtype x_dtype, int64_t planes, i
                               const void* dx_in, rc_dtype dx_in_dtype, const float* dx_scale, void* dx_out, void* stream) {
   RC_REQUIRE(dx_in != nullptr, "rc_tv_bwd_from: null dx_in");
   return tv_bwd_impl(x, x_dtype, planes, H, W, scale, dx_out, dx_in, dx_in_dtype, dx_scale, stream, "rc_tv_bwd_from");
+}
+
+extern "C" int rc_tv_bwd_codes(const uint32_t* codes, int64_t planes, int H, int W, const float* scale, const void* dx_in,
+                               rc_dtype dx_in_dtype, const float* dx_scale, float* dx_out, void* stream) {
+  using bf16 = __nv_bfloat16;
+  RC_REQUIRE(codes && scale && dx_out, "rc_tv_bwd_codes: null pointer");
+  RC_REQUIRE(planes >= 0 && H >= 1 && W >= 1, "rc_tv_bwd_codes: bad shape");
+  if (W % 8 != 0) return rc::fail(RC_ERR_UNSUPPORTED, "rc_tv_bwd_codes: W=%d must be a multiple of 8", W);
+  RC_REQUIRE((reinterpret_cast<uintptr_t>(dx_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx_in) & 15) == 0,
+             "rc_tv_bwd_codes: dx_in / dx_out must be 16-byte aligned");
+  if (planes == 0) return RC_OK;
+  const int64_t n = planes * (int64_t)H * (W / 8);
+  const int64_t nb = (n + 255) / 256, cap = (int64_t)rc::num_sms() * 16;
+  const int grid = (int)(nb < cap ? nb : cap);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dx_in != nullptr && dx_in_dtype == RC_BF16)
+    rc::tv_bwd_codes_kernel<bf16><<<grid, 256, 0, s>>>(codes, planes, H, W, scale, dx_out, (const bf16*)dx_in, dx_scale);
+  else
+    rc::tv_bwd_codes_kernel<float><<<grid, 256, 0, s>>>(codes, planes, H, W, scale, dx_out, (const float*)dx_in, dx_scale);
+  return rc::check_launch("rc_tv_bwd_codes");
 }

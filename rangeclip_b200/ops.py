@@ -179,7 +179,8 @@ def contrast_build(counts: torch.Tensor, sim_off: Optional[torch.Tensor], sim_it
 def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch.Tensor, inv_tau: float,
                 need_dx: bool, need_dt: bool, precision: str = "auto",
                 grad_scale: Optional[torch.Tensor] = None, t_bf16=None, rep: int = 1, keep_bf16: bool = False,
-                flags: int = 0, k_dev: Optional[torch.Tensor] = None, log_tau_dev: Optional[torch.Tensor] = None):
+                flags: int = 0, k_dev: Optional[torch.Tensor] = None, log_tau_dev: Optional[torch.Tensor] = None,
+                fuse_tv: bool = False):
     """One fused pass: returns dict(loss_sum, w_sum (double[1] tensors), lse, dx, dt, dlogtau).
     loss = loss_sum / w_sum; dx/dt/dlogtau are gradients of that mean loss times grad_scale.
     rep = 4: every row of x is the embedding shared by a 2x2 block of pixels (decoder.py:113, Q8);
@@ -187,8 +188,12 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
     keep_bf16: leave the tensor-core path's dx in bf16 whatever x's dtype (the autograd wrappers widen and scale it
     in one pass at backward time); flags: extra RC_INFONCE_* bits for rc_infonce_bf16 (e.g. RC_INFONCE_TS_KERNEL).
     k_dev / log_tau_dev (device int32[>=1] / float[1]): the sync-free form (rc_infonce_bf16_dyn) -- the number of valid rows of
-    t_norm and log(tau) are read by the kernel from device memory; ``inv_tau`` is ignored; CTA-pair kernel shapes only."""
+    t_norm and log(tau) are read by the kernel from device memory; ``inv_tau`` is ignored; CTA-pair kernel shapes only.
+    fuse_tv: the caller also wants tv_sums(x); where the launch has a pre-pass over x anyway (fp32 NCHW x on the tensor-core
+    path, W % 8 == 0) the sums come out of that pass (rc_infonce_prepass_tv) as ``tv_sums`` -- and with need_dx the difference
+    signs for tv_backward_codes as ``tv_codes`` --, else both keys are None."""
     _need_cuda(x, t_norm, y, w)
+    tv_hw = tuple(x.shape[2:]) if (fuse_tv and x.dim() == 4 and x.dtype == torch.float32 and x.shape[3] % 8 == 0) else None
     x, B, D, HW = _emb3(x)
     K = t_norm.shape[0]
     dev = x.device
@@ -215,7 +220,7 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
         if grad_scale is not None:
             dlt = dlt * grad_scale.detach().reshape(()).to(device=dev, dtype=torch.float64)
         return dict(loss_sum=r["loss"] * r["w_sum"], w_sum=r["w_sum"], dlogtau=dlt, lse=r["lse"], dx=dx, dt=None,
-                    precision="bf16-kblocked")
+                    precision="bf16-kblocked", tv_sums=None)
     dt_on_tc = need_dt and need_dx and D in (256, 512)       # tensor-core dText: pair kernel + split-K GEMM
     if precision == "auto":
         precision = "bf16" if (bf16_path_supported(D, HW, K) and (not need_dt or dt_on_tc)) else "fp32"
@@ -252,6 +257,16 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
         ws_bytes = int((L.rc_infonce_workspace_bytes_dt if need_dt else L.rc_infonce_workspace_bytes)(B, D, HW, K, xdt))
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         dxb = torch.empty(B, D, HW, device=dev, dtype=torch.bfloat16) if need_dx else None
+        tv = tv_codes = None
+        if tv_hw is not None and M > 0:
+            # fp32 x: the bf16 copy, the row norms, the smoothness sums and (for the backward) the signs of the differences,
+            # 4 bits per element, from one read of x
+            tv = torch.zeros(2, device=dev, dtype=torch.float64)
+            if need_dx:
+                tv_codes = torch.empty(B, D, int(tv_hw[0]), int(tv_hw[1]) // 8, device=dev, dtype=torch.int32)
+            check(L.rc_infonce_prepass_tv(_p(x), B, D, int(tv_hw[0]), int(tv_hw[1]), _p(ws), ws_bytes, _p(tv), _p(tv_codes), st),
+                  "rc_infonce_prepass_tv")
+            flags = int(flags) | RC_INFONCE_PREPASS_DONE
         if log_tau_dev is not None:
             if need_dt or D not in (256, 512):
                 raise RuntimeError("infonce: the device-parameter form needs D in (256, 512) and no dText")
@@ -264,7 +279,8 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
             dx = None
             if dxb is not None:
                 dx = dxb.view(x.shape) if (x.dtype == torch.bfloat16 or keep_bf16) else scale_to(dxb.view(x.shape), x.dtype)
-            return dict(loss_sum=acc[0], w_sum=acc[1], dlogtau=acc[2], lse=lse, dx=dx, dt=None, precision=precision)
+            return dict(loss_sum=acc[0], w_sum=acc[1], dlogtau=acc[2], lse=lse, dx=dx, dt=None, precision=precision, tv_sums=tv,
+                        tv_codes=tv_codes)
         entry = L.rc_infonce_bf16 if rep == 1 else L.rc_infonce_bf16_rep4
         check(entry(_p(x), xdt, B, D, HW, _p(tb), _p(ttb), K, _p(y), _p(w), float(inv_tau), _p(lse),
                     acc[0:].data_ptr(), acc[1:].data_ptr(),
@@ -276,10 +292,11 @@ def infonce_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor, w: torch
             dx = dxb.view(x.shape) if (x.dtype == torch.bfloat16 or keep_bf16) else scale_to(dxb.view(x.shape), x.dtype)
     else:
         raise RuntimeError(f"infonce: unknown precision {precision!r}")
-    return dict(loss_sum=acc[0], w_sum=acc[1], dlogtau=acc[2], lse=lse, dx=dx, dt=dt, precision=precision)
+    return dict(loss_sum=acc[0], w_sum=acc[1], dlogtau=acc[2], lse=lse, dx=dx, dt=dt, precision=precision,
+                tv_sums=tv if precision == "bf16" else None, tv_codes=tv_codes if precision == "bf16" else None)
 
 
-RC_INFONCE_KEEP_WEIGHT, RC_INFONCE_LSE_GIVEN, RC_INFONCE_TS_KERNEL, RC_INFONCE_ACCUMULATE_DX = 2, 4, 8, 16
+RC_INFONCE_PREPASS_DONE, RC_INFONCE_KEEP_WEIGHT, RC_INFONCE_LSE_GIVEN, RC_INFONCE_TS_KERNEL, RC_INFONCE_ACCUMULATE_DX = 1, 2, 4, 8, 16
 
 
 def kblocked_supported(D: int, HW: int) -> bool:
@@ -426,6 +443,24 @@ def tv_backward(x: torch.Tensor, scale: torch.Tensor, dx: Optional[torch.Tensor]
     ds = None if dx_scale is None else dx_scale.detach().reshape(1).to(device=x.device, dtype=torch.float32)
     check(_lib.lib().rc_tv_bwd_from(_p(x), _dt(x), B * D, H, W, _p(scale), _p(dx), _dt(dx), _p(ds), _p(out), _stream(x)),
           "rc_tv_bwd_from")
+    return out
+
+
+def tv_backward_codes(codes: torch.Tensor, scale: torch.Tensor, dx: Optional[torch.Tensor] = None,
+                      dx_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tv_backward of an fp32 x from the difference signs kept by the fused pre-pass (``codes`` int32 [B, D, H, W/8],
+    rc_infonce_prepass_tv) instead of from x: a FRESH fp32 [B, D, H, W] tensor (rc_tv_bwd_codes)."""
+    _need_cuda(codes, scale, dx)
+    B, D, H, W8 = codes.shape
+    out = torch.empty(B, D, H, W8 * 8, device=codes.device, dtype=torch.float32)
+    scale = scale.detach().to(device=codes.device, dtype=torch.float32).contiguous()
+    if dx is not None:
+        dx = dx.contiguous()
+        if dx.numel() != out.numel():
+            raise RuntimeError("tv_backward_codes: dx must have x's shape")
+    ds = None if (dx is None or dx_scale is None) else dx_scale.detach().reshape(1).to(device=codes.device, dtype=torch.float32)
+    check(_lib.lib().rc_tv_bwd_codes(_p(codes), B * D, H, W8 * 8, _p(scale), _p(dx), _dt(dx) if dx is not None else _lib.RC_F32, _p(ds),
+                                     _p(out), _stream(codes)), "rc_tv_bwd_codes")
     return out
 
 
@@ -701,16 +736,21 @@ def _op_infonce(x: torch.Tensor, t_norm: torch.Tensor, log_tau: torch.Tensor, y:
     the same fused launch (single pass over x).  dx stays in the kernel's dtype (bf16 on the tensor-core path).
     ``k_dev`` (int32 device tensor, first entry = valid rows of t_norm): the sync-free form -- the kernel reads the row
     count and log(tau) from device memory, nothing is read back here."""
+    return _infonce_forward(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, rep, t_bf16, tt_bf16, k_dev, False)[:4]
+
+
+def _infonce_forward(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, rep, t_bf16, tt_bf16, k_dev, fuse_tv):
+    """Body of rangeclip::infonce (and of the InfoNCE half of rangeclip::pixel_losses): (loss, dx, dt, dlogtau, tv_sums | None, tv_codes | None)."""
     tb = (t_bf16, tt_bf16) if (t_bf16 is not None and tt_bf16 is not None) else None
     if k_dev is not None:
         r = infonce_raw(x, t_norm, y, w, 0.0, need_grad, False, "bf16", t_bf16=tb, rep=rep, keep_bf16=True, k_dev=k_dev,
-                        log_tau_dev=log_tau)
+                        log_tau_dev=log_tau, fuse_tv=fuse_tv)
     else:
         inv_tau = float(torch.exp(-log_tau.detach().float()))          # one scalar sync, as .item() in the reference
-        r = infonce_raw(x, t_norm, y, w, inv_tau, need_grad, need_dt, precision, t_bf16=tb, rep=rep, keep_bf16=True)
+        r = infonce_raw(x, t_norm, y, w, inv_tau, need_grad, need_dt, precision, t_bf16=tb, rep=rep, keep_bf16=True, fuse_tv=fuse_tv)
     dx, dt = r["dx"], r["dt"]
     return (_mean_loss(r), dx if dx is not None else _empty(x), dt if dt is not None else _empty(t_norm),
-            r["dlogtau"].float().reshape(()))
+            r["dlogtau"].float().reshape(()), r.get("tv_sums"), r.get("tv_codes"))
 
 
 @_op_infonce.register_fake
@@ -768,15 +808,20 @@ _op_infonce.register_autograd(_infonce_backward, setup_context=_infonce_setup)
 @_op("rangeclip::pixel_losses", mutates_args=(), device_types="cuda")
 def _op_pixel_losses(x: torch.Tensor, t_norm: torch.Tensor, log_tau: torch.Tensor, y: torch.Tensor, w: torch.Tensor,
                      need_grad: bool, need_dt: bool, precision: str, t_bf16: Optional[torch.Tensor],
-                     tt_bf16: Optional[torch.Tensor], k_dev: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    """(text InfoNCE, smoothness, dx_text, dt, dlogtau) of the SAME pixel embeddings: one autograd node for both terms, so
-    that the backward is a single pass (model.py:272-291, 332-334 and their autograd)."""
-    loss, dx, dt, dlt = _op_infonce._init_fn(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, 1, t_bf16, tt_bf16, k_dev)
-    sums = tv_sums(x)
+                     tt_bf16: Optional[torch.Tensor], k_dev: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(text InfoNCE, smoothness, dx_text, dt, dlogtau, tv_codes) of the SAME pixel embeddings: one autograd node for both
+    terms, so that the backward is a single pass (model.py:272-291, 332-334 and their autograd).  tv_codes: the difference
+    signs the backward needs, when the fp32 pre-pass produced them with the sums (else empty)."""
+    loss, dx, dt, dlt, sums, codes = _infonce_forward(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, 1, t_bf16, tt_bf16,
+                                                      k_dev, True)
+    if sums is None:
+        sums = tv_sums(x)
+    if codes is None:
+        codes = torch.empty(0, device=x.device, dtype=torch.int32)
     dh, dv = tv_denominators(x.shape)
     nan = torch.full((), float("nan"), device=x.device, dtype=torch.float64)
     smooth = ((sums[0] / dh if dh > 0 else nan) + (sums[1] / dv if dv > 0 else nan)).float().reshape(())
-    return loss, smooth, dx, dt, dlt
+    return loss, smooth, dx, dt, dlt, codes
 
 
 @_op_pixel_losses.register_fake
@@ -784,18 +829,20 @@ def _(x, t_norm, log_tau, y, w, need_grad, need_dt, precision, t_bf16, tt_bf16, 
     plan = "bf16" if k_dev is not None else _infonce_plan(x, t_norm.shape[0], need_dt, precision, 1)
     dx_dtype = torch.bfloat16 if plan == "bf16" else x.dtype
     f32 = dict(device=x.device, dtype=torch.float32)
+    fused = (plan == "bf16" and need_grad and x.dim() == 4 and x.dtype == torch.float32 and x.shape[3] % 8 == 0 and x.numel() > 0)
     return (torch.empty((), **f32), torch.empty((), **f32),
             torch.empty(x.shape, device=x.device, dtype=dx_dtype) if need_grad else _empty(x),
-            torch.empty(t_norm.shape, **f32) if need_dt else _empty(t_norm), torch.empty((), **f32))
+            torch.empty(t_norm.shape, **f32) if need_dt else _empty(t_norm), torch.empty((), **f32),
+            torch.empty(tuple(x.shape[:3]) + (x.shape[3] // 8,) if fused else (0,), device=x.device, dtype=torch.int32))
 
 
 def _pixel_losses_setup(ctx, inputs, output):
-    ctx.save_for_backward(inputs[0], output[2], output[3], output[4])
+    ctx.save_for_backward(inputs[0], output[2], output[3], output[4], output[5])
     ctx.set_materialize_grads(False)         # see _infonce_setup
 
 
 def _pixel_losses_backward(ctx, g_text, g_smooth, *_unused):
-    x, dx, dt, dlt = ctx.saved_tensors
+    x, dx, dt, dlt, codes = ctx.saved_tensors
     need = ctx.needs_input_grad
     gx = None
     if g_text is None and g_smooth is None:
@@ -809,7 +856,10 @@ def _pixel_losses_backward(ctx, g_text, g_smooth, *_unused):
         gs = g_smooth.float()
         scale = torch.stack([gs / dh if dh > 0 else gs * 0, gs / dv if dv > 0 else gs * 0])
         # dX = g_text * dX_text (from the forward launch) + g_smooth * d(TV)/dX in ONE pass, into a fresh tensor
-        gx = torch.ops.rangeclip.tv_bwd(x, scale, dx, g_text.float())
+        if codes.numel():        # fp32 x: from the difference signs of the fused pre-pass, x is not read again
+            gx = torch.ops.rangeclip.tv_bwd_codes(codes, scale, dx, g_text.float())
+        else:
+            gx = torch.ops.rangeclip.tv_bwd(x, scale, dx, g_text.float())
     gt = dt * g_text if need[1] else None
     gl = (dlt * g_text).reshape(()) if need[2] else None
     return (gx, gt, gl) + (None,) * 8
@@ -886,6 +936,16 @@ def _op_tv_bwd(x: torch.Tensor, scale: torch.Tensor, dx: Optional[torch.Tensor],
 @_op_tv_bwd.register_fake
 def _(x, scale, dx, dx_scale):
     return torch.empty_like(x)
+
+
+@_op("rangeclip::tv_bwd_codes", mutates_args=(), device_types="cuda")
+def _op_tv_bwd_codes(codes: torch.Tensor, scale: torch.Tensor, dx: Optional[torch.Tensor], dx_scale: Optional[torch.Tensor]) -> torch.Tensor:
+    return tv_backward_codes(codes, scale, dx if (dx is not None and dx.numel()) else None, dx_scale)
+
+
+@_op_tv_bwd_codes.register_fake
+def _(codes, scale, dx, dx_scale):
+    return torch.empty(tuple(codes.shape[:3]) + (codes.shape[3] * 8,), device=codes.device, dtype=torch.float32)
 
 
 @_op("rangeclip::smoothness", mutates_args=(), device_types="cuda")

@@ -117,3 +117,47 @@ def test_fused_topk_histograms_with_an_odd_tile_count():
     ids = ops.eval_topk_hist(x, t, torch.arange(K, device=dev()), k, gt, E, cmap, hist, cnt)
     hist2, cnt2 = ops.eval_hist(gt, ids, E, cmap)
     assert torch.equal(hist, hist2) and torch.equal(cnt, cnt2) and int(cnt[2]) == B * H * W
+
+
+@pytest.mark.parametrize("B,D,H,W", [(2, 256, 6, 32), (1, 512, 7, 24), (3, 128, 1, 8), (1, 256, 9, 264), (2, 384, 4, 8), (1, 256, 5, 512)])
+def test_fused_prepass_smoothness_sums(B, D, H, W):
+    """fp32 X: rc_infonce_prepass_tv (bf16 copy + row norms + smoothness sums from one read) against the separate pre-pass and
+    rc_tv_fwd -- strips that end before a multiple of 4 rows, rows narrower / wider than a warp, units that do not fill a warp."""
+    from rangeclip_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(B * 1000 + H * 10 + W)
+    x = torch.randn(B, D, H, W, device=dev, generator=g)
+    x[:, :, :, ::3] = x[:, :, :, 1::3][:, :, :, : x[:, :, :, ::3].shape[3]] if W > 8 else x[:, :, :, ::3]     # some exact zeros in the differences
+    K = 40
+    t = torch.nn.functional.normalize(torch.randn(K, D, device=dev, generator=g), dim=1)
+    y = torch.randint(0, K, (B * H * W,), device=dev, generator=g, dtype=torch.int32)
+    w = torch.rand(B * H * W, device=dev, generator=g)
+    a = ops.infonce_raw(x, t, y, w, 1 / 0.07, True, False, "bf16", fuse_tv=True)
+    b = ops.infonce_raw(x, t, y, w, 1 / 0.07, True, False, "bf16", fuse_tv=False)
+    assert a["tv_sums"] is not None and b["tv_sums"] is None
+    assert torch.equal(a["lse"], b["lse"]) and torch.allclose(a["dx"], b["dx"], rtol=1e-2, atol=1e-7)
+    assert abs(float(a["loss_sum"]) - float(b["loss_sum"])) <= 1e-9 * abs(float(b["loss_sum"]))
+    ref = ops.tv_sums(x)
+    xd = x.double()
+    exact = torch.stack([(xd[..., 1:] - xd[..., :-1]).abs().sum(), (xd[:, :, 1:] - xd[:, :, :-1]).abs().sum()])
+    assert torch.allclose(a["tv_sums"], exact, rtol=2e-6, atol=1e-9), (a["tv_sums"], exact)
+    assert torch.allclose(ref, exact, rtol=2e-6, atol=1e-9)
+    # and through the operator: same losses, same gradient as the two-pass form
+    xg = x.clone().requires_grad_(True)
+    lt = torch.log(torch.tensor(0.07, device=dev))
+    loss, smooth = ops.pixel_losses(xg, t, lt, y, w, "bf16")
+    dh, dv = ops.tv_denominators(x.shape)
+    want = (exact[0] / dh if dh > 0 else float("nan")) + (exact[1] / dv if dv > 0 else float("nan"))
+    if dh > 0 and dv > 0:
+        assert abs(float(smooth) - float(want)) <= 2e-6 * abs(float(want))
+        (loss + 3.0 * smooth).backward()
+        # the backward runs from the 4-bit difference signs kept by the pre-pass; the two-pass form reads x again
+        scale = torch.tensor([3.0 / dh, 3.0 / dv], device=dev)
+        one = torch.ones((), device=dev)
+        want_g = ops.tv_backward(x, scale, b["dx"].view(x.shape), one)
+        got_g = ops.tv_backward_codes(a["tv_codes"], scale, b["dx"].view(x.shape), one)
+        assert torch.allclose(got_g, want_g, rtol=1e-6, atol=1e-10), float((got_g - want_g).abs().max())
+        # (the operator's own launch may round single dX values to the neighbouring bf16 -- the weight sum is an atomic double
+        # sum, exp(-log(tau)) is not 1 / tau to the last bit -- and the smoothness term may cancel most of such a value)
+        ulp = 2.0 ** -7 * float(b["dx"].abs().max())
+        assert torch.allclose(xg.grad, want_g, rtol=1e-2, atol=ulp), float((xg.grad - want_g).abs().max())
