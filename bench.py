@@ -642,7 +642,7 @@ def run_gpu(args):
                 torch.autograd.grad(total, params, allow_unused=True)
                 return info
             np.random.seed(0); torch.manual_seed(0)
-            t = timed(f, max(3, args.steps // 4), 2)
+            t = timed(f, max(5, args.steps // 2), 2)
             info = f()
             out[name] = {"ms_per_step": t, "value": world * M / (t * 1e-3) / 1e6, "unit": UNIT, "total_loss": info["total_loss"],
                          "text": info["text_contrastive_loss"], "image": info["image_contrastive_loss"], "smooth": info["smoothness_loss"]}
@@ -650,7 +650,8 @@ def run_gpu(args):
             torch.cuda.empty_cache()
         out["fp32_over_bf16"] = out["fp32"]["ms_per_step"] / out["bf16"]["ms_per_step"]
         out["note"] = ("compute_loss(W_text=1, W_image=0.5, W_smooth=200)+backward, one object per image (n=B), X on the device; "
-                       "fp32 X = what the reference decoder emits (decoder.py:115)")
+                       "fp32 X = what the reference decoder emits (decoder.py:115): one pre-pass gives the bf16 copy, the smoothness sums "
+                       "and the 4-bit difference signs (rc_infonce_prepass_tv), the backward runs from those signs (rc_tv_bwd_codes)")
         return out
     hybrid = None if args.no_hybrid else section(hybrid_section)
 

@@ -118,23 +118,26 @@ rownorm_kernel(const T* __restrict__ x, int B, int D, int64_t HW, __nv_bfloat16*
 #ifndef RC_PREPASS_TV_UNROLL
 #define RC_PREPASS_TV_UNROLL 1
 #endif
+#ifndef RC_PREPASS_TV_THREADS
+#define RC_PREPASS_TV_THREADS 128
+#endif
 #ifndef RC_PREPASS_TV_BLOCKS
-#define RC_PREPASS_TV_BLOCKS 2
+#define RC_PREPASS_TV_BLOCKS 4
 #endif
 constexpr int kPrepassTvUnroll = RC_PREPASS_TV_UNROLL;
-// 2-bit two's-complement sgn(d0) at bit 0 and sgn(d1) at bit 16: the pair is compared as packed bf16 (two results per
-// instruction); scaling by 2^64 first keeps a denormal difference from rounding to zero (an overflow to +-inf keeps its sign)
-__device__ __forceinline__ uint32_t sgn_codes2(float d0, float d1) {
-  const float k = 18446744073709551616.f;
-  uint32_t pk, g, l;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(d1 * k), "f"(d0 * k));
-  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(g) : "r"(pk), "r"(0u));
-  asm("set.lt.u32.bf16x2 %0, %1, %2;" : "=r"(l) : "r"(pk), "r"(0u));
-  return ((g | l) & 0x00010001u) | (l & 0x00020002u);
+constexpr int kPrepassTvThreads = RC_PREPASS_TV_THREADS;
+// acc + (2-bit two's-complement sgn(d)) * unit, in FLOAT arithmetic: d * 2^64 is normal for every non-zero d (an overflow
+// to +-inf keeps its sign), so sat(+-d * 2^64 * 2^100) is exactly 1 or 0; code = pos + 3 neg.  Four pixels x (horizontal,
+// vertical) codes = 16 bits per accumulator: exact in a float.  (Packed bf16 compares of the differences -- set.gt/lt.bf16x2,
+// two results per instruction -- and plain integer selects were measured too: the pass takes the same 2.7-2.8 ms with each.)
+__device__ __forceinline__ float add_sgn_code(float acc, float d, float unit) {
+  const float dd = d * 18446744073709551616.f;
+  const float pos = __saturatef(dd * 1.2676506002282294e30f), neg = __saturatef(dd * -1.2676506002282294e30f);
+  return fmaf(neg, 3.f * unit, fmaf(pos, unit, acc));
 }
 
 template <int R, bool kCodes>
-__global__ void __launch_bounds__(256, RC_PREPASS_TV_BLOCKS)
+__global__ void __launch_bounds__(kPrepassTvThreads, RC_PREPASS_TV_BLOCKS)
 rownorm_tv_kernel(const float* __restrict__ x, int B, int D, int H, int W, __nv_bfloat16* __restrict__ xb,
                   float* __restrict__ inv_norm, double* __restrict__ tv_sums, uint32_t* __restrict__ codes) {
   const int gpr = W >> 3;                                   // 8-pixel groups per row
@@ -196,12 +199,14 @@ rownorm_tv_kernel(const float* __restrict__ x, int B, int D, int H, int W, __nv_
           }
           if (live) *reinterpret_cast<uint4*>(dst + (int64_t)d * HW + (int64_t)r * W) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           if (kCodes) {
-            // word layout: pixel 2i at bits 4i.., pixel 2i+1 at bits 16+4i..; +0 horizontal, +2 vertical
-            uint32_t word = 0;
+            // word layout: pixel j at bits 4j..4j+3; +0 horizontal, +2 vertical
+            float lo = 0.f, hi = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              word |= (sgn_codes2(dh[2 * i], dh[2 * i + 1]) << (4 * i)) | (sgn_codes2(dv[2 * i], dv[2 * i + 1]) << (4 * i + 2));
-            if (live) cdst[((int64_t)d * H + r) * gpr] = word;
+            for (int j = 0; j < 4; ++j) {
+              lo = add_sgn_code(add_sgn_code(lo, dh[j], (float)(1 << (4 * j))), dv[j], (float)(4 << (4 * j)));
+              hi = add_sgn_code(add_sgn_code(hi, dh[j + 4], (float)(1 << (4 * j))), dv[j + 4], (float)(4 << (4 * j)));
+            }
+            if (live) cdst[((int64_t)d * H + r) * gpr] = __float2uint_rz(lo) | (__float2uint_rz(hi) << 16);
           }
         }
       }
@@ -220,12 +225,12 @@ rownorm_tv_kernel(const float* __restrict__ x, int B, int D, int H, int W, __nv_
   }
   acc_h = warp_sum(acc_h);
   acc_v = warp_sum(acc_v);
-  __shared__ double red[2][8];
+  __shared__ double red[2][kPrepassTvThreads / 32];
   if (lane == 0) { red[0][threadIdx.x >> 5] = acc_h; red[1][threadIdx.x >> 5] = acc_v; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double a = 0, c = 0;
-    for (int i = 0; i < 8; ++i) { a += red[0][i]; c += red[1][i]; }
+    for (int i = 0; i < kPrepassTvThreads / 32; ++i) { a += red[0][i]; c += red[1][i]; }
     atomicAdd(&tv_sums[0], a);
     atomicAdd(&tv_sums[1], c);
   }
@@ -918,10 +923,11 @@ extern "C" int rc_infonce_prepass_tv(const float* x, int B, int D, int H, int W,
   if (B == 0 || HW == 0) return RC_OK;
   constexpr int R = RC_PREPASS_TV_ROWS;
   const int64_t units = (int64_t)B * ((H + R - 1) / R) * (W / 8);
-  const int64_t blocks = (units + 255) / 256;
-  const int grid = (int)(blocks < (int64_t)num_sms() * 8 ? blocks : (int64_t)num_sms() * 8);
-  if (tv_codes != nullptr) rownorm_tv_kernel<R, true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, D, H, W, xb, inv_norm, tv_sums, tv_codes);
-  else rownorm_tv_kernel<R, false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, D, H, W, xb, inv_norm, tv_sums, nullptr);
+  constexpr int T = kPrepassTvThreads;
+  const int64_t blocks = (units + T - 1) / T;
+  const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
+  if (tv_codes != nullptr) rownorm_tv_kernel<R, true><<<grid, T, 0, (cudaStream_t)stream>>>(x, B, D, H, W, xb, inv_norm, tv_sums, tv_codes);
+  else rownorm_tv_kernel<R, false><<<grid, T, 0, (cudaStream_t)stream>>>(x, B, D, H, W, xb, inv_norm, tv_sums, nullptr);
   return check_launch("rc_infonce_prepass_tv");
 }
 

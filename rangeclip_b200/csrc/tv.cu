@@ -485,8 +485,7 @@ static int tv_allow_smem(K kernel, size_t bytes, const char* what) {
 
 // ------------------------------------------------------------------------------------------------
 // Smoothness backward from the difference signs the fused fp32 pre-pass kept (rc_infonce_prepass_tv: one word per 8-pixel
-// group, pixel j at bits 16 (j & 1) + 4 (j >> 1) .. +3 = {sgn(x[h][w] - x[h][w+1]), sgn(x[h][w] - x[h+1][w])} as 2-bit two's
-// complement):
+// group, pixel j at bits 4j .. 4j+3 = {sgn(x[h][w] - x[h][w+1]), sgn(x[h][w] - x[h+1][w])} as 2-bit two's complement):
 // dx = dx_scale * dx_in + sh * (c_h[w] - c_h[w-1]) + sv * (c_v[h] - c_v[h-1]) -- 0.5 bytes per element read instead of the
 // fp32 x (the same arithmetic as tv_bwd_vec_kernel up to the order of the +-sh / +-sv additions).
 // ------------------------------------------------------------------------------------------------
@@ -511,7 +510,7 @@ tv_bwd_codes_kernel(const uint32_t* __restrict__ codes, int64_t planes, int H, i
     int prev = sext2(lw, 28);               // pixel 7 of the group to the left
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int pos = 16 * (j & 1) + 4 * (j >> 1);
+      const int pos = 4 * j;
       const int ch = sext2(cw, pos);
       const int a = ch - prev;
       prev = ch;
