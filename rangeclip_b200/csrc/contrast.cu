@@ -147,9 +147,13 @@ contrast_build_kernel(const int32_t* __restrict__ counts, int C, const int32_t* 
   for (int c = threadIdx.x; c < C; c += kThreads) state[c] = (c >= first_label && counts[c] > 0) ? kPresent : 0;
   __syncthreads();
   if (sim_off != nullptr && n_curriculum > 0) {
-    for (int c = threadIdx.x; c < C; c += kThreads) {
+    // a warp per present label, its lanes along the similarity list (coalesced; one thread per label walks a list of a
+    // hundred entries as a chain of dependent loads)
+    const int lane = threadIdx.x & 31;
+    for (int c = threadIdx.x >> 5; c < C; c += kThreads / 32) {
       if (!(state[c] & kPresent)) continue;
-      for (int j = sim_off[c]; j < sim_off[c + 1]; ++j) {
+      const int end = sim_off[c + 1];
+      for (int j = sim_off[c] + lane; j < end; j += 32) {
         const int d = sim_items[j];
         if (d >= 0 && d < C && !(state[d] & kPresent)) state[d] = kCand;      // benign race: every writer stores kCand
       }
