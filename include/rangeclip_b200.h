@@ -163,8 +163,8 @@ int rc_infonce_prepass(const void* x, rc_dtype x_dtype, int B, int D, int64_t HW
 int rc_infonce_prepass_tv(const float* x, int B, int D, int H, int W, void* workspace,
                           int64_t workspace_bytes, double* tv_sums, uint32_t* tv_codes, void* stream);
 /* tv_codes (nullable, [B][D][H][W/8] words) keeps the SIGNS of those differences, 4 bits per element: pixel j of an 8-pixel
- * group at bits 4j .. 4j+3 = {sgn(x[h][w] - x[h][w+1]), sgn(x[h][w] - x[h+1][w])}, each a 2-bit
- * two's-complement -1/0/+1 (an opaque format between these two entry points).
+ * group at bits 4j .. 4j+3 = {sgn(x[h][w] - x[h][w+1]) + 1, sgn(x[h][w] - x[h+1][w]) + 1}, two bits each
+ * (an opaque format between these two entry points).
  * rc_tv_bwd_codes is rc_tv_bwd_from computed from them instead of from x (the autograd of model.py:332-334 needs nothing
  * else): dx_out (f32) = dx_scale[0] * dx_in (f32 | bf16, nullable) + scale[0] d(sum_w)/dx + scale[1] d(sum_h)/dx. */
 int rc_tv_bwd_codes(const uint32_t* codes, int64_t planes, int H, int W, const float* scale,

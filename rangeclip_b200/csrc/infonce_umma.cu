@@ -126,14 +126,14 @@ rownorm_kernel(const T* __restrict__ x, int B, int D, int64_t HW, __nv_bfloat16*
 #endif
 constexpr int kPrepassTvUnroll = RC_PREPASS_TV_UNROLL;
 constexpr int kPrepassTvThreads = RC_PREPASS_TV_THREADS;
-// acc + (2-bit two's-complement sgn(d)) * unit, in FLOAT arithmetic: d * 2^64 is normal for every non-zero d (an overflow
-// to +-inf keeps its sign), so sat(+-d * 2^64 * 2^100) is exactly 1 or 0; code = pos + 3 neg.  Four pixels x (horizontal,
-// vertical) codes = 16 bits per accumulator: exact in a float.  (Packed bf16 compares of the differences -- set.gt/lt.bf16x2,
-// two results per instruction -- and plain integer selects were measured too: the pass takes the same 2.7-2.8 ms with each.)
+// acc + (sgn(d) + 1) * unit in FLOAT arithmetic, three FMA-pipe instructions per difference: d * 2^64 is normal for every
+// non-zero d (an overflow to +-inf keeps its sign), so sat(d * 2^64 * 2^100 + 0.5) is exactly 0, 0.5 or 1 = (sgn(d) + 1) / 2.
+// Four pixels x (horizontal, vertical) codes = 16 bits per accumulator: exact in a float.  (Packed bf16 compares of the
+// differences -- set.gt/lt.bf16x2, two results per instruction --, integer selects and a two's-complement code from two
+// saturating multiplies were measured too: 2.7-2.8 ms each, the pass is bound by its instruction count.)
 __device__ __forceinline__ float add_sgn_code(float acc, float d, float unit) {
-  const float dd = d * 18446744073709551616.f;
-  const float pos = __saturatef(dd * 1.2676506002282294e30f), neg = __saturatef(dd * -1.2676506002282294e30f);
-  return fmaf(neg, 3.f * unit, fmaf(pos, unit, acc));
+  const float q = __saturatef(fmaf(d * 18446744073709551616.f, 1.2676506002282294e30f, 0.5f));
+  return fmaf(q, 2.f * unit, acc);
 }
 
 template <int R, bool kCodes>

@@ -485,40 +485,45 @@ static int tv_allow_smem(K kernel, size_t bytes, const char* what) {
 
 // ------------------------------------------------------------------------------------------------
 // Smoothness backward from the difference signs the fused fp32 pre-pass kept (rc_infonce_prepass_tv: one word per 8-pixel
-// group, pixel j at bits 4j .. 4j+3 = {sgn(x[h][w] - x[h][w+1]), sgn(x[h][w] - x[h+1][w])} as 2-bit two's complement):
+// group, pixel j at bits 4j .. 4j+3 = {sgn(x[h][w] - x[h][w+1]) + 1, sgn(x[h][w] - x[h+1][w]) + 1}, two bits each):
 // dx = dx_scale * dx_in + sh * (c_h[w] - c_h[w-1]) + sv * (c_v[h] - c_v[h-1]) -- 0.5 bytes per element read instead of the
 // fp32 x (the same arithmetic as tv_bwd_vec_kernel up to the order of the +-sh / +-sv additions).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sext2(uint32_t w, int pos) { return ((int)(w << (30 - pos))) >> 30; }
-
 template <typename TI>
 __global__ void __launch_bounds__(256)
 tv_bwd_codes_kernel(const uint32_t* __restrict__ codes, int64_t planes, int H, int W, const float* __restrict__ scale,
                     float* __restrict__ dx, const TI* __restrict__ dx_in, const float* __restrict__ dx_scale) {
   const int gpr = W >> 3;
-  const int64_t n = planes * (int64_t)H * gpr;
+  const int64_t rows = planes * (int64_t)H;
   const float sh = scale[0], sv = scale[1];
   const float ds = (dx_scale != nullptr) ? dx_scale[0] : 1.f;
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x) {
-    const int gi = (int)(g % gpr);
-    const int h = (int)((g / gpr) % H);
-    const uint32_t cw = __ldg(codes + g);
-    const uint32_t lw = gi > 0 ? __ldg(codes + g - 1) : 0u;
-    const uint32_t aw = h > 0 ? __ldg(codes + g - gpr) : 0u;
-    float e[8], o[8];
-    if (dx_in != nullptr) load8(dx_in + g * 8, e);
-    int prev = sext2(lw, 28);               // pixel 7 of the group to the left
+  constexpr uint32_t kLow2 = 0x33333333u, kNoDiff = 0x55555555u, kBias = 0x22222222u;
+  // a warp per image row, lanes along its 8-pixel groups; the row's h is carried along the grid stride (a 64-bit
+  // division per group made the first version of this kernel instruction bound)
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5), stride = (int64_t)gridDim.x * wpb;
+  const int h_step = (int)(stride % H);
+  int h = (int)(row0 % H);
+  for (int64_t row = row0; row < rows; row += stride, h = (h + h_step >= H) ? h + h_step - H : h + h_step) {
+    for (int gi = lane; gi < gpr; gi += 32) {
+      const int64_t g = row * gpr + gi;
+      const uint32_t cw = __ldg(codes + g);
+      const uint32_t lw = gi > 0 ? __ldg(codes + g - 1) : kNoDiff;          // no neighbour: code 1 = "no difference"
+      const uint32_t aw = h > 0 ? __ldg(codes + g - gpr) : kNoDiff;
+      float e[8], o[8];
+      if (dx_in != nullptr) load8(dx_in + g * 8, e);
+      // all eight pixels at once, one nibble each: (code - code of the previous pixel / the row above) + 2, in 0 .. 4
+      const uint32_t hd = (cw & kLow2) + kBias - (((cw << 4) | ((lw >> 28) & 3u)) & kLow2);
+      const uint32_t vd = ((cw >> 2) & kLow2) + kBias - ((aw >> 2) & kLow2);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int pos = 4 * j;
-      const int ch = sext2(cw, pos);
-      const int a = ch - prev;
-      prev = ch;
-      const int b = sext2(cw, pos + 2) - sext2(aw, pos + 2);
-      const float t = fmaf(sv, (float)b, sh * (float)a);
-      o[j] = dx_in != nullptr ? fmaf(ds, e[j], t) : t;
+      for (int j = 0; j < 8; ++j) {
+        const float a = (float)((hd >> (4 * j)) & 15u) - 2.f;
+        const float b = (float)((vd >> (4 * j)) & 15u) - 2.f;
+        const float t = fmaf(sv, b, sh * a);
+        o[j] = dx_in != nullptr ? fmaf(ds, e[j], t) : t;
+      }
+      store8(dx + g * 8, o);
     }
-    store8(dx + g * 8, o);
   }
 }
 
@@ -629,8 +634,7 @@ extern "C" int rc_tv_bwd_codes(const uint32_t* codes, int64_t planes, int H, int
   RC_REQUIRE((reinterpret_cast<uintptr_t>(dx_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx_in) & 15) == 0,
              "rc_tv_bwd_codes: dx_in / dx_out must be 16-byte aligned");
   if (planes == 0) return RC_OK;
-  const int64_t n = planes * (int64_t)H * (W / 8);
-  const int64_t nb = (n + 255) / 256, cap = (int64_t)rc::num_sms() * 16;
+  const int64_t nb = (planes * (int64_t)H + 7) / 8, cap = (int64_t)rc::num_sms() * 16;      // a warp per row, 8 warps per block
   const int grid = (int)(nb < cap ? nb : cap);
   cudaStream_t s = (cudaStream_t)stream;
   if (dx_in != nullptr && dx_in_dtype == RC_BF16)
