@@ -500,12 +500,15 @@ tv_bwd_codes_kernel(const uint32_t* __restrict__ codes, int64_t planes, int H, i
   constexpr uint32_t kLow2 = 0x33333333u, kNoDiff = 0x55555555u, kBias = 0x22222222u;
   // a warp per image row, lanes along its 8-pixel groups; the row's h is carried along the grid stride (a 64-bit
   // division per group made the first version of this kernel instruction bound)
+  // (rows narrower than a warp: 32 / gpr rows per warp when that divides)
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  const int64_t row0 = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5), stride = (int64_t)gridDim.x * wpb;
+  const int rpw = (gpr < 32 && 32 % gpr == 0) ? 32 / gpr : 1;
+  const int lane_gi = rpw > 1 ? lane % gpr : lane, lane_row = rpw > 1 ? lane / gpr : 0;
+  const int64_t row0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * rpw + lane_row, stride = (int64_t)gridDim.x * wpb * rpw;
   const int h_step = (int)(stride % H);
   int h = (int)(row0 % H);
   for (int64_t row = row0; row < rows; row += stride, h = (h + h_step >= H) ? h + h_step - H : h + h_step) {
-    for (int gi = lane; gi < gpr; gi += 32) {
+    for (int gi = lane_gi; gi < gpr; gi += 32) {
       const int64_t g = row * gpr + gi;
       const uint32_t cw = __ldg(codes + g);
       const uint32_t lw = gi > 0 ? __ldg(codes + g - 1) : kNoDiff;          // no neighbour: code 1 = "no difference"
@@ -634,7 +637,8 @@ extern "C" int rc_tv_bwd_codes(const uint32_t* codes, int64_t planes, int H, int
   RC_REQUIRE((reinterpret_cast<uintptr_t>(dx_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx_in) & 15) == 0,
              "rc_tv_bwd_codes: dx_in / dx_out must be 16-byte aligned");
   if (planes == 0) return RC_OK;
-  const int64_t nb = (planes * (int64_t)H + 7) / 8, cap = (int64_t)rc::num_sms() * 16;      // a warp per row, 8 warps per block
+  const int gpr = W / 8, rpw = (gpr < 32 && 32 % gpr == 0) ? 32 / gpr : 1;                   // a warp per row (or per 32 / gpr rows), 8 warps per block
+  const int64_t nb = (planes * (int64_t)H + 8 * rpw - 1) / (8 * rpw), cap = (int64_t)rc::num_sms() * 16;
   const int grid = (int)(nb < cap ? nb : cap);
   cudaStream_t s = (cudaStream_t)stream;
   if (dx_in != nullptr && dx_in_dtype == RC_BF16)
