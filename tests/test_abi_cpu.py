@@ -148,3 +148,21 @@ def test_device_contrast_builder_oracle_properties():
     assert Kc == 40 and flags_c == 2 and n_dis_c == 15 and set(present.tolist()) <= set(con_c[:Kc].tolist())
     _, _, (Ko, flags_o, _, n_dis_o) = O.contrast_build_device(counts, off, items, 20, 10, 16, 99)
     assert Ko == 16 and flags_o & 1 and n_dis_o == 0
+
+
+def test_fp32_single_read_entry_points_validate_on_cpu():
+    """rc_infonce_prepass_tv / rc_tv_bwd_codes reject null pointers and rows that are not whole 8-pixel groups before any launch."""
+    import ctypes
+    from rangeclip_b200 import _lib, ops
+    L = _lib.lib()
+    buf = (ctypes.c_uint8 * 4096)()
+    p = ctypes.addressof(buf)
+    assert L.rc_infonce_prepass_tv(None, 1, 4, 2, 8, None, 0, None, None, None) == -1
+    assert b"null pointer" in L.rc_last_error()
+    assert L.rc_infonce_prepass_tv(p, 1, 4, 2, 12, p, 4096, p, None, None) != 0
+    assert b"multiple of 8" in L.rc_last_error()
+    assert L.rc_tv_bwd_codes(None, 1, 2, 8, None, None, _lib.RC_BF16, None, None, None) == -1
+    assert L.rc_tv_bwd_codes(p, 1, 2, 12, p, None, _lib.RC_BF16, None, p, None) != 0
+    assert b"multiple of 8" in L.rc_last_error()
+    with pytest.raises(RuntimeError):                                      # CPU tensors
+        ops.tv_backward_codes(torch.zeros(1, 1, 2, 1, dtype=torch.int32), torch.zeros(2))
