@@ -323,7 +323,10 @@ def infonce_kblocked_raw(x: torch.Tensor, t_norm: torch.Tensor, y: torch.Tensor,
     xdt = _dt(x)
     ws_bytes = int(L.rc_infonce_workspace_bytes(B, D, HW, block, xdt))
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-    check(L.rc_infonce_prepass(_p(x), xdt, B, D, HW, _p(ws), ws_bytes, st), "rc_infonce_prepass")    # once for all launches
+    if x.dtype != torch.bfloat16:
+        # the bf16 copy of an fp32 x, once for all launches (a bf16 x needs no pre-pass: the CTA-pair kernel, the only one
+        # these shapes reach, takes the row norms from its operand tiles)
+        check(L.rc_infonce_prepass(_p(x), xdt, B, D, HW, _p(ws), ws_bytes, st), "rc_infonce_prepass")
     starts = list(range(0, K, block))
     nb = len(starts)
     if B == 1 and HW % 256 == 0 and block == 256:
